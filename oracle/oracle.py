@@ -1,0 +1,67 @@
+"""Python wrapper of the C oracle (oracle/wsi_oracle.c).
+
+TEST INFRASTRUCTURE: imported only by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package wsi_b200
+never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+from wsi_b200.backend.capi import ModelBuffers, WsiModelDesc
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libwsi_oracle.so")
+_LIB = None
+
+
+def build(force=False):
+    """Compile the C restatement with the system gcc (oracle/Makefile)."""
+    src = os.path.join(_HERE, "wsi_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "-s"])
+    return _SO
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_SO):
+            build()
+        _LIB = C.CDLL(_SO)
+        _LIB.wsi_oracle_run.argtypes = [C.POINTER(WsiModelDesc), C.c_int64, C.c_int64, C.c_int]
+        _LIB.wsi_oracle_run.restype = C.c_int
+    return _LIB
+
+
+class OracleRun:
+    """Result of one oracle simulation (host numpy arrays)."""
+
+    def __init__(self, buffers):
+        self.buffers = buffers
+        self.fm = buffers.fm
+        self.out_probe = buffers.array("out_probe")
+        self.out_mb = buffers.array("out_mb") if buffers.record_mb else None
+        self.mb_sums = buffers.array("mb_sums")
+        self.mb_count = buffers.array("mb_count")
+        self.node_flags = buffers.array("node_flags")
+        self.groups = {g: buffers.array("group_" + g) for g in self.fm.groups}
+
+
+def run(fm, probes=(), t0=0, t1=None, record_mb=False, n_threads=0, rec_t0=None, rec_T=None):
+    """Simulate timesteps [t0, t1) of flat model ``fm`` on the CPU oracle."""
+    t1 = fm.T if t1 is None else t1
+    buf = ModelBuffers(
+        fm,
+        device="numpy",
+        probes=probes,
+        rec_t0=t0 if rec_t0 is None else rec_t0,
+        rec_T=(t1 - t0) if rec_T is None else rec_T,
+        record_mb=record_mb,
+    )
+    rc = lib().wsi_oracle_run(C.byref(buf.desc), int(t0), int(t1), int(n_threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle returned {rc}")
+    return OracleRun(buf)

@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""Generate golden input/output fixtures by RUNNING THE REFERENCE (WSIMOD).
+
+Only runs in the build container, where the reference is mounted read-only at
+/root/reference.  For each scenario it
+
+  1. builds the model with the reference's own classes,
+  2. flattens the *initial* state with wsi_b200's flattener (duck-typed),
+  3. replays ``Model.run``'s loop (wsimod/orchestration/model.py:993-1176) through
+     the reference's public methods, capturing per step every arc VQIP, every
+     node's (in, ds, out) mass-balance terms and all tank / surface / pool state,
+  4. writes ``tests/golden/<name>.npz`` (flat model + reference outputs).
+
+The GPU box has no /root/reference: tests read only the committed .npz files.
+
+    PYTHONHASHSEED=0 PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py [names...]
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+import tempfile
+import zipfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+sys.dont_write_bytecode = True
+
+import pandas as pd  # noqa: E402
+import yaml  # noqa: E402
+from wsimod.core import constants  # noqa: E402
+from wsimod.orchestration.model import Model, to_datetime  # noqa: E402
+
+from wsi_b200.backend import flatten as F  # noqa: E402
+from wsi_b200.backend import layout as L  # noqa: E402
+from wsi_b200.backend.probes import SURF_OUT, SURF_POOLS, SURF_STATE  # noqa: E402
+
+
+# ------------------------------------------------------------------ harness
+def set_default_pollutants():
+    constants.set_default_pollutants()
+    constants.FLOAT_ACCURACY = 1e-11
+
+
+def vq(d):
+    return [d["volume"]] + [d[p] for p in constants.POLLUTANTS]
+
+
+def run_reference(model, dates):
+    """Replay Model.run (model.py:993-1176) and capture everything per step."""
+    nodes = list(model.nodes.values())
+    arcs = list(model.arcs.values())
+    lands = [n for n in nodes if n.__class__.__name__ == "Land"]
+    surfs = [s for n in lands for s in n.surfaces]
+    stores = [n for n in nodes if n.__class__.__name__ in F.STORE_TYPES]
+    sewers = [n for n in nodes if n.__class__.__name__ == "Sewer"]
+    V = len(constants.POLLUTANTS) + 1
+    T = len(dates)
+    out = {
+        "flows": np.zeros((T, len(arcs), V)),
+        "mb": np.zeros((T, len(nodes), 3, V)),
+        "land_tanks": np.zeros((T, len(lands), 3 * V)),
+        "surf_storage": np.zeros((T, len(surfs), V)),
+        "surf_out": np.zeros((T, len(surfs), len(SURF_OUT))),
+        "surf_state": np.zeros((T, len(surfs), len(SURF_STATE) + 10)),
+        "tank_storage": np.zeros((T, len(stores), V)),
+        "sewer_storage": np.zeros((T, len(sewers), V)),
+        "sewer_active": np.zeros((T, len(sewers), V)),
+    }
+    advisories = io.StringIO()
+    with contextlib.redirect_stdout(advisories):
+        for t, date in enumerate(dates):
+            for node in model.nodelist:
+                node.t = date
+                node.monthyear = date.to_period("M")
+            for item in model.orchestration:
+                for node_type, function in item.items():
+                    for node in model.nodes_type.get(node_type, {}).values():
+                        getattr(node, function)()
+            for name in model.river_discharge_order:
+                model.nodes[name].distribute()
+            for arc in arcs:
+                arc.arc_mass_balance()
+            for i, node in enumerate(nodes):
+                in_, ds_, out_ = node.node_mass_balance()
+                out["mb"][t, i, 0] = vq(in_)
+                out["mb"][t, i, 1] = vq(ds_)
+                out["mb"][t, i, 2] = vq(out_)
+            for i, arc in enumerate(arcs):
+                out["flows"][t, i] = vq(arc.vqip_out)
+            for i, n in enumerate(lands):
+                out["land_tanks"][t, i] = (
+                    vq(n.surface_runoff.storage) + vq(n.subsurface_runoff.storage) + vq(n.percolation.storage)
+                )
+            for i, s in enumerate(surfs):
+                out["surf_storage"][t, i] = vq(s.storage)
+                g = lambda a: getattr(s, a)["volume"] if hasattr(s, a) else 0.0  # noqa: E731
+                out["surf_out"][t, i] = [
+                    g("percolation"), g("subsurface_flow"), g("infiltration_excess"), g("evaporation"),
+                    g("precipitation"), getattr(s, "tank_recharge", 0.0),
+                ]
+                st = [
+                    getattr(s, "et0_coefficient", 0.0),
+                    (-1.0 if s.days_after_sow is None else s.days_after_sow) if hasattr(s, "days_after_sow") else 0.0,
+                    getattr(s, "crop_cover", 0.0), getattr(s, "ground_cover", 0.0), getattr(s, "crop_factor", 0.0),
+                ]
+                if hasattr(s, "nutrient_pool"):
+                    npool = s.nutrient_pool
+                    for pool in (npool.fast_pool, npool.humus_pool, npool.dissolved_inorganic_pool,
+                                 npool.dissolved_organic_pool, npool.adsorbed_inorganic_pool):
+                        st += [pool.storage["N"], pool.storage["P"]]
+                else:
+                    st += [0.0] * 10
+                out["surf_state"][t, i] = st
+            for i, n in enumerate(stores):
+                out["tank_storage"][t, i] = vq(n.tank.storage)
+            for i, n in enumerate(sewers):
+                out["sewer_storage"][t, i] = vq(n.sewer_tank.storage)
+                out["sewer_active"][t, i] = vq(n.sewer_tank.active_storage)
+            for node in nodes:
+                node.end_timestep()
+            for arc in arcs:
+                arc.end_timestep()
+    out["n_advisories"] = np.array([len(advisories.getvalue().splitlines())])
+    return out
+
+
+def flatten_ref(model, dates):
+    return F.flatten(
+        model, dates, constants.POLLUTANTS, constants.ADDITIVE_POLLUTANTS,
+        constants.NON_ADDITIVE_POLLUTANTS, constants.FLOAT_ACCURACY,
+    )
+
+
+def merge_replicas(fms):
+    """Stack R=1 flat models of identical structure into one R=len(fms) model."""
+    base = fms[0]
+    groups = {}
+    for g in base.groups:
+        cols = [fm.groups[g] for fm in fms]  # each [nf, n_obj]
+        groups[g] = np.ascontiguousarray(np.stack(cols, axis=2).reshape(cols[0].shape[0], -1))
+    kw = dict(base.__dict__)
+    kw.update(groups=groups, R=len(fms))
+    return F.FlatModel(**kw)
+
+
+def save(name, fm, ref, note):
+    d = fm.to_npz_dict()
+    for k, v in ref.items():
+        d["ref_" + k] = v
+    d["meta_note"] = np.array(note)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **d)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+# ------------------------------------------------------------------ scenarios
+def oxford_land_inputs():
+    df = pd.read_csv(os.path.join(REF, "docs/demo/data/processed/timeseries_data.csv"))
+    df = df.loc[df.site == "oxford_land"].copy()
+    df.loc[df.variable == "precipitation", "value"] *= constants.MM_TO_M
+    df.date = pd.to_datetime(df.date)
+    dates = sorted(df.date.drop_duplicates())
+    return df.set_index(["variable", "date"]).value.to_dict(), [pd.Timestamp(x) for x in dates]
+
+
+def build_quickstart(land_inputs, load_pol="phosphate"):
+    """docs/demo/scripts/quickstart_demo.py:84-190."""
+    sewer = {"type_": "Sewer", "capacity": 0.04, "name": "my_sewer"}
+    surface1 = {"type_": "ImperviousSurface", "surface": "urban", "area": 10, "pollutant_load": {load_pol: 1e-7}}
+    surface2 = {"type_": "PerviousSurface", "surface": "rural", "area": 100, "depth": 0.5,
+                "pollutant_load": {load_pol: 1e-7}}
+    land = {"type_": "Land", "data_input_dict": land_inputs, "surfaces": [surface1, surface2], "name": "my_land"}
+    gw = {"type_": "Groundwater", "area": 100, "capacity": 100, "name": "my_groundwater"}
+    node = {"type_": "Node", "name": "my_river"}
+    waste = {"type_": "Waste", "name": "my_outlet"}
+    arcs = [
+        ("urban_drainage", "my_land", "my_sewer"),
+        ("percolation", "my_land", "my_groundwater"),
+        ("runoff", "my_land", "my_river"),
+        ("storm_outflow", "my_sewer", "my_river"),
+        ("baseflow", "my_groundwater", "my_river"),
+        ("catchment_outflow", "my_river", "my_outlet"),
+    ]
+    m = Model()
+    m.add_nodes([sewer, land, gw, node, waste])
+    m.add_arcs([{"type_": "Arc", "name": a, "in_port": i, "out_port": o} for a, i, o in arcs])
+    return m
+
+
+def scenario_quickstart(T=500):
+    set_default_pollutants()
+    land_inputs, dates = oxford_land_inputs()
+    dates = dates[:T]
+    m = build_quickstart(land_inputs)
+    fm = flatten_ref(m, dates)
+    ref = run_reference(m, dates)
+    save("quickstart", fm, ref, "quickstart_demo.py model, default pollutants, first %d days" % T)
+
+
+def scenario_quickstart_simple(T=300):
+    constants.set_simple_pollutants()
+    constants.FLOAT_ACCURACY = 1e-11
+    land_inputs, dates = oxford_land_inputs()
+    dates = dates[200 : 200 + T]
+    m = build_quickstart(land_inputs)
+    fm = flatten_ref(m, dates)
+    ref = run_reference(m, dates)
+    save("quickstart_simple", fm, ref, "quickstart model with set_simple_pollutants (P=2)")
+    set_default_pollutants()
+
+
+def scenario_fixture3607(T=730):
+    """tests/test_model_data.zip reduced to the nodes on the GPU path (Land with 9
+    surfaces incl. 7 GrowingSurface + GardenSurface, storm Sewer, Groundwater, River
+    with biochemistry, junction, 2 Waste); csv date regime (to_datetime)."""
+    set_default_pollutants()
+    tmp = tempfile.mkdtemp()
+    zipfile.ZipFile(os.path.join(REF, "tests/test_model_data.zip")).extractall(tmp)
+    cfg = yaml.safe_load(open(os.path.join(tmp, "config.yml")))
+    keep = {k: v for k, v in cfg["nodes"].items()
+            if v["type_"] in ("Land", "Sewer", "Groundwater", "River", "Node", "Waste") and "foul" not in k}
+    cfg["nodes"] = keep
+    cfg["arcs"] = {k: a for k, a in cfg["arcs"].items() if a["in_port"] in keep and a["out_port"] in keep}
+    cfg["dates"] = cfg["dates"][:T]
+    cfg.pop("extensions", None)
+    yaml.safe_dump(cfg, open(os.path.join(tmp, "reduced.yml"), "w"))
+    m = Model()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.load(tmp, config_name="reduced.yml")
+    dates = m.dates
+    fm = flatten_ref(m, dates)
+    ref = run_reference(m, dates)
+    save("fixture3607", fm, ref, "reference test fixture 3607 reduced to supported nodes, %d days, csv dates" % T)
+
+
+def synthetic_forcing(dates, rng):
+    """SURVEY 8d config 2 forcing generator."""
+    doy = np.array([d.dayofyear for d in dates], dtype=float)
+    temperature = 10 + 8 * np.sin(2 * np.pi * (doy - 110) / 365) + rng.normal(0, 2, len(dates))
+    et0 = np.maximum(2e-4, 1e-3 * (1.5 + 1.2 * np.sin(2 * np.pi * (doy - 100) / 365)))
+    wet = rng.random(len(dates)) < 0.45
+    precipitation = wet * rng.gamma(0.8, 6e-3, len(dates))
+    d = {}
+    for t, date in enumerate(dates):
+        d[("precipitation", date)] = float(precipitation[t])
+        d[("et0", date)] = float(et0[t])
+        d[("temperature", date)] = float(temperature[t])
+    return d
+
+
+GROWING_TEMPLATE = dict(  # "Spring wheat" of the 3607 fixture
+    surface_coefficient=0.05, field_capacity=0.3577337861061096, wilting_point=0.14462512731552124,
+    crop_factor_stages=[0.0, 0.0, 0.3, 0.3, 1.15, 1.15, 0.325, 0.0, 0.0],
+    crop_factor_stage_dates=[0, 73, 74, 121, 166, 196, 274, 275, 366],
+    ihacres_p=10.0, rooting_depth=1.25, percolation_coefficient=0.25, total_porosity=0.4,
+    ET_depletion_factor=0.55, sowing_day=74, harvest_day=274, infiltration_capacity=0.06,
+)
+
+
+def config2_member(forcing, dates, scale, area_scale):
+    """One {Land(Impervious, Pervious, Growing) -> Sewer, Groundwater, Node -> Waste}
+    catchment of SURVEY 8d config 2; ``scale`` perturbs parameters."""
+    months = sorted({(d.year, d.month) for d in dates})
+    monthly = {}
+    for var in L.DEP_COLS:
+        for (y, mth) in months:
+            monthly[(var, pd.Timestamp(year=y, month=mth, day=1).to_period("M"))] = 1e-7
+    a_imp, a_perv, a_grow = 2.0e4 * area_scale, 5.0e4 * area_scale, 2.0e5 * area_scale
+    vol = a_grow * 1.25 * 0.4 * 0.9
+    init = {"do": 0.01, "org-phosphorus": vol * 1e-4, "phosphate": vol * 1e-4, "ammonia": vol * 5e-5,
+            "solids": vol * 1e-2, "bod": vol * 1e-3, "cod": vol * 2e-2, "ph": 7.0, "temperature": 11.0,
+            "nitrate": vol * 4e-3, "nitrite": vol * 2e-5, "org-nitrogen": vol * 5e-3, "volume": vol}
+    soil = {"org-phosphorus": vol * 5e-3, "phosphate": vol * 5e-3, "ammonia": 0.0, "nitrate": vol,
+            "nitrite": 0.0, "org-nitrogen": vol, "volume": vol}
+    grow = dict(GROWING_TEMPLATE)
+    grow.update(
+        type_="GrowingSurface", surface="crop", area=a_grow, pollutant_load={}, initial_storage=init,
+        initial_soil_storage=soil, data_input_dict=monthly,
+        decays={"ammonia": {"constant": 0.1 * scale, "exponent": 1.005},
+                "nitrite": {"constant": 0.05 * scale, "exponent": 1.005}},
+        field_capacity=GROWING_TEMPLATE["field_capacity"] * min(scale, 1.1),
+        infiltration_capacity=0.06 * scale, rooting_depth=1.25 * scale,
+    )
+    imp = {"type_": "ImperviousSurface", "surface": "urban", "area": a_imp, "pore_depth": 0.004 * scale,
+           "pollutant_load": {"phosphate": 1e-10, "solids": 1e-5, "bod": 1e-5, "ammonia": 1e-9,
+                              "temperature": 13.0, "do": 0.005, "ph": 7.5}}
+    perv = {"type_": "PerviousSurface", "surface": "rural", "area": a_perv, "depth": 0.5 * scale,
+            "pollutant_load": {"phosphate": 1e-7}, "initial_storage": a_perv * 0.5 * scale * 0.4 * 0.5,
+            "infiltration_capacity": 0.05}
+    land = {"type_": "Land", "name": "land", "data_input_dict": forcing, "surfaces": [imp, perv, grow],
+            "surface_residence_time": 2.0 * scale, "subsurface_residence_time": 10.0,
+            "percolation_residence_time": 30.0 / scale}
+    sewer = {"type_": "Sewer", "name": "sewer", "capacity": a_imp * 0.01 * scale}
+    gw = {"type_": "Groundwater", "name": "gw", "area": a_perv + a_grow, "capacity": (a_perv + a_grow) * 0.5,
+          "residence_time": 100.0 * scale, "initial_storage": (a_perv + a_grow) * 0.01}
+    node = {"type_": "Node", "name": "river"}
+    waste = {"type_": "Waste", "name": "outlet"}
+    arcs = [("land-sewer", "land", "sewer"), ("land-gw", "land", "gw"), ("land-river", "land", "river"),
+            ("sewer-river", "sewer", "river"), ("gw-river", "gw", "river"), ("river-outlet", "river", "outlet")]
+    m = Model()
+    m.add_nodes([sewer, land, gw, node, waste])
+    m.add_arcs([{"type_": "Arc", "name": a, "in_port": i, "out_port": o} for a, i, o in arcs])
+    return m
+
+
+def scenario_config2(T=730, R=4):
+    set_default_pollutants()
+    dates = [pd.Timestamp("2000-01-01") + pd.Timedelta(days=i) for i in range(T)]
+    rng = np.random.default_rng(20261019)
+    forcing = synthetic_forcing(dates, rng)
+    scales = [1.0, 0.85, 1.2, 0.95][:R]
+    areas = [1.0, 0.3, 4.0, 12.0][:R]
+    fms, refs = [], []
+    for s, a in zip(scales, areas):
+        m = config2_member(forcing, dates, s, a)
+        fms.append(flatten_ref(m, dates))
+        refs.append(run_reference(m, dates))
+    fm = merge_replicas(fms)
+    ref = {k: np.stack([r[k] for r in refs], axis=-1) for k in refs[0] if k != "n_advisories"}
+    ref["n_advisories"] = np.array([int(sum(r["n_advisories"][0] for r in refs))])
+    save("config2", fm, ref, "SURVEY 8d config 2 catchment, %d perturbed members, %d days" % (R, T))
+
+
+def scenario_rivernet(T=420):
+    """Catchments -> river network with junctions, decays, a multi-arc preference
+    split, a binding arc capacity, a Storage and an (inflow-less) Reservoir."""
+    set_default_pollutants()
+    dates = [pd.Timestamp("2001-01-01") + pd.Timedelta(days=i) for i in range(T)]
+    rng = np.random.default_rng(20261021)
+    forcing = synthetic_forcing(dates, rng)
+
+    def catch_data(seed, q):
+        r = np.random.default_rng(seed)
+        d = {}
+        flow = q * (1 + 0.5 * np.sin(np.arange(T) / 30.0)) * r.lognormal(0, 0.3, T)
+        for t, date in enumerate(dates):
+            d[("flow", date)] = float(flow[t])
+            for p in constants.POLLUTANTS:
+                if p == "temperature":
+                    d[(p, date)] = forcing[("temperature", date)] + 1.0
+                elif p == "ph":
+                    d[(p, date)] = 7.2
+                elif p == "do":
+                    d[(p, date)] = 0.009
+                else:
+                    d[(p, date)] = float(r.uniform(1e-5, 2e-3))
+        return d
+
+    tdata = {k: v for k, v in forcing.items() if k[0] == "temperature"}
+    init = lambda v: {"volume": v, "do": 0.008, "org-phosphorus": v * 2e-5, "phosphate": v * 5e-5,  # noqa: E731
+                      "ammonia": v * 1e-4, "solids": v * 1e-3, "bod": v * 1e-3, "cod": v * 2e-3, "ph": 7.1,
+                      "temperature": 8.0, "nitrate": v * 2e-3, "nitrite": v * 1e-5, "org-nitrogen": v * 3e-4}
+    decays = {"ammonia": {"constant": 0.03, "exponent": 1.01}, "bod": {"constant": 0.02, "exponent": 1.02}}
+    nodes = [
+        {"type_": "Catchment", "name": "c1", "data_input_dict": catch_data(1, 4e4)},
+        {"type_": "Catchment", "name": "c2", "data_input_dict": catch_data(2, 1e4)},
+        {"type_": "Catchment", "name": "c3", "data_input_dict": catch_data(3, 2e4)},
+        {"type_": "River", "name": "r1", "length": 8000, "width": 12, "data_input_dict": tdata,
+         "initial_storage": init(5e4)},
+        {"type_": "River", "name": "r2", "length": 3000, "width": 8, "data_input_dict": tdata,
+         "initial_storage": init(1e4), "decays": dict(decays)},
+        {"type_": "River", "name": "r3", "length": 12000, "width": 20, "damp": 0.2, "data_input_dict": tdata,
+         "initial_storage": init(9e4)},
+        {"type_": "River", "name": "r4", "length": 5000, "width": 25, "data_input_dict": tdata,
+         "initial_storage": 0},
+        {"type_": "Node", "name": "j1"},
+        {"type_": "Node", "name": "j2"},
+        {"type_": "Groundwater", "name": "gw", "area": 1e6, "capacity": 3e5, "residence_time": 40.0,
+         "initial_storage": init(1e5), "infiltration_threshold": 0.2, "infiltration_pct": 1e-6},
+        {"type_": "Sewer", "name": "sw", "capacity": 500.0, "pipe_time": 1},
+        {"type_": "Sewer", "name": "sw2", "capacity": 800.0},
+        {"type_": "Storage", "name": "pond", "capacity": 2000.0, "area": 500.0, "initial_storage": init(300.0),
+         "decays": {"nitrate": {"constant": 0.002, "exponent": 1.03}}, "data_input_dict": tdata},
+        {"type_": "Reservoir", "name": "res", "capacity": 1e5, "area": 1e4, "initial_storage": init(4e4),
+         "decays": dict(decays), "data_input_dict": tdata},
+        {"type_": "Land", "name": "land", "data_input_dict": forcing, "surfaces": [
+            {"type_": "ImperviousSurface", "surface": "urban", "area": 3e4, "pore_depth": 0.002,
+             "pollutant_load": {"solids": 1e-5, "phosphate": 1e-8}},
+            {"type_": "PerviousSurface", "surface": "rural", "area": 2e5, "depth": 0.6,
+             "initial_storage": init(2e4), "decays": {"ammonia": {"constant": 0.05, "exponent": 1.005}}},
+        ]},
+        {"type_": "Waste", "name": "out"},
+        {"type_": "Waste", "name": "out2"},
+    ]
+    arcs = [
+        ("c1-r1", "c1", "r1", {}), ("c2-r2", "c2", "r2", {}), ("c3-j1", "c3", "j1", {}),
+        ("r1-j1", "r1", "j1", {}), ("r2-r3", "r2", "r3", {}), ("j1-r3", "j1", "r3", {}),
+        ("r3-j2", "r3", "j2", {}), ("j2-r4", "j2", "r4", {"preference": 2.0}),
+        ("j2-out2", "j2", "out2", {"preference": 0.5, "capacity": 2.5e4}),
+        ("r4-out", "r4", "out", {}),
+        ("land-sw", "land", "sw", {}), ("land-gw", "land", "gw", {}),
+        ("land-r1", "land", "r1", {"preference": 1.0}), ("land-r2", "land", "r2", {"preference": 3.0, "capacity": 900.0}),
+        ("sw-sw2", "sw", "sw2", {"capacity": 300.0}), ("sw2-r3", "sw2", "r3", {}),
+        ("gw-r3", "gw", "r3", {}), ("gw-sw", "gw", "sw", {}),
+        ("pond-r4", "pond", "r4", {}), ("land-pond", "land", "pond", {}),
+    ]
+    m = Model()
+    m.orchestration.insert(8, {"Storage": "distribute"})  # after Groundwater.distribute
+    m.add_nodes(nodes)
+    m.add_arcs([dict({"type_": "Arc", "name": a, "in_port": i, "out_port": o}, **kw) for a, i, o, kw in arcs])
+    fm = flatten_ref(m, dates)
+    ref = run_reference(m, dates)
+    save("rivernet", fm, ref, "synthetic river/sewer network with decays, splits and binding capacities")
+
+
+SCENARIOS = {
+    "quickstart": scenario_quickstart,
+    "quickstart_simple": scenario_quickstart_simple,
+    "fixture3607": scenario_fixture3607,
+    "config2": scenario_config2,
+    "rivernet": scenario_rivernet,
+}
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(SCENARIOS)
+    for n in names:
+        SCENARIOS[n]()

@@ -1,0 +1,312 @@
+"""ctypes binding of ``libwsi_b200.so`` (include/wsi_b200.h).
+
+``WsiModelDesc`` mirrors the C struct field for field.  ``ModelBuffers`` owns every
+buffer a descriptor points at -- torch CUDA tensors for the product path, numpy
+arrays when the CPU oracle (tests only) is handed the same descriptor -- and keeps
+them alive for as long as the descriptor is in use.
+
+There is no CPU fallback here: :func:`load_library` raises if the CUDA extension
+has not been built, and ``ModelBuffers(device="cuda")`` raises without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import layout as L
+
+ABI_VERSION = 1
+
+RUN_SCHEDULE = 1
+RUN_MASS_BALANCE = 2
+RUN_RECORD = 4
+RUN_END_TIMESTEP = 8
+RUN_ALL = 15
+
+FLAG_NAMES = {
+    1: "mass_balance",
+    2: "maxiter",
+    4: "pool_mismatch",
+    8: "nan",
+    16: "junction_depth",
+    32: "push_denied",
+}
+
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+_u32p = C.POINTER(C.c_uint32)
+
+
+class WsiModelDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("P", C.c_int32),
+        ("V", C.c_int32),
+        ("R", C.c_int32),
+        ("T", C.c_int32),
+        ("n_nodes", C.c_int32),
+        ("n_arcs", C.c_int32),
+        ("n_land", C.c_int32),
+        ("n_surf", C.c_int32),
+        ("n_tank", C.c_int32),
+        ("n_river", C.c_int32),
+        ("n_sewer", C.c_int32),
+        ("n_catch", C.c_int32),
+        ("n_sched", C.c_int32),
+        ("nq", C.c_int32),
+        ("n_fseries", C.c_int32),
+        ("n_dep_series", C.c_int32),
+        ("n_months", C.c_int32),
+        ("n_cseries", C.c_int32),
+        ("n_probe", C.c_int32),
+        ("rec_t0", C.c_int32),
+        ("rec_T", C.c_int32),
+        ("record_mb", C.c_int32),
+        ("additive_mask", C.c_uint32),
+        ("idx", C.c_int32 * 8),
+        ("float_accuracy", C.c_double),
+        ("node_type", _i32p),
+        ("node_gidx", _i32p),
+        ("arc_in", _i32p),
+        ("arc_out", _i32p),
+        ("out_ptr", _i32p),
+        ("out_arcs", _i32p),
+        ("in_ptr", _i32p),
+        ("in_arcs", _i32p),
+        ("cand_ptr", _i32p),
+        ("cand_arcs", _i32p),
+        ("land_surf_ptr", _i32p),
+        ("land_surf", _i32p),
+        ("sched_op", _i32p),
+        ("sched_node", _i32p),
+        ("arc", _f64p),
+        ("land", _f64p),
+        ("surf", _f64p),
+        ("tank", _f64p),
+        ("river", _f64p),
+        ("sewer", _f64p),
+        ("catchm", _f64p),
+        ("node_forcing", _f64p),
+        ("surf_inputs", _f64p),
+        ("catch_inputs", _f64p),
+        ("month_idx", _i32p),
+        ("dayofyear", _i32p),
+        ("doy_adj", _i32p),
+        ("probe_group", _i32p),
+        ("probe_plane", _i32p),
+        ("probe_obj", _i32p),
+        ("out_probe", _f64p),
+        ("out_mb", _f64p),
+        ("mb_partial", _f64p),
+        ("mb_sums", _f64p),
+        ("mb_count", _i32p),
+        ("node_flags", _u32p),
+    ]
+
+
+_INT_ARRAYS = [
+    "node_type", "node_gidx", "arc_in", "arc_out", "out_ptr", "out_arcs", "in_ptr", "in_arcs",
+    "cand_ptr", "cand_arcs", "land_surf_ptr", "land_surf", "sched_op", "sched_node", "month_idx",
+    "dayofyear", "doy_adj",
+]
+_F64_ARRAYS = ["node_forcing", "surf_inputs", "catch_inputs"]
+_GROUP_FIELD = {"arc": "arc", "land": "land", "surf": "surf", "tank": "tank", "river": "river",
+                "sewer": "sewer", "catchm": "catchm"}
+
+_LIB = None
+_LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "libwsi_b200.so")
+
+
+class ExtensionMissingError(RuntimeError):
+    pass
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def load_library():
+    """Load ``libwsi_b200.so``; fail loudly when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_LIB_PATH):
+        raise ExtensionMissingError(
+            f"{_LIB_PATH} not found: build the CUDA extension first "
+            "(python -c 'import __graft_entry__ as g; g.build()'). wsi_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(_LIB_PATH)
+    lib.wsi_version.restype = C.c_int
+    lib.wsi_last_error.restype = C.c_char_p
+    lib.wsi_validate.argtypes = [C.POINTER(WsiModelDesc)]
+    lib.wsi_validate.restype = C.c_int
+    lib.wsi_num_blocks.argtypes = [C.POINTER(WsiModelDesc)]
+    lib.wsi_num_blocks.restype = C.c_int
+    lib.wsi_step.argtypes = [C.POINTER(WsiModelDesc), C.c_int64, C.c_void_p]
+    lib.wsi_step.restype = C.c_int
+    lib.wsi_run_steps.argtypes = [C.POINTER(WsiModelDesc), C.c_int64, C.c_int64, C.c_void_p]
+    lib.wsi_run_steps.restype = C.c_int
+    lib.wsi_sched_range.argtypes = [C.POINTER(WsiModelDesc), C.c_int64, C.c_int32, C.c_int32, C.c_uint32, C.c_void_p]
+    lib.wsi_sched_range.restype = C.c_int
+    lib.wsi_launch_count.restype = C.c_int64
+    if lib.wsi_version() != ABI_VERSION:
+        raise ExtensionMissingError("libwsi_b200.so ABI version mismatch; rebuild")
+    _LIB = lib
+    return lib
+
+
+def check(lib, rc):
+    if rc != 0:
+        msg = lib.wsi_last_error()
+        raise RuntimeError(f"wsi_b200 error {rc}: {msg.decode() if msg else ''}")
+
+
+class ModelBuffers:
+    """Owns the buffers of one flattened model on a device and its C descriptor."""
+
+    MAX_BLOCKS = 65536
+
+    def __init__(self, fm, device="cuda", probes=(), rec_t0=0, rec_T=None, record_mb=False):
+        self.fm = fm
+        self.device = device
+        self.probes = list(probes)
+        self.rec_t0 = int(rec_t0)
+        self.rec_T = int(fm.T if rec_T is None else rec_T)
+        self.record_mb = bool(record_mb)
+        self._keep = {}
+        if device == "numpy":
+            self._init_numpy()
+        else:
+            self._init_torch(device)
+        self.desc = self._build_desc()
+
+    # ---------------------------------------------------------------- backends
+    def _init_numpy(self):
+        fm = self.fm
+        k = self._keep
+        for name in _INT_ARRAYS:
+            k[name] = np.ascontiguousarray(getattr(fm, name), dtype=np.int32)
+        for name in _F64_ARRAYS:
+            k[name] = np.ascontiguousarray(getattr(fm, name), dtype=np.float64)
+        for g, arr in fm.groups.items():
+            k["group_" + g] = np.ascontiguousarray(arr, dtype=np.float64).copy()
+        pr = np.array(self.probes or [(0, 0, 0)], dtype=np.int32).reshape(-1, 3)
+        k["probe_group"] = np.ascontiguousarray(pr[:, 0])
+        k["probe_plane"] = np.ascontiguousarray(pr[:, 1])
+        k["probe_obj"] = np.ascontiguousarray(pr[:, 2])
+        npb = max(len(self.probes), 1)
+        k["out_probe"] = np.zeros((self.rec_T, npb, fm.R), dtype=np.float64)
+        k["out_mb"] = (
+            np.zeros((self.rec_T, len(fm.node_names), 3, fm.V, fm.R), dtype=np.float64)
+            if self.record_mb
+            else np.zeros(1, dtype=np.float64)
+        )
+        k["mb_partial"] = np.zeros((self.MAX_BLOCKS // 64, 3 * fm.V), dtype=np.float64)
+        k["mb_sums"] = np.zeros((fm.T, 3, fm.V), dtype=np.float64)
+        k["mb_count"] = np.zeros(fm.T, dtype=np.int32)
+        k["node_flags"] = np.zeros(len(fm.node_names) * fm.R, dtype=np.uint32)
+        self._ptr = lambda a: a.ctypes.data
+
+    def _init_torch(self, device):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("wsi_b200 needs a CUDA device (no CPU fallback on this path)")
+        fm = self.fm
+        k = self._keep
+        dev = torch.device(device)
+        self.torch_device = dev
+
+        def up(a, dtype):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).to(dev).contiguous()
+
+        for name in _INT_ARRAYS:
+            k[name] = up(getattr(fm, name), torch.int32)
+        for name in _F64_ARRAYS:
+            k[name] = up(getattr(fm, name), torch.float64)
+        for g, arr in fm.groups.items():
+            k["group_" + g] = up(arr, torch.float64)
+        pr = np.array(self.probes or [(0, 0, 0)], dtype=np.int32).reshape(-1, 3)
+        k["probe_group"] = up(pr[:, 0], torch.int32)
+        k["probe_plane"] = up(pr[:, 1], torch.int32)
+        k["probe_obj"] = up(pr[:, 2], torch.int32)
+        npb = max(len(self.probes), 1)
+        k["out_probe"] = torch.zeros((self.rec_T, npb, fm.R), dtype=torch.float64, device=dev)
+        k["out_mb"] = (
+            torch.zeros((self.rec_T, len(fm.node_names), 3, fm.V, fm.R), dtype=torch.float64, device=dev)
+            if self.record_mb
+            else torch.zeros(1, dtype=torch.float64, device=dev)
+        )
+        k["mb_partial"] = torch.zeros((self.MAX_BLOCKS, 3 * fm.V), dtype=torch.float64, device=dev)
+        k["mb_sums"] = torch.zeros((fm.T, 3, fm.V), dtype=torch.float64, device=dev)
+        k["mb_count"] = torch.zeros(fm.T, dtype=torch.int32, device=dev)
+        # uint32 flags carried as int32 storage
+        k["node_flags"] = torch.zeros(len(fm.node_names) * fm.R, dtype=torch.int32, device=dev)
+        self._ptr = lambda a: a.data_ptr()
+
+    # -------------------------------------------------------------- descriptor
+    def _build_desc(self):
+        fm = self.fm
+        k = self._keep
+        d = WsiModelDesc()
+        d.abi_version = ABI_VERSION
+        d.P, d.V, d.R, d.T = fm.P, fm.V, fm.R, fm.T
+        d.n_nodes = len(fm.node_names)
+        d.n_arcs = len(fm.arc_names)
+        d.n_land = fm.n_obj["land"]
+        d.n_surf = fm.n_obj["surf"]
+        d.n_tank = fm.n_obj["tank"]
+        d.n_river = fm.n_obj["river"]
+        d.n_sewer = fm.n_obj["sewer"]
+        d.n_catch = fm.n_obj["catchm"]
+        d.n_sched = int(len(fm.sched_op))
+        d.nq = fm.nq
+        d.n_fseries = fm.node_forcing.shape[1]
+        d.n_months = fm.surf_inputs.shape[0]
+        d.n_dep_series = fm.surf_inputs.shape[1]
+        d.n_cseries = fm.catch_inputs.shape[1]
+        d.n_probe = len(self.probes)
+        d.rec_t0 = self.rec_t0
+        d.rec_T = self.rec_T
+        d.record_mb = 1 if self.record_mb else 0
+        d.additive_mask = fm.additive_mask
+        for i, v in enumerate(fm.idx):
+            d.idx[i] = v
+        d.float_accuracy = fm.float_accuracy
+        P = self._ptr
+        for name in _INT_ARRAYS:
+            setattr(d, name, C.cast(P(k[name]), _i32p))
+        for name in _F64_ARRAYS:
+            setattr(d, name, C.cast(P(k[name]), _f64p))
+        for g, fld in _GROUP_FIELD.items():
+            setattr(d, fld, C.cast(P(k["group_" + g]), _f64p))
+        for name in ("probe_group", "probe_plane", "probe_obj", "mb_count"):
+            setattr(d, name, C.cast(P(k[name]), _i32p))
+        for name in ("out_probe", "out_mb", "mb_partial", "mb_sums"):
+            setattr(d, name, C.cast(P(k[name]), _f64p))
+        d.node_flags = C.cast(P(k["node_flags"]), _u32p)
+        return d
+
+    # ----------------------------------------------------------------- access
+    def group(self, name):
+        """Group tensor/array ``[n_fields, n_obj*R]``."""
+        return self._keep["group_" + name]
+
+    def array(self, name):
+        return self._keep[name]
+
+    def to_numpy(self, name):
+        a = self._keep[name]
+        if self.device == "numpy":
+            return a
+        return a.detach().cpu().numpy()
+
+    def groups_numpy(self):
+        return {g: self.to_numpy("group_" + g) for g in self.fm.groups}
+
+    def set_rec_window(self, rec_t0):
+        """Move the recording window (out_probe row 0 == timestep rec_t0)."""
+        self.rec_t0 = int(rec_t0)
+        self.desc.rec_t0 = int(rec_t0)

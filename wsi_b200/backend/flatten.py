@@ -1,0 +1,699 @@
+"""Flatten a WSIMOD object graph into the structure-of-arrays ``FlatModel``.
+
+The flattener is duck-typed: it reads the attributes the reference classes define
+(``wsimod/nodes/*.py``, ``wsimod/arcs/arcs.py``) and therefore works both on
+``wsi_b200``'s own host-side mirror classes and on objects of the reference
+package (that is how ``tests/golden/make_golden.py`` builds its fixtures).
+
+Anything outside the supported hot path raises :class:`UnsupportedModelError` --
+there is no CPU fallback (BASELINE.json north_star).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import layout as L
+
+
+class UnsupportedModelError(RuntimeError):
+    """The model uses a node/arc/orchestration feature outside the GPU hot path."""
+
+
+SUPPORTED_NODES = set(L.NODE_TYPES)
+SURFACE_CLASS_MAP = {
+    "Surface": "Surface",
+    "ImperviousSurface": "ImperviousSurface",
+    "PerviousSurface": "PerviousSurface",
+    "GrowingSurface": "GrowingSurface",
+    # GardenSurface only differs through Demand push handlers (land.py:2384-2437);
+    # Demand nodes are not on this path, so it behaves as a GrowingSurface.
+    "GardenSurface": "GrowingSurface",
+}
+STORE_TYPES = ("Groundwater", "Storage", "River", "Reservoir")
+
+# (class name, orchestration function) -> op
+ORCHESTRATION_OPS = {
+    ("Land", "run"): "LAND_RUN",
+    ("Land", "apply_irrigation"): "NOP",
+    ("Groundwater", "infiltrate"): "GW_INFILTRATE",
+    ("Groundwater", "distribute"): "GW_DISTRIBUTE",
+    ("Sewer", "make_discharge"): "SEWER_DISCHARGE",
+    ("River", "calculate_discharge"): "RIVER_CALC",
+    ("River", "distribute"): "RIVER_DISTRIBUTE",
+    ("Reservoir", "make_abstractions"): "RESERVOIR_ABSTRACT",
+    ("Catchment", "route"): "CATCHMENT_ROUTE",
+    ("Storage", "distribute"): "STORAGE_DISTRIBUTE",
+    ("Reservoir", "distribute"): "STORAGE_DISTRIBUTE",
+}
+
+
+@dataclass
+class FlatModel:
+    """Numpy image of a flattened model (see ``layout.py`` for the plane layout)."""
+
+    pollutants: list
+    additive: list
+    non_additive: list
+    float_accuracy: float
+    R: int
+    T: int
+    nq: int
+    # graph
+    node_names: list
+    node_type: np.ndarray
+    node_gidx: np.ndarray
+    arc_names: list
+    arc_in: np.ndarray
+    arc_out: np.ndarray
+    out_ptr: np.ndarray
+    out_arcs: np.ndarray
+    in_ptr: np.ndarray
+    in_arcs: np.ndarray
+    cand_ptr: np.ndarray
+    cand_arcs: np.ndarray
+    land_surf_ptr: np.ndarray
+    land_surf: np.ndarray
+    surf_names: list  # (land name, surface name)
+    sched_op: np.ndarray
+    sched_node: np.ndarray
+    # groups: name -> [n_fields, n_obj * R]
+    groups: dict
+    n_obj: dict
+    # forcing
+    node_forcing: np.ndarray  # [T, n_fseries, 3]
+    surf_inputs: np.ndarray  # [n_months, n_dep_series, N_DEP]
+    catch_inputs: np.ndarray  # [T, n_cseries, V]
+    month_idx: np.ndarray
+    dayofyear: np.ndarray
+    doy_adj: np.ndarray
+    dates: list = field(default_factory=list)
+
+    # ------------------------------------------------------------------ basics
+    @property
+    def P(self):
+        return len(self.pollutants)
+
+    @property
+    def V(self):
+        return self.P + 1
+
+    @property
+    def additive_mask(self):
+        m = 0
+        for p in self.additive:
+            m |= 1 << (self.pollutants.index(p) + 1)
+        return m
+
+    @property
+    def idx(self):
+        return [
+            (self.pollutants.index(n) + 1) if n in self.pollutants else -1 for n in L.NAMED
+        ]
+
+    def n_fields(self, group):
+        if group == "sewer":
+            return L.sewer_n_fields(self.V, self.nq)
+        return L.GROUPS[group].n_fields(self.V)
+
+    def plane(self, group, name, k=0):
+        """Plane index of field ``name`` (+k) in ``group``."""
+        return L.GROUPS[group].offset(name, self.V) + k
+
+    def view(self, group, name, n=None):
+        """View ``[n_planes, n_obj, R]`` of a field (writable)."""
+        g = L.GROUPS[group]
+        o = g.offset(name, self.V)
+        if n is None:
+            n = g.size(name, self.V)
+        arr = self.groups[group]
+        return arr[o : o + n].reshape(n, self.n_obj[group], self.R)
+
+    # ------------------------------------------------------------- replication
+    def replicate(self, R):
+        """Return a copy with every object replicated ``R`` times (ensemble)."""
+        if self.R != 1:
+            raise ValueError("replicate() expects an R == 1 template")
+        groups = {k: np.ascontiguousarray(np.repeat(v, R, axis=1)) for k, v in self.groups.items()}
+        kw = dict(self.__dict__)
+        kw.update(groups=groups, R=int(R))
+        return FlatModel(**kw)
+
+    def take_replicas(self, sel):
+        """Sub-ensemble made of replicas ``sel`` (used to check a slice on the CPU)."""
+        sel = np.asarray(sel)
+        groups = {}
+        for k, v in self.groups.items():
+            n = self.n_obj[k]
+            groups[k] = np.ascontiguousarray(
+                v.reshape(v.shape[0], n, self.R)[:, :, sel].reshape(v.shape[0], n * len(sel))
+            )
+        kw = dict(self.__dict__)
+        kw.update(groups=groups, R=int(len(sel)))
+        return FlatModel(**kw)
+
+    def copy(self):
+        kw = dict(self.__dict__)
+        kw["groups"] = {k: v.copy() for k, v in self.groups.items()}
+        return FlatModel(**kw)
+
+    # ------------------------------------------------------------------ probes
+    def probes_for_arc(self, arc):
+        a = self.arc_names.index(arc) if isinstance(arc, str) else int(arc)
+        o = self.plane("arc", "vqip_in")
+        return [(L.GROUP_ID["arc"], o + p, a) for p in range(self.V)]
+
+    def probes_for_field(self, group, name, obj, n=None):
+        g = L.GROUPS[group]
+        if n is None:
+            n = g.size(name, self.V)
+        o = g.offset(name, self.V)
+        return [(L.GROUP_ID[group], o + p, int(obj)) for p in range(n)]
+
+    # --------------------------------------------------------------------- I/O
+    _ARRAYS = [
+        "node_type", "node_gidx", "arc_in", "arc_out", "out_ptr", "out_arcs", "in_ptr",
+        "in_arcs", "cand_ptr", "cand_arcs", "land_surf_ptr", "land_surf", "sched_op",
+        "sched_node", "node_forcing", "surf_inputs", "catch_inputs", "month_idx",
+        "dayofyear", "doy_adj",
+    ]
+
+    def to_npz_dict(self):
+        d = {k: getattr(self, k) for k in self._ARRAYS}
+        for k, v in self.groups.items():
+            d["group_" + k] = v
+        d["meta_pollutants"] = np.array(self.pollutants)
+        d["meta_additive"] = np.array(self.additive)
+        d["meta_non_additive"] = np.array(self.non_additive)
+        d["meta_scalars"] = np.array([self.float_accuracy, self.R, self.T, self.nq], dtype=np.float64)
+        d["meta_node_names"] = np.array(self.node_names)
+        d["meta_arc_names"] = np.array(self.arc_names)
+        d["meta_surf_names"] = np.array(["\t".join(x) for x in self.surf_names] or [""])
+        d["meta_n_obj"] = np.array([self.n_obj[k] for k in L.GROUPS], dtype=np.int64)
+        return d
+
+    @classmethod
+    def from_npz_dict(cls, d):
+        sc = d["meta_scalars"]
+        n_obj = {k: int(v) for k, v in zip(L.GROUPS, d["meta_n_obj"])}
+        surf_names = [tuple(x.split("\t")) for x in d["meta_surf_names"].tolist() if x]
+        kw = {k: np.ascontiguousarray(d[k]) for k in cls._ARRAYS}
+        return cls(
+            pollutants=[str(x) for x in d["meta_pollutants"].tolist()],
+            additive=[str(x) for x in d["meta_additive"].tolist()],
+            non_additive=[str(x) for x in d["meta_non_additive"].tolist()],
+            float_accuracy=float(sc[0]),
+            R=int(sc[1]),
+            T=int(sc[2]),
+            nq=int(sc[3]),
+            node_names=[str(x) for x in d["meta_node_names"].tolist()],
+            arc_names=[str(x) for x in d["meta_arc_names"].tolist()],
+            surf_names=surf_names,
+            groups={k: np.ascontiguousarray(d["group_" + k]) for k in L.GROUPS},
+            n_obj=n_obj,
+            **kw,
+        )
+
+
+# ---------------------------------------------------------------------- helpers
+def _cls(obj):
+    return obj.__class__.__name__
+
+
+def _vq(vqip, pollutants):
+    """dict VQIP -> list [volume, pollutants...]."""
+    return [float(vqip.get("volume", 0.0))] + [float(vqip.get(p, 0.0)) for p in pollutants]
+
+
+def _decay_fields(obj, pollutants):
+    """(n, pol, const, exp, total, pre) for a DecayObj-like ``obj``."""
+    decays = getattr(obj, "decays", None) or {}
+    if len(decays) > L.MAX_DECAY:
+        raise UnsupportedModelError(f"more than {L.MAX_DECAY} decaying pollutants on one store")
+    n = len(decays)
+    pol = [0.0] * L.MAX_DECAY
+    const = [0.0] * L.MAX_DECAY
+    exp_ = [0.0] * L.MAX_DECAY
+    total = [0.0] * L.MAX_DECAY
+    pre = [0.0] * L.MAX_DECAY
+    td = getattr(obj, "total_decayed", None) or {}
+    st_ = getattr(obj, "storage_", None) or {}
+    for i, (p, pars) in enumerate(decays.items()):
+        if p not in pollutants:
+            raise UnsupportedModelError(f"decay for unknown pollutant {p}")
+        pol[i] = float(pollutants.index(p) + 1)
+        const[i] = float(pars["constant"])
+        exp_[i] = float(pars["exponent"])
+        total[i] = float(td.get(p, 0.0))
+        pre[i] = float(st_.get(p, 0.0))
+    return n, pol, const, exp_, total, pre
+
+
+class _GroupBuilder:
+    def __init__(self, name, V, nq=2):
+        self.g = L.GROUPS[name]
+        self.name = name
+        self.V = V
+        self.nf = L.sewer_n_fields(V, nq) if name == "sewer" else self.g.n_fields(V)
+        self.cols = []
+
+    def new(self):
+        col = np.zeros(self.nf, dtype=np.float64)
+        self.cols.append(col)
+        return col
+
+    def set(self, col, name, value, k=0):
+        o = self.g.offset(name, self.V)
+        if isinstance(value, (list, tuple, np.ndarray)):
+            col[o + k : o + k + len(value)] = value
+        else:
+            col[o + k] = float(value)
+
+    def array(self):
+        if not self.cols:
+            return np.zeros((self.nf, 0), dtype=np.float64)
+        return np.ascontiguousarray(np.stack(self.cols, axis=1))
+
+
+def _series_from_dict(did, dates, variables, required=True):
+    out = np.zeros((len(dates), len(variables)), dtype=np.float64)
+    for j, var in enumerate(variables):
+        if var is None:
+            continue
+        for t, date in enumerate(dates):
+            try:
+                out[t, j] = did[(var, date)]
+            except KeyError:
+                if required:
+                    raise UnsupportedModelError(f"missing input ({var!r}, {date})") from None
+                out[t, j] = np.nan
+    return out
+
+
+# --------------------------------------------------------------------- flatten
+def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
+    """Flatten ``model`` for the timesteps ``dates`` (the objects used as
+    ``data_input_dict`` keys, ``model.py:993-997``)."""
+    pollutants = list(pollutants)
+    additive = list(additive)
+    non_additive = list(non_additive)
+    P = len(pollutants)
+    V = P + 1
+    if P > L.MAXP:
+        raise UnsupportedModelError(f"{P} pollutants > {L.MAXP}")
+    if set(additive) | set(non_additive) != set(pollutants) or set(additive) & set(non_additive):
+        raise UnsupportedModelError("POLLUTANTS must be the disjoint union of additive and non-additive")
+    has_nitrate = "nitrate" in pollutants
+    if has_nitrate:
+        needed = {"nitrite", "ammonia", "phosphate", "org-phosphorus", "org-nitrogen", "temperature"}
+        if not needed <= set(pollutants):
+            raise UnsupportedModelError(f"'nitrate' modelled without {sorted(needed - set(pollutants))}")
+    dates = list(dates)
+    T = len(dates)
+
+    nodes = list(model.nodes.values())
+    node_names = [n.name for n in nodes]
+    node_index = {n.name: i for i, n in enumerate(nodes)}
+    arcs = list(model.arcs.values())
+    arc_names = [a.name for a in arcs]
+    arc_index = {a.name: i for i, a in enumerate(arcs)}
+
+    for n in nodes:
+        if _cls(n) not in SUPPORTED_NODES:
+            raise UnsupportedModelError(
+                f"node {n.name!r} of class {_cls(n)} is outside the GPU hot path "
+                f"(supported: {sorted(SUPPORTED_NODES)})"
+            )
+    for a in arcs:
+        if _cls(a) != "Arc":
+            raise UnsupportedModelError(f"arc {a.name!r} of class {_cls(a)} is not supported (plain Arc only)")
+        if _cls(a.out_port) in ("Land", "Catchment"):
+            raise UnsupportedModelError(f"arc {a.name!r} pushes into a {_cls(a.out_port)} node")
+
+    # ---- graph CSR -----------------------------------------------------------
+    node_type = np.array([L.NT[_cls(n)] for n in nodes], dtype=np.int32)
+    arc_in = np.array([node_index[a.in_port.name] for a in arcs], dtype=np.int32)
+    arc_out = np.array([node_index[a.out_port.name] for a in arcs], dtype=np.int32)
+
+    def csr(lists):
+        ptr = np.zeros(len(lists) + 1, dtype=np.int32)
+        flat = []
+        for i, l in enumerate(lists):
+            flat.extend(l)
+            ptr[i + 1] = len(flat)
+        return ptr, np.array(flat if flat else [0], dtype=np.int32)[: max(len(flat), 1)]
+
+    out_lists = [[arc_index[k] for k in n.out_arcs.keys()] for n in nodes]
+    in_lists = [[arc_index[k] for k in n.in_arcs.keys()] for n in nodes]
+    out_ptr, out_arcs = csr(out_lists)
+    in_ptr, in_arcs = csr(in_lists)
+    cand_lists = []
+    for n in nodes:
+        for fname in L.FILTER_NAMES:
+            types = L.FILTERS[fname]
+            if types is None:
+                cand_lists.append([arc_index[k] for k in n.out_arcs.keys()])
+            else:
+                # get_direction_arcs (nodes.py:257-265): per type, in of_type order
+                lst = []
+                for ty in types:
+                    lst += [arc_index[k] for k in n.out_arcs_type.get(ty, {}).keys()]
+                cand_lists.append(lst)
+    cand_ptr, cand_arcs = csr(cand_lists)
+
+    # ---- forcing series ------------------------------------------------------
+    fseries_ids = {}
+    fseries = []
+
+    def forcing_series(did, variables):
+        key = (id(did), tuple(variables))
+        if key not in fseries_ids:
+            fseries_ids[key] = len(fseries)
+            fseries.append(_series_from_dict(did, dates, variables))
+        return fseries_ids[key]
+
+    months = []
+    month_of = {}
+    month_idx = np.zeros(T, dtype=np.int32)
+    for t, date in enumerate(dates):
+        m = date.to_period("M")
+        if m not in month_of:
+            month_of[m] = len(months)
+            months.append(m)
+        month_idx[t] = month_of[m]
+    dep_ids = {}
+    dep_series = []
+
+    def dep_series_id(did, need):
+        key = id(did)
+        if key not in dep_ids:
+            arr = np.zeros((len(months), L.N_DEP), dtype=np.float64)
+            present = set(x[0] for x in did.keys())
+            for j, var in enumerate(L.DEP_COLS):
+                if var in present:
+                    for mi, m in enumerate(months):
+                        try:
+                            arr[mi, j] = did[(var, m)]
+                        except KeyError:
+                            raise UnsupportedModelError(f"surface input ({var!r}, {m}) missing") from None
+                elif var in need:
+                    raise UnsupportedModelError(f"surface data_input_dict lacks {var!r}")
+            dep_ids[key] = len(dep_series)
+            dep_series.append(arr)
+        return dep_ids[key]
+
+    dayofyear = np.array([int(d.dayofyear) for d in dates], dtype=np.int32)
+    # land.py:1524-1529: `if self.parent.t.is_leap_year:` -- a bound method (csv/yaml
+    # dates, model.py:114) is always truthy, a pandas bool is not.
+    doy_adj = dayofyear.copy()
+    for t, d in enumerate(dates):
+        if bool(d.is_leap_year) and doy_adj[t] > 59:
+            doy_adj[t] -= 1
+
+    # ---- groups --------------------------------------------------------------
+    sewers = [n for n in nodes if _cls(n) == "Sewer"]
+    nq = 2
+    for w in sewers:
+        keys = list(w.sewer_tank.internal_arc.queue.keys())
+        nq = max(nq, max([1, int(w.pipe_time)] + [int(k) for k in keys]) + 1)
+    if nq > 16:
+        raise UnsupportedModelError("sewer travel time > 15 timesteps")
+
+    gb = {k: _GroupBuilder(k, V, nq) for k in L.GROUPS}
+    node_gidx = np.zeros(len(nodes), dtype=np.int32)
+    land_surf_lists = []
+    surf_names = []
+    catch_series = []
+
+    for a in arcs:
+        col = gb["arc"].new()
+        gb["arc"].set(col, "capacity", a.capacity)
+        gb["arc"].set(col, "preference", a.preference)
+        gb["arc"].set(col, "flow_in", a.flow_in)
+        gb["arc"].set(col, "vqip_in", _vq(a.vqip_in, pollutants))
+
+    def add_store(n):
+        col = gb["tank"].new()
+        tk = n.tank
+        b = gb["tank"]
+        b.set(col, "capacity", tk.capacity)
+        b.set(col, "area", tk.area)
+        b.set(col, "residence_time", getattr(n, "residence_time", 1.0))
+        b.set(col, "infiltration_threshold", getattr(n, "infiltration_threshold", 1.0))
+        b.set(col, "infiltration_pct", getattr(n, "infiltration_pct", 0.0))
+        is_decay = _cls(tk) == "DecayTank"
+        if _cls(tk) not in ("Tank", "DecayTank"):
+            raise UnsupportedModelError(f"{n.name}: tank class {_cls(tk)} unsupported")
+        b.set(col, "is_decay", 1.0 if is_decay else 0.0)
+        need_T = (is_decay and len(tk.decays) > 0) or (_cls(n) == "River" and has_nitrate)
+        fid = 0
+        if need_T:
+            fid = forcing_series(n.data_input_dict, (None, None, "temperature"))
+        b.set(col, "forcing_id", fid)
+        if is_decay:
+            nd, pol, const, exp_, total, pre = _decay_fields(tk, pollutants)
+            b.set(col, "n_decay", nd)
+            b.set(col, "decay_pol", pol)
+            b.set(col, "decay_const", const)
+            b.set(col, "decay_exp", exp_)
+            b.set(col, "total_decayed", total)
+            b.set(col, "pre_decay", pre)
+        b.set(col, "storage", _vq(tk.storage, pollutants))
+        b.set(col, "storage_", _vq(tk.storage_, pollutants))
+        return len(gb["tank"].cols) - 1
+
+    for i, n in enumerate(nodes):
+        c = _cls(n)
+        if c == "Land":
+            node_gidx[i] = len(gb["land"].cols)
+            col = gb["land"].new()
+            b = gb["land"]
+            b.set(col, "res_surface", n.surface_runoff.residence_time)
+            b.set(col, "res_subsurface", n.subsurface_runoff.residence_time)
+            b.set(col, "res_percolation", n.percolation.residence_time)
+            b.set(col, "forcing_id", forcing_series(n.data_input_dict, ("precipitation", "et0", "temperature")))
+            b.set(col, "surface_runoff", _vq(n.surface_runoff.storage, pollutants))
+            b.set(col, "subsurface_runoff", _vq(n.subsurface_runoff.storage, pollutants))
+            b.set(col, "percolation", _vq(n.percolation.storage, pollutants))
+            lst = []
+            for s in n.surfaces:
+                lst.append(len(gb["surf"].cols))
+                surf_names.append((n.name, str(s.surface)))
+                _flatten_surface(gb["surf"], s, pollutants, additive, has_nitrate, dep_series_id)
+            land_surf_lists.append(lst)
+        elif c in STORE_TYPES:
+            ti = add_store(n)
+            if c == "Reservoir" and len(n.in_arcs) > 0:
+                raise UnsupportedModelError(f"{n.name}: Reservoir abstractions (pulls) are not on the GPU path yet")
+            if c == "River":
+                node_gidx[i] = len(gb["river"].cols)
+                _flatten_river(gb["river"], n, ti)
+            else:
+                node_gidx[i] = ti
+        elif c == "Sewer":
+            node_gidx[i] = len(gb["sewer"].cols)
+            col = gb["sewer"].new()
+            b = gb["sewer"]
+            tk = n.sewer_tank
+            if any(_cls(a.out_port) == "Land" for a in n.out_arcs.values()):
+                raise UnsupportedModelError(f"{n.name}: sewer flooding onto Land (sewer.py:236) is unsupported")
+            if int(n.pipe_time) != n.pipe_time or n.pipe_time < 0:
+                raise UnsupportedModelError("non-integer pipe_time")
+            b.set(col, "capacity", tk.capacity)
+            b.set(col, "pipe_time", n.pipe_time)
+            qmask = 0
+            for k, v in tk.internal_arc.queue.items():
+                qmask |= 1 << int(k)
+                b.set(col, "queue", _vq(v, pollutants), k=int(k) * V)
+            b.set(col, "qmask", qmask)
+            b.set(col, "storage", _vq(tk.storage, pollutants))
+            b.set(col, "storage_", _vq(tk.storage_, pollutants))
+            b.set(col, "active_storage", _vq(tk.active_storage, pollutants))
+        elif c == "Catchment":
+            node_gidx[i] = len(gb["catchm"].cols)
+            col = gb["catchm"].new()
+            col[0] = len(catch_series)
+            catch_series.append(_series_from_dict(n.data_input_dict, dates, ["flow"] + pollutants))
+        else:  # Node, Waste
+            node_gidx[i] = 0
+
+    land_surf_ptr, land_surf = csr(land_surf_lists)
+
+    # ---- schedule ------------------------------------------------------------
+    sched = []
+    for item in model.orchestration:
+        for type_key, fn in item.items():
+            for n in model.nodes_type.get(type_key, {}).values():
+                op = ORCHESTRATION_OPS.get((_cls(n), fn))
+                if op is None:
+                    raise UnsupportedModelError(f"orchestration entry {type_key}.{fn} on {_cls(n)} {n.name!r} unsupported")
+                if op != "NOP":
+                    sched.append((L.OP[op], node_index[n.name]))
+    for name in model.river_discharge_order:
+        sched.append((L.OP["RIVER_DISTRIBUTE"], node_index[name]))
+    sched_op = np.array([s[0] for s in sched] or [L.OP["NOP"]], dtype=np.int32)
+    sched_node = np.array([s[1] for s in sched] or [0], dtype=np.int32)
+
+    groups = {k: b.array() for k, b in gb.items()}
+    n_obj = {k: v.shape[1] for k, v in groups.items()}
+    node_forcing = (
+        np.stack(fseries, axis=1) if fseries else np.zeros((T, 1, 3), dtype=np.float64)
+    )
+    node_forcing = np.nan_to_num(np.ascontiguousarray(node_forcing), nan=0.0)
+    surf_inputs = (
+        np.stack(dep_series, axis=1) if dep_series else np.zeros((max(len(months), 1), 1, L.N_DEP))
+    )
+    catch_inputs = (
+        np.stack(catch_series, axis=1) if catch_series else np.zeros((T, 1, V), dtype=np.float64)
+    )
+    return FlatModel(
+        pollutants=pollutants,
+        additive=additive,
+        non_additive=non_additive,
+        float_accuracy=float(float_accuracy),
+        R=1,
+        T=T,
+        nq=nq,
+        node_names=node_names,
+        node_type=node_type,
+        node_gidx=node_gidx,
+        arc_names=arc_names,
+        arc_in=arc_in,
+        arc_out=arc_out,
+        out_ptr=out_ptr,
+        out_arcs=out_arcs,
+        in_ptr=in_ptr,
+        in_arcs=in_arcs,
+        cand_ptr=cand_ptr,
+        cand_arcs=cand_arcs,
+        land_surf_ptr=land_surf_ptr,
+        land_surf=land_surf,
+        surf_names=surf_names,
+        sched_op=sched_op,
+        sched_node=sched_node,
+        groups=groups,
+        n_obj=n_obj,
+        node_forcing=np.ascontiguousarray(node_forcing, dtype=np.float64),
+        surf_inputs=np.ascontiguousarray(surf_inputs, dtype=np.float64),
+        catch_inputs=np.ascontiguousarray(catch_inputs, dtype=np.float64),
+        month_idx=month_idx,
+        dayofyear=dayofyear,
+        doy_adj=doy_adj,
+        dates=dates,
+    )
+
+
+def _flatten_surface(b, s, pollutants, additive, has_nitrate, dep_series_id):
+    cname = _cls(s)
+    if cname not in SURFACE_CLASS_MAP:
+        raise UnsupportedModelError(
+            f"surface class {cname} is outside the GPU hot path (pull-driven irrigation / variable area)"
+        )
+    kind = SURFACE_CLASS_MAP[cname]
+    col = b.new()
+    b.set(col, "type", L.ST[kind])
+    b.set(col, "area", s.area)
+    b.set(col, "capacity", s.capacity)
+    b.set(col, "depth", s.depth)
+    load = getattr(s, "pollutant_load", {}) or {}
+    b.set(col, "has_load", 1.0 if len(load) > 0 else 0.0)
+    lv = [0.0] + [float(load.get(p, 0.0)) for p in pollutants]
+    b.set(col, "load", lv)
+    did = getattr(s, "data_input_dict", {}) or {}
+    present = set(x[0] for x in did.keys())
+    has_dep = "nhx-dry" in present
+    b.set(col, "has_dep", 1.0 if has_dep else 0.0)
+    need = set()
+    if has_dep:
+        need |= set(L.DEP_COLS[:6])
+    if kind == "GrowingSurface" and has_nitrate:
+        need |= set(L.DEP_COLS[6:])
+    if need:
+        b.set(col, "dep_id", dep_series_id(did, need))
+    nd, pol, const, exp_, total, pre = _decay_fields(s, pollutants)
+    b.set(col, "n_decay", nd)
+    b.set(col, "decay_pol", pol)
+    b.set(col, "decay_const", const)
+    b.set(col, "decay_exp", exp_)
+    b.set(col, "total_decayed", total)
+    b.set(col, "pre_decay", pre)
+    b.set(col, "storage", _vq(s.storage, pollutants))
+    if kind == "ImperviousSurface":
+        b.set(col, "et0_to_e", s.et0_to_e)
+    if kind in ("PerviousSurface", "GrowingSurface"):
+        for name in (
+            "field_capacity_m", "wilting_point_m", "infiltration_capacity", "surface_coefficient",
+            "percolation_coefficient", "subsurface_coefficient", "ihacres_p", "et0_coefficient",
+            "soil_temp_w_prev", "soil_temp_w_air", "soil_temp_w_deep", "soil_temp_deep",
+        ):
+            b.set(col, name, getattr(s, name))
+    if kind == "GrowingSurface":
+        for name in (
+            "rooting_depth", "ET_depletion_factor", "total_available_water", "readily_available_water",
+            "sowing_day", "harvest_day", "satact", "thetaupp", "thetalow", "thetapow", "uptake1",
+            "uptake2", "uptake3", "uptake_PNratio", "erodibility", "sreroexp", "cohesion", "slope",
+            "srfilt", "macrofilt", "limpar", "exppar", "hsatINs", "denpar", "kfr", "nfr", "kadsdes",
+            "bulk_density", "crop_cover", "ground_cover", "crop_factor",
+        ):
+            b.set(col, name, getattr(s, name))
+        b.set(col, "adsorption_nr_limit", s.adosorption_nr_limit)  # sic (land.py:1243)
+        b.set(col, "adsorption_nr_maxiter", s.adsorption_nr_maxiter)
+        b.set(col, "autumn_sow", 1.0 if s.autumn_sow else 0.0)
+        ns = len(s.crop_factor_stages)
+        if ns > L.MAX_STAGE or ns != len(s.crop_factor_stage_dates):
+            raise UnsupportedModelError("crop_factor_stages table too long / inconsistent")
+        b.set(col, "n_stage", ns)
+        b.set(col, "stage_dates", [float(x) for x in s.crop_factor_stage_dates])
+        b.set(col, "stage_vals", [float(x) for x in s.crop_factor_stages])
+        b.set(col, "hs_calendar", [float(x) for x in s.harvest_sow_calendar])
+        b.set(col, "ground_cover_stages", [float(x) for x in s.ground_cover_stages])
+        b.set(col, "crop_cover_stages", [float(x) for x in s.crop_cover_stages])
+        b.set(col, "days_after_sow", -1.0 if s.days_after_sow is None else float(s.days_after_sow))
+        npool = s.nutrient_pool
+        b.set(col, "frac_dry_n_to_dis_inorg", npool.fraction_dry_n_to_dissolved_inorganic)
+        b.set(col, "frac_dry_n_to_fast", npool.fraction_dry_n_to_fast)
+        NP = ("N", "P")
+        b.set(col, "frac_manure_to_dis_inorg", [npool.fraction_manure_to_dissolved_inorganic[x] for x in NP])
+        b.set(col, "frac_manure_to_fast", [npool.fraction_manure_to_fast[x] for x in NP])
+        for name in ("degrhpar", "dishpar", "minfpar", "disfpar", "immobdpar"):
+            b.set(col, name, [getattr(npool, name)[x] for x in NP])
+        b.set(col, "pool_fast", [npool.fast_pool.storage[x] for x in NP])
+        b.set(col, "pool_humus", [npool.humus_pool.storage[x] for x in NP])
+        b.set(col, "pool_dis_inorg", [npool.dissolved_inorganic_pool.storage[x] for x in NP])
+        b.set(col, "pool_dis_org", [npool.dissolved_organic_pool.storage[x] for x in NP])
+        b.set(col, "pool_ads_inorg", [npool.adsorbed_inorganic_pool.storage[x] for x in NP])
+
+
+def _flatten_river(b, n, tank_index):
+    col = b.new()
+    b.set(col, "tank", tank_index)
+    # get_riverrc (storage.py:900-915), evaluated with the host libm so the
+    # constant is bit-identical to the reference's
+    total_time = n.length / n.velocity
+    kt = n.damp * total_time
+    riverrc = 1 - kt + kt * math.exp(-1 / kt) if kt != 0 else 1
+    b.set(col, "riverrc", riverrc)
+    b.set(col, "area", n.area)
+    for name in (
+        "uptake_PNratio", "denpar_w", "T_wdays", "halfsatINwater", "hsatTP", "limpppar", "prodNpar",
+        "prodPpar", "muptNpar", "muptPpar", "max_temp_lag", "max_phosphorus_lag",
+    ):
+        b.set(col, name, getattr(n, name))
+    if n.max_temp_lag + 1 > L.LAG_T or n.max_phosphorus_lag + 1 > L.LAG_TP:
+        raise UnsupportedModelError("river lag longer than the ring buffers")
+    if getattr(n, "mrf", 0) not in (0, 0.0):
+        pass  # mrf only limits pulls (storage.py:676-684), which are not on this path
+    lt = list(n.lagged_temperatures)
+    ltp = list(n.lagged_total_phosphorus)
+    b.set(col, "n_lag_T", len(lt))
+    b.set(col, "head_T", 0)
+    b.set(col, "n_lag_TP", len(ltp))
+    b.set(col, "head_TP", 0)
+    if lt:
+        b.set(col, "lag_T", [float(x) for x in lt])
+    if ltp:
+        b.set(col, "lag_TP", [float(x) for x in ltp])
+    b.set(col, "bio_in", [0.0])
+    b.set(col, "bio_out", [0.0])
