@@ -1,0 +1,80 @@
+"""Drive the CUDA kernels over a flattened model (product path; CUDA only)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class GpuRunner:
+    """Holds a flattened model on one GPU and steps it through ``libwsi_b200.so``.
+
+    Parameters mirror what ``Model.run`` needs: which planes to record every step
+    (``probes``), how many steps the record buffer covers (``rec_T``) and whether the
+    per-node mass-balance terms are kept (``record_mb``).
+    """
+
+    def __init__(self, fm, probes=(), rec_t0=0, rec_T=None, record_mb=False, device="cuda:0",
+                 system_sums=True):
+        import torch
+
+        self.torch = torch
+        self.lib = capi.load_library()
+        self.fm = fm
+        self.device = torch.device(device)
+        self.buffers = capi.ModelBuffers(fm, device=device, probes=probes, rec_t0=rec_t0, rec_T=rec_T,
+                                         record_mb=record_mb)
+        self.desc = self.buffers.desc
+        if not system_sums:
+            self.desc.mb_sums = C.cast(None, C.POINTER(C.c_double))
+        if self.lib.wsi_num_blocks(C.byref(self.desc)) > capi.ModelBuffers.MAX_BLOCKS:
+            raise RuntimeError("too many replicas for the mb_partial scratch")
+        capi.check(self.lib, self.lib.wsi_validate(C.byref(self.desc)))
+
+    def _stream(self, stream):
+        if stream is None:
+            stream = self.torch.cuda.current_stream(self.device)
+        return C.c_void_p(stream.cuda_stream)
+
+    def run(self, t0, t1, stream=None):
+        """Timesteps [t0, t1) back to back (asynchronous on the stream)."""
+        with self.torch.cuda.device(self.device):
+            capi.check(self.lib, self.lib.wsi_run_steps(C.byref(self.desc), int(t0), int(t1), self._stream(stream)))
+
+    def step(self, t, stream=None):
+        with self.torch.cuda.device(self.device):
+            capi.check(self.lib, self.lib.wsi_step(C.byref(self.desc), int(t), self._stream(stream)))
+
+    def sched_range(self, t, begin, end, flags, stream=None):
+        with self.torch.cuda.device(self.device):
+            capi.check(
+                self.lib,
+                self.lib.wsi_sched_range(C.byref(self.desc), int(t), int(begin), int(end), int(flags), self._stream(stream)),
+            )
+
+    def synchronize(self):
+        self.torch.cuda.synchronize(self.device)
+
+    # ---- results ----
+    def out_probe(self):
+        return self.buffers.to_numpy("out_probe")
+
+    def out_mb(self):
+        return self.buffers.to_numpy("out_mb") if self.buffers.record_mb else None
+
+    def mb_sums(self):
+        return self.buffers.to_numpy("mb_sums")
+
+    def mb_count(self):
+        return self.buffers.to_numpy("mb_count")
+
+    def node_flags(self):
+        return self.buffers.to_numpy("node_flags").view(np.uint32)
+
+    def groups(self):
+        return self.buffers.groups_numpy()
+
+    def launch_count(self):
+        return int(self.lib.wsi_launch_count())

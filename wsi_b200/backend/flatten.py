@@ -697,3 +697,98 @@ def _flatten_river(b, n, tank_index):
         b.set(col, "lag_TP", [float(x) for x in ltp])
     b.set(col, "bio_in", [0.0])
     b.set(col, "bio_out", [0.0])
+
+
+# ------------------------------------------------------------------ scatter back
+def scatter_back(model, fm, groups, last_date=None):
+    """Write the final SoA state (``groups``: name -> ``[n_fields, n_obj]`` arrays of an
+    ``R == 1`` run) back into the Python objects, so that follow-on ``run()`` calls,
+    ``node.tank.storage[...]`` inspection and pickling keep working."""
+    if fm.R != 1:
+        raise ValueError("scatter_back needs an R == 1 model")
+    pol = fm.pollutants
+    V = fm.V
+
+    def vq_dict(group, name, obj, k=0):
+        o = L.GROUPS[group].offset(name, V) + k * V
+        col = groups[group][o : o + V, obj]
+        d = {"volume": float(col[0])}
+        d.update({p: float(col[i + 1]) for i, p in enumerate(pol)})
+        return d
+
+    def sc(group, name, obj, k=0):
+        return float(groups[group][L.GROUPS[group].offset(name, V) + k, obj])
+
+    def decay_back(tank, group, obj):
+        decays = getattr(tank, "decays", None) or {}
+        tank.total_decayed = dict.fromkeys(pol + ["volume"], 0)
+        for i, p in enumerate(decays):
+            tank.total_decayed[p] = sc(group, "total_decayed", obj, i)
+            tank.storage_[p] = sc(group, "pre_decay", obj, i)
+
+    si = ti = ri = wi = li = 0
+    for n in model.nodes.values():
+        c = _cls(n)
+        n.t = last_date
+        if c == "Land":
+            for name in ("surface_runoff", "subsurface_runoff", "percolation"):
+                tank = getattr(n, name)
+                tank.storage = vq_dict("land", name, li)
+                tank.storage_ = dict(tank.storage)
+            for s in n.surfaces:
+                s.storage = vq_dict("surf", "storage", si)
+                s.storage_ = dict(s.storage)
+                decay_back(s, "surf", si)
+                kind = SURFACE_CLASS_MAP[_cls(s)]
+                if kind in ("PerviousSurface", "GrowingSurface"):
+                    s.tank_recharge = sc("surf", "out_tank_recharge", si)
+                    for attr, f in (("percolation", "out_percolation"), ("subsurface_flow", "out_subsurface"),
+                                    ("infiltration_excess", "out_surface"), ("evaporation", "out_evaporation"),
+                                    ("precipitation", "out_precipitation")):
+                        d = dict.fromkeys(pol + ["volume"], 0)
+                        d["volume"] = sc("surf", f, si)
+                        setattr(s, attr, d)
+                if kind == "GrowingSurface":
+                    das = sc("surf", "days_after_sow", si)
+                    s.days_after_sow = None if das < 0 else int(das)
+                    s.crop_cover = sc("surf", "crop_cover", si)
+                    s.ground_cover = sc("surf", "ground_cover", si)
+                    s.crop_factor = sc("surf", "crop_factor", si)
+                    s.et0_coefficient = sc("surf", "et0_coefficient", si)
+                    npool = s.nutrient_pool
+                    for pool, f in ((npool.fast_pool, "pool_fast"), (npool.humus_pool, "pool_humus"),
+                                    (npool.dissolved_inorganic_pool, "pool_dis_inorg"),
+                                    (npool.dissolved_organic_pool, "pool_dis_org"),
+                                    (npool.adsorbed_inorganic_pool, "pool_ads_inorg")):
+                        pool.storage["N"] = sc("surf", f, si, 0)
+                        pool.storage["P"] = sc("surf", f, si, 1)
+                si += 1
+            li += 1
+        elif c in STORE_TYPES:
+            n.tank.storage = vq_dict("tank", "storage", ti)
+            n.tank.storage_ = vq_dict("tank", "storage_", ti)
+            if _cls(n.tank) == "DecayTank":
+                decay_back(n.tank, "tank", ti)
+            if c == "River":
+                nT, hT = int(sc("river", "n_lag_T", ri)), int(sc("river", "head_T", ri))
+                n.lagged_temperatures = [sc("river", "lag_T", ri, (hT + k) % L.LAG_T) for k in range(nT)]
+                nP, hP = int(sc("river", "n_lag_TP", ri)), int(sc("river", "head_TP", ri))
+                n.lagged_total_phosphorus = [sc("river", "lag_TP", ri, (hP + k) % L.LAG_TP) for k in range(nP)]
+                ri += 1
+            ti += 1
+        elif c == "Sewer":
+            tk = n.sewer_tank
+            tk.storage = vq_dict("sewer", "storage", wi)
+            tk.storage_ = vq_dict("sewer", "storage_", wi)
+            tk.active_storage = vq_dict("sewer", "active_storage", wi)
+            qmask = int(sc("sewer", "qmask", wi))
+            tk.internal_arc.queue = {
+                k: vq_dict("sewer", "queue", wi, k) for k in range(fm.nq) if qmask & (1 << k)
+            }
+            tk.internal_arc.max_travel = max([1] + list(tk.internal_arc.queue))
+            wi += 1
+    for a in model.arcs.values():
+        a.flow_in = 0
+        a.flow_out = 0
+        a.vqip_in = dict.fromkeys(pol + ["volume"], 0)
+        a.vqip_out = a.vqip_in

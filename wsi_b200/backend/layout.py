@@ -302,6 +302,7 @@ SEWER = Group(
         S("capacity"),
         S("pipe_time"),
         S("qmask"),  # state: which travel-time keys exist in internal_arc.queue
+        S("ia_flow_in"),  # per-step transient: internal_arc.flow_in (arcs.py:427)
         Q("storage"),
         Q("storage_"),
         Q("active_storage"),

@@ -1,0 +1,484 @@
+// Per-replica timestep logic of the wsi_b200 kernels.
+//
+// One thread advances one replica (ensemble member / independent catchment) of the
+// template graph through one model timestep: the orchestration schedule, river routing,
+// per-node mass balance, recording and end_timestep -- the body of the loop at
+// wsimod/orchestration/model.py:993-1176.  State lives in the SoA group tensors
+// (include/wsi_layout.h); plane `f` of object `o` for replica `r` is at
+// base[(f * n_obj + o) * R + r], so a warp of 32 consecutive replicas reads 256
+// contiguous bytes per plane.
+//
+// Everything here is __host__ __device__: the shipped library only instantiates it inside
+// __global__ kernels (wsi_api.cu); tests/hostsim compiles the same code for the CPU so the
+// CPU-only CI can exercise the kernel logic (it is never loaded by the product).
+#pragma once
+
+#include "../../include/wsi_b200.h"
+#include "../../include/wsi_layout.h"
+#include "wsi_vq.cuh"
+
+namespace wsi {
+
+constexpr double kUnbounded = 1e15;  // constants.UNBOUNDED_CAPACITY
+constexpr int kMaxIter = 5;          // constants.MAXITER
+constexpr int kMaxCand = 8;          // arcs one push_distributed call can split over
+constexpr int kJunctionDepth = 3;    // nested junction Nodes a push may traverse
+
+template <class CFG>
+struct Ctx {
+  static constexpr int P = CFG::P;
+  static constexpr int V = P + 1;
+  using Vq = VQ<P>;
+
+  const WsiModelDesc* d;
+  CFG cfg;
+  size_t R;
+  int r;
+  int t;
+  uint32_t add;
+  double FA;
+  uint32_t run_flags;
+  int viol;        // mass-balance violations found for this replica this step
+  double* mb_acc;  // [3*V] per-thread system-total accumulators (stride mb_stride) or null
+  int mb_stride;
+
+  // ---- plane addressing ----
+  WSI_HD double* pl(double* base, int n_obj, int plane, int obj) const {
+    return base + ((size_t)plane * (size_t)n_obj + (size_t)obj) * R + (size_t)r;
+  }
+  WSI_HD double* arc(int plane, int a) const { return pl(d->arc, d->n_arcs, plane, a); }
+  WSI_HD double* land(int plane, int i) const { return pl(d->land, d->n_land, plane, i); }
+  WSI_HD double* surf(int plane, int i) const { return pl(d->surf, d->n_surf, plane, i); }
+  WSI_HD double* tank(int plane, int i) const { return pl(d->tank, d->n_tank, plane, i); }
+  WSI_HD double* river(int plane, int i) const { return pl(d->river, d->n_river, plane, i); }
+  WSI_HD double* sewer(int plane, int i) const { return pl(d->sewer, d->n_sewer, plane, i); }
+  WSI_HD size_t s_arc() const { return (size_t)d->n_arcs * R; }
+  WSI_HD size_t s_land() const { return (size_t)d->n_land * R; }
+  WSI_HD size_t s_surf() const { return (size_t)d->n_surf * R; }
+  WSI_HD size_t s_tank() const { return (size_t)d->n_tank * R; }
+  WSI_HD size_t s_river() const { return (size_t)d->n_river * R; }
+  WSI_HD size_t s_sewer() const { return (size_t)d->n_sewer * R; }
+
+  WSI_HD Vq ldv(const double* p, size_t stride) const {
+    Vq v;
+#pragma unroll
+    for (int i = 0; i < V; i++) v.x[i] = p[(size_t)i * stride];
+    return v;
+  }
+  WSI_HD void stv(double* p, size_t stride, const Vq& v) const {
+#pragma unroll
+    for (int i = 0; i < V; i++) p[(size_t)i * stride] = v.x[i];
+  }
+  WSI_HD void flag(int node, uint32_t f) const { d->node_flags[(size_t)node * R + r] |= f; }
+
+  // ---- forcing ----
+  WSI_HD double forcing(int fid, int col) const {
+    return d->node_forcing[((size_t)t * d->n_fseries + fid) * 3 + col];
+  }
+  WSI_HD double dep(int dep_id, int col) const {
+    return d->surf_inputs[((size_t)d->month_idx[t] * d->n_dep_series + dep_id) * WSI_N_DEP + col];
+  }
+
+  // ---- algebra shorthands ----
+  WSI_HD Vq sum(const Vq& a, const Vq& b) const { return vq_sum<P>(add, a, b); }
+  WSI_HD Vq extract(const Vq& a, const Vq& b) const { return vq_extract<P>(add, a, b); }
+  WSI_HD Vq vchange(const Vq& a, double v) const { return vq_vchange<P>(add, a, v); }
+};
+
+// =========================================================================================
+// Tanks addressed in place (global memory read-modify-write)
+// =========================================================================================
+template <class C>
+struct TankRef {
+  double* st;     // plane 0 of the storage VQIP
+  size_t stride;  // distance between planes
+  double capacity;
+};
+
+// Tank.push_storage(force=True) tanks.py:189-192
+template <class C>
+WSI_HD void tank_push_force(const C& c, double* st, size_t stride, const typename C::Vq& v) {
+  c.stv(st, stride, c.sum(c.ldv(st, stride), v));
+}
+// Tank.get_excess()["volume"] tanks.py:132-158
+WSI_HD double tank_excess_vol(double capacity, double vol, bool has_v, double v_vol) {
+  double e = pymax(capacity - vol, 0.0);
+  if (has_v) e = pymin(v_vol, e);
+  return vol_vchange(vol, e);
+}
+// Tank.push_storage tanks.py:194-205 (capacity limited); returns the reply
+template <class C>
+WSI_HD typename C::Vq tank_push(const C& c, double* st, size_t stride, double capacity,
+                                const typename C::Vq& v) {
+  typename C::Vq s = c.ldv(st, stride);
+  const double excess = tank_excess_vol(capacity, s.x[0], false, 0.0);
+  typename C::Vq reply = c.vchange(v, pymax(v.x[0] - excess, 0.0));
+  typename C::Vq entered = c.vchange(v, v.x[0] - reply.x[0]);
+  c.stv(st, stride, c.sum(s, entered));
+  return reply;
+}
+// Tank.pull_storage tanks.py:207-239 on a register-resident storage
+template <class C>
+WSI_HD typename C::Vq vq_pull(const C& c, typename C::Vq& s, double vol) {
+  if (s.x[0] == 0) return vq_zero<C::P>();
+  typename C::Vq reply = c.vchange(s, pymin(vol, s.x[0]));
+  s = c.extract(s, reply);
+  return reply;
+}
+template <class C>
+WSI_HD typename C::Vq tank_pull(const C& c, double* st, size_t stride, double vol) {
+  typename C::Vq s = c.ldv(st, stride);
+  if (s.x[0] == 0) return vq_zero<C::P>();
+  typename C::Vq reply = vq_pull(c, s, vol);
+  c.stv(st, stride, s);
+  return reply;
+}
+// Tank.pull_pollutants tanks.py:241-266: clips the request (in place) and extracts it
+template <class C>
+WSI_HD void vq_pull_pollutants(const C& c, typename C::Vq& s, typename C::Vq& req) {
+#pragma unroll
+  for (int p = 1; p <= C::P; p++)
+    if (bit(c.add, p)) req.x[p] = pymin(s.x[p], req.x[p]);
+  req.x[0] = pymin(s.x[0], req.x[0]);
+  s = c.extract(s, req);
+}
+
+// =========================================================================================
+// Push protocol: Arc.send_push_check / send_push_request (arcs.py:112-257),
+// Node.push_distributed / check_basic (nodes.py:409-508) and the push handlers of every
+// supported node class.  D is the number of junction `Node`s the call may still traverse.
+// =========================================================================================
+template <int D, class C>
+WSI_HDN double arc_excess_vol(C& c, int a, bool has_v, double v_vol);
+template <int D, class C>
+WSI_HDN typename C::Vq arc_send_push_request(C& c, int a, const typename C::Vq& vqip);
+template <int D, class C>
+WSI_HDN typename C::Vq push_distributed(C& c, int node, const typename C::Vq& vqip, int filter);
+
+// sewer QueueTank helpers -------------------------------------------------------------------
+template <class C>
+WSI_HD void sewer_update_queue(C& c, int w) {  // AltQueueArc.update_queue arcs.py:603-638
+  constexpr int V = C::V;
+  const size_t s = c.s_sewer();
+  double* q0 = c.sewer(WSI_SEWER_QUEUE(V), w);
+  double* act = c.sewer(WSI_SEWER_ACTIVE_STORAGE(V), w);
+  c.stv(act, s, c.sum(c.ldv(act, s), c.ldv(q0, s)));  // QueueTank.push_set tanks.py:610-629
+  c.stv(q0, s, vq_zero<C::P>());
+}
+// QueueTank.push_storage(vqip, time) tanks.py:513-539 through AltQueueArc (arcs.py:360-407).
+template <class C>
+WSI_HDN typename C::Vq sewer_push_storage(C& c, int w, const typename C::Vq& v0, int time) {
+  constexpr int V = C::V;
+  using Vq = typename C::Vq;
+  const size_t s = c.s_sewer();
+  double* st = c.sewer(WSI_SEWER_STORAGE(V), w);
+  Vq reply;
+  if (v0.x[0] < c.FA) {
+    reply = vq_zero<C::P>();
+  } else {
+    const double cap = *c.sewer(WSI_SEWER_CAPACITY, w);
+    double* ia_flow_in = c.sewer(WSI_SEWER_IA_FLOW_IN, w);
+    const double pipe_excess = kUnbounded - *ia_flow_in;
+    const double svol = st[0];
+    double ne = vol_vchange(svol, pymax(cap - svol, 0.0));  // get_excess()
+    ne = pymin(v0.x[0], ne);                                // QueueTank.push_check tanks.py:605-608
+    const double excess_in = vol_vchange(ne, pymin(pipe_excess, ne));
+    Vq not_pushed = c.vchange(v0, pymax(v0.x[0] - excess_in, 0.0));
+    Vq v = c.extract(v0, not_pushed);
+    *ia_flow_in = *ia_flow_in + v.x[0] / (double)(time + 1);  // enter_arc arcs.py:423-427
+    double* qm = c.sewer(WSI_SEWER_QMASK, w);
+    unsigned qmask = (unsigned)*qm;
+    double* q = c.sewer(WSI_SEWER_QUEUE(V) + time * V, w);
+    if (qmask & (1u << time)) {  // AltQueueArc.enter_queue arcs.py:595-601
+      c.stv(q, s, c.sum(c.ldv(q, s), v));
+    } else {
+      c.stv(q, s, v);
+      *qm = (double)(qmask | (1u << time));
+    }
+    sewer_update_queue(c, w);
+    reply = c.sum(not_pushed, vq_zero<C::P>());  // + (empty) backflow
+  }
+  Vq entered = c.vchange(v0, v0.x[0] - reply.x[0]);
+  c.stv(st, s, c.sum(c.ldv(st, s), entered));
+  return reply;
+}
+
+template <int D, class C>
+WSI_HDN double node_push_check_vol(C& c, int node, bool has_v, double v_vol) {
+  const WsiModelDesc* d = c.d;
+  const int g = d->node_gidx[node];
+  constexpr int V = C::V;
+  switch (d->node_type[node]) {
+    case WSI_NT_NODE: {  // push_check_basic nodes.py:529-545 -> check_basic :480-508
+      if constexpr (D == 0) {
+        c.flag(node, WSI_FLAG_DEPTH);
+        return 0.0;
+      } else {
+        const int b = d->cand_ptr[node * WSI_NF + WSI_FILTER_NRWR];
+        const int e = d->cand_ptr[node * WSI_NF + WSI_FILTER_NRWR + 1];
+        double avail = 0.0;
+        for (int i = b; i < e; i++) avail = avail + arc_excess_vol<D - 1>(c, d->cand_arcs[i], false, 0.0);
+        if (has_v) avail = vol_vchange(avail, pymin(avail, v_vol));
+        return avail;
+      }
+    }
+    case WSI_NT_WASTE:  // push_check_accept nodes.py:611-623
+    case WSI_NT_RIVER:
+      return has_v ? v_vol : kUnbounded;
+    case WSI_NT_GROUNDWATER:
+    case WSI_NT_STORAGE:
+    case WSI_NT_RESERVOIR:  // tank.get_excess storage.py:71
+      return tank_excess_vol(*c.tank(WSI_TANK_CAPACITY, g), *c.tank(WSI_TANK_STORAGE(V), g), has_v,
+                             v_vol);
+    case WSI_NT_SEWER: {  // push_check_sewer sewer.py:145-161
+      const double vol = *c.sewer(WSI_SEWER_STORAGE(V), g);
+      const double ex = vol_vchange(vol, pymax(*c.sewer(WSI_SEWER_CAPACITY, g) - vol, 0.0));
+      if (!has_v) return ex;
+      return vol_vchange(ex, pymin(ex, v_vol));
+    }
+    default:  // Land / Catchment deny pushes (nodes.py:595-609)
+      c.flag(node, WSI_FLAG_DENY);
+      return 0.0;
+  }
+}
+
+template <int D, class C>
+WSI_HDN typename C::Vq node_push_set(C& c, int node, const typename C::Vq& vqip) {
+  const WsiModelDesc* d = c.d;
+  const int g = d->node_gidx[node];
+  constexpr int V = C::V;
+  switch (d->node_type[node]) {
+    case WSI_NT_NODE:  // junction: forward (nodes.py:62-66)
+      if constexpr (D == 0) {
+        c.flag(node, WSI_FLAG_DEPTH);
+        return vqip;
+      } else {
+        return push_distributed<D - 1>(c, node, vqip, WSI_FILTER_NRWR);
+      }
+    case WSI_NT_WASTE:  // waste.py:40-49
+      return vq_zero<C::P>();
+    case WSI_NT_RIVER: {  // push_set_river storage.py:711-721
+      const int tk = (int)*c.river(WSI_RIVER_TANK, g);
+      tank_push_force(c, c.tank(WSI_TANK_STORAGE(V), tk), c.s_tank(), vqip);
+      return vq_zero<C::P>();
+    }
+    case WSI_NT_GROUNDWATER:
+    case WSI_NT_STORAGE:
+    case WSI_NT_RESERVOIR:  // push_set_storage storage.py:106-118
+      return tank_push(c, c.tank(WSI_TANK_STORAGE(V), g), c.s_tank(), *c.tank(WSI_TANK_CAPACITY, g),
+                       vqip);
+    case WSI_NT_SEWER:  // push_set_sewer sewer.py:163-176
+      return sewer_push_storage(c, g, vqip, (int)*c.sewer(WSI_SEWER_PIPE_TIME, g));
+    default:
+      c.flag(node, WSI_FLAG_DENY);
+      return vqip;
+  }
+}
+
+// Arc.get_excess(direction="push")["volume"] arcs.py:230-257
+template <int D, class C>
+WSI_HDN double arc_excess_vol(C& c, int a, bool has_v, double v_vol) {
+  const double pipe_excess = *c.arc(WSI_ARC_CAPACITY, a) - *c.arc(WSI_ARC_FLOW_IN, a);
+  const double ne = node_push_check_vol<D>(c, c.d->arc_out[a], has_v, v_vol);
+  return vol_vchange(ne, pymin(pipe_excess, ne));
+}
+
+// Arc.send_push_request arcs.py:112-158
+template <int D, class C>
+WSI_HDN typename C::Vq arc_send_push_request(C& c, int a, const typename C::Vq& vqip) {
+  using Vq = typename C::Vq;
+  constexpr int V = C::V;
+  const double excess_in = arc_excess_vol<D>(c, a, true, vqip.x[0]);
+  const Vq not_pushed = c.vchange(vqip, pymax(vqip.x[0] - excess_in, 0.0));
+  const Vq v = c.extract(vqip, not_pushed);
+  Vq reply = node_push_set<D>(c, c.d->arc_out[a], v);
+  const Vq sent = c.extract(v, reply);
+  reply = c.sum(reply, not_pushed);
+  double* fi = c.arc(WSI_ARC_FLOW_IN, a);
+  *fi = *fi + sent.x[0];
+  double* vi = c.arc(WSI_ARC_VQIP_IN(V), a);
+  c.stv(vi, c.s_arc(), c.sum(c.ldv(vi, c.s_arc()), sent));
+  return reply;
+}
+
+// Node.push_distributed nodes.py:409-478
+template <int D, class C>
+WSI_HDN typename C::Vq push_distributed(C& c, int node, const typename C::Vq& vqip, int filter) {
+  using Vq = typename C::Vq;
+  const WsiModelDesc* d = c.d;
+  const int cb = d->cand_ptr[node * WSI_NF + filter];
+  int nc = d->cand_ptr[node * WSI_NF + filter + 1] - cb;
+  const int* cand = d->cand_arcs + cb;
+  const int n_out = d->out_ptr[node + 1] - d->out_ptr[node];
+  if (n_out == 1) {
+    if (nc > 0) return arc_send_push_request<D>(c, d->out_arcs[d->out_ptr[node]], vqip);
+    return vqip;
+  }
+  if (nc > kMaxCand) nc = kMaxCand;
+  double not_pushed = vqip.x[0];
+  Vq not_pushed_ = vqip;
+  double alloc[kMaxCand], cap_[kMaxCand];
+  double avail = 0.0, priority = 0.0;
+  // get_connected nodes.py:271-317
+  for (int i = 0; i < nc; i++) {
+    double a = arc_excess_vol<D>(c, cand[i], false, 0.0);
+    if (a < c.FA) a = 0.0;
+    const double pref = *c.arc(WSI_ARC_PREFERENCE, cand[i]);
+    avail += a;
+    priority += a * pref;
+    alloc[i] = a * pref;
+    cap_[i] = a;
+  }
+  if (not_pushed > avail) {
+    priority = avail;
+    for (int i = 0; i < nc; i++) alloc[i] = cap_[i];
+  }
+  int iter = 0;
+  while (not_pushed > c.FA && avail > c.FA && iter < kMaxIter) {
+    const double amount = pymin(avail, not_pushed);
+    for (int i = 0; i < nc; i++) {
+      const Vq to_send = c.vchange(not_pushed_, amount * alloc[i] / priority);
+      const Vq reply = arc_send_push_request<D>(c, cand[i], to_send);
+      const Vq sent = c.extract(to_send, reply);
+      not_pushed_ = c.extract(not_pushed_, sent);
+    }
+    not_pushed = not_pushed_.x[0];
+    avail = 0.0;
+    priority = 0.0;
+    for (int i = 0; i < nc; i++) {
+      double a = arc_excess_vol<D>(c, cand[i], false, 0.0);
+      if (a < c.FA) a = 0.0;
+      const double pref = *c.arc(WSI_ARC_PREFERENCE, cand[i]);
+      avail += a;
+      priority += a * pref;
+      alloc[i] = a * pref;
+    }
+    iter++;
+  }
+  if (iter == kMaxIter) c.flag(node, WSI_FLAG_MAXITER);
+  return not_pushed_;
+}
+
+// =========================================================================================
+// Mass-balance bookkeeping
+// =========================================================================================
+// (in, ds, out) of one object checked as WSIObj.mass_balance does (core.py:403-427);
+// optionally recorded and accumulated into the per-thread system totals.
+template <class C>
+WSI_HD void mb_check(C& c, int node, const typename C::Vq& in_, const typename C::Vq& ds_,
+                     const typename C::Vq& out_) {
+  constexpr int V = C::V;
+  int viol = 0;
+#pragma unroll
+  for (int p = 0; p <= C::P; p++) {
+    if (p != 0 && !bit(c.add, p)) continue;
+    const double a = in_.x[p], o = out_.x[p], dd = ds_.x[p];
+    const double largest = pymax(pymax(a, o), dd);
+    double in10 = a, out10 = o, ds10 = dd;
+    if (largest > c.FA) {
+      const double magnitude = pow(10.0, (double)(int)log10(largest));
+      in10 = a / magnitude;
+      out10 = o / magnitude;
+      ds10 = dd / magnitude;
+    }
+    if (fabs(in10 - ds10 - out10) > c.FA) viol++;
+  }
+  if (viol) {
+    c.flag(node, WSI_FLAG_MASS_BALANCE);
+    c.viol += viol;
+  }
+  if (c.mb_acc) {
+#pragma unroll
+    for (int p = 0; p <= C::P; p++) {
+      if (p != 0 && !bit(c.add, p)) continue;
+      c.mb_acc[(0 * V + p) * c.mb_stride] += in_.x[p];
+      c.mb_acc[(1 * V + p) * c.mb_stride] += ds_.x[p];
+      c.mb_acc[(2 * V + p) * c.mb_stride] += out_.x[p];
+    }
+  }
+  const WsiModelDesc* d = c.d;
+  const int row = c.t - d->rec_t0;
+  if (d->record_mb && row >= 0 && row < d->rec_T) {
+    double* o = d->out_mb + ((size_t)row * d->n_nodes + node) * 3 * V * c.R + c.r;
+#pragma unroll
+    for (int p = 0; p < V; p++) {
+      o[(size_t)(0 * V + p) * c.R] = in_.x[p];
+      o[(size_t)(1 * V + p) * c.R] = ds_.x[p];
+      o[(size_t)(2 * V + p) * c.R] = out_.x[p];
+    }
+  }
+}
+
+// Node.total_in / total_out nodes.py:104-132
+template <class C>
+WSI_HD typename C::Vq total_in(const C& c, int node) {
+  const WsiModelDesc* d = c.d;
+  typename C::Vq v = vq_zero<C::P>();
+  for (int i = d->in_ptr[node]; i < d->in_ptr[node + 1]; i++)
+    v = c.sum(v, c.ldv(c.arc(WSI_ARC_VQIP_IN(C::V), d->in_arcs[i]), c.s_arc()));
+  return v;
+}
+template <class C>
+WSI_HD typename C::Vq total_out(const C& c, int node) {
+  const WsiModelDesc* d = c.d;
+  typename C::Vq v = vq_zero<C::P>();
+  for (int i = d->out_ptr[node]; i < d->out_ptr[node + 1]; i++)
+    v = c.sum(v, c.ldv(c.arc(WSI_ARC_VQIP_IN(C::V), d->out_arcs[i]), c.s_arc()));
+  return v;
+}
+// ds_ accumulation of mass_balance (core.py:397-401): volume + additive only
+template <class C>
+WSI_HD void ds_add(const C& c, typename C::Vq& acc, const typename C::Vq& v) {
+#pragma unroll
+  for (int p = 0; p <= C::P; p++)
+    if (p == 0 || bit(c.add, p)) acc.x[p] += v.x[p];
+}
+
+// =========================================================================================
+// Decay (core.py:474-521) on a register-resident storage; decay slots of a group start at
+// plane `f_n` (n_decay, pol[4], const[4], exp[4], total[4], pre[4])
+// =========================================================================================
+template <class C, class PlaneFn>
+WSI_HD void decay_end_timestep(const C& c, typename C::Vq& st, PlaneFn plane, int f_n,
+                               double temperature) {
+  const int n = (int)*plane(f_n);
+  for (int i = 0; i < WSI_MAX_DECAY; i++) {
+    if (i >= n) break;
+    const int pol = (int)*plane(f_n + 1 + i);
+    const double k = *plane(f_n + 1 + WSI_MAX_DECAY + i);
+    const double e = *plane(f_n + 1 + 2 * WSI_MAX_DECAY + i);
+    const double x = vget<C::P>(st, pol);
+    const double f = k * pow(e, temperature - 20.0);  // constants.DECAY_REFERENCE_TEMPERATURE
+    const double diff = x * pymin(f, 1.0);
+    *plane(f_n + 1 + 4 * WSI_MAX_DECAY + i) = x;  // storage_[pol] (tanks.py:445)
+    vset<C::P>(st, pol, x - diff);
+    // total_decayed = sum_vqip(empty, diff): only additive lanes accumulate (core.py:491)
+    *plane(f_n + 1 + 3 * WSI_MAX_DECAY + i) = bit(c.add, pol) ? 0.0 + diff : 0.0;
+  }
+}
+// total_decayed as a VQIP (zero volume)
+template <class C, class PlaneFn>
+WSI_HD typename C::Vq decay_total(const C& c, PlaneFn plane, int f_n) {
+  typename C::Vq td = vq_zero<C::P>();
+  const int n = (int)*plane(f_n);
+  for (int i = 0; i < WSI_MAX_DECAY; i++) {
+    if (i >= n) break;
+    vset<C::P>(td, (int)*plane(f_n + 1 + i), *plane(f_n + 1 + 3 * WSI_MAX_DECAY + i));
+  }
+  return td;
+}
+template <class PlaneFn>
+WSI_HD double decay_total_of(PlaneFn plane, int f_n, int pol) {
+  const int n = (int)*plane(f_n);
+  double r = 0.0;
+  for (int i = 0; i < WSI_MAX_DECAY; i++) {
+    if (i >= n) break;
+    if ((int)*plane(f_n + 1 + i) == pol) r = *plane(f_n + 1 + 3 * WSI_MAX_DECAY + i);
+  }
+  return r;
+}
+
+}  // namespace wsi
+
+#include "wsi_land.cuh"
+#include "wsi_nodes.cuh"

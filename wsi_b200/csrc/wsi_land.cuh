@@ -1,0 +1,742 @@
+// Land node and its surfaces (reference: wsimod/nodes/land.py, nodes/nutrient_pool.py).
+//
+// A surface's soil-water VQIP, its nutrient pools and its three outgoing flow VQIPs are held
+// in registers while its inflow/process/outflow function lists run; every parameter plane is
+// read exactly once where it is used.  Included by wsi_device.cuh.
+#pragma once
+
+namespace wsi {
+
+// vol + additive accumulation used for running_inflow_mb / running_outflow_mb
+// (land.py:441-449): the non-additive lanes of those VQIPs never reach a comparison.
+template <class C>
+WSI_HD void mb_acc(const C& c, typename C::Vq& acc, const typename C::Vq& v) {
+#pragma unroll
+  for (int p = 0; p <= C::P; p++)
+    if (p == 0 || bit(c.add, p)) acc.x[p] += v.x[p];
+}
+
+// NutrientStore.extract nutrient_pool.py:542-556
+WSI_HD double pool_extract(double& store, double amount) {
+  const double r = pymin(store, amount);
+  store -= r;
+  return r;
+}
+
+// NutrientPool state of one GrowingSurface, [N, P] pairs
+struct Pools {
+  double fast[2], humus[2], dis_inorg[2], dis_org[2], ads_inorg[2];
+  double tdf, smdf;  // temperature / soil-moisture dependence factors
+};
+
+// temp_soil_process nutrient_pool.py:452-481
+WSI_HD void temp_soil_process(const Pools& pl, const double par0, const double par1, double* ext,
+                              double* rcv, double* amount) {
+  amount[0] = par0 * pl.tdf * pl.smdf * ext[0];
+  amount[1] = par1 * pl.tdf * pl.smdf * ext[1];
+  amount[0] = pool_extract(ext[0], amount[0]);
+  amount[1] = pool_extract(ext[1], amount[1]);
+  rcv[0] += amount[0];
+  rcv[1] += amount[1];
+}
+
+// GrowingSurface.quick_interp land.py:1495-1512: bisect_left + Python negative-index wrap.
+// xp/yp are table planes (stride `st` doubles apart)
+WSI_HD double quick_interp(double x, const double* xp, const double* yp, size_t st, int n) {
+  int i = 0;
+  while (i < n && xp[(size_t)i * st] < x) i++;
+  int il = i - 1;
+  if (il < 0) il += n;
+  if (i >= n) i = n - 1;  // the reference raises IndexError here
+  const double x_left = xp[(size_t)il * st], x_right = xp[(size_t)i * st];
+  const double y_left = yp[(size_t)il * st], y_right = yp[(size_t)i * st];
+  return y_left + (y_right - y_left) * (x - x_left) / (x_right - x_left);
+}
+
+// GrowingSurface.adjust_vqip_to_liquid land.py:1574-1603
+template <class C>
+WSI_HD void adjust_to_liquid(const C& c, typename C::Vq& v, double depN, double depP, double inN,
+                             double inP) {
+  if (c.cfg.no3() < 0) return;
+  if (depN > 0) {
+    vmul<C::P>(v, c.cfg.no3(), inN / depN);
+    vmul<C::P>(v, c.cfg.nh4(), inN / depN);
+    vmul<C::P>(v, c.cfg.orgn(), inN / depN);
+  }
+  if (depP > 0) {
+    vmul<C::P>(v, c.cfg.po4(), inP / depP);
+    vmul<C::P>(v, c.cfg.orgp(), inP / depP);
+  }
+}
+
+// One surface of a Land node: Surface.run land.py:425-449 with the function lists of
+// Surface / ImperviousSurface / PerviousSurface / GrowingSurface (land.py:375-382, 619-621,
+// 830-841, 1275-1291).  Accumulates the parent's running mass-balance VQIPs and, when
+// `want_ds`, the surface's ds term.
+template <class C>
+WSI_HDN void surface_run(C& c, int node, int L, int u, double precip, double et0, double temperature,
+                         typename C::Vq& mb_in, typename C::Vq& mb_out, typename C::Vq& ds_acc,
+                         bool want_ds) {
+  using Vq = typename C::Vq;
+  constexpr int P = C::P;
+  constexpr int V = C::V;
+  const size_t ss = c.s_surf();
+  auto S = [&](int plane) -> double* { return c.surf(plane, u); };
+  const int type = (int)*S(WSI_SURF_TYPE);
+  const double area = *S(WSI_SURF_AREA);
+  double* stp = S(WSI_SURF_STORAGE(V));
+  Vq st = c.ldv(stp, ss);
+  const auto& cfg = c.cfg;
+
+  // nitrification hand-over from last step's decay (land.py:427-439)
+  if (cfg.no2() >= 0) {
+    const double dn2 = decay_total_of(S, WSI_SURF_N_DECAY, cfg.no2());
+    vadd<P>(st, cfg.no3(), dn2);
+    vadd<P>(mb_in, cfg.no3(), dn2);
+    const double dnh = decay_total_of(S, WSI_SURF_N_DECAY, cfg.nh4());
+    vadd<P>(st, cfg.no2(), dnh);
+    vadd<P>(mb_in, cfg.no2(), dnh);
+  }
+
+  const bool growing = type == WSI_ST_GROWINGSURFACE;
+  const bool nutrients = growing && cfg.no3() >= 0;
+  Pools pl;
+  if (growing) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      pl.fast[k] = *S(WSI_SURF_POOL_FAST + k);
+      pl.humus[k] = *S(WSI_SURF_POOL_HUMUS + k);
+      pl.dis_inorg[k] = *S(WSI_SURF_POOL_DIS_INORG + k);
+      pl.dis_org[k] = *S(WSI_SURF_POOL_DIS_ORG + k);
+      pl.ads_inorg[k] = *S(WSI_SURF_POOL_ADS_INORG + k);
+    }
+    pl.tdf = 0.0;
+    pl.smdf = 0.0;
+  }
+  double et0_coef = *S(WSI_SURF_ET0_COEFFICIENT);
+  double days_after_sow = 0.0, crop_cover = 0.0, ground_cover = 0.0;
+
+  // ---- inflows --------------------------------------------------------------------------
+  if (growing) {  // calc_crop_cover land.py:1514-1572
+    const double doy = (double)c.d->doy_adj[c.t];
+    const double dayofyear = (double)c.d->dayofyear[c.t];
+    days_after_sow = *S(WSI_SURF_DAYS_AFTER_SOW);
+    crop_cover = *S(WSI_SURF_CROP_COVER);
+    ground_cover = *S(WSI_SURF_GROUND_COVER);
+    if (days_after_sow < 0) {
+      if (dayofyear == *S(WSI_SURF_SOWING_DAY)) days_after_sow = 0.0;
+    } else {
+      if (dayofyear == *S(WSI_SURF_HARVEST_DAY)) {
+        days_after_sow = -1.0;
+        crop_cover = 0.0;
+        ground_cover = 0.0;
+      } else {
+        days_after_sow += 1.0;
+      }
+    }
+    const double crop_factor = quick_interp(doy, S(WSI_SURF_STAGE_DATES), S(WSI_SURF_STAGE_VALS), ss,
+                                            (int)*S(WSI_SURF_N_STAGE));
+    if (days_after_sow > 0) {
+      crop_cover = quick_interp(doy, S(WSI_SURF_HS_CALENDAR), S(WSI_SURF_CROP_COVER_STAGES), ss, 5);
+      ground_cover = quick_interp(doy, S(WSI_SURF_HS_CALENDAR), S(WSI_SURF_GROUND_COVER_STAGES), ss, 5);
+    }
+    const double fc_m = *S(WSI_SURF_FIELD_CAPACITY_M);
+    const double rzd = pymax(fc_m - st.x[0] / area, 0.0);
+    double stress;
+    if (rzd < *S(WSI_SURF_READILY_AVAILABLE_WATER)) {
+      stress = 1.0;
+    } else {
+      const double taw = *S(WSI_SURF_TOTAL_AVAILABLE_WATER);
+      stress = pymax(0.0, (taw - rzd) / ((1 - *S(WSI_SURF_ET_DEPLETION_FACTOR)) * taw));
+    }
+    et0_coef = stress * crop_factor;
+    *S(WSI_SURF_DAYS_AFTER_SOW) = days_after_sow;
+    *S(WSI_SURF_CROP_COVER) = crop_cover;
+    *S(WSI_SURF_GROUND_COVER) = ground_cover;
+    *S(WSI_SURF_CROP_FACTOR) = crop_factor;
+    *S(WSI_SURF_ET0_COEFFICIENT) = et0_coef;
+  }
+
+  const int dep_id = (int)*S(WSI_SURF_DEP_ID);
+  if (*S(WSI_SURF_HAS_DEP) != 0.0) {
+    // atmospheric_deposition / precipitation_deposition land.py:528-581 (dry, then wet)
+#pragma unroll
+    for (int wet = 0; wet < 2; wet++) {
+      const int b = wet ? WSI_DEP_NHX_WET : WSI_DEP_NHX_DRY;
+      const double nhx = c.dep(dep_id, b) * area;
+      const double noy = c.dep(dep_id, b + 1) * area;
+      const double srp = c.dep(dep_id, b + 2) * area;
+      Vq v = vq_zero<P>();
+      vset<P>(v, cfg.nh4(), nhx);
+      vset<P>(v, cfg.no3(), noy);
+      vset<P>(v, cfg.po4(), srp);
+      if (growing) {  // dry/wet_deposition_to_tank land.py:2267-2311
+        const double depN = noy + nhx, depP = srp;
+        double inN, inP;
+        if (!wet) {  // allocate_dry_deposition nutrient_pool.py:226-248
+          const double f_di = *S(WSI_SURF_FRAC_DRY_N_TO_DIS_INORG);
+          pl.fast[0] += depN * *S(WSI_SURF_FRAC_DRY_N_TO_FAST);
+          pl.dis_inorg[0] += depN * f_di;
+          pl.ads_inorg[1] += depP;
+          inN = depN * f_di;
+          inP = 0.0;
+        } else {  // allocate_wet_deposition nutrient_pool.py:250-265
+          pl.dis_inorg[0] += depN;
+          pl.dis_inorg[1] += depP;
+          inN = depN;
+          inP = depP;
+        }
+        adjust_to_liquid(c, v, depN, depP, inN, inP);
+      }
+      st = c.sum(st, v);
+      mb_acc(c, mb_in, v);
+    }
+  }
+  if (*S(WSI_SURF_HAS_LOAD) != 0.0) {  // simple_deposition land.py:505-526
+    Vq pol;
+    pol.x[0] = 0.0;
+    const double* lp = S(WSI_SURF_LOAD(V));
+#pragma unroll
+    for (int p = 1; p <= P; p++) pol.x[p] = bit(c.add, p) ? lp[(size_t)p * ss] * area : lp[(size_t)p * ss];
+    st = c.sum(st, pol);
+    mb_acc(c, mb_in, pol);
+  }
+
+  Vq ie = vq_zero<P>(), sf = vq_zero<P>(), pc = vq_zero<P>();  // infiltration_excess, subsurface_flow, percolation
+  double out_evap = 0.0, out_precip = 0.0, out_recharge = 0.0;
+
+  if (type == WSI_ST_IMPERVIOUSSURFACE) {
+    // precipitation_evaporation land.py:645-697
+    const double evaporation_depth = et0 * *S(WSI_SURF_ET0_TO_E);
+    double total_evaporation;
+    if (precip < evaporation_depth) {
+      double e = (evaporation_depth - precip) * area;
+      e = pymin(e, st.x[0]);  // Tank.evaporate tanks.py:303-317
+      st.x[0] -= e;
+      total_evaporation = e + precip * area;
+    } else {
+      Vq np = vq_volume<P>((precip - evaporation_depth) * area);
+      vset<P>(np, cfg.temp(), temperature);
+      st = c.sum(st, np);
+      total_evaporation = evaporation_depth * area;
+    }
+    out_evap = total_evaporation;
+    out_precip = precip * area;
+    mb_in.x[0] += out_precip;
+    mb_out.x[0] += out_evap;
+    // push_to_sewers land.py:699-721: pull_ponded, push to Sewers, force the reply back
+    const double ponded = pymax(st.x[0] - *S(WSI_SURF_CAPACITY), 0.0);
+    Vq runoff = vq_pull(c, st, ponded);
+    Vq reply = push_distributed<kJunctionDepth>(c, node, runoff, WSI_FILTER_SEWER);
+    st = c.sum(st, reply);
+  } else if (type >= WSI_ST_PERVIOUSSURFACE) {
+    // ihacres land.py:913-1044
+    const double depth = *S(WSI_SURF_DEPTH);
+    const double capacity = *S(WSI_SURF_CAPACITY);
+    const double fc_m = *S(WSI_SURF_FIELD_CAPACITY_M);
+    const double wp_m = *S(WSI_SURF_WILTING_POINT_M);
+    const double evaporation_depth = et0 * et0_coef;  // get_climate land.py:903-911
+    const double inf_cap = *S(WSI_SURF_INFILTRATION_CAPACITY);
+    const double infiltrated = pymin(precip, inf_cap);
+    double infiltration_excess = pymax(precip - infiltrated, 0.0);
+    const double cmd = tank_excess_vol(capacity, st.x[0], false, 0.0) / area;  // get_cmd land.py:886
+    double evaporation = evaporation_depth * pymin(1.0, exp(2 * (1 - cmd / (depth - wp_m))));
+    const double outflow =
+        infiltrated * (1 - pymin(1.0, pow(cmd / (depth - fc_m), *S(WSI_SURF_IHACRES_P))));
+    evaporation = pymin(evaporation, precip + st.x[0] / area);
+    const double surf_coef = *S(WSI_SURF_SURFACE_COEFFICIENT);
+    const double surface = outflow * surf_coef * area;
+    const double percolation = outflow * (1 - surf_coef) * *S(WSI_SURF_PERCOLATION_COEFFICIENT) * area;
+    const double subsurface_flow = outflow * (1 - surf_coef) * *S(WSI_SURF_SUBSURFACE_COEFFICIENT) * area;
+    const double tank_recharge = (infiltrated - evaporation - outflow) * area;
+    infiltration_excess *= area;
+    infiltration_excess += surface;
+    evaporation *= area;
+    const double precipitation = precip * area;
+    const double total = tank_recharge + subsurface_flow + percolation;
+    if (total > 0) {
+      Vq tw = vq_volume<P>(total);
+      vset<P>(tw, cfg.temp(), temperature);
+      st = c.sum(st, tw);
+      // pull_storage: Tank version (tanks.py:207-239) or GrowingSurface override (land.py:1433-1493)
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const double want = k == 0 ? subsurface_flow : percolation;
+        Vq reply = vq_zero<P>();
+        if (st.x[0] != 0) {
+          reply = c.vchange(st, pymin(want, st.x[0]));
+          if (nutrients) {
+            const double prop = reply.x[0] / st.x[0];
+            // extract_dissolved nutrient_pool.py:330-356
+            const double diN = pool_extract(pl.dis_inorg[0], pl.dis_inorg[0] * prop);
+            const double diP = pool_extract(pl.dis_inorg[1], pl.dis_inorg[1] * prop);
+            const double doN = pool_extract(pl.dis_org[0], pl.dis_org[0] * prop);
+            const double doP = pool_extract(pl.dis_org[1], pl.dis_org[1] * prop);
+            const double sno3 = vget<P>(st, cfg.no3()), snh4 = vget<P>(st, cfg.nh4()),
+                         sno2 = vget<P>(st, cfg.no2());
+            const double den = sno3 + snh4 + sno2;
+            if (den == 0) c.flag(node, WSI_FLAG_NAN);
+            vset<P>(reply, cfg.no3(), diN * sno3 / den);
+            vset<P>(reply, cfg.nh4(), diN * snh4 / den);
+            vset<P>(reply, cfg.no2(), diN * sno2 / den);
+            vset<P>(reply, cfg.po4(), diP);
+            vset<P>(reply, cfg.orgp(), doP);
+            vset<P>(reply, cfg.orgn(), doN);
+          }
+          st = c.extract(st, reply);
+        }
+        if (k == 0)
+          sf = reply;
+        else
+          pc = reply;
+      }
+    } else {
+      const double e = pymin(-total, st.x[0]);  // Tank.evaporate
+      st.x[0] -= e;
+    }
+    ie = vq_volume<P>(infiltration_excess);
+    vset<P>(ie, cfg.temp(), temperature);
+    out_evap = evaporation;
+    out_precip = precipitation;
+    out_recharge = tank_recharge;
+    mb_in.x[0] += precipitation;
+    mb_out.x[0] += evaporation;
+
+    if (nutrients) {
+      // effective_precipitation_flushing land.py:1605-1647
+      {
+        const int a = cfg.nh4(), b = cfg.no2(), n3 = cfg.no3();
+        double N = vget<P>(sf, a) + vget<P>(sf, b) + vget<P>(sf, n3) + vget<P>(pc, a) + vget<P>(pc, b) +
+                   vget<P>(pc, n3) + vget<P>(ie, a) + vget<P>(ie, b) + vget<P>(ie, n3);
+        double Pp = vget<P>(sf, cfg.po4()) + vget<P>(pc, cfg.po4()) + vget<P>(ie, cfg.po4());
+        (void)pool_extract(pl.dis_inorg[0], N);
+        (void)pool_extract(pl.dis_inorg[1], Pp);
+        N = vget<P>(sf, cfg.orgn()) + vget<P>(pc, cfg.orgn()) + vget<P>(ie, cfg.orgn());
+        Pp = vget<P>(sf, cfg.orgp()) + vget<P>(pc, cfg.orgp()) + vget<P>(ie, cfg.orgp());
+        (void)pool_extract(pl.dis_org[0], N);
+        (void)pool_extract(pl.dis_org[1], Pp);
+      }
+      // fertiliser land.py:1649-1679, manure land.py:1681-1710
+#pragma unroll
+      for (int manure = 0; manure < 2; manure++) {
+        const int b = manure ? WSI_DEP_NHX_MANURE : WSI_DEP_NHX_FERTILISER;
+        const double nhx = c.dep(dep_id, b) * area;
+        const double noy = c.dep(dep_id, b + 1) * area;
+        const double srp = c.dep(dep_id, b + 2) * area;
+        Vq v = vq_zero<P>();
+        vset<P>(v, cfg.nh4(), nhx);
+        vset<P>(v, cfg.no3(), noy);
+        vset<P>(v, cfg.po4(), srp);
+        const double depN = noy + nhx, depP = srp;
+        double inN, inP;
+        if (!manure) {  // allocate_fertiliser nutrient_pool.py:314-328
+          pl.dis_inorg[0] += depN;
+          pl.dis_inorg[1] += depP;
+          inN = depN;
+          inP = depP;
+        } else {  // allocate_manure nutrient_pool.py:267-290
+          const double fN = *S(WSI_SURF_FRAC_MANURE_TO_DIS_INORG), fP = *S(WSI_SURF_FRAC_MANURE_TO_DIS_INORG + 1);
+          pl.dis_inorg[0] += depN * fN;
+          pl.dis_inorg[1] += depP * fP;
+          pl.fast[0] += depN * *S(WSI_SURF_FRAC_MANURE_TO_FAST);
+          pl.fast[1] += depP * *S(WSI_SURF_FRAC_MANURE_TO_FAST + 1);
+          inN = depN * fN;
+          inP = depP * fP;
+        }
+        adjust_to_liquid(c, v, depN, depP, inN, inP);
+        st = c.sum(st, v);
+        mb_acc(c, mb_in, v);
+      }
+    }
+
+    // ---- processes ----------------------------------------------------------------------
+    if (cfg.temp() >= 0) {  // calculate_soil_temperature land.py:1060-1079
+      const double w_prev = *S(WSI_SURF_SOIL_TEMP_W_PREV), w_air = *S(WSI_SURF_SOIL_TEMP_W_AIR),
+                   w_deep = *S(WSI_SURF_SOIL_TEMP_W_DEEP);
+      const double au = vget<P>(st, cfg.temp()) * w_prev;
+      const double air = temperature * w_air;
+      const double total_weight = w_air + w_deep + w_prev;
+      vset<P>(st, cfg.temp(), (au + air + *S(WSI_SURF_SOIL_TEMP_DEEP) * w_deep) / total_weight);
+    }
+    if (nutrients) {
+      const double rooting_depth = *S(WSI_SURF_ROOTING_DEPTH);
+      const double soilT = vget<P>(st, cfg.temp());
+      // calc_temperature_dependence_factor land.py:1813-1831
+      if (soilT > 5)
+        pl.tdf = pow(2.0, (soilT - 20) / 10);
+      else if (soilT > 0)
+        pl.tdf = soilT / 5;
+      else
+        pl.tdf = 0.0;
+      // calc_soil_moisture_dependence_factor land.py:1833-1856
+      {
+        const double smc = st.x[0] / area;
+        const double satact = *S(WSI_SURF_SATACT);
+        if (smc >= fc_m) {
+          pl.smdf = satact;
+        } else if (smc <= wp_m) {
+          pl.smdf = 0.0;
+        } else {
+          const double thetapow = *S(WSI_SURF_THETAPOW);
+          double fc_comp = pow((fc_m - smc) / (*S(WSI_SURF_THETAUPP) * rooting_depth), thetapow);
+          fc_comp = (1 - satact) * fc_comp + satact;
+          const double wp_comp = pow((smc - wp_m) / (*S(WSI_SURF_THETALOW) * rooting_depth), thetapow);
+          pl.smdf = pymin(pymin(1.0, wp_comp), fc_comp);
+        }
+      }
+      // soil_pool_transformation land.py:1744-1811 + nutrient_pool.py:396-450
+      {
+        const double sno3 = vget<P>(st, cfg.no3()), snh4 = vget<P>(st, cfg.nh4());
+        if (sno3 + snh4 == 0) c.flag(node, WSI_FLAG_NAN);
+        const double nitrate_proportion = sno3 / (sno3 + snh4);
+        double inc_di[2] = {0.0, 0.0}, inc_do[2] = {0.0, 0.0}, amount[2];
+        temp_soil_process(pl, *S(WSI_SURF_DEGRHPAR), *S(WSI_SURF_DEGRHPAR + 1), pl.humus, pl.fast, amount);
+        temp_soil_process(pl, *S(WSI_SURF_DISHPAR), *S(WSI_SURF_DISHPAR + 1), pl.humus, pl.dis_org, amount);
+        inc_do[0] = inc_do[0] + amount[0];
+        inc_do[1] = inc_do[1] + amount[1];
+        temp_soil_process(pl, *S(WSI_SURF_MINFPAR), *S(WSI_SURF_MINFPAR + 1), pl.fast, pl.dis_inorg, amount);
+        inc_di[0] = inc_di[0] + amount[0];
+        inc_di[1] = inc_di[1] + amount[1];
+        temp_soil_process(pl, *S(WSI_SURF_DISFPAR), *S(WSI_SURF_DISFPAR + 1), pl.fast, pl.dis_org, amount);
+        inc_do[0] = inc_do[0] + amount[0];
+        inc_do[1] = inc_do[1] + amount[1];
+        temp_soil_process(pl, *S(WSI_SURF_IMMOBDPAR), *S(WSI_SURF_IMMOBDPAR + 1), pl.dis_inorg, pl.fast, amount);
+        inc_di[0] = inc_di[0] - amount[0];
+        inc_di[1] = inc_di[1] - amount[1];
+        Vq in_ = vq_zero<P>(), out_ = vq_zero<P>();
+        if (inc_di[0] > 0) {
+          vset<P>(in_, cfg.no3(), inc_di[0] * nitrate_proportion);
+          vset<P>(in_, cfg.nh4(), inc_di[0] * (1 - nitrate_proportion));
+        } else {
+          vset<P>(out_, cfg.no3(), -inc_di[0] * nitrate_proportion);
+          vset<P>(out_, cfg.nh4(), -inc_di[0] * (1 - nitrate_proportion));
+        }
+        if (inc_do[0] > 0)
+          vset<P>(in_, cfg.orgn(), inc_do[0]);
+        else
+          vset<P>(out_, cfg.orgn(), -inc_do[0]);
+        if (inc_di[1] > 0)
+          vset<P>(in_, cfg.po4(), inc_di[1]);
+        else
+          vset<P>(out_, cfg.po4(), -inc_di[1]);
+        if (inc_do[1] > 0)
+          vset<P>(in_, cfg.orgp(), inc_do[1]);
+        else
+          vset<P>(out_, cfg.orgp(), -inc_do[1]);
+        st = c.sum(st, in_);
+        vq_pull_pollutants(c, st, out_);  // clips out_ in place (tanks.py:261-262)
+        mb_acc(c, mb_in, in_);
+        mb_acc(c, mb_out, out_);
+      }
+      // calc_crop_uptake land.py:1858-1926
+      if (days_after_sow > 0) {
+        double das = days_after_sow;
+        double temp_func = 1.0;
+        if (*S(WSI_SURF_AUTUMN_SOW) != 0.0) {
+          temp_func = pymax(0.0, pymin(1.0, (vget<P>(st, cfg.temp()) - 5) / 20));
+          das -= 25;
+        }
+        const double u1 = *S(WSI_SURF_UPTAKE1), u2 = *S(WSI_SURF_UPTAKE2), u3 = *S(WSI_SURF_UPTAKE3);
+        const double uptake_par = (u1 - u2) * exp(-u3 * das);
+        double N_common = 0.0;
+        if (uptake_par + u2 > 0) N_common = u1 * u2 * u3 * uptake_par / ((u2 + uptake_par) * (u2 + uptake_par));
+        N_common *= temp_func * 1e-3 * area;  // G_M2_TO_KG_M2
+        const double P_common = N_common * *S(WSI_SURF_UPTAKE_PNRATIO);
+        const double frac = pymax(0.0, st.x[0] - wp_m * area) / st.x[0];
+        const double N_max = frac * pl.dis_inorg[0];
+        const double P_max = frac * pl.dis_inorg[1];
+        const double gotP = pool_extract(pl.dis_inorg[1], pymin(P_common, P_max));
+        const double gotN = pool_extract(pl.dis_inorg[0], pymin(N_common, N_max));
+        Vq out_ = vq_zero<P>();
+        vset<P>(out_, cfg.no3(), gotN);
+        vset<P>(out_, cfg.po4(), gotP);
+        vq_pull_pollutants(c, st, out_);
+        mb_acc(c, mb_out, out_);
+      }
+      // erosion land.py:1928-2094
+      {
+        const double precipitation_depth = precip * 1e3;  // M_TO_MM
+        double mobilised_rain = 0.0, mobilised_flow = 0.0;
+        if (precipitation_depth > 5) {
+          const double dayofyear = (double)c.d->dayofyear[c.t];
+          double rainfall_energy =
+              8.95 + 8.44 * log10(precipitation_depth *
+                                  (0.257 + sin(2 * 3.141592653589793 * ((dayofyear - 70) / 365)) * 0.09) * 2);
+          rainfall_energy *= precipitation_depth;
+          mobilised_rain = rainfall_energy * (1 - crop_cover) * *S(WSI_SURF_ERODIBILITY);
+        }
+        if (ie.x[0] > 0) {
+          mobilised_flow = pow(ie.x[0] / area * 1e3 * 365, *S(WSI_SURF_SREROEXP));
+          mobilised_flow *= (1 - ground_cover) * (1 / (0.5 * *S(WSI_SURF_COHESION))) *
+                            sin(*S(WSI_SURF_SLOPE) / 100) / 365;
+        }
+        const double total_flows = ie.x[0] + sf.x[0] + pc.x[0];
+        const double erodingflow = total_flows / area * 1e3;
+        const double transportfactor = pymin(1.0, pow(erodingflow / 4, 1.3));
+        double erodedsed = 1000 * (mobilised_flow + mobilised_rain) * transportfactor;
+        double enrichment = 0.0;
+        bool active = true;
+        if (erodingflow > 4)
+          enrichment = 1.5;
+        else if (erodingflow > 0)
+          enrichment = 4 - (4 - 1.5) * erodingflow / 4;
+        else
+          active = false;  // early return land.py:1996-1997
+        if (active) {
+          const double erodableP = (pl.ads_inorg[1] + pl.humus[1]) / area * 1e6;  // KG_M2_TO_KG_KM2
+          const double bulk_density = *S(WSI_SURF_BULK_DENSITY);
+          double erodedP = erodedsed * (erodableP / (rooting_depth * 1e-3 * bulk_density * 1e9)) * enrichment;
+          erodedP *= area * 1e-6;
+          erodedsed *= area * 1e-6;
+          const double srfilt = *S(WSI_SURF_SRFILT), macrofilt = *S(WSI_SURF_MACROFILT);
+          const double surface_erodedP = srfilt * ie.x[0] / total_flows * erodedP;
+          const double surface_erodedsed = srfilt * ie.x[0] / total_flows * erodedsed;
+          const double subsurface_erodedP = macrofilt * sf.x[0] / total_flows * erodedP;
+          const double subsurface_erodedsed = macrofilt * sf.x[0] / total_flows * erodedsed;
+          const double percolation_erodedP = macrofilt * pc.x[0] / total_flows * erodedP;
+          const double percolation_erodedsed = macrofilt * pc.x[0] / total_flows * erodedsed;
+          const double eff_erodedP = percolation_erodedP + surface_erodedP + subsurface_erodedP;
+          if (eff_erodedP > 0) {
+            // erode_P nutrient_pool.py:367-394
+            const double fraction_adsorbed = pl.ads_inorg[1] / (pl.ads_inorg[1] + pl.humus[1]);
+            const double inorg_removed = pool_extract(pl.ads_inorg[1], eff_erodedP * fraction_adsorbed);
+            const double org_removed = pool_extract(pl.humus[1], eff_erodedP * (1 - fraction_adsorbed));
+            vadd<P>(ie, cfg.orgp(), surface_erodedP * org_removed / eff_erodedP);
+            vadd<P>(sf, cfg.orgp(), subsurface_erodedP * org_removed / eff_erodedP);
+            vadd<P>(pc, cfg.orgp(), percolation_erodedP * org_removed / eff_erodedP);
+            vadd<P>(ie, cfg.po4(), surface_erodedP * inorg_removed / eff_erodedP);
+            vadd<P>(sf, cfg.po4(), subsurface_erodedP * inorg_removed / eff_erodedP);
+            vadd<P>(pc, cfg.po4(), percolation_erodedP * inorg_removed / eff_erodedP);
+            vadd<P>(mb_in, cfg.po4(), inorg_removed);
+            vadd<P>(mb_in, cfg.orgp(), org_removed);
+          }
+          if (cfg.solids() >= 0) {
+            vadd<P>(ie, cfg.solids(), surface_erodedsed);
+            vadd<P>(sf, cfg.solids(), subsurface_erodedsed);
+            vadd<P>(pc, cfg.solids(), percolation_erodedsed);
+            vadd<P>(mb_in, cfg.solids(), surface_erodedsed + subsurface_erodedsed + percolation_erodedsed);
+          }
+        }
+      }
+      // denitrification land.py:2096-2152
+      {
+        const double smc = st.x[0] / area;
+        double dep_f = -1.0;
+        const double limpar = *S(WSI_SURF_LIMPAR);
+        if (smc > fc_m)
+          dep_f = 1.0;
+        else if (smc / fc_m > limpar)
+          dep_f = pow(((smc / fc_m) - limpar) / (1 - limpar), *S(WSI_SURF_EXPPAR));
+        if (dep_f >= 0) {
+          double din_conc = pl.dis_inorg[0] / st.x[0];
+          din_conc *= 1e3;  // KG_M3_TO_MG_L
+          const double hs = din_conc / (din_conc + *S(WSI_SURF_HSATINS));
+          const double denitrified = pl.dis_inorg[0] * hs * dep_f * pl.tdf * *S(WSI_SURF_DENPAR);
+          const double got = pool_extract(pl.dis_inorg[0], denitrified);
+          Vq out_ = vq_zero<P>();
+          vset<P>(out_, cfg.no3(), got);
+          vq_pull_pollutants(c, st, out_);
+          mb_acc(c, mb_out, out_);
+        }
+      }
+      // adsorption land.py:2154-2265 (Freundlich isotherm, Newton-Raphson)
+      {
+        const double bulk_density = *S(WSI_SURF_BULK_DENSITY);
+        double ad_de_P_pool = pl.ads_inorg[1] + pl.dis_inorg[1];
+        ad_de_P_pool /= area * 1e-6;
+        if (ad_de_P_pool != 0) {
+          const double kfr = *S(WSI_SURF_KFR), nfr = *S(WSI_SURF_NFR);
+          const double smc_mm = st.x[0] / area * 1e3;
+          const double conc_sol = pl.ads_inorg[1] * 1e6 / (bulk_density * rooting_depth * area);
+          const double coeff = kfr * bulk_density * rooting_depth;
+          double ad_P_equi_conc;
+          if (conc_sol <= 0) {
+            const double xn_1 = ad_de_P_pool / (smc_mm + coeff);
+            ad_P_equi_conc = kfr * xn_1;
+          } else {
+            const double limit = *S(WSI_SURF_ADSORPTION_NR_LIMIT);
+            const int maxiter = (int)*S(WSI_SURF_ADSORPTION_NR_MAXITER);
+            const double x0 = exp((log(conc_sol) - log(kfr)) / nfr);
+            double fxn = x0 * smc_mm + coeff * pow(x0, nfr) - ad_de_P_pool;
+            double xn = x0, xn_1 = x0;
+            int j = 0;
+            while (fabs(fxn) > limit && j < maxiter) {
+              fxn = xn * smc_mm + coeff * pow(xn, nfr) - ad_de_P_pool;
+              const double fprimxn = smc_mm + nfr * coeff * pow(xn, nfr - 1);
+              const double dx = fxn / fprimxn;
+              if (fabs(dx) < 0.000001 * xn) break;
+              xn_1 = xn - dx;
+              if (xn_1 <= 0) xn_1 = 1e-10;
+              xn = xn_1;
+              j++;
+            }
+            ad_P_equi_conc = kfr * pow(xn_1, nfr);
+          }
+          if (fabs(ad_P_equi_conc - conc_sol) > 1e-6) {
+            const double adsdes = (ad_P_equi_conc - conc_sol) * (1 - exp(-*S(WSI_SURF_KADSDES)));
+            double req = adsdes * bulk_density * rooting_depth * (area * 1e-6);
+            if (req > 0) {
+              const double adsorbed = pool_extract(pl.dis_inorg[1], req);
+              pl.ads_inorg[1] += adsorbed;
+              Vq out_ = vq_zero<P>();
+              vset<P>(out_, cfg.po4(), adsorbed);
+              vq_pull_pollutants(c, st, out_);
+              mb_acc(c, mb_out, out_);
+            } else {
+              req = -req;
+              const double desorbed = pool_extract(pl.ads_inorg[1], req);
+              pl.dis_inorg[1] += desorbed;
+              Vq in_ = vq_zero<P>();
+              vset<P>(in_, cfg.po4(), desorbed);
+              st = c.sum(st, in_);
+              mb_acc(c, mb_in, in_);
+            }
+          }
+        }
+      }
+    }
+    // ---- outflows: route land.py:1046-1058 -------------------------------------------------
+    tank_push_force(c, c.land(WSI_LAND_SURFACE_RUNOFF(V), L), c.s_land(), ie);
+    tank_push_force(c, c.land(WSI_LAND_SUBSURFACE_RUNOFF(V), L), c.s_land(), sf);
+    tank_push_force(c, c.land(WSI_LAND_PERCOLATION(V), L), c.s_land(), pc);
+  }
+
+  // ---- write back ---------------------------------------------------------------------------
+  if (want_ds) {
+    // decay_ds tanks.py:449-457: (storage - storage_) + total_decayed, where storage_ is what
+    // is still in memory except for the decayed pollutants (pre_decay)
+    Vq old = c.ldv(stp, ss);
+    const int n = (int)*S(WSI_SURF_N_DECAY);
+    for (int i = 0; i < WSI_MAX_DECAY; i++) {
+      if (i >= n) break;
+      vset<P>(old, (int)*S(WSI_SURF_DECAY_POL + i), *S(WSI_SURF_PRE_DECAY + i));
+    }
+    Vq dsv;
+#pragma unroll
+    for (int p = 0; p <= P; p++) dsv.x[p] = (p == 0 || bit(c.add, p)) ? st.x[p] - old.x[p] : 0.0;
+    dsv = c.sum(dsv, decay_total<C>(c, S, WSI_SURF_N_DECAY));
+    ds_add(c, ds_acc, dsv);
+  }
+  c.stv(stp, ss, st);
+  if (growing) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      *S(WSI_SURF_POOL_FAST + k) = pl.fast[k];
+      *S(WSI_SURF_POOL_HUMUS + k) = pl.humus[k];
+      *S(WSI_SURF_POOL_DIS_INORG + k) = pl.dis_inorg[k];
+      *S(WSI_SURF_POOL_DIS_ORG + k) = pl.dis_org[k];
+      *S(WSI_SURF_POOL_ADS_INORG + k) = pl.ads_inorg[k];
+    }
+  }
+  if (c.d->n_probe > 0) {  // per-step diagnostics recorded by Model.run (model.py:1081-1118)
+    *S(WSI_SURF_OUT_PERCOLATION) = pc.x[0];
+    *S(WSI_SURF_OUT_SUBSURFACE) = sf.x[0];
+    *S(WSI_SURF_OUT_SURFACE) = ie.x[0];
+    *S(WSI_SURF_OUT_EVAPORATION) = out_evap;
+    *S(WSI_SURF_OUT_PRECIPITATION) = out_precip;
+    *S(WSI_SURF_OUT_TANK_RECHARGE) = out_recharge;
+  }
+}
+
+// ResidenceTank.pull_outflow tanks.py:387-400 on an in-memory tank
+template <class C>
+WSI_HD typename C::Vq residence_pull(const C& c, double* st, size_t stride, double residence_time) {
+  typename C::Vq s = c.ldv(st, stride);
+  const double outflow = vol_vchange(s.x[0], s.x[0] / residence_time);
+  typename C::Vq o = vq_pull(c, s, outflow);
+  c.stv(st, stride, s);
+  return o;
+}
+
+// Land.run land.py:200-244, followed (when requested) by the node's mass balance
+// (core.py:370-429 with Land's term lists, land.py:113,158-162)
+template <class C>
+WSI_HDN void land_run(C& c, int node) {
+  using Vq = typename C::Vq;
+  constexpr int P = C::P;
+  constexpr int V = C::V;
+  const WsiModelDesc* d = c.d;
+  const int L = d->node_gidx[node];
+  const size_t sl = c.s_land();
+  const bool want_mb = (c.run_flags & WSI_RUN_MASS_BALANCE) != 0;
+  const int fid = (int)*c.land(WSI_LAND_FORCING_ID, L);
+  const double precip = c.forcing(fid, 0), et0 = c.forcing(fid, 1), temperature = c.forcing(fid, 2);
+
+  double* t_surf = c.land(WSI_LAND_SURFACE_RUNOFF(V), L);
+  double* t_sub = c.land(WSI_LAND_SUBSURFACE_RUNOFF(V), L);
+  double* t_perc = c.land(WSI_LAND_PERCOLATION(V), L);
+  Vq ds = vq_zero<P>();
+  // the three ResidenceTanks' storage_ are whatever is in memory at the start of the step
+  Vq neg0 = vq_zero<P>(), neg1 = vq_zero<P>(), neg2 = vq_zero<P>();
+  if (want_mb) {
+    neg0 = c.ldv(t_surf, sl);
+    neg1 = c.ldv(t_sub, sl);
+    neg2 = c.ldv(t_perc, sl);
+  }
+  Vq mb_in = vq_zero<P>(), mb_out = vq_zero<P>();
+  for (int i = d->land_surf_ptr[L]; i < d->land_surf_ptr[L + 1]; i++)
+    surface_run(c, node, L, d->land_surf[i], precip, et0, temperature, mb_in, mb_out, ds, want_mb);
+
+  // percolation -> Groundwater (land.py:207-215)
+  {
+    Vq percolation = residence_pull(c, t_perc, sl, *c.land(WSI_LAND_RES_PERCOLATION, L));
+    Vq reply = push_distributed<kJunctionDepth>(c, node, percolation, WSI_FILTER_GROUNDWATER);
+    if (reply.x[0] > c.FA) tank_push_force(c, t_perc, sl, reply);
+  }
+  // surface + subsurface runoff -> River / junction Node (land.py:217-244)
+  {
+    Vq surface_runoff = residence_pull(c, t_surf, sl, *c.land(WSI_LAND_RES_SURFACE, L));
+    Vq subsurface_runoff = residence_pull(c, t_sub, sl, *c.land(WSI_LAND_RES_SUBSURFACE, L));
+    Vq total_runoff = c.sum(surface_runoff, subsurface_runoff);
+    if (total_runoff.x[0] > 0) {
+      Vq reply = push_distributed<kJunctionDepth>(c, node, total_runoff, WSI_FILTER_RIVER_NODE);
+      if (reply.x[0] > 0) {
+        Vq rs = c.vchange(reply, reply.x[0] * surface_runoff.x[0] / total_runoff.x[0]);
+        Vq rss = c.vchange(reply, reply.x[0] * subsurface_runoff.x[0] / total_runoff.x[0]);
+        if (rs.x[0] > 0) tank_push_force(c, t_surf, sl, rs);
+        if (rss.x[0] > 0) tank_push_force(c, t_sub, sl, rss);
+      }
+    }
+  }
+  if (want_mb) {
+    Vq in_ = c.sum(vq_zero<P>(), total_in(c, node));
+    Vq out_ = c.sum(vq_zero<P>(), total_out(c, node));
+#pragma unroll
+    for (int p = 0; p <= P; p++)
+      if (p == 0 || bit(c.add, p)) {
+        in_.x[p] += mb_in.x[p];
+        out_.x[p] += mb_out.x[p];
+      }
+    Vq f0 = c.ldv(t_surf, sl), f1 = c.ldv(t_sub, sl), f2 = c.ldv(t_perc, sl);
+#pragma unroll
+    for (int p = 0; p <= P; p++)
+      if (p == 0 || bit(c.add, p)) {
+        ds.x[p] += f0.x[p] - neg0.x[p];
+        ds.x[p] += f1.x[p] - neg1.x[p];
+        ds.x[p] += f2.x[p] - neg2.x[p];
+      }
+    mb_check(c, node, in_, ds, out_);
+  }
+}
+
+// Land.end_timestep land.py:266-275: surfaces are DecayTanks (tanks.py:442-447); the
+// residence tanks only refresh storage_, which is implicit here.
+template <class C>
+WSI_HD void land_end_timestep(C& c, int node) {
+  constexpr int V = C::V;
+  const WsiModelDesc* d = c.d;
+  const int L = d->node_gidx[node];
+  const double temperature = c.forcing((int)*c.land(WSI_LAND_FORCING_ID, L), 2);
+  for (int i = d->land_surf_ptr[L]; i < d->land_surf_ptr[L + 1]; i++) {
+    const int u = d->land_surf[i];
+    auto S = [&](int plane) -> double* { return c.surf(plane, u); };
+    if ((int)*S(WSI_SURF_N_DECAY) > 0) {
+      double* stp = S(WSI_SURF_STORAGE(V));
+      typename C::Vq st = c.ldv(stp, c.s_surf());
+      decay_end_timestep(c, st, S, WSI_SURF_N_DECAY, temperature);
+      c.stv(stp, c.s_surf(), st);
+    }
+  }
+}
+
+}  // namespace wsi

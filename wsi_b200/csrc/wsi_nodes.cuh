@@ -1,0 +1,507 @@
+// Storage / Groundwater / River / Reservoir / Sewer / Catchment operations, per-node mass
+// balance, recording, end_timestep and the per-replica step driver
+// (reference: wsimod/nodes/storage.py, sewer.py, catchment.py, waste.py, core/core.py,
+// orchestration/model.py:993-1176).  Included by wsi_device.cuh.
+#pragma once
+
+namespace wsi {
+
+// ---- Groundwater / Storage / Reservoir ----------------------------------------------------
+template <class C>
+WSI_HDN void gw_infiltrate(C& c, int node) {  // storage.py:231-245
+  constexpr int V = C::V;
+  const int g = c.d->node_gidx[node];
+  double* st = c.tank(WSI_TANK_STORAGE(V), g);
+  double avail = st[0];
+  avail = pymax(avail - *c.tank(WSI_TANK_CAPACITY, g) * *c.tank(WSI_TANK_INFILTRATION_THRESHOLD, g), 0.0);
+  avail = pow(avail * *c.tank(WSI_TANK_INFILTRATION_PCT, g), 0.5);
+  typename C::Vq to_send = tank_pull(c, st, c.s_tank(), avail);
+  typename C::Vq retained = push_distributed<kJunctionDepth>(c, node, to_send, WSI_FILTER_SEWER);
+  tank_push_force(c, st, c.s_tank(), retained);
+}
+template <class C>
+WSI_HDN void gw_distribute(C& c, int node) {  // storage.py:222-229
+  constexpr int V = C::V;
+  const int g = c.d->node_gidx[node];
+  double* st = c.tank(WSI_TANK_STORAGE(V), g);
+  const double avail = st[0] / *c.tank(WSI_TANK_RESIDENCE_TIME, g);
+  typename C::Vq to_send = tank_pull(c, st, c.s_tank(), avail);
+  typename C::Vq retained = push_distributed<kJunctionDepth>(c, node, to_send, WSI_FILTER_NRW);
+  tank_push_force(c, st, c.s_tank(), retained);
+}
+template <class C>
+WSI_HDN void storage_distribute(C& c, int node) {  // storage.py:120-127
+  constexpr int V = C::V;
+  const int g = c.d->node_gidx[node];
+  double* st = c.tank(WSI_TANK_STORAGE(V), g);
+  typename C::Vq storage = tank_pull(c, st, c.s_tank(), st[0]);
+  typename C::Vq retained = push_distributed<kJunctionDepth>(c, node, storage, WSI_FILTER_ALL);
+  tank_push_force(c, st, c.s_tank(), retained);
+}
+// Reservoir.make_abstractions storage.py:983-989 with no in-arcs: pull_distributed returns
+// an empty VQIP (nodes.py:376-407), which is then pushed (twice) into the tank.
+template <class C>
+WSI_HDN void reservoir_abstract(C& c, int node) {
+  constexpr int V = C::V;
+  const int g = c.d->node_gidx[node];
+  double* st = c.tank(WSI_TANK_STORAGE(V), g);
+  typename C::Vq spill = tank_push(c, st, c.s_tank(), *c.tank(WSI_TANK_CAPACITY, g), vq_zero<C::P>());
+  tank_push_force(c, st, c.s_tank(), spill);
+}
+
+// ---- River --------------------------------------------------------------------------------
+// Python's sum() over a list slice (CPython >= 3.12: Neumaier compensated summation) on a
+// ring buffer stored as planes; entries [first, first+n) counted from the oldest.
+WSI_HD double ring_sum(const double* ring, size_t stride, int cap, int head, int first, int n) {
+  if (n <= 0) return 0.0;
+  double f = ring[(size_t)((head + first) % cap) * stride], comp = 0.0;
+  for (int k = 1; k < n; k++) {
+    const double x = ring[(size_t)((head + first + k) % cap) * stride];
+    const double t = f + x;
+    if (fabs(f) >= fabs(x))
+      comp += (f - t) + x;
+    else
+      comp += (x - t) + f;
+    f = t;
+  }
+  if (comp != 0.0 && isfinite(comp)) f += comp;
+  return f;
+}
+
+// River.calculate_discharge -> biochemical_processes storage.py:738-898, 917-924
+template <class C>
+WSI_HDN void river_calc(C& c, int node) {
+  using Vq = typename C::Vq;
+  constexpr int P = C::P;
+  constexpr int V = C::V;
+  const auto& cfg = c.cfg;
+  if (cfg.no3() < 0) return;
+  const int g = c.d->node_gidx[node];
+  auto Rv = [&](int plane) -> double* { return c.river(plane, g); };
+  const int tk = (int)*Rv(WSI_RIVER_TANK);
+  const size_t sr = c.s_river();
+  double* stp = c.tank(WSI_TANK_STORAGE(V), tk);
+  Vq st = c.ldv(stp, c.s_tank());
+  Vq in_ = vq_zero<P>(), out_ = vq_zero<P>();
+  const double area = *Rv(WSI_RIVER_AREA);
+  const double current_depth = st.x[0] / area;  // update_depth storage.py:723-725
+  const double T_wdays = *Rv(WSI_RIVER_T_WDAYS);
+  const double airT = c.forcing((int)*c.tank(WSI_TANK_FORCING_ID, tk), 2);
+  double T = (1 - 1 / T_wdays) * vget<P>(st, cfg.temp()) + (1 / T_wdays) * airT;
+  vset<P>(st, cfg.temp(), T);
+  // lagged lists storage.py:753-763
+  int nT = (int)*Rv(WSI_RIVER_N_LAG_T), hT = (int)*Rv(WSI_RIVER_HEAD_T);
+  if (nT > (int)*Rv(WSI_RIVER_MAX_TEMP_LAG)) {
+    hT = (hT + 1) % WSI_LAG_T;
+    nT--;
+  }
+  *Rv(WSI_RIVER_LAG_T + (hT + nT) % WSI_LAG_T) = T;
+  nT++;
+  *Rv(WSI_RIVER_N_LAG_T) = (double)nT;
+  *Rv(WSI_RIVER_HEAD_T) = (double)hT;
+  int nTP = (int)*Rv(WSI_RIVER_N_LAG_TP), hTP = (int)*Rv(WSI_RIVER_HEAD_TP);
+  const double max_p_lag = *Rv(WSI_RIVER_MAX_PHOSPHORUS_LAG);
+  if (nTP > (int)max_p_lag) {
+    hTP = (hTP + 1) % WSI_LAG_TP;
+    nTP--;
+  }
+  *Rv(WSI_RIVER_LAG_TP + (hTP + nTP) % WSI_LAG_TP) = vget<P>(st, cfg.po4()) + vget<P>(st, cfg.orgp());
+  nTP++;
+  *Rv(WSI_RIVER_N_LAG_TP) = (double)nTP;
+  *Rv(WSI_RIVER_HEAD_TP) = (double)hTP;
+
+  if (!(st.x[0] < c.FA) && !(T <= 0)) {
+    const int dc[2] = {cfg.nh4(), cfg.no3()};  // din_components storage.py:566
+    double tempfcn = pow(2.0, (T - 20) / 10);
+    if (T < 5) tempfcn *= T / 5;
+    double din = 0.0 + vget<P>(st, dc[0]) + vget<P>(st, dc[1]);
+    const double din_concentration = din / st.x[0];
+    const double confcn = din_concentration / (din_concentration + *Rv(WSI_RIVER_HALFSATINWATER));
+    const double denitri_water = *Rv(WSI_RIVER_DENPAR_W) * area * tempfcn * confcn;
+    const double river_denitrification = pymin(denitri_water, 0.5 * din);
+    const double din_ = din - river_denitrification;
+    if (din > 0) {
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const double loss = (din - din_) / din * vget<P>(st, dc[k]);
+        vadd<P>(out_, dc[k], loss);
+        vsub<P>(st, dc[k], loss);
+      }
+    }
+    din = 0.0 + vget<P>(st, dc[0]) + vget<P>(st, dc[1]);
+    const int n10 = nT < 10 ? nT : 10, n20 = nT < 20 ? nT : 20;
+    const double temp_10_day = ring_sum(Rv(WSI_RIVER_LAG_T), sr, WSI_LAG_T, hT, nT - n10, n10) / 10;
+    const double temp_20_day = ring_sum(Rv(WSI_RIVER_LAG_T), sr, WSI_LAG_T, hT, nT - n20, n20) / 20;
+    const double total_phos_365_day = ring_sum(Rv(WSI_RIVER_LAG_TP), sr, WSI_LAG_TP, hTP, 0, nTP) / max_p_lag;
+    tempfcn = T / 20 * (temp_10_day - temp_20_day) / 5;
+    const double limpppar = *Rv(WSI_RIVER_LIMPPPAR), hsatTP = *Rv(WSI_RIVER_HSATTP);
+    double totalphosfcn = 0.0;
+    if (total_phos_365_day - limpppar + hsatTP > 0)
+      totalphosfcn = (total_phos_365_day - limpppar) / (total_phos_365_day - limpppar + hsatTP);
+    double minprodN = *Rv(WSI_RIVER_PRODNPAR) * totalphosfcn * tempfcn * area * current_depth;
+    double minprodP =
+        *Rv(WSI_RIVER_PRODPPAR) * totalphosfcn * tempfcn * area * current_depth * *Rv(WSI_RIVER_UPTAKE_PNRATIO);
+    if (minprodN > 0) {  // production (inorganic -> organic)
+      minprodN = pymin(0.5 * din, minprodN);
+      minprodP = pymin(0.5 * vget<P>(st, cfg.po4()), minprodP);
+      vset<P>(out_, cfg.po4(), minprodP);
+      vsub<P>(st, cfg.po4(), minprodP);
+      vset<P>(in_, cfg.orgp(), minprodP);
+      vadd<P>(st, cfg.orgp(), minprodP);
+      if (din > 0) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          const double loss = minprodN * vget<P>(st, dc[k]) / din;
+          vadd<P>(out_, dc[k], loss);
+          vsub<P>(st, dc[k], loss);
+        }
+      }
+      vset<P>(in_, cfg.orgn(), minprodN);
+      vadd<P>(st, cfg.orgn(), minprodN);
+    } else {  // mineralisation (organic -> inorganic)
+      minprodN = pymin(0.5 * vget<P>(st, cfg.orgn()), -minprodN);
+      minprodP = pymin(0.5 * vget<P>(st, cfg.orgp()), -minprodP);
+      vset<P>(in_, cfg.po4(), minprodP);
+      vadd<P>(st, cfg.po4(), minprodP);
+      vset<P>(out_, cfg.orgp(), minprodP);
+      vsub<P>(st, cfg.orgp(), minprodP);
+      if (din > 0) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          const double gain = minprodN * vget<P>(st, dc[k]) / din;
+          vadd<P>(in_, dc[k], gain);
+          vadd<P>(st, dc[k], gain);
+        }
+      }
+      vset<P>(out_, cfg.orgn(), minprodN);
+      vsub<P>(st, cfg.orgn(), minprodN);
+    }
+    din = 0.0 + vget<P>(st, dc[0]) + vget<P>(st, dc[1]);
+    const double tempfcn1 = pow(pymax(0.0, T) / 20, 0.3);
+    const double tempfcn2 = (T - temp_20_day) / 5;
+    tempfcn = pymax(0.0, tempfcn1 * tempfcn2);
+    const double macrouptN = *Rv(WSI_RIVER_MUPTNPAR) * tempfcn * area;
+    const double mN = pymin(0.5 * din, macrouptN);
+    if (din > 0) {
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const double loss = mN * vget<P>(st, dc[k]) / din;
+        vadd<P>(out_, dc[k], loss);
+        vsub<P>(st, dc[k], loss);
+      }
+    }
+    const double macrouptP = *Rv(WSI_RIVER_MUPTPPAR) * tempfcn * pymax(0.0, totalphosfcn) * area;
+    const double mP = pymin(0.5 * vget<P>(st, cfg.po4()), macrouptP);
+    vadd<P>(out_, cfg.po4(), mP);
+    vsub<P>(st, cfg.po4(), mP);
+  }
+  c.stv(stp, c.s_tank(), st);
+  c.stv(Rv(WSI_RIVER_BIO_IN(V)), sr, in_);
+  c.stv(Rv(WSI_RIVER_BIO_OUT(V)), sr, out_);
+}
+
+template <class C>
+WSI_HDN void river_distribute(C& c, int node) {  // storage.py:926-936
+  constexpr int V = C::V;
+  const int g = c.d->node_gidx[node];
+  const int tk = (int)*c.river(WSI_RIVER_TANK, g);
+  double* st = c.tank(WSI_TANK_STORAGE(V), tk);
+  typename C::Vq outflow = tank_pull(c, st, c.s_tank(), st[0] * *c.river(WSI_RIVER_RIVERRC, g));
+  typename C::Vq reply = push_distributed<kJunctionDepth>(c, node, outflow, WSI_FILTER_NRW);
+  tank_push_force(c, st, c.s_tank(), reply);
+}
+
+// ---- Sewer --------------------------------------------------------------------------------
+template <class C>
+WSI_HDN void sewer_discharge(C& c, int node) {  // sewer.py:201-239
+  using Vq = typename C::Vq;
+  constexpr int V = C::V;
+  const int w = c.d->node_gidx[node];
+  const size_t s = c.s_sewer();
+  sewer_update_queue(c, w);
+  double* act = c.sewer(WSI_SEWER_ACTIVE_STORAGE(V), w);
+  double* st = c.sewer(WSI_SEWER_STORAGE(V), w);
+  Vq active = c.ldv(act, s);
+  Vq remaining = push_distributed<kJunctionDepth>(c, node, active, WSI_FILTER_ALL);
+  active = c.ldv(act, s);
+  Vq sent = c.extract(active, remaining);
+  // pull_storage_exact tanks.py:566-586
+  Vq reply = sent;
+  reply.x[0] = pymin(reply.x[0], active.x[0]);
+#pragma unroll
+  for (int p = 1; p <= C::P; p++)
+    if (bit(c.add, p)) reply.x[p] = pymin(reply.x[p], active.x[p]);
+  active = c.extract(active, reply);
+  Vq storage = c.extract(c.ldv(st, s), reply);
+  // pull_ponded tanks.py:78-100 -> QueueTank.pull_storage tanks.py:541-564
+  const double ponded_v = pymax(storage.x[0] - *c.sewer(WSI_SEWER_CAPACITY, w), 0.0);
+  Vq ponded = c.vchange(active, pymin(ponded_v, active.x[0]));
+  active = c.extract(active, ponded);
+  storage = c.extract(storage, ponded);
+  if (ponded.x[0] > c.FA) {
+    // push_distributed(ponded, of_type=["Land"]) has no eligible arc (the flattener refuses
+    // Sewer->Land arcs), so everything is forced back (sewer.py:236-237, tanks.py:526-530)
+    storage = c.sum(storage, ponded);
+    active = c.sum(active, ponded);
+  }
+  c.stv(act, s, active);
+  c.stv(st, s, storage);
+}
+
+// QueueTank._end_timestep tanks.py:631-635 + AltQueueArc.end_timestep arcs.py:640-660
+template <class C>
+WSI_HD void sewer_end_timestep(C& c, int w) {
+  using Vq = typename C::Vq;
+  constexpr int V = C::V;
+  const size_t s = c.s_sewer();
+  const int nq = c.d->nq;
+  *c.sewer(WSI_SEWER_IA_FLOW_IN, w) = 0.0;
+  unsigned keys = (unsigned)*c.sewer(WSI_SEWER_QMASK, w);
+  int max_travel = 1;
+  for (int k = 2; k < nq; k++)
+    if (keys & (1u << k)) max_travel = k;
+  double* q = c.sewer(WSI_SEWER_QUEUE(V), w);
+  const Vq q0 = c.ldv(q, s);
+  const Vq q1 = c.ldv(q + (size_t)V * s, s);
+  // arcs.py:653-658: queue[i] = queue_[i+1]; queue[i+1] = empty, for the keys that exist
+  unsigned newkeys = keys | 1u;
+  for (int i = 1; i < nq; i++) {
+    const bool take = (i < max_travel) && ((keys >> (i + 1)) & 1u);
+    if (take) {
+      c.stv(q + (size_t)i * V * s, s, c.ldv(q + (size_t)(i + 1) * V * s, s));
+      newkeys |= 1u << i;
+    } else if ((keys >> i) & 1u) {
+      c.stv(q + (size_t)i * V * s, s, vq_zero<C::P>());
+    }
+  }
+  *c.sewer(WSI_SEWER_QMASK, w) = (double)newkeys;
+  // queue[0] = sum_vqip(queue_[0], queue_[1]), then update_queue() empties it into active
+  const Vq merged = c.sum(q0, q1);
+  double* act = c.sewer(WSI_SEWER_ACTIVE_STORAGE(V), w);
+  c.stv(act, s, c.sum(c.ldv(act, s), merged));
+  c.stv(q, s, vq_zero<C::P>());
+  // storage_ = copy(storage)
+  c.stv(c.sewer(WSI_SEWER_STORAGE_LAG(V), w), s, c.ldv(c.sewer(WSI_SEWER_STORAGE(V), w), s));
+}
+
+// ---- Catchment ------------------------------------------------------------------------------
+template <class C>
+WSI_HD typename C::Vq catch_get_flow(const C& c, int g) {  // catchment.py:60-75
+  const WsiModelDesc* d = c.d;
+  const int cid = (int)d->catchm[(size_t)g * c.R + c.r];
+  const double* row = d->catch_inputs + ((size_t)c.t * d->n_cseries + cid) * C::V;
+  typename C::Vq v;
+#pragma unroll
+  for (int p = 0; p <= C::P; p++) v.x[p] = row[p];
+#pragma unroll
+  for (int p = 1; p <= C::P; p++)
+    if (bit(c.add, p)) v.x[p] *= v.x[0];
+  return v;
+}
+// Catchment.route catchment.py:77-88; returns unrouted_water (needed by the mass balance)
+template <class C>
+WSI_HDN void catchment_route(C& c, int node) {
+  using Vq = typename C::Vq;
+  const WsiModelDesc* d = c.d;
+  const int g = d->node_gidx[node];
+  Vq avail = catch_get_flow(c, g);
+  for (int i = d->out_ptr[node]; i < d->out_ptr[node + 1]; i++)  // get_avail catchment.py:90-104
+    avail = c.vchange(avail, avail.x[0] - *c.arc(WSI_ARC_VQIP_IN(C::V), d->out_arcs[i]));
+  const Vq flow = avail;
+  Vq reply = push_distributed<kJunctionDepth>(c, node, flow, WSI_FILTER_NRW);
+  if (c.run_flags & WSI_RUN_MASS_BALANCE) {
+    // in = total_in + get_flow(); out = total_out + unrouted_water (catchment.py:55-56)
+    Vq in_ = c.sum(c.sum(vq_zero<C::P>(), total_in(c, node)), catch_get_flow(c, g));
+    Vq out_ = c.sum(c.sum(vq_zero<C::P>(), total_out(c, node)), c.sum(vq_zero<C::P>(), reply));
+    mb_check(c, node, in_, vq_zero<C::P>(), out_);
+  }
+}
+
+// ---- mass balance of the remaining node classes (core.py:370-429) --------------------------
+template <class C>
+WSI_HD typename C::Vq tank_ds(const C& c, int tk) {  // tanks.py:70-76 / 449-457
+  constexpr int V = C::V;
+  using Vq = typename C::Vq;
+  const Vq st = c.ldv(c.tank(WSI_TANK_STORAGE(V), tk), c.s_tank());
+  const Vq st_ = c.ldv(c.tank(WSI_TANK_STORAGE_LAG(V), tk), c.s_tank());
+  Vq dsv;
+#pragma unroll
+  for (int p = 0; p <= C::P; p++) dsv.x[p] = (p == 0 || bit(c.add, p)) ? st.x[p] - st_.x[p] : 0.0;
+  if (*c.tank(WSI_TANK_IS_DECAY, tk) != 0.0) {
+    auto Tk = [&](int plane) -> double* { return c.tank(plane, tk); };
+    dsv = c.sum(dsv, decay_total<C>(c, Tk, WSI_TANK_N_DECAY));
+  }
+  return dsv;
+}
+
+template <class C>
+WSI_HDN void node_mass_balance(C& c, int node) {
+  using Vq = typename C::Vq;
+  constexpr int V = C::V;
+  const WsiModelDesc* d = c.d;
+  const int g = d->node_gidx[node];
+  const int type = d->node_type[node];
+  if (type == WSI_NT_LAND || type == WSI_NT_CATCHMENT) return;  // fused into their ops
+  const Vq tin = total_in(c, node);
+  Vq in_ = c.sum(vq_zero<C::P>(), tin);
+  Vq out_ = c.sum(vq_zero<C::P>(), total_out(c, node));
+  Vq ds = vq_zero<C::P>();
+  switch (type) {
+    case WSI_NT_WASTE:  // waste.py:38
+      out_ = c.sum(out_, tin);
+      break;
+    case WSI_NT_SEWER: {
+      const Vq st = c.ldv(c.sewer(WSI_SEWER_STORAGE(V), g), c.s_sewer());
+      const Vq st_ = c.ldv(c.sewer(WSI_SEWER_STORAGE_LAG(V), g), c.s_sewer());
+#pragma unroll
+      for (int p = 0; p <= C::P; p++)
+        if (p == 0 || bit(c.add, p)) ds.x[p] += st.x[p] - st_.x[p];
+      break;
+    }
+    case WSI_NT_GROUNDWATER:
+    case WSI_NT_STORAGE:
+    case WSI_NT_RESERVOIR:
+      ds_add(c, ds, tank_ds(c, g));
+      break;
+    case WSI_NT_RIVER: {
+      in_ = c.sum(in_, c.ldv(c.river(WSI_RIVER_BIO_IN(V), g), c.s_river()));
+      out_ = c.sum(out_, c.ldv(c.river(WSI_RIVER_BIO_OUT(V), g), c.s_river()));
+      ds_add(c, ds, tank_ds(c, (int)*c.river(WSI_RIVER_TANK, g)));
+      break;
+    }
+    default:
+      break;
+  }
+  mb_check(c, node, in_, ds, out_);
+}
+
+// ---- end_timestep (model.py:1172-1176) ------------------------------------------------------
+template <class C>
+WSI_HD void store_end_timestep(C& c, int tk) {  // tanks.py:348-351 / 442-447
+  constexpr int V = C::V;
+  double* stp = c.tank(WSI_TANK_STORAGE(V), tk);
+  typename C::Vq st = c.ldv(stp, c.s_tank());
+  c.stv(c.tank(WSI_TANK_STORAGE_LAG(V), tk), c.s_tank(), st);
+  if (*c.tank(WSI_TANK_IS_DECAY, tk) != 0.0 && (int)*c.tank(WSI_TANK_N_DECAY, tk) > 0) {
+    auto Tk = [&](int plane) -> double* { return c.tank(plane, tk); };
+    decay_end_timestep(c, st, Tk, WSI_TANK_N_DECAY, c.forcing((int)*c.tank(WSI_TANK_FORCING_ID, tk), 2));
+    c.stv(stp, c.s_tank(), st);
+  }
+}
+
+template <class C>
+WSI_HDN void end_timestep(C& c) {
+  constexpr int V = C::V;
+  const WsiModelDesc* d = c.d;
+  for (int n = 0; n < d->n_nodes; n++) {
+    const int g = d->node_gidx[n];
+    switch (d->node_type[n]) {
+      case WSI_NT_LAND:
+        land_end_timestep(c, n);
+        break;
+      case WSI_NT_SEWER:
+        sewer_end_timestep(c, g);
+        break;
+      case WSI_NT_GROUNDWATER:
+      case WSI_NT_STORAGE:
+      case WSI_NT_RESERVOIR:
+        store_end_timestep(c, g);
+        break;
+      case WSI_NT_RIVER:  // storage.py:951-955
+        store_end_timestep(c, (int)*c.river(WSI_RIVER_TANK, g));
+        c.stv(c.river(WSI_RIVER_BIO_IN(V), g), c.s_river(), vq_zero<C::P>());
+        c.stv(c.river(WSI_RIVER_BIO_OUT(V), g), c.s_river(), vq_zero<C::P>());
+        break;
+      default:
+        break;
+    }
+  }
+  for (int a = 0; a < d->n_arcs; a++) {  // Arc.end_timestep arcs.py:259-265
+    *c.arc(WSI_ARC_FLOW_IN, a) = 0.0;
+    c.stv(c.arc(WSI_ARC_VQIP_IN(V), a), c.s_arc(), vq_zero<C::P>());
+  }
+}
+
+// ---- recording (model.py:1063-1170): copy probe planes into out_probe[t, k, r] ---------------
+template <class C>
+WSI_HD void record(const C& c) {
+  const WsiModelDesc* d = c.d;
+  const int row = c.t - d->rec_t0;
+  if (d->n_probe <= 0 || row < 0 || row >= d->rec_T) return;
+  double* out = d->out_probe + (size_t)row * d->n_probe * c.R + c.r;
+  for (int k = 0; k < d->n_probe; k++) {
+    const int plane = d->probe_plane[k], obj = d->probe_obj[k];
+    const double* src;
+    switch (d->probe_group[k]) {
+      case 0: src = c.arc(plane, obj); break;
+      case 1: src = c.land(plane, obj); break;
+      case 2: src = c.surf(plane, obj); break;
+      case 3: src = c.tank(plane, obj); break;
+      case 4: src = c.river(plane, obj); break;
+      default: src = c.sewer(plane, obj); break;
+    }
+    out[(size_t)k * c.R] = *src;
+  }
+}
+
+// ---- one schedule entry -----------------------------------------------------------------------
+template <class C>
+WSI_HD void run_op(C& c, int op, int node) {
+  switch (op) {
+    case WSI_OP_LAND_RUN: land_run(c, node); break;
+    case WSI_OP_GW_INFILTRATE: gw_infiltrate(c, node); break;
+    case WSI_OP_SEWER_DISCHARGE: sewer_discharge(c, node); break;
+    case WSI_OP_GW_DISTRIBUTE: gw_distribute(c, node); break;
+    case WSI_OP_RIVER_CALC: river_calc(c, node); break;
+    case WSI_OP_RESERVOIR_ABSTRACT: reservoir_abstract(c, node); break;
+    case WSI_OP_CATCHMENT_ROUTE: catchment_route(c, node); break;
+    case WSI_OP_RIVER_DISTRIBUTE: river_distribute(c, node); break;
+    case WSI_OP_STORAGE_DISTRIBUTE: storage_distribute(c, node); break;
+    default: break;
+  }
+}
+
+// ---- the whole timestep of one replica --------------------------------------------------------
+template <class C>
+WSI_HD void replica_step(C& c, int sched_begin, int sched_end) {
+  const WsiModelDesc* d = c.d;
+  if (c.run_flags & WSI_RUN_SCHEDULE)
+    for (int k = sched_begin; k < sched_end; k++) run_op(c, d->sched_op[k], d->sched_node[k]);
+  if (c.run_flags & WSI_RUN_MASS_BALANCE) {
+    // arcs are trivially balanced (vqip_in is vqip_out, arcs.py:83-85, 155-156); they only
+    // feed the system totals of model.py:1016-1023
+    if (c.mb_acc) {
+      for (int a = 0; a < d->n_arcs; a++) {
+        const typename C::Vq v = c.ldv(c.arc(WSI_ARC_VQIP_IN(C::V), a), c.s_arc());
+#pragma unroll
+        for (int p = 0; p <= C::P; p++)
+          if (p == 0 || bit(c.add, p)) {
+            c.mb_acc[(0 * C::V + p) * c.mb_stride] += v.x[p];
+            c.mb_acc[(2 * C::V + p) * c.mb_stride] += v.x[p];
+          }
+      }
+    }
+    for (int n = 0; n < d->n_nodes; n++) node_mass_balance(c, n);
+  }
+  if (c.run_flags & WSI_RUN_RECORD) record(c);
+  if (c.run_flags & WSI_RUN_END_TIMESTEP) end_timestep(c);
+}
+
+template <class CFG>
+WSI_HD Ctx<CFG> make_ctx(const WsiModelDesc* d, const CFG& cfg, int r, int t, uint32_t flags) {
+  Ctx<CFG> c;
+  c.d = d;
+  c.cfg = cfg;
+  c.R = (size_t)d->R;
+  c.r = r;
+  c.t = t;
+  c.add = cfg.add_mask();
+  c.FA = d->float_accuracy;
+  c.run_flags = flags;
+  c.viol = 0;
+  c.mb_acc = nullptr;
+  c.mb_stride = 1;
+  return c;
+}
+
+}  // namespace wsi
