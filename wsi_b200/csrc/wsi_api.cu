@@ -122,8 +122,10 @@ int launch(const WsiModelDesc* d, const CFG& cfg, int64_t t, int b, int e, uint3
 
 int dispatch(const WsiModelDesc* d, int64_t t, int b, int e, uint32_t flags, cudaStream_t s) {
   if (is_default12(d)) return launch(d, CfgDefault12(), t, b, e, flags, s);
+#ifndef WSI_ONLY_DEFAULT12  // development builds instantiate a single configuration
   if (d->P == 12) return launch(d, runtime_cfg<12>(d), t, b, e, flags, s);
   if (d->P == 2) return launch(d, runtime_cfg<2>(d), t, b, e, flags, s);
+#endif
   return fail(WSI_ERR_UNSUPPORTED, "no kernel instantiated for this number of pollutants%s");
 }
 

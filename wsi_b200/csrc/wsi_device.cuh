@@ -22,7 +22,14 @@ namespace wsi {
 constexpr double kUnbounded = 1e15;  // constants.UNBOUNDED_CAPACITY
 constexpr int kMaxIter = 5;          // constants.MAXITER
 constexpr int kMaxCand = 8;          // arcs one push_distributed call can split over
-constexpr int kJunctionDepth = 3;    // nested junction Nodes a push may traverse
+constexpr int kJunctionDepth = 2;    // nested junction Nodes a push may traverse
+
+// One object's column in a group tensor: plane k lives at p[k * s]
+struct Obj {
+  double* p;
+  size_t s;
+  WSI_HD double* operator()(int plane) const { return p + (size_t)plane * s; }
+};
 
 template <class CFG>
 struct Ctx {
@@ -52,6 +59,12 @@ struct Ctx {
   WSI_HD double* tank(int plane, int i) const { return pl(d->tank, d->n_tank, plane, i); }
   WSI_HD double* river(int plane, int i) const { return pl(d->river, d->n_river, plane, i); }
   WSI_HD double* sewer(int plane, int i) const { return pl(d->sewer, d->n_sewer, plane, i); }
+  WSI_HD Obj arc_obj(int a) const { return Obj{d->arc + (size_t)a * R + r, (size_t)d->n_arcs * R}; }
+  WSI_HD Obj land_obj(int i) const { return Obj{d->land + (size_t)i * R + r, (size_t)d->n_land * R}; }
+  WSI_HD Obj surf_obj(int i) const { return Obj{d->surf + (size_t)i * R + r, (size_t)d->n_surf * R}; }
+  WSI_HD Obj tank_obj(int i) const { return Obj{d->tank + (size_t)i * R + r, (size_t)d->n_tank * R}; }
+  WSI_HD Obj river_obj(int i) const { return Obj{d->river + (size_t)i * R + r, (size_t)d->n_river * R}; }
+  WSI_HD Obj sewer_obj(int i) const { return Obj{d->sewer + (size_t)i * R + r, (size_t)d->n_sewer * R}; }
   WSI_HD size_t s_arc() const { return (size_t)d->n_arcs * R; }
   WSI_HD size_t s_land() const { return (size_t)d->n_land * R; }
   WSI_HD size_t s_surf() const { return (size_t)d->n_surf * R; }
@@ -364,6 +377,37 @@ WSI_HDN typename C::Vq push_distributed(C& c, int node, const typename C::Vq& vq
 // =========================================================================================
 // (in, ds, out) of one object checked as WSIObj.mass_balance does (core.py:403-427);
 // optionally recorded and accumulated into the per-thread system totals.
+// 10 ** int(log10(x)) of core.py:410 without transcendental calls or table look-ups (a table
+// indexed by a per-thread exponent serialises in the constant cache).  10^k for 0 <= k <= 22 is
+// exact in binary64 and is built from exact products; int() truncates towards zero, so the
+// magnitude is 10^floor(log10 x) for x >= 1 and 1/10^j with the smallest 10^-j >= x below 1
+// (Python evaluates 10 ** -j as the correctly rounded float, which 1.0 / 10^j reproduces).
+WSI_HD double pow10i(int k) {  // 0 <= k <= 22
+  double p = 1.0;
+  if (k & 1) p *= 1e1;
+  if (k & 2) p *= 1e2;
+  if (k & 4) p *= 1e4;
+  if (k & 8) p *= 1e8;
+  if (k & 16) p *= 1e16;
+  return p;
+}
+WSI_HD double magnitude10(double x) {
+  if (!(x > 1e-22 && x < 1e22)) return pow(10.0, (double)(int)log10(x));
+  int e2;
+  (void)frexp(x, &e2);  // x = m * 2^e2, m in [0.5, 1)
+  if (x >= 1.0) {
+    int k = (int)((double)(e2 - 1) * 0.30102999566398120);  // <= floor(log10 x), off by at most 1
+    if (k < 0) k = 0;
+    if (k < 22 && pow10i(k + 1) <= x) k++;
+    return pow10i(k);
+  }
+  // x < 1: j = number of leading decimal zeros, magnitude 10^-j with 10^-j >= x > 10^-(j+1)
+  int j = (int)((double)(-e2) * 0.30102999566398120);  // <= true j, off by at most 1
+  if (j < 0) j = 0;
+  if (j < 22 && 1.0 / pow10i(j + 1) >= x) j++;
+  return 1.0 / pow10i(j);
+}
+
 template <class C>
 WSI_HD void mb_check(C& c, int node, const typename C::Vq& in_, const typename C::Vq& ds_,
                      const typename C::Vq& out_) {
@@ -374,14 +418,18 @@ WSI_HD void mb_check(C& c, int node, const typename C::Vq& in_, const typename C
     if (p != 0 && !bit(c.add, p)) continue;
     const double a = in_.x[p], o = out_.x[p], dd = ds_.x[p];
     const double largest = pymax(pymax(a, o), dd);
-    double in10 = a, out10 = o, ds10 = dd;
-    if (largest > c.FA) {
-      const double magnitude = pow(10.0, (double)(int)log10(largest));
-      in10 = a / magnitude;
-      out10 = o / magnitude;
-      ds10 = dd / magnitude;
-    }
-    if (fabs(in10 - ds10 - out10) > c.FA) viol++;
+    const double magnitude = largest > c.FA ? magnitude10(largest) : 1.0;
+    // core.py:411-419 compares |in/m - ds/m - out/m| with FLOAT_ACCURACY; the three divisions
+    // are only needed when the residual is within 1 % of the threshold
+    const double resid = fabs(a - dd - o), thr = c.FA * magnitude;
+    bool bad;
+    if (c.FA >= 1e-12 && resid < 0.99 * thr)
+      bad = false;
+    else if (c.FA >= 1e-12 && resid > 1.01 * thr)
+      bad = true;
+    else
+      bad = fabs(a / magnitude - dd / magnitude - o / magnitude) > c.FA;
+    if (bad) viol++;
   }
   if (viol) {
     c.flag(node, WSI_FLAG_MASS_BALANCE);

@@ -81,7 +81,7 @@ WSI_HDN void surface_run(C& c, int node, int L, int u, double precip, double et0
   constexpr int P = C::P;
   constexpr int V = C::V;
   const size_t ss = c.s_surf();
-  auto S = [&](int plane) -> double* { return c.surf(plane, u); };
+  const Obj S = c.surf_obj(u);
   const int type = (int)*S(WSI_SURF_TYPE);
   const double area = *S(WSI_SURF_AREA);
   double* stp = S(WSI_SURF_STORAGE(V));
@@ -729,7 +729,7 @@ WSI_HD void land_end_timestep(C& c, int node) {
   const double temperature = c.forcing((int)*c.land(WSI_LAND_FORCING_ID, L), 2);
   for (int i = d->land_surf_ptr[L]; i < d->land_surf_ptr[L + 1]; i++) {
     const int u = d->land_surf[i];
-    auto S = [&](int plane) -> double* { return c.surf(plane, u); };
+    const Obj S = c.surf_obj(u);
     if ((int)*S(WSI_SURF_N_DECAY) > 0) {
       double* stp = S(WSI_SURF_STORAGE(V));
       typename C::Vq st = c.ldv(stp, c.s_surf());

@@ -77,7 +77,7 @@ WSI_HDN void river_calc(C& c, int node) {
   const auto& cfg = c.cfg;
   if (cfg.no3() < 0) return;
   const int g = c.d->node_gidx[node];
-  auto Rv = [&](int plane) -> double* { return c.river(plane, g); };
+  const Obj Rv = c.river_obj(g);
   const int tk = (int)*Rv(WSI_RIVER_TANK);
   const size_t sr = c.s_river();
   double* stp = c.tank(WSI_TANK_STORAGE(V), tk);
@@ -328,7 +328,7 @@ WSI_HD typename C::Vq tank_ds(const C& c, int tk) {  // tanks.py:70-76 / 449-457
 #pragma unroll
   for (int p = 0; p <= C::P; p++) dsv.x[p] = (p == 0 || bit(c.add, p)) ? st.x[p] - st_.x[p] : 0.0;
   if (*c.tank(WSI_TANK_IS_DECAY, tk) != 0.0) {
-    auto Tk = [&](int plane) -> double* { return c.tank(plane, tk); };
+    const Obj Tk = c.tank_obj(tk);
     dsv = c.sum(dsv, decay_total<C>(c, Tk, WSI_TANK_N_DECAY));
   }
   return dsv;
@@ -383,7 +383,7 @@ WSI_HD void store_end_timestep(C& c, int tk) {  // tanks.py:348-351 / 442-447
   typename C::Vq st = c.ldv(stp, c.s_tank());
   c.stv(c.tank(WSI_TANK_STORAGE_LAG(V), tk), c.s_tank(), st);
   if (*c.tank(WSI_TANK_IS_DECAY, tk) != 0.0 && (int)*c.tank(WSI_TANK_N_DECAY, tk) > 0) {
-    auto Tk = [&](int plane) -> double* { return c.tank(plane, tk); };
+    const Obj Tk = c.tank_obj(tk);
     decay_end_timestep(c, st, Tk, WSI_TANK_N_DECAY, c.forcing((int)*c.tank(WSI_TANK_FORCING_ID, tk), 2));
     c.stv(stp, c.s_tank(), st);
   }
