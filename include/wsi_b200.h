@@ -46,7 +46,8 @@ extern "C" {
 #define WSI_RUN_MASS_BALANCE 2u  /* per-node mass balance (core.py:370) */
 #define WSI_RUN_RECORD 4u        /* copy probe planes into out_probe (model.py:1063-1170) */
 #define WSI_RUN_END_TIMESTEP 8u  /* node/arc end_timestep (model.py:1172-1176) */
-#define WSI_RUN_ALL 15u
+#define WSI_RUN_SURFACES 16u     /* Surface.run of every Land surface (land.py:425-449) */
+#define WSI_RUN_ALL 31u
 
 typedef struct WsiModelDesc {
   /* ---- sizes ---- */
@@ -81,6 +82,13 @@ typedef struct WsiModelDesc {
   const int32_t* cand_arcs;
   const int32_t* land_surf_ptr; /* [n_land+1] CSR land -> surface slots */
   const int32_t* land_surf;
+  const int32_t* surf_order; /* [n_surf] surface slots sorted by surface class */
+  int32_t surf_class_ptr[5]; /* CSR over surf_order: class k = [ptr[k], ptr[k+1]) */
+  int32_t reserved0;
+  const int32_t* end_kind;   /* [n_end] end_timestep items: group id (0 arc, 2 surf, 3 tank, 4 river, 5 sewer) */
+  const int32_t* end_obj;    /* [n_end] object slot */
+  int32_t n_end;
+  int32_t reserved1;
   const int32_t* sched_op;   /* [n_sched] WSI_OP_* */
   const int32_t* sched_node; /* [n_sched] node slot */
 
@@ -107,7 +115,10 @@ typedef struct WsiModelDesc {
   const int32_t* probe_obj;   /* [n_probe] object slot */
   double* out_probe;          /* [rec_T][n_probe][R] */
   double* out_mb;             /* [rec_T][n_nodes][3][V][R] or NULL */
-  double* mb_partial;         /* [n_blocks][3*V] scratch for the block reduction */
+  double* mb_terms;           /* [n_fused][3][V][R] scratch: (in, ds, out) of nodes whose terms are formed
+                                 inside their schedule op (Land, Catchment) */
+  const int32_t* mb_term_slot; /* [n_nodes] row of mb_terms, -1 for other nodes */
+  double* mb_partial;         /* [wsi_num_blocks()][3*V] scratch for the block reduction */
   double* mb_sums;            /* [T][3][V] system totals sys_in, sys_ds, sys_out */
   int32_t* mb_count;          /* [T] number of (node, component) violations */
   uint32_t* node_flags;       /* [n_nodes*R] sticky WSI_FLAG_* */
@@ -122,7 +133,7 @@ const char* wsi_last_error(void);
 /* Structural checks on a descriptor (no device access). */
 int wsi_validate(const WsiModelDesc* d);
 
-/* Number of thread blocks wsi_step launches for this descriptor (sizes mb_partial). */
+/* Rows of mb_partial a timestep may write (blocks that reduce mass-balance partials). */
 int wsi_num_blocks(const WsiModelDesc* d);
 
 /* One model timestep `t` for every replica: orchestration schedule, river
@@ -134,7 +145,11 @@ int wsi_step(const WsiModelDesc* d, int64_t t, void* stream);
 int wsi_run_steps(const WsiModelDesc* d, int64_t t0, int64_t t1, void* stream);
 
 /* Part of a timestep: schedule entries [begin, end) and the phases in `flags`
- * (WSI_RUN_*).  wsi_step == wsi_sched_range(d, t, 0, n_sched, WSI_RUN_ALL). */
+ * (WSI_RUN_*).  wsi_step == wsi_sched_range(d, t, 0, n_sched, WSI_RUN_ALL).
+ * WSI_RUN_SURFACES launches the surface kernels (one thread per surface, one launch per
+ * surface class) before the per-replica schedule kernel; a LAND_RUN schedule entry then
+ * only runs the Land's own tanks and pushes.  Land / Catchment mass balances are fused into
+ * their ops, so WSI_RUN_MASS_BALANCE must accompany WSI_RUN_SURFACES | WSI_RUN_SCHEDULE. */
 int wsi_sched_range(const WsiModelDesc* d, int64_t t, int32_t begin, int32_t end,
                     uint32_t flags, void* stream);
 

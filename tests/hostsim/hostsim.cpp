@@ -21,10 +21,10 @@ static int run_cfg(const WsiModelDesc* d, const CFG& cfg, int64_t t0, int64_t t1
     memset(acc, 0, sizeof(double) * 3 * V);
     int viol = 0;
     for (int r = 0; r < d->R; r++) {
-      Ctx<CFG> c = make_ctx(d, cfg, r, (int)t, WSI_RUN_ALL);
+      Ctx<CFG> c = make_ctx(d, 0, cfg, r, (int)t, WSI_RUN_ALL);
       c.mb_acc = d->mb_sums ? acc : nullptr;
       c.mb_stride = 1;
-      replica_step(c, 0, d->n_sched);
+      replica_step<true>(c, 0, d->n_sched);
       viol += c.viol;
     }
     if (d->mb_sums) memcpy(d->mb_sums + (size_t)t * 3 * V, acc, sizeof(double) * 3 * V);

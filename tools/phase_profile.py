@@ -32,6 +32,7 @@ def timed(fn, reps=10):
 
 res = {}
 res["full_step"] = timed(lambda: run.step(10))
+res["surfaces_only"] = timed(lambda: run.sched_range(10, 0, 0, capi.RUN_SURFACES))
 res["schedule_only"] = timed(lambda: run.sched_range(10, 0, n, capi.RUN_SCHEDULE))
 res["schedule+mb"] = timed(lambda: run.sched_range(10, 0, n, capi.RUN_SCHEDULE | capi.RUN_MASS_BALANCE))
 for k, name in enumerate(ops):

@@ -23,7 +23,8 @@ RUN_SCHEDULE = 1
 RUN_MASS_BALANCE = 2
 RUN_RECORD = 4
 RUN_END_TIMESTEP = 8
-RUN_ALL = 15
+RUN_SURFACES = 16
+RUN_ALL = 31
 
 FLAG_NAMES = {
     1: "mass_balance",
@@ -79,6 +80,13 @@ class WsiModelDesc(C.Structure):
         ("cand_arcs", _i32p),
         ("land_surf_ptr", _i32p),
         ("land_surf", _i32p),
+        ("surf_order", _i32p),
+        ("surf_class_ptr", C.c_int32 * 5),
+        ("reserved0", C.c_int32),
+        ("end_kind", _i32p),
+        ("end_obj", _i32p),
+        ("n_end", C.c_int32),
+        ("reserved1", C.c_int32),
         ("sched_op", _i32p),
         ("sched_node", _i32p),
         ("arc", _f64p),
@@ -99,6 +107,8 @@ class WsiModelDesc(C.Structure):
         ("probe_obj", _i32p),
         ("out_probe", _f64p),
         ("out_mb", _f64p),
+        ("mb_terms", _f64p),
+        ("mb_term_slot", _i32p),
         ("mb_partial", _f64p),
         ("mb_sums", _f64p),
         ("mb_count", _i32p),
@@ -107,7 +117,7 @@ class WsiModelDesc(C.Structure):
 
 
 _INT_ARRAYS = [
-    "node_type", "node_gidx", "arc_in", "arc_out", "out_ptr", "out_arcs", "in_ptr", "in_arcs",
+    "surf_order", "end_kind", "end_obj", "mb_term_slot", "node_type", "node_gidx", "arc_in", "arc_out", "out_ptr", "out_arcs", "in_ptr", "in_arcs",
     "cand_ptr", "cand_arcs", "land_surf_ptr", "land_surf", "sched_op", "sched_node", "month_idx",
     "dayofyear", "doy_adj",
 ]
@@ -166,9 +176,32 @@ def check(lib, rc):
 class ModelBuffers:
     """Owns the buffers of one flattened model on a device and its C descriptor."""
 
-    MAX_BLOCKS = 65536
+    STEP_BLOCK = 64   # replicas per block of wsi_step_kernel (kBlock in wsi_api.cu)
+    OBJ_BLOCK = 128   # replicas per block of the object-parallel kernels (kObjBlock)
+
+    def partial_rows(self):
+        fm = self.fm
+        nb_obj = -(-fm.R // self.OBJ_BLOCK)
+        return (len(fm.node_names) + len(fm.arc_names)) * nb_obj
 
     def __init__(self, fm, device="cuda", probes=(), rec_t0=0, rec_T=None, record_mb=False):
+        # surface slots sorted by surface class (stable), for the per-class surface kernels
+        types = fm.view("surf", "type")[0, :, 0].astype(np.int64) if fm.n_obj["surf"] else np.zeros(0, np.int64)
+        order = np.argsort(types, kind="stable").astype(np.int32)
+        # end_timestep items: every arc, decaying surfaces, tanks, rivers, sewers
+        nd = fm.view("surf", "n_decay")[0].max(axis=1) if fm.n_obj["surf"] else np.zeros(0)
+        items = [(0, a) for a in range(fm.n_obj["arc"])] + [(2, u) for u in range(fm.n_obj["surf"]) if nd[u] > 0]
+        items += [(3, i) for i in range(fm.n_obj["tank"])] + [(4, i) for i in range(fm.n_obj["river"])]
+        items += [(5, i) for i in range(fm.n_obj["sewer"])]
+        self.n_end = len(items)
+        it = np.array(items or [(0, 0)], dtype=np.int32).reshape(-1, 2)
+        fused = [int(t) in (L.NT["Land"], L.NT["Catchment"]) for t in fm.node_type]
+        slot = np.full(len(fm.node_type), -1, dtype=np.int32)
+        slot[np.nonzero(fused)[0]] = np.arange(int(np.sum(fused)), dtype=np.int32)
+        self.n_fused = int(np.sum(fused))
+        self._extra_int = {"surf_order": order if len(order) else np.zeros(1, np.int32), "mb_term_slot": slot,
+                           "end_kind": np.ascontiguousarray(it[:, 0]), "end_obj": np.ascontiguousarray(it[:, 1])}
+        self.surf_class_ptr = [int(np.searchsorted(types[order], k, side="left")) for k in range(4)] + [len(order)]
         self.fm = fm
         self.device = device
         self.probes = list(probes)
@@ -187,7 +220,8 @@ class ModelBuffers:
         fm = self.fm
         k = self._keep
         for name in _INT_ARRAYS:
-            k[name] = np.ascontiguousarray(getattr(fm, name), dtype=np.int32)
+            src = self._extra_int[name] if name in self._extra_int else getattr(fm, name)
+            k[name] = np.ascontiguousarray(src, dtype=np.int32)
         for name in _F64_ARRAYS:
             k[name] = np.ascontiguousarray(getattr(fm, name), dtype=np.float64)
         for g, arr in fm.groups.items():
@@ -203,7 +237,8 @@ class ModelBuffers:
             if self.record_mb
             else np.zeros(1, dtype=np.float64)
         )
-        k["mb_partial"] = np.zeros((self.MAX_BLOCKS // 64, 3 * fm.V), dtype=np.float64)
+        k["mb_partial"] = np.zeros((8, 3 * fm.V), dtype=np.float64)
+        k["mb_terms"] = np.zeros((max(self.n_fused, 1), 3, fm.V, fm.R), dtype=np.float64)
         k["mb_sums"] = np.zeros((fm.T, 3, fm.V), dtype=np.float64)
         k["mb_count"] = np.zeros(fm.T, dtype=np.int32)
         k["node_flags"] = np.zeros(len(fm.node_names) * fm.R, dtype=np.uint32)
@@ -223,7 +258,7 @@ class ModelBuffers:
             return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).to(dev).contiguous()
 
         for name in _INT_ARRAYS:
-            k[name] = up(getattr(fm, name), torch.int32)
+            k[name] = up(self._extra_int[name] if name in self._extra_int else getattr(fm, name), torch.int32)
         for name in _F64_ARRAYS:
             k[name] = up(getattr(fm, name), torch.float64)
         for g, arr in fm.groups.items():
@@ -239,7 +274,8 @@ class ModelBuffers:
             if self.record_mb
             else torch.zeros(1, dtype=torch.float64, device=dev)
         )
-        k["mb_partial"] = torch.zeros((self.MAX_BLOCKS, 3 * fm.V), dtype=torch.float64, device=dev)
+        k["mb_partial"] = torch.zeros((self.partial_rows(), 3 * fm.V), dtype=torch.float64, device=dev)
+        k["mb_terms"] = torch.zeros((max(self.n_fused, 1), 3, fm.V, fm.R), dtype=torch.float64, device=dev)
         k["mb_sums"] = torch.zeros((fm.T, 3, fm.V), dtype=torch.float64, device=dev)
         k["mb_count"] = torch.zeros(fm.T, dtype=torch.int32, device=dev)
         # uint32 flags carried as int32 storage
@@ -262,6 +298,9 @@ class ModelBuffers:
         d.n_sewer = fm.n_obj["sewer"]
         d.n_catch = fm.n_obj["catchm"]
         d.n_sched = int(len(fm.sched_op))
+        for i, v in enumerate(self.surf_class_ptr):
+            d.surf_class_ptr[i] = v
+        d.n_end = self.n_end
         d.nq = fm.nq
         d.n_fseries = fm.node_forcing.shape[1]
         d.n_months = fm.surf_inputs.shape[0]
@@ -284,7 +323,7 @@ class ModelBuffers:
             setattr(d, fld, C.cast(P(k["group_" + g]), _f64p))
         for name in ("probe_group", "probe_plane", "probe_obj", "mb_count"):
             setattr(d, name, C.cast(P(k[name]), _i32p))
-        for name in ("out_probe", "out_mb", "mb_partial", "mb_sums"):
+        for name in ("out_probe", "out_mb", "mb_partial", "mb_sums", "mb_terms"):
             setattr(d, name, C.cast(P(k[name]), _f64p))
         d.node_flags = C.cast(P(k["node_flags"]), _u32p)
         return d

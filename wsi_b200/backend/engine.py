@@ -29,8 +29,8 @@ class GpuRunner:
         self.desc = self.buffers.desc
         if not system_sums:
             self.desc.mb_sums = C.cast(None, C.POINTER(C.c_double))
-        if self.lib.wsi_num_blocks(C.byref(self.desc)) > capi.ModelBuffers.MAX_BLOCKS:
-            raise RuntimeError("too many replicas for the mb_partial scratch")
+        if self.lib.wsi_num_blocks(C.byref(self.desc)) > self.buffers.partial_rows():
+            raise RuntimeError("mb_partial scratch smaller than the library needs (block sizes out of sync)")
         capi.check(self.lib, self.lib.wsi_validate(C.byref(self.desc)))
 
     def _stream(self, stream):

@@ -474,6 +474,7 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
             b.set(col, "res_subsurface", n.subsurface_runoff.residence_time)
             b.set(col, "res_percolation", n.percolation.residence_time)
             b.set(col, "forcing_id", forcing_series(n.data_input_dict, ("precipitation", "et0", "temperature")))
+            b.set(col, "node", i)
             b.set(col, "surface_runoff", _vq(n.surface_runoff.storage, pollutants))
             b.set(col, "subsurface_runoff", _vq(n.subsurface_runoff.storage, pollutants))
             b.set(col, "percolation", _vq(n.percolation.storage, pollutants))
@@ -482,6 +483,7 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
                 lst.append(len(gb["surf"].cols))
                 surf_names.append((n.name, str(s.surface)))
                 _flatten_surface(gb["surf"], s, pollutants, additive, has_nitrate, dep_series_id)
+                gb["surf"].set(gb["surf"].cols[-1], "land", node_gidx[i])
             land_surf_lists.append(lst)
         elif c in STORE_TYPES:
             ti = add_store(n)

@@ -149,6 +149,7 @@ LAND = Group(
         S("res_subsurface"),
         S("res_percolation"),
         S("forcing_id"),
+        S("node"),  # node slot of this Land (status flags)
         Q("surface_runoff"),  # ResidenceTank storages (land.py:138-149)
         Q("subsurface_runoff"),
         Q("percolation"),
@@ -159,6 +160,7 @@ SURF = Group(
     "surf",
     [
         S("type"),
+        S("land"),  # index of the parent Land in the land group
         S("area"),
         S("capacity"),
         S("depth"),
@@ -248,6 +250,13 @@ SURF = Group(
         S("out_tank_recharge"),
         Q("storage"),
         Q("load"),  # pollutant_load (plane 0 unused)
+        # per-step exchange between the surface kernels and the land phase (scratch)
+        Q("flow_a"),  # infiltration_excess (pervious) / ponded runoff (impervious)
+        Q("flow_b"),  # subsurface_flow
+        Q("flow_c"),  # percolation
+        Q("mb_in"),  # this surface's share of running_inflow_mb (volume + additive lanes)
+        Q("mb_out"),  # ... of running_outflow_mb
+        Q("mb_ds"),  # surface.ds() (tanks.py:449-457)
     ],
 )
 

@@ -1,11 +1,15 @@
 // libwsi_b200.so: sm_100a kernels and the C ABI of include/wsi_b200.h.
 //
 // Kernels
-//   wsi_step_kernel<CFG>  one thread per replica runs wsi::replica_step (wsi_device.cuh):
-//                         schedule, mass balance, recording, end_timestep of one timestep.
-//                         The per-block mass-balance partials (violation count, system
-//                         totals) are reduced in shared memory / with warp shuffles.
+//   wsi_surface_kernel<CFG,TYPE>  one thread per (surface, replica): Surface.run of one
+//                         surface class (wsi_land.cuh surface_phase); one launch per class.
+//   wsi_step_kernel<CFG>  one thread per replica: the orchestration schedule (routing) with the
+//                         Land / Catchment mass balances fused in.
+//   wsi_mb_kernel<CFG>    one thread per (node | arc, replica): remaining mass balances; per-block
+//                         partials (violation count, system totals) via shared memory / shuffles.
 //   wsi_mb_finalize       fixed-order reduction of the per-block partials -> mb_sums[t].
+//   wsi_record_kernel     one thread per (probe, replica): recording is a strided copy.
+//   wsi_end_kernel        one thread per (end_timestep item, replica).
 //
 // The path is HBM-bound fp64 element-wise work: no tensor cores.  Grid sizing,
 // coalescing and the byte accounting are described in DESIGN.md.
@@ -29,50 +33,145 @@ int fail(int code, const char* fmt, const char* detail = "") {
   return code;
 }
 
-constexpr int kBlock = 64;
+// Minimum resident blocks per SM requested from ptxas (caps registers per thread): the kernels
+// are latency-bound, so occupancy matters more than avoiding a few spills.
+#ifndef WSI_SURF_MINB
+#define WSI_SURF_MINB 3
+#endif
+#ifndef WSI_STEP_MINB
+#define WSI_STEP_MINB 12
+#endif
+#ifndef WSI_OBJ_MINB
+#define WSI_OBJ_MINB 6
+#endif
+constexpr int kBlock = 64;      // replicas per block of the per-replica schedule kernel
+constexpr int kSurfBlock = 128; // surfaces per block of the surface kernels
+constexpr int kObjBlock = 128;  // replicas per block of the object-parallel kernels
 
+// One thread per (surface slot, replica).  blockIdx.y selects the slot inside the surface
+// class being launched, so every block (and warp) is homogeneous in surface class and reads
+// 256 contiguous bytes per plane.
+template <class CFG, int TYPE>
+__global__ void __launch_bounds__(kSurfBlock, WSI_SURF_MINB)
+    wsi_surface_kernel(const int slot, const CFG cfg, const int t, const uint32_t flags) {
+  const WsiModelDesc& d = g_wsi_desc[slot];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= d.R) return;
+  const int u = d.surf_order[d.surf_class_ptr[TYPE] + blockIdx.y];
+  Ctx<CFG> c = make_ctx(nullptr, slot, cfg, r, t, flags);
+  surface_phase<TYPE>(c, u);
+}
+
+// One thread per replica: the orchestration schedule (Land.run after its surfaces, Groundwater,
+// Sewer, River, Catchment ops and river routing, in the reference's order).  Land / Catchment
+// form their mass-balance terms here (everything is still at hand) and leave them in mb_terms.
+// Routing is sequential inside a replica by construction.
 template <class CFG>
-__global__ void __launch_bounds__(kBlock)
-    wsi_step_kernel(const __grid_constant__ WsiModelDesc d, const CFG cfg, const int t, const int sched_begin,
-                    const int sched_end, const uint32_t flags) {
-  extern __shared__ double s_acc[];  // [3*V][blockDim.x] system-total accumulators
+__global__ void __launch_bounds__(kBlock, WSI_STEP_MINB)
+    wsi_step_kernel(const int slot, const CFG cfg, const int t, const int sched_begin, const int sched_end,
+                    const uint32_t flags) {
+  const WsiModelDesc& d = g_wsi_desc[slot];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= d.R) return;
+  Ctx<CFG> c = make_ctx(nullptr, slot, cfg, r, t, flags);
+  for (int k = sched_begin; k < sched_end; k++) run_op(c, d.sched_op[k], d.sched_node[k]);
+}
+
+// One thread per (node or arc, replica): WSIObj.mass_balance (core.py:370-429) of every node and
+// the system totals of model.py:1016-1036.  Block-reduced: violations via warp shuffle + one
+// atomic per warp; the (in, ds, out) lanes via warp shuffles, a fixed cross-warp sum, and one
+// row of mb_partial per block (summed in block order by wsi_mb_finalize: deterministic).
+template <class CFG>
+__global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
+    wsi_mb_kernel(const int slot, const CFG cfg, const int t, const uint32_t flags) {
   constexpr int V = CFG::P + 1;
+  constexpr int kWarps = kObjBlock / 32;
+  __shared__ double s_w[kWarps][3 * V];
+  const WsiModelDesc& d = g_wsi_desc[slot];
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = r < d.R;
-  const bool want_sums = (flags & WSI_RUN_MASS_BALANCE) && d.mb_sums != nullptr;
-  Ctx<CFG> c = make_ctx(&d, cfg, active ? r : 0, t, flags);
-  if (want_sums) {
-    for (int j = 0; j < 3 * V; j++) s_acc[j * blockDim.x + threadIdx.x] = 0.0;
-    c.mb_acc = s_acc + threadIdx.x;
-    c.mb_stride = blockDim.x;
+  const bool want_sums = d.mb_sums != nullptr;
+  Ctx<CFG> c = make_ctx(nullptr, slot, cfg, active ? r : 0, t, flags);
+  using Vq = typename Ctx<CFG>::Vq;
+  Vq term[3];
+  term[0] = vq_zero<CFG::P>();
+  term[1] = vq_zero<CFG::P>();
+  term[2] = vq_zero<CFG::P>();
+  const int item = blockIdx.y;
+  if (active) {
+    if (item < d.n_nodes) {
+      node_mass_balance(c, item, term[0], term[1], term[2]);
+    } else {  // arcs are trivially balanced; they only feed the system totals
+      term[0] = c.ldv_add(c.arc(WSI_ARC_VQIP_IN(V), item - d.n_nodes), c.s_arc());
+      term[2] = term[0];
+    }
   }
-  if (active) replica_step(c, sched_begin, sched_end);
-
-  if (flags & WSI_RUN_MASS_BALANCE) {
-    // block-reduced mass-balance check: violations via warp shuffle + one atomic per warp
-    int v = active ? c.viol : 0;
+  int v = active ? c.viol : 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v != 0 && d.mb_count) atomicAdd(&d.mb_count[t], v);
-    if (want_sums) {
-      __syncthreads();
-      // one thread per (term, lane) row sums the block's columns in a fixed order
-      for (int j = threadIdx.x; j < 3 * V; j += blockDim.x) {
-        double acc = 0.0;
-        for (int k = 0; k < (int)blockDim.x; k++) acc += s_acc[j * blockDim.x + k];
-        d.mb_partial[(size_t)blockIdx.x * 3 * V + j] = acc;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v != 0 && d.mb_count) atomicAdd(&d.mb_count[t], v);
+  if (want_sums) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+      for (int p = 0; p < V; p++) {
+        if (p != 0 && !bit(c.add, p)) continue;
+        double x = active ? term[k].x[p] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) s_w[warp][k * V + p] = x;
       }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * V) {
+      const int p = threadIdx.x % V;
+      double acc = 0.0;
+      if (p == 0 || bit(c.add, p))
+        for (int w = 0; w < kWarps; w++) acc += s_w[w][threadIdx.x];
+      d.mb_partial[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 3 * V + threadIdx.x] = acc;
     }
   }
 }
 
-__global__ void wsi_mb_finalize(const double* __restrict__ partial, double* __restrict__ sums, int n_blocks,
-                                int n) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+// One thread per (probe, replica): Model.run's recording (model.py:1063-1170) is a strided copy.
+template <class CFG>
+__global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
+    wsi_record_kernel(const int slot, const CFG cfg, const int t, const int row) {
+  const WsiModelDesc& d = g_wsi_desc[slot];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= d.R) return;
+  Ctx<CFG> c = make_ctx(nullptr, slot, cfg, r, t, 0u);
+  record_probe(c, row, (int)blockIdx.y);
+}
+
+// One thread per (end_timestep item, replica): arcs reset, DecayTank decay, QueueTank shift.
+template <class CFG>
+__global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
+    wsi_end_kernel(const int slot, const CFG cfg, const int t) {
+  const WsiModelDesc& d = g_wsi_desc[slot];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= d.R) return;
+  Ctx<CFG> c = make_ctx(nullptr, slot, cfg, r, t, 0u);
+  end_item(c, d.end_kind[blockIdx.y], d.end_obj[blockIdx.y]);
+}
+
+// Sum the mass-balance partial rows of one timestep: block j reduces column j of
+// partial[n_rows][n] with a fixed strided pass + fixed shared-memory tree (deterministic).
+constexpr int kFinBlock = 256;
+__global__ void __launch_bounds__(kFinBlock)
+    wsi_mb_finalize(const double* __restrict__ partial, double* __restrict__ sums, int n_rows, int n) {
+  __shared__ double s[kFinBlock];
+  const int j = blockIdx.x;
   double acc = 0.0;
-  for (int b = 0; b < n_blocks; b++) acc += partial[(size_t)b * n + j];
-  sums[j] = acc;
+  for (int b = threadIdx.x; b < n_rows; b += kFinBlock) acc += partial[(size_t)b * n + j];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = kFinBlock / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sums[j] = s[0];
 }
 
 template <int P>
@@ -99,32 +198,90 @@ bool is_default12(const WsiModelDesc* d) {
 }
 
 int n_blocks(const WsiModelDesc* d) { return (d->R + kBlock - 1) / kBlock; }
+int n_obj_blocks(const WsiModelDesc* d) { return (d->R + kObjBlock - 1) / kObjBlock; }
+int n_partial_rows(const WsiModelDesc* d) { return (d->n_nodes + d->n_arcs) * n_obj_blocks(d); }
 
+#define WSI_CHECK_LAUNCH(name)                                                                         \
+  do {                                                                                                 \
+    g_launches++;                                                                                      \
+    cudaError_t err_ = cudaGetLastError();                                                             \
+    if (err_ != cudaSuccess) return fail(WSI_ERR_LAUNCH, name " launch failed: %s", cudaGetErrorString(err_)); \
+  } while (0)
+
+template <class CFG, int TYPE>
+int launch_surfaces(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, uint32_t flags, cudaStream_t s) {
+  const int n = d->surf_class_ptr[TYPE + 1] - d->surf_class_ptr[TYPE];
+  if (n <= 0) return WSI_OK;
+  const dim3 grid((d->R + kSurfBlock - 1) / kSurfBlock, n);
+  wsi_surface_kernel<CFG, TYPE><<<grid, kSurfBlock, 0, s>>>(slot, cfg, (int)t, flags);
+  WSI_CHECK_LAUNCH("wsi_surface_kernel");
+  return WSI_OK;
+}
+
+// One timestep = surface kernels (one per class) -> schedule kernel -> mass-balance kernel ->
+// finalize -> record kernel -> end_timestep kernel, all on one stream.
 template <class CFG>
-int launch(const WsiModelDesc* d, const CFG& cfg, int64_t t, int b, int e, uint32_t flags, cudaStream_t s) {
+int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, int e, uint32_t flags, cudaStream_t s) {
   constexpr int V = CFG::P + 1;
-  const bool want_sums = (flags & WSI_RUN_MASS_BALANCE) && d->mb_sums != nullptr;
-  const size_t smem = want_sums ? (size_t)3 * V * kBlock * sizeof(double) : 0;
-  const int nb = n_blocks(d);
-  wsi_step_kernel<CFG><<<nb, kBlock, smem, s>>>(*d, cfg, (int)t, b, e, flags);
-  g_launches++;
-  cudaError_t err = cudaGetLastError();
-  if (err != cudaSuccess) return fail(WSI_ERR_LAUNCH, "wsi_step_kernel launch failed: %s", cudaGetErrorString(err));
-  if (want_sums) {
-    const int n = 3 * V;
-    wsi_mb_finalize<<<1, 64, 0, s>>>(d->mb_partial, d->mb_sums + (size_t)t * n, nb, n);
-    g_launches++;
-    err = cudaGetLastError();
-    if (err != cudaSuccess) return fail(WSI_ERR_LAUNCH, "wsi_mb_finalize launch failed: %s", cudaGetErrorString(err));
+  const bool want_mb = (flags & WSI_RUN_MASS_BALANCE) != 0;
+  const bool want_sums = want_mb && d->mb_sums != nullptr;
+  if (flags & WSI_RUN_SURFACES) {
+    int rc = launch_surfaces<CFG, WSI_ST_SURFACE>(d, slot, cfg, t, flags, s);
+    if (!rc) rc = launch_surfaces<CFG, WSI_ST_IMPERVIOUSSURFACE>(d, slot, cfg, t, flags, s);
+    if (!rc) rc = launch_surfaces<CFG, WSI_ST_PERVIOUSSURFACE>(d, slot, cfg, t, flags, s);
+    if (!rc) rc = launch_surfaces<CFG, WSI_ST_GROWINGSURFACE>(d, slot, cfg, t, flags, s);
+    if (rc) return rc;
+  }
+  if ((flags & WSI_RUN_SCHEDULE) && e > b) {
+    wsi_step_kernel<CFG><<<n_blocks(d), kBlock, 0, s>>>(slot, cfg, (int)t, b, e, flags);
+    WSI_CHECK_LAUNCH("wsi_step_kernel");
+  }
+  if (want_mb) {
+    const int items = d->n_nodes + (want_sums ? d->n_arcs : 0);
+    if (items > 0) {
+      const dim3 grid(n_obj_blocks(d), items);
+      wsi_mb_kernel<CFG><<<grid, kObjBlock, 0, s>>>(slot, cfg, (int)t, flags);
+      WSI_CHECK_LAUNCH("wsi_mb_kernel");
+    }
+    if (want_sums) {
+      const int n = 3 * V;
+      wsi_mb_finalize<<<n, kFinBlock, 0, s>>>(d->mb_partial, d->mb_sums + (size_t)t * n, items * n_obj_blocks(d), n);
+      WSI_CHECK_LAUNCH("wsi_mb_finalize");
+    }
+  }
+  if (flags & WSI_RUN_RECORD) {
+    const int row = (int)t - d->rec_t0;
+    if (d->n_probe > 0 && row >= 0 && row < d->rec_T) {
+      const dim3 grid(n_obj_blocks(d), d->n_probe);
+      wsi_record_kernel<CFG><<<grid, kObjBlock, 0, s>>>(slot, cfg, (int)t, row);
+      WSI_CHECK_LAUNCH("wsi_record_kernel");
+    }
+  }
+  if ((flags & WSI_RUN_END_TIMESTEP) && d->n_end > 0) {
+    const dim3 grid(n_obj_blocks(d), d->n_end);
+    wsi_end_kernel<CFG><<<grid, kObjBlock, 0, s>>>(slot, cfg, (int)t);
+    WSI_CHECK_LAUNCH("wsi_end_kernel");
   }
   return WSI_OK;
 }
 
-int dispatch(const WsiModelDesc* d, int64_t t, int b, int e, uint32_t flags, cudaStream_t s) {
-  if (is_default12(d)) return launch(d, CfgDefault12(), t, b, e, flags, s);
+// Copy the descriptor into a constant-memory slot, ordered on the launching stream.  Slots are
+// handed out round-robin per call so that models stepped concurrently on different streams do
+// not overwrite each other's descriptor (up to WSI_DESC_SLOTS in flight).
+std::atomic<unsigned> g_next_slot{0};
+int upload_desc(const WsiModelDesc* d, cudaStream_t s, int* slot) {
+  *slot = (int)(g_next_slot.fetch_add(1) % WSI_DESC_SLOTS);
+  cudaError_t err = cudaMemcpyToSymbolAsync(g_wsi_desc, d, sizeof(WsiModelDesc), (size_t)*slot * sizeof(WsiModelDesc),
+                                            cudaMemcpyHostToDevice, s);
+  if (err != cudaSuccess) return fail(WSI_ERR_LAUNCH, "descriptor upload failed: %s", cudaGetErrorString(err));
+  return WSI_OK;
+}
+
+int dispatch(const WsiModelDesc* d, int slot, int64_t t, int b, int e, uint32_t flags, cudaStream_t s) {
+  if (is_default12(d)) return launch(d, slot, CfgDefault12(), t, b, e, flags, s);
 #ifndef WSI_ONLY_DEFAULT12  // development builds instantiate a single configuration
-  if (d->P == 12) return launch(d, runtime_cfg<12>(d), t, b, e, flags, s);
-  if (d->P == 2) return launch(d, runtime_cfg<2>(d), t, b, e, flags, s);
+  if (d->P == 12) return launch(d, slot, runtime_cfg<12>(d), t, b, e, flags, s);
+  if (d->P == 2) return launch(d, slot, runtime_cfg<2>(d), t, b, e, flags, s);
 #endif
   return fail(WSI_ERR_UNSUPPORTED, "no kernel instantiated for this number of pollutants%s");
 }
@@ -147,6 +304,11 @@ int wsi_validate(const WsiModelDesc* d) {
   if (d->n_nodes > 0 && (!d->node_type || !d->node_gidx || !d->out_ptr || !d->in_ptr || !d->cand_ptr))
     return fail(WSI_ERR_BAD_DESC, "graph arrays missing%s");
   if (d->n_sched > 0 && (!d->sched_op || !d->sched_node)) return fail(WSI_ERR_BAD_DESC, "schedule missing%s");
+  if (d->n_end > 0 && (!d->end_kind || !d->end_obj)) return fail(WSI_ERR_BAD_DESC, "end_timestep items missing%s");
+  if (d->n_probe > 65535 || d->n_end > 65535 || d->n_nodes + d->n_arcs > 65535)
+    return fail(WSI_ERR_UNSUPPORTED, "more than 65535 probes / nodes+arcs / end items per template%s");
+  if (d->n_surf > 0 && (!d->surf_order || d->surf_class_ptr[0] != 0 || d->surf_class_ptr[4] != d->n_surf))
+    return fail(WSI_ERR_BAD_DESC, "surface class order missing%s");
   if ((d->n_arcs > 0 && !d->arc) || (d->n_land > 0 && !d->land) || (d->n_surf > 0 && !d->surf) ||
       (d->n_tank > 0 && !d->tank) || (d->n_river > 0 && !d->river) || (d->n_sewer > 0 && !d->sewer) ||
       (d->n_catch > 0 && !d->catchm))
@@ -157,20 +319,24 @@ int wsi_validate(const WsiModelDesc* d) {
     return fail(WSI_ERR_BAD_DESC, "probe arrays missing%s");
   if (d->record_mb && !d->out_mb) return fail(WSI_ERR_BAD_DESC, "record_mb without out_mb%s");
   if (d->mb_sums && !d->mb_partial) return fail(WSI_ERR_BAD_DESC, "mb_sums without mb_partial%s");
+  if (d->n_nodes > 0 && (!d->mb_terms || !d->mb_term_slot)) return fail(WSI_ERR_BAD_DESC, "mb_terms missing%s");
   if (!d->node_flags) return fail(WSI_ERR_BAD_DESC, "node_flags missing%s");
   if (!(is_default12(d) || d->P == 12 || d->P == 2))
     return fail(WSI_ERR_UNSUPPORTED, "kernels are instantiated for P in {2, 12}%s");
   return WSI_OK;
 }
 
-int wsi_num_blocks(const WsiModelDesc* d) { return d ? n_blocks(d) : 0; }
+int wsi_num_blocks(const WsiModelDesc* d) { return d ? n_partial_rows(d) : 0; }
 
 int wsi_sched_range(const WsiModelDesc* d, int64_t t, int32_t begin, int32_t end, uint32_t flags, void* stream) {
   int rc = wsi_validate(d);
   if (rc) return rc;
   if (t < 0 || t >= d->T) return fail(WSI_ERR_BAD_DESC, "timestep outside the forcing tables%s");
   if (begin < 0 || end > d->n_sched || begin > end) return fail(WSI_ERR_BAD_DESC, "bad schedule range%s");
-  return dispatch(d, t, begin, end, flags, (cudaStream_t)stream);
+  int slot;
+  rc = upload_desc(d, (cudaStream_t)stream, &slot);
+  if (rc) return rc;
+  return dispatch(d, slot, t, begin, end, flags, (cudaStream_t)stream);
 }
 
 int wsi_step(const WsiModelDesc* d, int64_t t, void* stream) {
@@ -182,8 +348,11 @@ int wsi_run_steps(const WsiModelDesc* d, int64_t t0, int64_t t1, void* stream) {
   int rc = wsi_validate(d);
   if (rc) return rc;
   if (t0 < 0 || t1 > d->T || t0 > t1) return fail(WSI_ERR_BAD_DESC, "timestep range outside the forcing tables%s");
+  int slot;
+  rc = upload_desc(d, (cudaStream_t)stream, &slot);
+  if (rc) return rc;
   for (int64_t t = t0; t < t1; t++) {
-    rc = dispatch(d, t, 0, d->n_sched, WSI_RUN_ALL, (cudaStream_t)stream);
+    rc = dispatch(d, slot, t, 0, d->n_sched, WSI_RUN_ALL, (cudaStream_t)stream);
     if (rc) return rc;
   }
   return WSI_OK;

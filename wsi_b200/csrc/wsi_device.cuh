@@ -24,6 +24,16 @@ constexpr int kMaxIter = 5;          // constants.MAXITER
 constexpr int kMaxCand = 8;          // arcs one push_distributed call can split over
 constexpr int kJunctionDepth = 2;    // nested junction Nodes a push may traverse
 
+// The model descriptor lives in constant memory on the device (direct constant-bank loads with
+// immediate offsets from every function, inlined or not); wsi_api.cu copies it into a slot
+// before launching.  The host build (tests/hostsim) reads it through a pointer.
+#ifndef WSI_DESC_SLOTS
+#define WSI_DESC_SLOTS 8
+#endif
+#if defined(__CUDACC__)
+__constant__ WsiModelDesc g_wsi_desc[WSI_DESC_SLOTS];
+#endif
+
 // One object's column in a group tensor: plane k lives at p[k * s]
 struct Obj {
   double* p;
@@ -37,7 +47,8 @@ struct Ctx {
   static constexpr int V = P + 1;
   using Vq = VQ<P>;
 
-  const WsiModelDesc* d;
+  const WsiModelDesc* host_d;  // host build only
+  int slot;                    // constant-memory slot of the descriptor (device)
   CFG cfg;
   size_t R;
   int r;
@@ -49,28 +60,36 @@ struct Ctx {
   double* mb_acc;  // [3*V] per-thread system-total accumulators (stride mb_stride) or null
   int mb_stride;
 
+  WSI_HD const WsiModelDesc& D() const {
+#if defined(__CUDA_ARCH__)
+    return g_wsi_desc[slot];
+#else
+    return *host_d;
+#endif
+  }
+
   // ---- plane addressing ----
   WSI_HD double* pl(double* base, int n_obj, int plane, int obj) const {
     return base + ((size_t)plane * (size_t)n_obj + (size_t)obj) * R + (size_t)r;
   }
-  WSI_HD double* arc(int plane, int a) const { return pl(d->arc, d->n_arcs, plane, a); }
-  WSI_HD double* land(int plane, int i) const { return pl(d->land, d->n_land, plane, i); }
-  WSI_HD double* surf(int plane, int i) const { return pl(d->surf, d->n_surf, plane, i); }
-  WSI_HD double* tank(int plane, int i) const { return pl(d->tank, d->n_tank, plane, i); }
-  WSI_HD double* river(int plane, int i) const { return pl(d->river, d->n_river, plane, i); }
-  WSI_HD double* sewer(int plane, int i) const { return pl(d->sewer, d->n_sewer, plane, i); }
-  WSI_HD Obj arc_obj(int a) const { return Obj{d->arc + (size_t)a * R + r, (size_t)d->n_arcs * R}; }
-  WSI_HD Obj land_obj(int i) const { return Obj{d->land + (size_t)i * R + r, (size_t)d->n_land * R}; }
-  WSI_HD Obj surf_obj(int i) const { return Obj{d->surf + (size_t)i * R + r, (size_t)d->n_surf * R}; }
-  WSI_HD Obj tank_obj(int i) const { return Obj{d->tank + (size_t)i * R + r, (size_t)d->n_tank * R}; }
-  WSI_HD Obj river_obj(int i) const { return Obj{d->river + (size_t)i * R + r, (size_t)d->n_river * R}; }
-  WSI_HD Obj sewer_obj(int i) const { return Obj{d->sewer + (size_t)i * R + r, (size_t)d->n_sewer * R}; }
-  WSI_HD size_t s_arc() const { return (size_t)d->n_arcs * R; }
-  WSI_HD size_t s_land() const { return (size_t)d->n_land * R; }
-  WSI_HD size_t s_surf() const { return (size_t)d->n_surf * R; }
-  WSI_HD size_t s_tank() const { return (size_t)d->n_tank * R; }
-  WSI_HD size_t s_river() const { return (size_t)d->n_river * R; }
-  WSI_HD size_t s_sewer() const { return (size_t)d->n_sewer * R; }
+  WSI_HD double* arc(int plane, int a) const { return pl(D().arc, D().n_arcs, plane, a); }
+  WSI_HD double* land(int plane, int i) const { return pl(D().land, D().n_land, plane, i); }
+  WSI_HD double* surf(int plane, int i) const { return pl(D().surf, D().n_surf, plane, i); }
+  WSI_HD double* tank(int plane, int i) const { return pl(D().tank, D().n_tank, plane, i); }
+  WSI_HD double* river(int plane, int i) const { return pl(D().river, D().n_river, plane, i); }
+  WSI_HD double* sewer(int plane, int i) const { return pl(D().sewer, D().n_sewer, plane, i); }
+  WSI_HD Obj arc_obj(int a) const { return Obj{D().arc + (size_t)a * R + r, (size_t)D().n_arcs * R}; }
+  WSI_HD Obj land_obj(int i) const { return Obj{D().land + (size_t)i * R + r, (size_t)D().n_land * R}; }
+  WSI_HD Obj surf_obj(int i) const { return Obj{D().surf + (size_t)i * R + r, (size_t)D().n_surf * R}; }
+  WSI_HD Obj tank_obj(int i) const { return Obj{D().tank + (size_t)i * R + r, (size_t)D().n_tank * R}; }
+  WSI_HD Obj river_obj(int i) const { return Obj{D().river + (size_t)i * R + r, (size_t)D().n_river * R}; }
+  WSI_HD Obj sewer_obj(int i) const { return Obj{D().sewer + (size_t)i * R + r, (size_t)D().n_sewer * R}; }
+  WSI_HD size_t s_arc() const { return (size_t)D().n_arcs * R; }
+  WSI_HD size_t s_land() const { return (size_t)D().n_land * R; }
+  WSI_HD size_t s_surf() const { return (size_t)D().n_surf * R; }
+  WSI_HD size_t s_tank() const { return (size_t)D().n_tank * R; }
+  WSI_HD size_t s_river() const { return (size_t)D().n_river * R; }
+  WSI_HD size_t s_sewer() const { return (size_t)D().n_sewer * R; }
 
   WSI_HD Vq ldv(const double* p, size_t stride) const {
     Vq v;
@@ -82,14 +101,26 @@ struct Ctx {
 #pragma unroll
     for (int i = 0; i < V; i++) p[(size_t)i * stride] = v.x[i];
   }
-  WSI_HD void flag(int node, uint32_t f) const { d->node_flags[(size_t)node * R + r] |= f; }
+  // volume + additive lanes only (everything a mass balance reads, core.py:400-404)
+  WSI_HD Vq ldv_add(const double* p, size_t stride) const {
+    Vq v;
+#pragma unroll
+    for (int i = 0; i < V; i++) v.x[i] = (i == 0 || bit(add, i)) ? p[(size_t)i * stride] : 0.0;
+    return v;
+  }
+  WSI_HD void stv_add(double* p, size_t stride, const Vq& v) const {
+#pragma unroll
+    for (int i = 0; i < V; i++)
+      if (i == 0 || bit(add, i)) p[(size_t)i * stride] = v.x[i];
+  }
+  WSI_HD void flag(int node, uint32_t f) const { D().node_flags[(size_t)node * R + r] |= f; }
 
   // ---- forcing ----
   WSI_HD double forcing(int fid, int col) const {
-    return d->node_forcing[((size_t)t * d->n_fseries + fid) * 3 + col];
+    return D().node_forcing[((size_t)t * D().n_fseries + fid) * 3 + col];
   }
   WSI_HD double dep(int dep_id, int col) const {
-    return d->surf_inputs[((size_t)d->month_idx[t] * d->n_dep_series + dep_id) * WSI_N_DEP + col];
+    return D().surf_inputs[((size_t)D().month_idx[t] * D().n_dep_series + dep_id) * WSI_N_DEP + col];
   }
 
   // ---- algebra shorthands ----
@@ -162,9 +193,11 @@ WSI_HD void vq_pull_pollutants(const C& c, typename C::Vq& s, typename C::Vq& re
 // supported node class.  D is the number of junction `Node`s the call may still traverse.
 // =========================================================================================
 template <int D, class C>
-WSI_HDN double arc_excess_vol(C& c, int a, bool has_v, double v_vol);
+WSI_HD double arc_excess_vol(C& c, int a, bool has_v, double v_vol);
 template <int D, class C>
-WSI_HDN typename C::Vq arc_send_push_request(C& c, int a, const typename C::Vq& vqip);
+WSI_HD typename C::Vq arc_send_push_request(C& c, int a, const typename C::Vq& vqip);
+template <int D, class C>
+WSI_HD typename C::Vq node_push_set(C& c, int node, const typename C::Vq& vqip);
 template <int D, class C>
 WSI_HDN typename C::Vq push_distributed(C& c, int node, const typename C::Vq& vqip, int filter);
 
@@ -180,7 +213,7 @@ WSI_HD void sewer_update_queue(C& c, int w) {  // AltQueueArc.update_queue arcs.
 }
 // QueueTank.push_storage(vqip, time) tanks.py:513-539 through AltQueueArc (arcs.py:360-407).
 template <class C>
-WSI_HDN typename C::Vq sewer_push_storage(C& c, int w, const typename C::Vq& v0, int time) {
+WSI_HD typename C::Vq sewer_push_storage(C& c, int w, const typename C::Vq& v0, int time) {
   constexpr int V = C::V;
   using Vq = typename C::Vq;
   const size_t s = c.s_sewer();
@@ -217,20 +250,21 @@ WSI_HDN typename C::Vq sewer_push_storage(C& c, int w, const typename C::Vq& v0,
 }
 
 template <int D, class C>
-WSI_HDN double node_push_check_vol(C& c, int node, bool has_v, double v_vol) {
-  const WsiModelDesc* d = c.d;
-  const int g = d->node_gidx[node];
+WSI_HD double node_push_check_vol(C& c, int node, bool has_v, double v_vol) {
+  const WsiModelDesc& d = c.D();
+  const int g = d.node_gidx[node];
   constexpr int V = C::V;
-  switch (d->node_type[node]) {
+  switch (d.node_type[node]) {
     case WSI_NT_NODE: {  // push_check_basic nodes.py:529-545 -> check_basic :480-508
       if constexpr (D == 0) {
         c.flag(node, WSI_FLAG_DEPTH);
         return 0.0;
       } else {
-        const int b = d->cand_ptr[node * WSI_NF + WSI_FILTER_NRWR];
-        const int e = d->cand_ptr[node * WSI_NF + WSI_FILTER_NRWR + 1];
+        const int b = d.cand_ptr[node * WSI_NF + WSI_FILTER_NRWR];
+        const int e = d.cand_ptr[node * WSI_NF + WSI_FILTER_NRWR + 1];
         double avail = 0.0;
-        for (int i = b; i < e; i++) avail = avail + arc_excess_vol<D - 1>(c, d->cand_arcs[i], false, 0.0);
+#pragma unroll 1
+        for (int i = b; i < e; i++) avail = avail + arc_excess_vol<D - 1>(c, d.cand_arcs[i], false, 0.0);
         if (has_v) avail = vol_vchange(avail, pymin(avail, v_vol));
         return avail;
       }
@@ -256,11 +290,11 @@ WSI_HDN double node_push_check_vol(C& c, int node, bool has_v, double v_vol) {
 }
 
 template <int D, class C>
-WSI_HDN typename C::Vq node_push_set(C& c, int node, const typename C::Vq& vqip) {
-  const WsiModelDesc* d = c.d;
-  const int g = d->node_gidx[node];
+WSI_HD typename C::Vq node_push_set(C& c, int node, const typename C::Vq& vqip) {
+  const WsiModelDesc& d = c.D();
+  const int g = d.node_gidx[node];
   constexpr int V = C::V;
-  switch (d->node_type[node]) {
+  switch (d.node_type[node]) {
     case WSI_NT_NODE:  // junction: forward (nodes.py:62-66)
       if constexpr (D == 0) {
         c.flag(node, WSI_FLAG_DEPTH);
@@ -290,23 +324,51 @@ WSI_HDN typename C::Vq node_push_set(C& c, int node, const typename C::Vq& vqip)
 
 // Arc.get_excess(direction="push")["volume"] arcs.py:230-257
 template <int D, class C>
-WSI_HDN double arc_excess_vol(C& c, int a, bool has_v, double v_vol) {
+WSI_HD double arc_excess_vol(C& c, int a, bool has_v, double v_vol) {
   const double pipe_excess = *c.arc(WSI_ARC_CAPACITY, a) - *c.arc(WSI_ARC_FLOW_IN, a);
-  const double ne = node_push_check_vol<D>(c, c.d->arc_out[a], has_v, v_vol);
+  const double ne = node_push_check_vol<D>(c, c.D().arc_out[a], has_v, v_vol);
   return vol_vchange(ne, pymin(pipe_excess, ne));
 }
 
-// Arc.send_push_request arcs.py:112-158
+// volume and additive lanes all zero (non-additive lanes of a zero-volume VQIP never reach a
+// result: they are always multiplied by the volume)
+template <class C>
+WSI_HD bool vq_is_empty(const C& c, const typename C::Vq& v) {
+  bool z = v.x[0] == 0.0;
+#pragma unroll
+  for (int p = 1; p <= C::P; p++)
+    if (bit(c.add, p)) z = z && v.x[p] == 0.0;
+  return z;
+}
+
+// Arc.send_push_request arcs.py:112-158.  When the whole volume is admitted
+// (max(vol - excess, 0) == 0) not_pushed = v_change_vqip(vqip, 0) has zero volume and zero
+// additive lanes and extract_vqip(vqip, not_pushed) is vqip itself; when the receiver then hands
+// nothing back, sent == vqip and sum_vqip(reply, not_pushed) leaves the reply unchanged.  Those
+// identities skip four VQIP operations on the common path without changing any value.
 template <int D, class C>
-WSI_HDN typename C::Vq arc_send_push_request(C& c, int a, const typename C::Vq& vqip) {
+WSI_HD typename C::Vq arc_send_push_request(C& c, int a, const typename C::Vq& vqip) {
   using Vq = typename C::Vq;
   constexpr int V = C::V;
   const double excess_in = arc_excess_vol<D>(c, a, true, vqip.x[0]);
-  const Vq not_pushed = c.vchange(vqip, pymax(vqip.x[0] - excess_in, 0.0));
-  const Vq v = c.extract(vqip, not_pushed);
-  Vq reply = node_push_set<D>(c, c.d->arc_out[a], v);
-  const Vq sent = c.extract(v, reply);
-  reply = c.sum(reply, not_pushed);
+  const double np = pymax(vqip.x[0] - excess_in, 0.0);
+  const bool admitted = np == 0.0 && vqip.x[0] > 0;
+  Vq not_pushed, v;
+  if (admitted) {
+    v = vqip;
+  } else {
+    not_pushed = c.vchange(vqip, np);
+    v = c.extract(vqip, not_pushed);
+  }
+  Vq reply = node_push_set<D>(c, c.D().arc_out[a], v);
+  Vq sent;
+  if (admitted && vq_is_empty(c, reply)) {
+    sent = v;
+  } else {
+    if (admitted) not_pushed = c.vchange(vqip, np);
+    sent = c.extract(v, reply);
+    reply = c.sum(reply, not_pushed);
+  }
   double* fi = c.arc(WSI_ARC_FLOW_IN, a);
   *fi = *fi + sent.x[0];
   double* vi = c.arc(WSI_ARC_VQIP_IN(V), a);
@@ -318,46 +380,54 @@ WSI_HDN typename C::Vq arc_send_push_request(C& c, int a, const typename C::Vq& 
 template <int D, class C>
 WSI_HDN typename C::Vq push_distributed(C& c, int node, const typename C::Vq& vqip, int filter) {
   using Vq = typename C::Vq;
-  const WsiModelDesc* d = c.d;
-  const int cb = d->cand_ptr[node * WSI_NF + filter];
-  int nc = d->cand_ptr[node * WSI_NF + filter + 1] - cb;
-  const int* cand = d->cand_arcs + cb;
-  const int n_out = d->out_ptr[node + 1] - d->out_ptr[node];
-  if (n_out == 1) {
-    if (nc > 0) return arc_send_push_request<D>(c, d->out_arcs[d->out_ptr[node]], vqip);
-    return vqip;
-  }
+  const WsiModelDesc& d = c.D();
+  const int cb = d.cand_ptr[node * WSI_NF + filter];
+  int nc = d.cand_ptr[node * WSI_NF + filter + 1] - cb;
+  const int* cand = d.cand_arcs + cb;
+  const int n_out = d.out_ptr[node + 1] - d.out_ptr[node];
+  const bool single = n_out == 1;  // nodes.py:424-438: one out-arc -> send everything down it
+  if (single && nc <= 0) return vqip;
   if (nc > kMaxCand) nc = kMaxCand;
   double not_pushed = vqip.x[0];
   Vq not_pushed_ = vqip;
   double alloc[kMaxCand], cap_[kMaxCand];
   double avail = 0.0, priority = 0.0;
-  // get_connected nodes.py:271-317
-  for (int i = 0; i < nc; i++) {
-    double a = arc_excess_vol<D>(c, cand[i], false, 0.0);
-    if (a < c.FA) a = 0.0;
-    const double pref = *c.arc(WSI_ARC_PREFERENCE, cand[i]);
-    avail += a;
-    priority += a * pref;
-    alloc[i] = a * pref;
-    cap_[i] = a;
-  }
-  if (not_pushed > avail) {
-    priority = avail;
-    for (int i = 0; i < nc; i++) alloc[i] = cap_[i];
+  if (!single) {
+    // get_connected nodes.py:271-317
+#pragma unroll 1
+    for (int i = 0; i < nc; i++) {
+      double a = arc_excess_vol<D>(c, cand[i], false, 0.0);
+      if (a < c.FA) a = 0.0;
+      const double pref = *c.arc(WSI_ARC_PREFERENCE, cand[i]);
+      avail += a;
+      priority += a * pref;
+      alloc[i] = a * pref;
+      cap_[i] = a;
+    }
+    if (not_pushed > avail) {
+      priority = avail;
+#pragma unroll 1
+      for (int i = 0; i < nc; i++) alloc[i] = cap_[i];
+    }
   }
   int iter = 0;
-  while (not_pushed > c.FA && avail > c.FA && iter < kMaxIter) {
+#pragma unroll 1
+  while (single || (not_pushed > c.FA && avail > c.FA && iter < kMaxIter)) {
     const double amount = pymin(avail, not_pushed);
-    for (int i = 0; i < nc; i++) {
-      const Vq to_send = c.vchange(not_pushed_, amount * alloc[i] / priority);
-      const Vq reply = arc_send_push_request<D>(c, cand[i], to_send);
+    const int n_send = single ? 1 : nc;
+#pragma unroll 1
+    for (int i = 0; i < n_send; i++) {
+      const int arc = single ? d.out_arcs[d.out_ptr[node]] : cand[i];
+      const Vq to_send = single ? vqip : c.vchange(not_pushed_, amount * alloc[i] / priority);
+      const Vq reply = arc_send_push_request<D>(c, arc, to_send);
+      if (single) return reply;
       const Vq sent = c.extract(to_send, reply);
       not_pushed_ = c.extract(not_pushed_, sent);
     }
     not_pushed = not_pushed_.x[0];
     avail = 0.0;
     priority = 0.0;
+#pragma unroll 1
     for (int i = 0; i < nc; i++) {
       double a = arc_excess_vol<D>(c, cand[i], false, 0.0);
       if (a < c.FA) a = 0.0;
@@ -391,7 +461,7 @@ WSI_HD double pow10i(int k) {  // 0 <= k <= 22
   if (k & 16) p *= 1e16;
   return p;
 }
-WSI_HD double magnitude10(double x) {
+WSI_HDN double magnitude10(double x) {
   if (!(x > 1e-22 && x < 1e22)) return pow(10.0, (double)(int)log10(x));
   int e2;
   (void)frexp(x, &e2);  // x = m * 2^e2, m in [0.5, 1)
@@ -418,17 +488,26 @@ WSI_HD void mb_check(C& c, int node, const typename C::Vq& in_, const typename C
     if (p != 0 && !bit(c.add, p)) continue;
     const double a = in_.x[p], o = out_.x[p], dd = ds_.x[p];
     const double largest = pymax(pymax(a, o), dd);
-    const double magnitude = largest > c.FA ? magnitude10(largest) : 1.0;
-    // core.py:411-419 compares |in/m - ds/m - out/m| with FLOAT_ACCURACY; the three divisions
-    // are only needed when the residual is within 1 % of the threshold
-    const double resid = fabs(a - dd - o), thr = c.FA * magnitude;
+    // core.py:404-419: |in/m - ds/m - out/m| > FLOAT_ACCURACY with m = 10**int(log10(largest))
+    // (m = 1 when largest <= FLOAT_ACCURACY).  m lies in (x/10, x] for x >= 1 and in [x, 10x)
+    // below 1, so most lanes are decided from those bounds; the exact power of ten (and the
+    // three divisions) are only evaluated when the residual is within 1 % of a possible threshold.
+    const double resid = fabs(a - dd - o);
     bool bad;
-    if (c.FA >= 1e-12 && resid < 0.99 * thr)
-      bad = false;
-    else if (c.FA >= 1e-12 && resid > 1.01 * thr)
-      bad = true;
-    else
-      bad = fabs(a / magnitude - dd / magnitude - o / magnitude) > c.FA;
+    if (!(largest > c.FA)) {
+      bad = resid > c.FA;
+    } else {
+      const double m_lo = largest >= 1.0 ? largest * 0.1 : largest;
+      const double m_hi = largest >= 1.0 ? largest : largest * 10.0;
+      if (c.FA >= 1e-12 && resid < 0.99 * c.FA * m_lo) {
+        bad = false;
+      } else if (c.FA >= 1e-12 && resid > 1.01 * c.FA * m_hi) {
+        bad = true;
+      } else {
+        const double magnitude = magnitude10(largest);
+        bad = fabs(a / magnitude - dd / magnitude - o / magnitude) > c.FA;
+      }
+    }
     if (bad) viol++;
   }
   if (viol) {
@@ -444,10 +523,10 @@ WSI_HD void mb_check(C& c, int node, const typename C::Vq& in_, const typename C
       c.mb_acc[(2 * V + p) * c.mb_stride] += out_.x[p];
     }
   }
-  const WsiModelDesc* d = c.d;
-  const int row = c.t - d->rec_t0;
-  if (d->record_mb && row >= 0 && row < d->rec_T) {
-    double* o = d->out_mb + ((size_t)row * d->n_nodes + node) * 3 * V * c.R + c.r;
+  const WsiModelDesc& d = c.D();
+  const int row = c.t - d.rec_t0;
+  if (d.record_mb && row >= 0 && row < d.rec_T) {
+    double* o = d.out_mb + ((size_t)row * d.n_nodes + node) * 3 * V * c.R + c.r;
 #pragma unroll
     for (int p = 0; p < V; p++) {
       o[(size_t)(0 * V + p) * c.R] = in_.x[p];
@@ -457,21 +536,48 @@ WSI_HD void mb_check(C& c, int node, const typename C::Vq& in_, const typename C
   }
 }
 
-// Node.total_in / total_out nodes.py:104-132
+// (in, ds, out) of a node whose terms are formed inside its schedule op (Land, Catchment) are
+// handed to the mass-balance pass through mb_terms[slot][3][V][R]
+template <class C>
+WSI_HD void store_mb_terms(const C& c, int node, const typename C::Vq& in_, const typename C::Vq& ds_,
+                           const typename C::Vq& out_) {
+  const WsiModelDesc& d = c.D();
+  double* p = d.mb_terms + (size_t)d.mb_term_slot[node] * 3 * C::V * c.R + c.r;
+  c.stv_add(p, c.R, in_);
+  c.stv_add(p + (size_t)C::V * c.R, c.R, ds_);
+  c.stv_add(p + (size_t)2 * C::V * c.R, c.R, out_);
+}
+template <class C>
+WSI_HD void load_mb_terms(const C& c, int node, typename C::Vq& in_, typename C::Vq& ds_, typename C::Vq& out_) {
+  const WsiModelDesc& d = c.D();
+  const double* p = d.mb_terms + (size_t)d.mb_term_slot[node] * 3 * C::V * c.R + c.r;
+  in_ = c.ldv_add(p, c.R);
+  ds_ = c.ldv_add(p + (size_t)C::V * c.R, c.R);
+  out_ = c.ldv_add(p + (size_t)2 * C::V * c.R, c.R);
+}
+
+// Node.total_in / total_out nodes.py:104-132, volume + additive lanes (the non-additive lanes
+// of a mass-balance term are never compared, core.py:400-404, so they are not blended here)
 template <class C>
 WSI_HD typename C::Vq total_in(const C& c, int node) {
-  const WsiModelDesc* d = c.d;
+  const WsiModelDesc& d = c.D();
   typename C::Vq v = vq_zero<C::P>();
-  for (int i = d->in_ptr[node]; i < d->in_ptr[node + 1]; i++)
-    v = c.sum(v, c.ldv(c.arc(WSI_ARC_VQIP_IN(C::V), d->in_arcs[i]), c.s_arc()));
+  for (int i = d.in_ptr[node]; i < d.in_ptr[node + 1]; i++) {
+    const typename C::Vq a = c.ldv_add(c.arc(WSI_ARC_VQIP_IN(C::V), d.in_arcs[i]), c.s_arc());
+#pragma unroll
+    for (int p = 0; p <= C::P; p++) v.x[p] += a.x[p];
+  }
   return v;
 }
 template <class C>
 WSI_HD typename C::Vq total_out(const C& c, int node) {
-  const WsiModelDesc* d = c.d;
+  const WsiModelDesc& d = c.D();
   typename C::Vq v = vq_zero<C::P>();
-  for (int i = d->out_ptr[node]; i < d->out_ptr[node + 1]; i++)
-    v = c.sum(v, c.ldv(c.arc(WSI_ARC_VQIP_IN(C::V), d->out_arcs[i]), c.s_arc()));
+  for (int i = d.out_ptr[node]; i < d.out_ptr[node + 1]; i++) {
+    const typename C::Vq a = c.ldv_add(c.arc(WSI_ARC_VQIP_IN(C::V), d.out_arcs[i]), c.s_arc());
+#pragma unroll
+    for (int p = 0; p <= C::P; p++) v.x[p] += a.x[p];
+  }
   return v;
 }
 // ds_ accumulation of mass_balance (core.py:397-401): volume + additive only

@@ -71,18 +71,26 @@ WSI_HD void adjust_to_liquid(const C& c, typename C::Vq& v, double depN, double 
 
 // One surface of a Land node: Surface.run land.py:425-449 with the function lists of
 // Surface / ImperviousSurface / PerviousSurface / GrowingSurface (land.py:375-382, 619-621,
-// 830-841, 1275-1291).  Accumulates the parent's running mass-balance VQIPs and, when
-// `want_ds`, the surface's ds term.
-template <class C>
-WSI_HDN void surface_run(C& c, int node, int L, int u, double precip, double et0, double temperature,
-                         typename C::Vq& mb_in, typename C::Vq& mb_out, typename C::Vq& ds_acc,
-                         bool want_ds) {
+// 830-841, 1275-1291).  Runs as its own thread (wsi_surface_kernel: one thread per surface, a
+// block is homogeneous in surface type) or inline in the per-replica step.  What the parent
+// Land needs afterwards goes through the surface's scratch planes: the flows of `route`
+// (land.py:1046-1058) or the ponded runoff of `push_to_sewers` (land.py:699-721), and its share
+// of running_inflow_mb / running_outflow_mb / ds.  TYPE >= 0 fixes the surface class at compile
+// time (-1: read it from the type plane).
+template <int TYPE, class C>
+WSI_HD void surface_phase(C& c, int u) {
   using Vq = typename C::Vq;
   constexpr int P = C::P;
   constexpr int V = C::V;
   const size_t ss = c.s_surf();
   const Obj S = c.surf_obj(u);
-  const int type = (int)*S(WSI_SURF_TYPE);
+  const int type = TYPE >= 0 ? TYPE : (int)*S(WSI_SURF_TYPE);
+  const int L = (int)*S(WSI_SURF_LAND);
+  const Obj Lo = c.land_obj(L);
+  const int fid = (int)*Lo(WSI_LAND_FORCING_ID);
+  const double precip = c.forcing(fid, 0), et0 = c.forcing(fid, 1), temperature = c.forcing(fid, 2);
+  const bool want_ds = (c.run_flags & WSI_RUN_MASS_BALANCE) != 0;
+  Vq mb_in = vq_zero<P>(), mb_out = vq_zero<P>();
   const double area = *S(WSI_SURF_AREA);
   double* stp = S(WSI_SURF_STORAGE(V));
   Vq st = c.ldv(stp, ss);
@@ -118,8 +126,8 @@ WSI_HDN void surface_run(C& c, int node, int L, int u, double precip, double et0
 
   // ---- inflows --------------------------------------------------------------------------
   if (growing) {  // calc_crop_cover land.py:1514-1572
-    const double doy = (double)c.d->doy_adj[c.t];
-    const double dayofyear = (double)c.d->dayofyear[c.t];
+    const double doy = (double)c.D().doy_adj[c.t];
+    const double dayofyear = (double)c.D().dayofyear[c.t];
     days_after_sow = *S(WSI_SURF_DAYS_AFTER_SOW);
     crop_cover = *S(WSI_SURF_CROP_COVER);
     ground_cover = *S(WSI_SURF_GROUND_COVER);
@@ -224,11 +232,10 @@ WSI_HDN void surface_run(C& c, int node, int L, int u, double precip, double et0
     out_precip = precip * area;
     mb_in.x[0] += out_precip;
     mb_out.x[0] += out_evap;
-    // push_to_sewers land.py:699-721: pull_ponded, push to Sewers, force the reply back
+    // push_to_sewers land.py:699-721, first half: pull_ponded.  The push to the Sewers and
+    // forcing the reply back into this tank happen in land_phase (the sewer is shared state).
     const double ponded = pymax(st.x[0] - *S(WSI_SURF_CAPACITY), 0.0);
-    Vq runoff = vq_pull(c, st, ponded);
-    Vq reply = push_distributed<kJunctionDepth>(c, node, runoff, WSI_FILTER_SEWER);
-    st = c.sum(st, reply);
+    ie = vq_pull(c, st, ponded);
   } else if (type >= WSI_ST_PERVIOUSSURFACE) {
     // ihacres land.py:913-1044
     const double depth = *S(WSI_SURF_DEPTH);
@@ -275,7 +282,7 @@ WSI_HDN void surface_run(C& c, int node, int L, int u, double precip, double et0
             const double sno3 = vget<P>(st, cfg.no3()), snh4 = vget<P>(st, cfg.nh4()),
                          sno2 = vget<P>(st, cfg.no2());
             const double den = sno3 + snh4 + sno2;
-            if (den == 0) c.flag(node, WSI_FLAG_NAN);
+            if (den == 0) c.flag((int)*Lo(WSI_LAND_NODE), WSI_FLAG_NAN);
             vset<P>(reply, cfg.no3(), diN * sno3 / den);
             vset<P>(reply, cfg.nh4(), diN * snh4 / den);
             vset<P>(reply, cfg.no2(), diN * sno2 / den);
@@ -387,7 +394,7 @@ WSI_HDN void surface_run(C& c, int node, int L, int u, double precip, double et0
       // soil_pool_transformation land.py:1744-1811 + nutrient_pool.py:396-450
       {
         const double sno3 = vget<P>(st, cfg.no3()), snh4 = vget<P>(st, cfg.nh4());
-        if (sno3 + snh4 == 0) c.flag(node, WSI_FLAG_NAN);
+        if (sno3 + snh4 == 0) c.flag((int)*Lo(WSI_LAND_NODE), WSI_FLAG_NAN);
         const double nitrate_proportion = sno3 / (sno3 + snh4);
         double inc_di[2] = {0.0, 0.0}, inc_do[2] = {0.0, 0.0}, amount[2];
         temp_soil_process(pl, *S(WSI_SURF_DEGRHPAR), *S(WSI_SURF_DEGRHPAR + 1), pl.humus, pl.fast, amount);
@@ -458,7 +465,7 @@ WSI_HDN void surface_run(C& c, int node, int L, int u, double precip, double et0
         const double precipitation_depth = precip * 1e3;  // M_TO_MM
         double mobilised_rain = 0.0, mobilised_flow = 0.0;
         if (precipitation_depth > 5) {
-          const double dayofyear = (double)c.d->dayofyear[c.t];
+          const double dayofyear = (double)c.D().dayofyear[c.t];
           double rainfall_energy =
               8.95 + 8.44 * log10(precipitation_depth *
                                   (0.257 + sin(2 * 3.141592653589793 * ((dayofyear - 70) / 365)) * 0.09) * 2);
@@ -595,27 +602,36 @@ WSI_HDN void surface_run(C& c, int node, int L, int u, double precip, double et0
         }
       }
     }
-    // ---- outflows: route land.py:1046-1058 -------------------------------------------------
-    tank_push_force(c, c.land(WSI_LAND_SURFACE_RUNOFF(V), L), c.s_land(), ie);
-    tank_push_force(c, c.land(WSI_LAND_SUBSURFACE_RUNOFF(V), L), c.s_land(), sf);
-    tank_push_force(c, c.land(WSI_LAND_PERCOLATION(V), L), c.s_land(), pc);
   }
-
   // ---- write back ---------------------------------------------------------------------------
+  if (type != WSI_ST_SURFACE) {  // flows for the parent's tanks / sewers
+    c.stv(S(WSI_SURF_FLOW_A(V)), ss, ie);
+    if (type >= WSI_ST_PERVIOUSSURFACE) {
+      c.stv(S(WSI_SURF_FLOW_B(V)), ss, sf);
+      c.stv(S(WSI_SURF_FLOW_C(V)), ss, pc);
+    }
+  }
   if (want_ds) {
-    // decay_ds tanks.py:449-457: (storage - storage_) + total_decayed, where storage_ is what
-    // is still in memory except for the decayed pollutants (pre_decay)
-    Vq old = c.ldv(stp, ss);
+    // storage_ is what is still in memory, except for the decayed pollutants (pre_decay)
+    Vq old = c.ldv_add(stp, ss);
     const int n = (int)*S(WSI_SURF_N_DECAY);
     for (int i = 0; i < WSI_MAX_DECAY; i++) {
       if (i >= n) break;
       vset<P>(old, (int)*S(WSI_SURF_DECAY_POL + i), *S(WSI_SURF_PRE_DECAY + i));
     }
-    Vq dsv;
+    if (type == WSI_ST_IMPERVIOUSSURFACE) {
+      // the tank still receives the sewers' reply: land_phase forms ds from storage_
+      c.stv_add(S(WSI_SURF_MB_DS(V)), ss, old);
+    } else {
+      // decay_ds tanks.py:449-457: (storage - storage_) + total_decayed
+      Vq dsv;
 #pragma unroll
-    for (int p = 0; p <= P; p++) dsv.x[p] = (p == 0 || bit(c.add, p)) ? st.x[p] - old.x[p] : 0.0;
-    dsv = c.sum(dsv, decay_total<C>(c, S, WSI_SURF_N_DECAY));
-    ds_add(c, ds_acc, dsv);
+      for (int p = 0; p <= P; p++) dsv.x[p] = (p == 0 || bit(c.add, p)) ? st.x[p] - old.x[p] : 0.0;
+      dsv = c.sum(dsv, decay_total<C>(c, S, WSI_SURF_N_DECAY));
+      c.stv_add(S(WSI_SURF_MB_DS(V)), ss, dsv);
+    }
+    c.stv_add(S(WSI_SURF_MB_IN(V)), ss, mb_in);
+    c.stv_add(S(WSI_SURF_MB_OUT(V)), ss, mb_out);
   }
   c.stv(stp, ss, st);
   if (growing) {
@@ -628,10 +644,10 @@ WSI_HDN void surface_run(C& c, int node, int L, int u, double precip, double et0
       *S(WSI_SURF_POOL_ADS_INORG + k) = pl.ads_inorg[k];
     }
   }
-  if (c.d->n_probe > 0) {  // per-step diagnostics recorded by Model.run (model.py:1081-1118)
+  if (c.D().n_probe > 0) {  // per-step diagnostics recorded by Model.run (model.py:1081-1118)
     *S(WSI_SURF_OUT_PERCOLATION) = pc.x[0];
     *S(WSI_SURF_OUT_SUBSURFACE) = sf.x[0];
-    *S(WSI_SURF_OUT_SURFACE) = ie.x[0];
+    *S(WSI_SURF_OUT_SURFACE) = type == WSI_ST_IMPERVIOUSSURFACE ? 0.0 : ie.x[0];
     *S(WSI_SURF_OUT_EVAPORATION) = out_evap;
     *S(WSI_SURF_OUT_PRECIPITATION) = out_precip;
     *S(WSI_SURF_OUT_TANK_RECHARGE) = out_recharge;
@@ -648,19 +664,19 @@ WSI_HD typename C::Vq residence_pull(const C& c, double* st, size_t stride, doub
   return o;
 }
 
-// Land.run land.py:200-244, followed (when requested) by the node's mass balance
-// (core.py:370-429 with Land's term lists, land.py:113,158-162)
+// Land.run land.py:200-244 after its surfaces have run (surface_phase), followed (when
+// requested) by the node's mass balance (core.py:370-429 with Land's term lists,
+// land.py:113,158-162)
 template <class C>
-WSI_HDN void land_run(C& c, int node) {
+WSI_HDN void land_phase(C& c, int node) {
   using Vq = typename C::Vq;
   constexpr int P = C::P;
   constexpr int V = C::V;
-  const WsiModelDesc* d = c.d;
-  const int L = d->node_gidx[node];
+  const WsiModelDesc& d = c.D();
+  const int L = d.node_gidx[node];
   const size_t sl = c.s_land();
+  const size_t ss = c.s_surf();
   const bool want_mb = (c.run_flags & WSI_RUN_MASS_BALANCE) != 0;
-  const int fid = (int)*c.land(WSI_LAND_FORCING_ID, L);
-  const double precip = c.forcing(fid, 0), et0 = c.forcing(fid, 1), temperature = c.forcing(fid, 2);
 
   double* t_surf = c.land(WSI_LAND_SURFACE_RUNOFF(V), L);
   double* t_sub = c.land(WSI_LAND_SUBSURFACE_RUNOFF(V), L);
@@ -669,13 +685,42 @@ WSI_HDN void land_run(C& c, int node) {
   // the three ResidenceTanks' storage_ are whatever is in memory at the start of the step
   Vq neg0 = vq_zero<P>(), neg1 = vq_zero<P>(), neg2 = vq_zero<P>();
   if (want_mb) {
-    neg0 = c.ldv(t_surf, sl);
-    neg1 = c.ldv(t_sub, sl);
-    neg2 = c.ldv(t_perc, sl);
+    neg0 = c.ldv_add(t_surf, sl);
+    neg1 = c.ldv_add(t_sub, sl);
+    neg2 = c.ldv_add(t_perc, sl);
   }
   Vq mb_in = vq_zero<P>(), mb_out = vq_zero<P>();
-  for (int i = d->land_surf_ptr[L]; i < d->land_surf_ptr[L + 1]; i++)
-    surface_run(c, node, L, d->land_surf[i], precip, et0, temperature, mb_in, mb_out, ds, want_mb);
+  for (int i = d.land_surf_ptr[L]; i < d.land_surf_ptr[L + 1]; i++) {
+    const Obj S = c.surf_obj(d.land_surf[i]);
+    const int type = (int)*S(WSI_SURF_TYPE);
+    if (type == WSI_ST_IMPERVIOUSSURFACE) {
+      // push_to_sewers land.py:699-721, second half
+      const Vq runoff = c.ldv(S(WSI_SURF_FLOW_A(V)), ss);
+      const Vq reply = push_distributed<kJunctionDepth>(c, node, runoff, WSI_FILTER_SEWER);
+      double* stp = S(WSI_SURF_STORAGE(V));
+      const Vq st = c.sum(c.ldv(stp, ss), reply);
+      c.stv(stp, ss, st);
+      if (want_mb) {
+        const Vq old = c.ldv_add(S(WSI_SURF_MB_DS(V)), ss);
+        Vq dsv;
+#pragma unroll
+        for (int p = 0; p <= P; p++) dsv.x[p] = (p == 0 || bit(c.add, p)) ? st.x[p] - old.x[p] : 0.0;
+        dsv = c.sum(dsv, decay_total<C>(c, S, WSI_SURF_N_DECAY));
+        ds_add(c, ds, dsv);
+      }
+    } else {
+      if (type >= WSI_ST_PERVIOUSSURFACE) {  // route land.py:1046-1058
+        tank_push_force(c, t_surf, sl, c.ldv(S(WSI_SURF_FLOW_A(V)), ss));
+        tank_push_force(c, t_sub, sl, c.ldv(S(WSI_SURF_FLOW_B(V)), ss));
+        tank_push_force(c, t_perc, sl, c.ldv(S(WSI_SURF_FLOW_C(V)), ss));
+      }
+      if (want_mb) ds_add(c, ds, c.ldv_add(S(WSI_SURF_MB_DS(V)), ss));
+    }
+    if (want_mb) {
+      mb_acc(c, mb_in, c.ldv_add(S(WSI_SURF_MB_IN(V)), ss));
+      mb_acc(c, mb_out, c.ldv_add(S(WSI_SURF_MB_OUT(V)), ss));
+    }
+  }
 
   // percolation -> Groundwater (land.py:207-215)
   {
@@ -699,15 +744,15 @@ WSI_HDN void land_run(C& c, int node) {
     }
   }
   if (want_mb) {
-    Vq in_ = c.sum(vq_zero<P>(), total_in(c, node));
-    Vq out_ = c.sum(vq_zero<P>(), total_out(c, node));
+    Vq in_ = total_in(c, node);
+    Vq out_ = total_out(c, node);
 #pragma unroll
     for (int p = 0; p <= P; p++)
       if (p == 0 || bit(c.add, p)) {
         in_.x[p] += mb_in.x[p];
         out_.x[p] += mb_out.x[p];
       }
-    Vq f0 = c.ldv(t_surf, sl), f1 = c.ldv(t_sub, sl), f2 = c.ldv(t_perc, sl);
+    Vq f0 = c.ldv_add(t_surf, sl), f1 = c.ldv_add(t_sub, sl), f2 = c.ldv_add(t_perc, sl);
 #pragma unroll
     for (int p = 0; p <= P; p++)
       if (p == 0 || bit(c.add, p)) {
@@ -715,7 +760,7 @@ WSI_HDN void land_run(C& c, int node) {
         ds.x[p] += f1.x[p] - neg1.x[p];
         ds.x[p] += f2.x[p] - neg2.x[p];
       }
-    mb_check(c, node, in_, ds, out_);
+    store_mb_terms(c, node, in_, ds, out_);
   }
 }
 
@@ -724,11 +769,11 @@ WSI_HDN void land_run(C& c, int node) {
 template <class C>
 WSI_HD void land_end_timestep(C& c, int node) {
   constexpr int V = C::V;
-  const WsiModelDesc* d = c.d;
-  const int L = d->node_gidx[node];
+  const WsiModelDesc& d = c.D();
+  const int L = d.node_gidx[node];
   const double temperature = c.forcing((int)*c.land(WSI_LAND_FORCING_ID, L), 2);
-  for (int i = d->land_surf_ptr[L]; i < d->land_surf_ptr[L + 1]; i++) {
-    const int u = d->land_surf[i];
+  for (int i = d.land_surf_ptr[L]; i < d.land_surf_ptr[L + 1]; i++) {
+    const int u = d.land_surf[i];
     const Obj S = c.surf_obj(u);
     if ((int)*S(WSI_SURF_N_DECAY) > 0) {
       double* stp = S(WSI_SURF_STORAGE(V));

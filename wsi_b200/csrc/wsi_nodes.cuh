@@ -10,7 +10,7 @@ namespace wsi {
 template <class C>
 WSI_HDN void gw_infiltrate(C& c, int node) {  // storage.py:231-245
   constexpr int V = C::V;
-  const int g = c.d->node_gidx[node];
+  const int g = c.D().node_gidx[node];
   double* st = c.tank(WSI_TANK_STORAGE(V), g);
   double avail = st[0];
   avail = pymax(avail - *c.tank(WSI_TANK_CAPACITY, g) * *c.tank(WSI_TANK_INFILTRATION_THRESHOLD, g), 0.0);
@@ -22,7 +22,7 @@ WSI_HDN void gw_infiltrate(C& c, int node) {  // storage.py:231-245
 template <class C>
 WSI_HDN void gw_distribute(C& c, int node) {  // storage.py:222-229
   constexpr int V = C::V;
-  const int g = c.d->node_gidx[node];
+  const int g = c.D().node_gidx[node];
   double* st = c.tank(WSI_TANK_STORAGE(V), g);
   const double avail = st[0] / *c.tank(WSI_TANK_RESIDENCE_TIME, g);
   typename C::Vq to_send = tank_pull(c, st, c.s_tank(), avail);
@@ -32,7 +32,7 @@ WSI_HDN void gw_distribute(C& c, int node) {  // storage.py:222-229
 template <class C>
 WSI_HDN void storage_distribute(C& c, int node) {  // storage.py:120-127
   constexpr int V = C::V;
-  const int g = c.d->node_gidx[node];
+  const int g = c.D().node_gidx[node];
   double* st = c.tank(WSI_TANK_STORAGE(V), g);
   typename C::Vq storage = tank_pull(c, st, c.s_tank(), st[0]);
   typename C::Vq retained = push_distributed<kJunctionDepth>(c, node, storage, WSI_FILTER_ALL);
@@ -43,7 +43,7 @@ WSI_HDN void storage_distribute(C& c, int node) {  // storage.py:120-127
 template <class C>
 WSI_HDN void reservoir_abstract(C& c, int node) {
   constexpr int V = C::V;
-  const int g = c.d->node_gidx[node];
+  const int g = c.D().node_gidx[node];
   double* st = c.tank(WSI_TANK_STORAGE(V), g);
   typename C::Vq spill = tank_push(c, st, c.s_tank(), *c.tank(WSI_TANK_CAPACITY, g), vq_zero<C::P>());
   tank_push_force(c, st, c.s_tank(), spill);
@@ -76,7 +76,7 @@ WSI_HDN void river_calc(C& c, int node) {
   constexpr int V = C::V;
   const auto& cfg = c.cfg;
   if (cfg.no3() < 0) return;
-  const int g = c.d->node_gidx[node];
+  const int g = c.D().node_gidx[node];
   const Obj Rv = c.river_obj(g);
   const int tk = (int)*Rv(WSI_RIVER_TANK);
   const size_t sr = c.s_river();
@@ -203,7 +203,7 @@ WSI_HDN void river_calc(C& c, int node) {
 template <class C>
 WSI_HDN void river_distribute(C& c, int node) {  // storage.py:926-936
   constexpr int V = C::V;
-  const int g = c.d->node_gidx[node];
+  const int g = c.D().node_gidx[node];
   const int tk = (int)*c.river(WSI_RIVER_TANK, g);
   double* st = c.tank(WSI_TANK_STORAGE(V), tk);
   typename C::Vq outflow = tank_pull(c, st, c.s_tank(), st[0] * *c.river(WSI_RIVER_RIVERRC, g));
@@ -216,7 +216,7 @@ template <class C>
 WSI_HDN void sewer_discharge(C& c, int node) {  // sewer.py:201-239
   using Vq = typename C::Vq;
   constexpr int V = C::V;
-  const int w = c.d->node_gidx[node];
+  const int w = c.D().node_gidx[node];
   const size_t s = c.s_sewer();
   sewer_update_queue(c, w);
   double* act = c.sewer(WSI_SEWER_ACTIVE_STORAGE(V), w);
@@ -254,7 +254,7 @@ WSI_HD void sewer_end_timestep(C& c, int w) {
   using Vq = typename C::Vq;
   constexpr int V = C::V;
   const size_t s = c.s_sewer();
-  const int nq = c.d->nq;
+  const int nq = c.D().nq;
   *c.sewer(WSI_SEWER_IA_FLOW_IN, w) = 0.0;
   unsigned keys = (unsigned)*c.sewer(WSI_SEWER_QMASK, w);
   int max_travel = 1;
@@ -287,9 +287,9 @@ WSI_HD void sewer_end_timestep(C& c, int w) {
 // ---- Catchment ------------------------------------------------------------------------------
 template <class C>
 WSI_HD typename C::Vq catch_get_flow(const C& c, int g) {  // catchment.py:60-75
-  const WsiModelDesc* d = c.d;
-  const int cid = (int)d->catchm[(size_t)g * c.R + c.r];
-  const double* row = d->catch_inputs + ((size_t)c.t * d->n_cseries + cid) * C::V;
+  const WsiModelDesc& d = c.D();
+  const int cid = (int)d.catchm[(size_t)g * c.R + c.r];
+  const double* row = d.catch_inputs + ((size_t)c.t * d.n_cseries + cid) * C::V;
   typename C::Vq v;
 #pragma unroll
   for (int p = 0; p <= C::P; p++) v.x[p] = row[p];
@@ -302,18 +302,20 @@ WSI_HD typename C::Vq catch_get_flow(const C& c, int g) {  // catchment.py:60-75
 template <class C>
 WSI_HDN void catchment_route(C& c, int node) {
   using Vq = typename C::Vq;
-  const WsiModelDesc* d = c.d;
-  const int g = d->node_gidx[node];
+  const WsiModelDesc& d = c.D();
+  const int g = d.node_gidx[node];
   Vq avail = catch_get_flow(c, g);
-  for (int i = d->out_ptr[node]; i < d->out_ptr[node + 1]; i++)  // get_avail catchment.py:90-104
-    avail = c.vchange(avail, avail.x[0] - *c.arc(WSI_ARC_VQIP_IN(C::V), d->out_arcs[i]));
+  for (int i = d.out_ptr[node]; i < d.out_ptr[node + 1]; i++)  // get_avail catchment.py:90-104
+    avail = c.vchange(avail, avail.x[0] - *c.arc(WSI_ARC_VQIP_IN(C::V), d.out_arcs[i]));
   const Vq flow = avail;
   Vq reply = push_distributed<kJunctionDepth>(c, node, flow, WSI_FILTER_NRW);
   if (c.run_flags & WSI_RUN_MASS_BALANCE) {
     // in = total_in + get_flow(); out = total_out + unrouted_water (catchment.py:55-56)
-    Vq in_ = c.sum(c.sum(vq_zero<C::P>(), total_in(c, node)), catch_get_flow(c, g));
-    Vq out_ = c.sum(c.sum(vq_zero<C::P>(), total_out(c, node)), c.sum(vq_zero<C::P>(), reply));
-    mb_check(c, node, in_, vq_zero<C::P>(), out_);
+    Vq in_ = total_in(c, node);
+    ds_add(c, in_, catch_get_flow(c, g));
+    Vq out_ = total_out(c, node);
+    ds_add(c, out_, reply);
+    store_mb_terms(c, node, in_, vq_zero<C::P>(), out_);
   }
 }
 
@@ -322,8 +324,8 @@ template <class C>
 WSI_HD typename C::Vq tank_ds(const C& c, int tk) {  // tanks.py:70-76 / 449-457
   constexpr int V = C::V;
   using Vq = typename C::Vq;
-  const Vq st = c.ldv(c.tank(WSI_TANK_STORAGE(V), tk), c.s_tank());
-  const Vq st_ = c.ldv(c.tank(WSI_TANK_STORAGE_LAG(V), tk), c.s_tank());
+  const Vq st = c.ldv_add(c.tank(WSI_TANK_STORAGE(V), tk), c.s_tank());
+  const Vq st_ = c.ldv_add(c.tank(WSI_TANK_STORAGE_LAG(V), tk), c.s_tank());
   Vq dsv;
 #pragma unroll
   for (int p = 0; p <= C::P; p++) dsv.x[p] = (p == 0 || bit(c.add, p)) ? st.x[p] - st_.x[p] : 0.0;
@@ -334,43 +336,59 @@ WSI_HD typename C::Vq tank_ds(const C& c, int tk) {  // tanks.py:70-76 / 449-457
   return dsv;
 }
 
+// arcs are trivially balanced (vqip_in is vqip_out, arcs.py:83-85, 155-156); they only feed the
+// system totals of model.py:1016-1023
 template <class C>
-WSI_HDN void node_mass_balance(C& c, int node) {
+WSI_HD void arc_system_totals(C& c, int a) {
+  const typename C::Vq v = c.ldv_add(c.arc(WSI_ARC_VQIP_IN(C::V), a), c.s_arc());
+#pragma unroll
+  for (int p = 0; p <= C::P; p++)
+    if (p == 0 || bit(c.add, p)) {
+      c.mb_acc[(0 * C::V + p) * c.mb_stride] += v.x[p];
+      c.mb_acc[(2 * C::V + p) * c.mb_stride] += v.x[p];
+    }
+}
+
+template <class C>
+WSI_HD void node_mass_balance(C& c, int node, typename C::Vq& in_, typename C::Vq& ds, typename C::Vq& out_) {
   using Vq = typename C::Vq;
   constexpr int V = C::V;
-  const WsiModelDesc* d = c.d;
-  const int g = d->node_gidx[node];
-  const int type = d->node_type[node];
-  if (type == WSI_NT_LAND || type == WSI_NT_CATCHMENT) return;  // fused into their ops
-  const Vq tin = total_in(c, node);
-  Vq in_ = c.sum(vq_zero<C::P>(), tin);
-  Vq out_ = c.sum(vq_zero<C::P>(), total_out(c, node));
-  Vq ds = vq_zero<C::P>();
-  switch (type) {
-    case WSI_NT_WASTE:  // waste.py:38
-      out_ = c.sum(out_, tin);
-      break;
-    case WSI_NT_SEWER: {
-      const Vq st = c.ldv(c.sewer(WSI_SEWER_STORAGE(V), g), c.s_sewer());
-      const Vq st_ = c.ldv(c.sewer(WSI_SEWER_STORAGE_LAG(V), g), c.s_sewer());
+  const WsiModelDesc& d = c.D();
+  const int g = d.node_gidx[node];
+  const int type = d.node_type[node];
+  if (type == WSI_NT_LAND || type == WSI_NT_CATCHMENT) {  // formed inside their ops
+    load_mb_terms(c, node, in_, ds, out_);
+  } else {
+    const Vq tin = total_in(c, node);
+    in_ = tin;
+    out_ = total_out(c, node);
+    ds = vq_zero<C::P>();
+    switch (type) {
+      case WSI_NT_WASTE:  // waste.py:38
+        ds_add(c, out_, tin);
+        break;
+      case WSI_NT_SEWER: {
+        const Vq st = c.ldv_add(c.sewer(WSI_SEWER_STORAGE(V), g), c.s_sewer());
+        const Vq st_ = c.ldv_add(c.sewer(WSI_SEWER_STORAGE_LAG(V), g), c.s_sewer());
 #pragma unroll
-      for (int p = 0; p <= C::P; p++)
-        if (p == 0 || bit(c.add, p)) ds.x[p] += st.x[p] - st_.x[p];
-      break;
+        for (int p = 0; p <= C::P; p++)
+          if (p == 0 || bit(c.add, p)) ds.x[p] += st.x[p] - st_.x[p];
+        break;
+      }
+      case WSI_NT_GROUNDWATER:
+      case WSI_NT_STORAGE:
+      case WSI_NT_RESERVOIR:
+        ds_add(c, ds, tank_ds(c, g));
+        break;
+      case WSI_NT_RIVER: {
+        ds_add(c, in_, c.ldv_add(c.river(WSI_RIVER_BIO_IN(V), g), c.s_river()));
+        ds_add(c, out_, c.ldv_add(c.river(WSI_RIVER_BIO_OUT(V), g), c.s_river()));
+        ds_add(c, ds, tank_ds(c, (int)*c.river(WSI_RIVER_TANK, g)));
+        break;
+      }
+      default:
+        break;
     }
-    case WSI_NT_GROUNDWATER:
-    case WSI_NT_STORAGE:
-    case WSI_NT_RESERVOIR:
-      ds_add(c, ds, tank_ds(c, g));
-      break;
-    case WSI_NT_RIVER: {
-      in_ = c.sum(in_, c.ldv(c.river(WSI_RIVER_BIO_IN(V), g), c.s_river()));
-      out_ = c.sum(out_, c.ldv(c.river(WSI_RIVER_BIO_OUT(V), g), c.s_river()));
-      ds_add(c, ds, tank_ds(c, (int)*c.river(WSI_RIVER_TANK, g)));
-      break;
-    }
-    default:
-      break;
   }
   mb_check(c, node, in_, ds, out_);
 }
@@ -389,66 +407,79 @@ WSI_HD void store_end_timestep(C& c, int tk) {  // tanks.py:348-351 / 442-447
   }
 }
 
+// end_timestep of one object; `kind` indexes the group (0 arc, 2 surface, 3 tank, 4 river,
+// 5 sewer).  Objects are independent here, so the CUDA library runs one thread per
+// (object, replica) (wsi_end_kernel); the fused per-replica step loops over the same list.
+template <class C>
+WSI_HD void end_item(C& c, int kind, int obj) {
+  constexpr int V = C::V;
+  switch (kind) {
+    case 0:  // Arc.end_timestep arcs.py:259-265
+      *c.arc(WSI_ARC_FLOW_IN, obj) = 0.0;
+      c.stv(c.arc(WSI_ARC_VQIP_IN(V), obj), c.s_arc(), vq_zero<C::P>());
+      break;
+    case 2: {  // Surface (DecayTank) end_timestep tanks.py:442-447, land.py:266-275
+      const Obj S = c.surf_obj(obj);
+      if ((int)*S(WSI_SURF_N_DECAY) > 0) {
+        const int L = (int)*S(WSI_SURF_LAND);
+        const double temperature = c.forcing((int)*c.land(WSI_LAND_FORCING_ID, L), 2);
+        double* stp = S(WSI_SURF_STORAGE(V));
+        typename C::Vq st = c.ldv(stp, c.s_surf());
+        decay_end_timestep(c, st, S, WSI_SURF_N_DECAY, temperature);
+        c.stv(stp, c.s_surf(), st);
+      }
+      break;
+    }
+    case 3:
+      store_end_timestep(c, obj);
+      break;
+    case 4:  // River.end_timestep_ storage.py:951-955 (its tank is a kind-3 item)
+      c.stv(c.river(WSI_RIVER_BIO_IN(V), obj), c.s_river(), vq_zero<C::P>());
+      c.stv(c.river(WSI_RIVER_BIO_OUT(V), obj), c.s_river(), vq_zero<C::P>());
+      break;
+    case 5:
+      sewer_end_timestep(c, obj);
+      break;
+    default:
+      break;
+  }
+}
+
 template <class C>
 WSI_HDN void end_timestep(C& c) {
-  constexpr int V = C::V;
-  const WsiModelDesc* d = c.d;
-  for (int n = 0; n < d->n_nodes; n++) {
-    const int g = d->node_gidx[n];
-    switch (d->node_type[n]) {
-      case WSI_NT_LAND:
-        land_end_timestep(c, n);
-        break;
-      case WSI_NT_SEWER:
-        sewer_end_timestep(c, g);
-        break;
-      case WSI_NT_GROUNDWATER:
-      case WSI_NT_STORAGE:
-      case WSI_NT_RESERVOIR:
-        store_end_timestep(c, g);
-        break;
-      case WSI_NT_RIVER:  // storage.py:951-955
-        store_end_timestep(c, (int)*c.river(WSI_RIVER_TANK, g));
-        c.stv(c.river(WSI_RIVER_BIO_IN(V), g), c.s_river(), vq_zero<C::P>());
-        c.stv(c.river(WSI_RIVER_BIO_OUT(V), g), c.s_river(), vq_zero<C::P>());
-        break;
-      default:
-        break;
-    }
-  }
-  for (int a = 0; a < d->n_arcs; a++) {  // Arc.end_timestep arcs.py:259-265
-    *c.arc(WSI_ARC_FLOW_IN, a) = 0.0;
-    c.stv(c.arc(WSI_ARC_VQIP_IN(V), a), c.s_arc(), vq_zero<C::P>());
-  }
+  const WsiModelDesc& d = c.D();
+  for (int i = 0; i < d.n_end; i++) end_item(c, d.end_kind[i], d.end_obj[i]);
 }
 
 // ---- recording (model.py:1063-1170): copy probe planes into out_probe[t, k, r] ---------------
 template <class C>
-WSI_HD void record(const C& c) {
-  const WsiModelDesc* d = c.d;
-  const int row = c.t - d->rec_t0;
-  if (d->n_probe <= 0 || row < 0 || row >= d->rec_T) return;
-  double* out = d->out_probe + (size_t)row * d->n_probe * c.R + c.r;
-  for (int k = 0; k < d->n_probe; k++) {
-    const int plane = d->probe_plane[k], obj = d->probe_obj[k];
-    const double* src;
-    switch (d->probe_group[k]) {
-      case 0: src = c.arc(plane, obj); break;
-      case 1: src = c.land(plane, obj); break;
-      case 2: src = c.surf(plane, obj); break;
-      case 3: src = c.tank(plane, obj); break;
-      case 4: src = c.river(plane, obj); break;
-      default: src = c.sewer(plane, obj); break;
-    }
-    out[(size_t)k * c.R] = *src;
+WSI_HD void record_probe(const C& c, int row, int k) {
+  const WsiModelDesc& d = c.D();
+  const int plane = d.probe_plane[k], obj = d.probe_obj[k];
+  const double* src;
+  switch (d.probe_group[k]) {
+    case 0: src = c.arc(plane, obj); break;
+    case 1: src = c.land(plane, obj); break;
+    case 2: src = c.surf(plane, obj); break;
+    case 3: src = c.tank(plane, obj); break;
+    case 4: src = c.river(plane, obj); break;
+    default: src = c.sewer(plane, obj); break;
   }
+  d.out_probe[((size_t)row * d.n_probe + k) * c.R + c.r] = *src;
+}
+template <class C>
+WSI_HD void record(const C& c) {
+  const WsiModelDesc& d = c.D();
+  const int row = c.t - d.rec_t0;
+  if (d.n_probe <= 0 || row < 0 || row >= d.rec_T) return;
+  for (int k = 0; k < d.n_probe; k++) record_probe(c, row, k);
 }
 
 // ---- one schedule entry -----------------------------------------------------------------------
 template <class C>
 WSI_HD void run_op(C& c, int op, int node) {
   switch (op) {
-    case WSI_OP_LAND_RUN: land_run(c, node); break;
+    case WSI_OP_LAND_RUN: land_phase(c, node); break;
     case WSI_OP_GW_INFILTRATE: gw_infiltrate(c, node); break;
     case WSI_OP_SEWER_DISCHARGE: sewer_discharge(c, node); break;
     case WSI_OP_GW_DISTRIBUTE: gw_distribute(c, node); break;
@@ -462,41 +493,40 @@ WSI_HD void run_op(C& c, int op, int node) {
 }
 
 // ---- the whole timestep of one replica --------------------------------------------------------
-template <class C>
+// FUSED_SURFACES: this thread also runs the replica's surfaces (host build / tiny models);
+// the CUDA library runs them in wsi_surface_kernel instead and instantiates <false>.
+template <bool FUSED_SURFACES, class C>
 WSI_HD void replica_step(C& c, int sched_begin, int sched_end) {
-  const WsiModelDesc* d = c.d;
+  const WsiModelDesc& d = c.D();
+  if constexpr (FUSED_SURFACES) {
+    if (c.run_flags & WSI_RUN_SURFACES)
+      for (int u = 0; u < d.n_surf; u++) surface_phase<-1>(c, u);
+  }
   if (c.run_flags & WSI_RUN_SCHEDULE)
-    for (int k = sched_begin; k < sched_end; k++) run_op(c, d->sched_op[k], d->sched_node[k]);
+    for (int k = sched_begin; k < sched_end; k++) run_op(c, d.sched_op[k], d.sched_node[k]);
   if (c.run_flags & WSI_RUN_MASS_BALANCE) {
-    // arcs are trivially balanced (vqip_in is vqip_out, arcs.py:83-85, 155-156); they only
-    // feed the system totals of model.py:1016-1023
-    if (c.mb_acc) {
-      for (int a = 0; a < d->n_arcs; a++) {
-        const typename C::Vq v = c.ldv(c.arc(WSI_ARC_VQIP_IN(C::V), a), c.s_arc());
-#pragma unroll
-        for (int p = 0; p <= C::P; p++)
-          if (p == 0 || bit(c.add, p)) {
-            c.mb_acc[(0 * C::V + p) * c.mb_stride] += v.x[p];
-            c.mb_acc[(2 * C::V + p) * c.mb_stride] += v.x[p];
-          }
-      }
+    if (c.mb_acc)
+      for (int a = 0; a < d.n_arcs; a++) arc_system_totals(c, a);
+    for (int n = 0; n < d.n_nodes; n++) {
+      typename C::Vq a, b, o;
+      node_mass_balance(c, n, a, b, o);
     }
-    for (int n = 0; n < d->n_nodes; n++) node_mass_balance(c, n);
   }
   if (c.run_flags & WSI_RUN_RECORD) record(c);
   if (c.run_flags & WSI_RUN_END_TIMESTEP) end_timestep(c);
 }
 
 template <class CFG>
-WSI_HD Ctx<CFG> make_ctx(const WsiModelDesc* d, const CFG& cfg, int r, int t, uint32_t flags) {
+WSI_HD Ctx<CFG> make_ctx(const WsiModelDesc* host_d, int slot, const CFG& cfg, int r, int t, uint32_t flags) {
   Ctx<CFG> c;
-  c.d = d;
+  c.host_d = host_d;
+  c.slot = slot;
   c.cfg = cfg;
-  c.R = (size_t)d->R;
+  c.R = (size_t)c.D().R;
   c.r = r;
   c.t = t;
   c.add = cfg.add_mask();
-  c.FA = d->float_accuracy;
+  c.FA = c.D().float_accuracy;
   c.run_flags = flags;
   c.viol = 0;
   c.mb_acc = nullptr;

@@ -120,12 +120,18 @@ WSI_HD VQ<P> vq_sum(uint32_t add, const VQ<P>& a, const VQ<P>& b) {
   VQ<P> t;
   t.x[0] = a.x[0] + b.x[0];
   const bool wet = t.x[0] > 0;
+  const double den = wet ? t.x[0] : 1.0;  // a zero denominator would take the slow division path
 #pragma unroll
   for (int p = 1; p <= P; p++) {
     if (bit(add, p))
       t.x[p] = a.x[p] + b.x[p];
     else
-      t.x[p] = wet ? (b.x[p] * b.x[0] + a.x[p] * a.x[0]) / t.x[0] : a.x[p];
+    {
+      // 0/den is +-0 with the numerator's sign: return it directly -- a zero numerator would
+      // send the fp64 division down its slow path
+      const double num = b.x[p] * b.x[0] + a.x[p] * a.x[0];
+      t.x[p] = wet ? (num == 0.0 ? num : num / den) : a.x[p];
+    }
   }
   return t;
 }
@@ -145,7 +151,7 @@ template <int P>
 WSI_HD VQ<P> vq_vchange(uint32_t add, const VQ<P>& a, double v) {
   VQ<P> t = a;
   if (a.x[0] > 0) {
-    const double ratio = v / a.x[0];
+    const double ratio = v == 0.0 ? v : v / a.x[0];  // (+-0)/x is +-0; skip the slow division path
     t.x[0] = a.x[0] * ratio;
 #pragma unroll
     for (int p = 1; p <= P; p++)
@@ -156,7 +162,7 @@ WSI_HD VQ<P> vq_vchange(uint32_t add, const VQ<P>& a, double v) {
   return t;
 }
 // the volume lane of v_change_vqip alone
-WSI_HD double vol_vchange(double vol, double v) { return vol > 0 ? vol * (v / vol) : v; }
+WSI_HD double vol_vchange(double vol, double v) { return vol > 0 ? vol * (v == 0.0 ? v : v / vol) : v; }
 
 // a VQIP that carries only a volume: v_change_vqip(empty_vqip(), v)
 template <int P>
