@@ -36,25 +36,46 @@ def test_golden_parity(name):
     assert run.launch_count() > 0
 
 
+STATE_FIELDS = {
+    "surf": ["storage", "total_decayed", "pre_decay", "et0_coefficient", "days_after_sow", "crop_cover",
+             "ground_cover", "crop_factor", "pool_fast", "pool_humus", "pool_dis_inorg", "pool_dis_org",
+             "pool_ads_inorg"],
+    "land": ["surface_runoff", "subsurface_runoff", "percolation"],
+    "tank": ["storage", "storage_", "total_decayed"],
+    "sewer": ["storage", "storage_", "active_storage", "qmask"],
+    "river": ["n_lag_T", "head_T", "n_lag_TP", "head_TP", "lag_T", "lag_TP"],
+    "arc": ["flow_in", "vqip_in"],
+}
+
+
 @pytest.mark.parametrize("name", ["config2", "rivernet"])
 def test_final_state_matches_oracle(name):
-    """State left in the SoA tensors after the run equals the oracle's (scatter-back input)."""
+    """Persistent state left in the SoA tensors after the run equals the oracle's (this is what
+    scatter_back writes into the Python objects and what a follow-on run starts from)."""
     from oracle import oracle
+    from wsi_b200.backend import layout as L
     from wsi_b200.backend.probes import ProbeSet
-    from parity_util import compare
 
     fm, _ = load_golden(name)
     ps = ProbeSet(fm).add_flows()
     run = _run_gpu(fm, ps, record_mb=False)
     ora = oracle.run(fm, probes=ps.probes)
     got = run.groups()
-    for g, arr in ora.groups.items():
-        if arr.size == 0:
+    nonadd = [fm.pollutants.index(p) + 1 for p in fm.non_additive]
+    for g, fields in STATE_FIELDS.items():
+        if fm.n_obj[g] == 0:
             continue
-        ok, rep = compare(g, got[g].T[None], arr.T[None], fm.float_accuracy, rtol=1e-9, time_axis=0)
-        # time_axis=0 over a single row: scale per entry
-        assert ok, rep
-    # system totals and violation counts
+        for f in fields:
+            o = L.GROUPS[g].offset(f, fm.V)
+            n = L.GROUPS[g].size(f, fm.V)
+            a, b = got[g][o:o + n].copy(), ora.groups[g][o:o + n].copy()
+            if any(x.name == f and x.vqip for x in L.GROUPS[g].fields):
+                # non-additive lanes of (nearly) empty stores are not comparable (parity_util)
+                dry = np.maximum(np.abs(a[0]), np.abs(b[0])) <= 1e-6 * max(np.abs(b[0]).max(), 1e-30)
+                for p in nonadd:
+                    a[p][dry] = b[p][dry]
+            scale = max(np.abs(b).max(), 1e-300)
+            np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-11 * scale, err_msg=f"{g}.{f}")
     np.testing.assert_allclose(run.mb_sums(), ora.mb_sums, rtol=1e-8, atol=1e-6)
 
 
