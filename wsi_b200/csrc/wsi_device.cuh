@@ -139,9 +139,34 @@ struct TankRef {
   double capacity;
 };
 
-// Tank.push_storage(force=True) tanks.py:189-192
+// volume and additive lanes all zero (non-additive lanes of a zero-volume VQIP never reach a
+// result: they are always multiplied by the volume)
+template <class C>
+WSI_HD bool vq_is_empty(const C& c, const typename C::Vq& v) {
+  bool z = v.x[0] == 0.0;
+#pragma unroll
+  for (int p = 1; p <= C::P; p++)
+    if (bit(c.add, p)) z = z && v.x[p] == 0.0;
+  return z;
+}
+
+// Tank.push_storage(force=True) tanks.py:189-192: storage = sum_vqip(storage, v).  When v is
+// empty the volume and additive lanes are unchanged (x + 0) and only the non-additive lanes are
+// re-blended, (v_p * 0 + s_p * vol) / vol, so only those are read and written.
 template <class C>
 WSI_HD void tank_push_force(const C& c, double* st, size_t stride, const typename C::Vq& v) {
+  if (vq_is_empty(c, v)) {
+    const double vol = st[0];
+    if (vol > 0) {
+#pragma unroll
+      for (int p = 1; p <= C::P; p++)
+        if (!bit(c.add, p)) {
+          const double num = v.x[p] * v.x[0] + st[(size_t)p * stride] * vol;
+          st[(size_t)p * stride] = num == 0.0 ? num : num / vol;
+        }
+    }
+    return;
+  }
   c.stv(st, stride, c.sum(c.ldv(st, stride), v));
 }
 // Tank.get_excess()["volume"] tanks.py:132-158
@@ -208,8 +233,14 @@ WSI_HD void sewer_update_queue(C& c, int w) {  // AltQueueArc.update_queue arcs.
   const size_t s = c.s_sewer();
   double* q0 = c.sewer(WSI_SEWER_QUEUE(V), w);
   double* act = c.sewer(WSI_SEWER_ACTIVE_STORAGE(V), w);
-  c.stv(act, s, c.sum(c.ldv(act, s), c.ldv(q0, s)));  // QueueTank.push_set tanks.py:610-629
-  c.stv(q0, s, vq_zero<C::P>());
+  const typename C::Vq q = c.ldv(q0, s);
+  tank_push_force(c, act, s, q);  // QueueTank.push_set tanks.py:610-629: active = sum(active, q)
+  if (!vq_is_empty(c, q) || q.x[0] != 0.0) c.stv(q0, s, vq_zero<C::P>());
+  else {
+#pragma unroll
+    for (int p = 1; p <= C::P; p++)
+      if (!bit(c.add, p)) q0[(size_t)p * s] = 0.0;
+  }
 }
 // QueueTank.push_storage(vqip, time) tanks.py:513-539 through AltQueueArc (arcs.py:360-407).
 template <class C>
@@ -328,17 +359,6 @@ WSI_HD double arc_excess_vol(C& c, int a, bool has_v, double v_vol) {
   const double pipe_excess = *c.arc(WSI_ARC_CAPACITY, a) - *c.arc(WSI_ARC_FLOW_IN, a);
   const double ne = node_push_check_vol<D>(c, c.D().arc_out[a], has_v, v_vol);
   return vol_vchange(ne, pymin(pipe_excess, ne));
-}
-
-// volume and additive lanes all zero (non-additive lanes of a zero-volume VQIP never reach a
-// result: they are always multiplied by the volume)
-template <class C>
-WSI_HD bool vq_is_empty(const C& c, const typename C::Vq& v) {
-  bool z = v.x[0] == 0.0;
-#pragma unroll
-  for (int p = 1; p <= C::P; p++)
-    if (bit(c.add, p)) z = z && v.x[p] == 0.0;
-  return z;
 }
 
 // Arc.send_push_request arcs.py:112-158.  When the whole volume is admitted

@@ -654,113 +654,148 @@ WSI_HD void surface_phase(C& c, int u) {
   }
 }
 
-// ResidenceTank.pull_outflow tanks.py:387-400 on an in-memory tank
+// ResidenceTank.pull_outflow tanks.py:387-400 on a register-resident tank
 template <class C>
-WSI_HD typename C::Vq residence_pull(const C& c, double* st, size_t stride, double residence_time) {
-  typename C::Vq s = c.ldv(st, stride);
+WSI_HD typename C::Vq residence_pull(const C& c, typename C::Vq& s, double residence_time) {
   const double outflow = vol_vchange(s.x[0], s.x[0] / residence_time);
-  typename C::Vq o = vq_pull(c, s, outflow);
-  c.stv(st, stride, s);
-  return o;
+  return vq_pull(c, s, outflow);
 }
 
-// Land.run land.py:200-244 after its surfaces have run (surface_phase), followed (when
-// requested) by the node's mass balance (core.py:370-429 with Land's term lists,
-// land.py:113,158-162)
+// push_to_sewers land.py:699-721, second half: the ponded runoff left by surface_phase goes to
+// the Sewers and whatever they do not take is forced back into the surface tank.
+template <class C>
+WSI_HDN void land_impervious_push(C& c, int node, int u) {
+  using Vq = typename C::Vq;
+  constexpr int V = C::V;
+  const Obj S = c.surf_obj(u);
+  const size_t ss = c.s_surf();
+  const Vq runoff = c.ldv(S(WSI_SURF_FLOW_A(V)), ss);
+  const Vq reply = push_distributed<kJunctionDepth>(c, node, runoff, WSI_FILTER_SEWER);
+  tank_push_force(c, S(WSI_SURF_STORAGE(V)), ss, reply);
+}
+
+// Mass-balance terms of a Land node (core.py:370-429 with land.py:113,158-162), assembled by
+// the mass-balance pass from what is in memory after Land.run: the surfaces' shares (scratch planes), the out-arcs,
+// and the three ResidenceTanks whose storage_ land_phase parked in the node's mb_terms row.
+template <class C>
+WSI_HD void land_mass_balance_terms(const C& c, int node, typename C::Vq& in_, typename C::Vq& ds, typename C::Vq& out_) {
+  using Vq = typename C::Vq;
+  constexpr int P = C::P;
+  constexpr int V = C::V;
+  const WsiModelDesc& d = c.D();
+  const int L = d.node_gidx[node];
+  const size_t sl = c.s_land(), ss = c.s_surf();
+  in_ = total_in(c, node);
+  out_ = total_out(c, node);
+  ds = vq_zero<P>();
+  for (int i = d.land_surf_ptr[L]; i < d.land_surf_ptr[L + 1]; i++) {
+    const Obj S = c.surf_obj(d.land_surf[i]);
+    mb_acc(c, in_, c.ldv_add(S(WSI_SURF_MB_IN(V)), ss));
+    mb_acc(c, out_, c.ldv_add(S(WSI_SURF_MB_OUT(V)), ss));
+  }
+  for (int i = d.land_surf_ptr[L]; i < d.land_surf_ptr[L + 1]; i++) {
+    const Obj S = c.surf_obj(d.land_surf[i]);
+    if ((int)*S(WSI_SURF_TYPE) == WSI_ST_IMPERVIOUSSURFACE) {
+      // its tank changed again after surface_phase: ds from the parked storage_
+      const Vq st = c.ldv_add(S(WSI_SURF_STORAGE(V)), ss);
+      const Vq old = c.ldv_add(S(WSI_SURF_MB_DS(V)), ss);
+      Vq dsv;
+#pragma unroll
+      for (int p = 0; p <= P; p++) dsv.x[p] = (p == 0 || bit(c.add, p)) ? st.x[p] - old.x[p] : 0.0;
+      dsv = c.sum(dsv, decay_total<C>(c, S, WSI_SURF_N_DECAY));
+      ds_add(c, ds, dsv);
+    } else {
+      ds_add(c, ds, c.ldv_add(S(WSI_SURF_MB_DS(V)), ss));
+    }
+  }
+  // surface_runoff.ds, subsurface_runoff.ds, percolation.ds (land.py:160-162)
+  const double* parked = d.mb_terms + (size_t)d.mb_term_slot[node] * 3 * V * c.R + c.r;
+  const int tank_plane[3] = {WSI_LAND_SURFACE_RUNOFF(V), WSI_LAND_SUBSURFACE_RUNOFF(V), WSI_LAND_PERCOLATION(V)};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const Vq fin = c.ldv_add(c.land(tank_plane[k], L), sl);
+    const Vq ini = c.ldv_add(parked + (size_t)k * V * c.R, c.R);
+#pragma unroll
+    for (int p = 0; p <= P; p++)
+      if (p == 0 || bit(c.add, p)) ds.x[p] += fin.x[p] - ini.x[p];
+  }
+}
+
+// Land.run land.py:200-244 after its surfaces have run (surface_phase).  The surfaces' route()
+// pushes (land.py:1046-1058) are applied tank by tank -- each tank still receives them in
+// surface order, so every sum is the reference's -- which lets each ResidenceTank be loaded and
+// stored once and keeps nothing large alive across the calls into the push protocol.
 template <class C>
 WSI_HDN void land_phase(C& c, int node) {
   using Vq = typename C::Vq;
-  constexpr int P = C::P;
   constexpr int V = C::V;
   const WsiModelDesc& d = c.D();
   const int L = d.node_gidx[node];
   const size_t sl = c.s_land();
   const size_t ss = c.s_surf();
   const bool want_mb = (c.run_flags & WSI_RUN_MASS_BALANCE) != 0;
+  const int s0 = d.land_surf_ptr[L], s1 = d.land_surf_ptr[L + 1];
+  double* parked = d.mb_terms + (size_t)d.mb_term_slot[node] * 3 * V * c.R + c.r;
 
-  double* t_surf = c.land(WSI_LAND_SURFACE_RUNOFF(V), L);
-  double* t_sub = c.land(WSI_LAND_SUBSURFACE_RUNOFF(V), L);
-  double* t_perc = c.land(WSI_LAND_PERCOLATION(V), L);
-  Vq ds = vq_zero<P>();
-  // the three ResidenceTanks' storage_ are whatever is in memory at the start of the step
-  Vq neg0 = vq_zero<P>(), neg1 = vq_zero<P>(), neg2 = vq_zero<P>();
-  if (want_mb) {
-    neg0 = c.ldv_add(t_surf, sl);
-    neg1 = c.ldv_add(t_sub, sl);
-    neg2 = c.ldv_add(t_perc, sl);
-  }
-  Vq mb_in = vq_zero<P>(), mb_out = vq_zero<P>();
-  for (int i = d.land_surf_ptr[L]; i < d.land_surf_ptr[L + 1]; i++) {
-    const Obj S = c.surf_obj(d.land_surf[i]);
-    const int type = (int)*S(WSI_SURF_TYPE);
-    if (type == WSI_ST_IMPERVIOUSSURFACE) {
-      // push_to_sewers land.py:699-721, second half
-      const Vq runoff = c.ldv(S(WSI_SURF_FLOW_A(V)), ss);
-      const Vq reply = push_distributed<kJunctionDepth>(c, node, runoff, WSI_FILTER_SEWER);
-      double* stp = S(WSI_SURF_STORAGE(V));
-      const Vq st = c.sum(c.ldv(stp, ss), reply);
-      c.stv(stp, ss, st);
-      if (want_mb) {
-        const Vq old = c.ldv_add(S(WSI_SURF_MB_DS(V)), ss);
-        Vq dsv;
-#pragma unroll
-        for (int p = 0; p <= P; p++) dsv.x[p] = (p == 0 || bit(c.add, p)) ? st.x[p] - old.x[p] : 0.0;
-        dsv = c.sum(dsv, decay_total<C>(c, S, WSI_SURF_N_DECAY));
-        ds_add(c, ds, dsv);
-      }
-    } else {
-      if (type >= WSI_ST_PERVIOUSSURFACE) {  // route land.py:1046-1058
-        tank_push_force(c, t_surf, sl, c.ldv(S(WSI_SURF_FLOW_A(V)), ss));
-        tank_push_force(c, t_sub, sl, c.ldv(S(WSI_SURF_FLOW_B(V)), ss));
-        tank_push_force(c, t_perc, sl, c.ldv(S(WSI_SURF_FLOW_C(V)), ss));
-      }
-      if (want_mb) ds_add(c, ds, c.ldv_add(S(WSI_SURF_MB_DS(V)), ss));
-    }
-    if (want_mb) {
-      mb_acc(c, mb_in, c.ldv_add(S(WSI_SURF_MB_IN(V)), ss));
-      mb_acc(c, mb_out, c.ldv_add(S(WSI_SURF_MB_OUT(V)), ss));
-    }
+  // impervious surfaces -> Sewers (independent of the Land's own tanks)
+  for (int i = s0; i < s1; i++) {
+    const int u = d.land_surf[i];
+    if ((int)*c.surf(WSI_SURF_TYPE, u) == WSI_ST_IMPERVIOUSSURFACE) land_impervious_push(c, node, u);
   }
 
-  // percolation -> Groundwater (land.py:207-215)
+  // percolation tank -> Groundwater (land.py:207-215)
   {
-    Vq percolation = residence_pull(c, t_perc, sl, *c.land(WSI_LAND_RES_PERCOLATION, L));
-    Vq reply = push_distributed<kJunctionDepth>(c, node, percolation, WSI_FILTER_GROUNDWATER);
-    if (reply.x[0] > c.FA) tank_push_force(c, t_perc, sl, reply);
+    double* tp = c.land(WSI_LAND_PERCOLATION(V), L);
+    Vq T = c.ldv(tp, sl);
+    if (want_mb) c.stv_add(parked + (size_t)2 * V * c.R, c.R, T);  // storage_ for the mass balance
+    for (int i = s0; i < s1; i++) {
+      const Obj S = c.surf_obj(d.land_surf[i]);
+      if ((int)*S(WSI_SURF_TYPE) >= WSI_ST_PERVIOUSSURFACE) T = c.sum(T, c.ldv(S(WSI_SURF_FLOW_C(V)), ss));
+    }
+    const Vq percolation = residence_pull(c, T, *c.land(WSI_LAND_RES_PERCOLATION, L));
+    c.stv(tp, sl, T);
+    const Vq reply = push_distributed<kJunctionDepth>(c, node, percolation, WSI_FILTER_GROUNDWATER);
+    if (reply.x[0] > c.FA) tank_push_force(c, tp, sl, reply);
   }
   // surface + subsurface runoff -> River / junction Node (land.py:217-244)
   {
-    Vq surface_runoff = residence_pull(c, t_surf, sl, *c.land(WSI_LAND_RES_SURFACE, L));
-    Vq subsurface_runoff = residence_pull(c, t_sub, sl, *c.land(WSI_LAND_RES_SUBSURFACE, L));
-    Vq total_runoff = c.sum(surface_runoff, subsurface_runoff);
+    double* t_surf = c.land(WSI_LAND_SURFACE_RUNOFF(V), L);
+    double* t_sub = c.land(WSI_LAND_SUBSURFACE_RUNOFF(V), L);
+    Vq total_runoff;
+    double v_surf, v_sub;
+    {
+      Vq T = c.ldv(t_surf, sl);
+      if (want_mb) c.stv_add(parked, c.R, T);
+      for (int i = s0; i < s1; i++) {
+        const Obj S = c.surf_obj(d.land_surf[i]);
+        if ((int)*S(WSI_SURF_TYPE) >= WSI_ST_PERVIOUSSURFACE) T = c.sum(T, c.ldv(S(WSI_SURF_FLOW_A(V)), ss));
+      }
+      total_runoff = residence_pull(c, T, *c.land(WSI_LAND_RES_SURFACE, L));
+      v_surf = total_runoff.x[0];
+      c.stv(t_surf, sl, T);
+    }
+    {
+      Vq T = c.ldv(t_sub, sl);
+      if (want_mb) c.stv_add(parked + (size_t)V * c.R, c.R, T);
+      for (int i = s0; i < s1; i++) {
+        const Obj S = c.surf_obj(d.land_surf[i]);
+        if ((int)*S(WSI_SURF_TYPE) >= WSI_ST_PERVIOUSSURFACE) T = c.sum(T, c.ldv(S(WSI_SURF_FLOW_B(V)), ss));
+      }
+      const Vq subsurface_runoff = residence_pull(c, T, *c.land(WSI_LAND_RES_SUBSURFACE, L));
+      v_sub = subsurface_runoff.x[0];
+      c.stv(t_sub, sl, T);
+      total_runoff = c.sum(total_runoff, subsurface_runoff);
+    }
     if (total_runoff.x[0] > 0) {
-      Vq reply = push_distributed<kJunctionDepth>(c, node, total_runoff, WSI_FILTER_RIVER_NODE);
+      const double v_total = total_runoff.x[0];
+      const Vq reply = push_distributed<kJunctionDepth>(c, node, total_runoff, WSI_FILTER_RIVER_NODE);
       if (reply.x[0] > 0) {
-        Vq rs = c.vchange(reply, reply.x[0] * surface_runoff.x[0] / total_runoff.x[0]);
-        Vq rss = c.vchange(reply, reply.x[0] * subsurface_runoff.x[0] / total_runoff.x[0]);
+        const Vq rs = c.vchange(reply, reply.x[0] * v_surf / v_total);
+        const Vq rss = c.vchange(reply, reply.x[0] * v_sub / v_total);
         if (rs.x[0] > 0) tank_push_force(c, t_surf, sl, rs);
         if (rss.x[0] > 0) tank_push_force(c, t_sub, sl, rss);
       }
     }
-  }
-  if (want_mb) {
-    Vq in_ = total_in(c, node);
-    Vq out_ = total_out(c, node);
-#pragma unroll
-    for (int p = 0; p <= P; p++)
-      if (p == 0 || bit(c.add, p)) {
-        in_.x[p] += mb_in.x[p];
-        out_.x[p] += mb_out.x[p];
-      }
-    Vq f0 = c.ldv_add(t_surf, sl), f1 = c.ldv_add(t_sub, sl), f2 = c.ldv_add(t_perc, sl);
-#pragma unroll
-    for (int p = 0; p <= P; p++)
-      if (p == 0 || bit(c.add, p)) {
-        ds.x[p] += f0.x[p] - neg0.x[p];
-        ds.x[p] += f1.x[p] - neg1.x[p];
-        ds.x[p] += f2.x[p] - neg2.x[p];
-      }
-    store_mb_terms(c, node, in_, ds, out_);
   }
 }
 

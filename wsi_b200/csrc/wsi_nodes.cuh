@@ -356,7 +356,9 @@ WSI_HD void node_mass_balance(C& c, int node, typename C::Vq& in_, typename C::V
   const WsiModelDesc& d = c.D();
   const int g = d.node_gidx[node];
   const int type = d.node_type[node];
-  if (type == WSI_NT_LAND || type == WSI_NT_CATCHMENT) {  // formed inside their ops
+  if (type == WSI_NT_LAND) {
+    land_mass_balance_terms(c, node, in_, ds, out_);
+  } else if (type == WSI_NT_CATCHMENT) {  // formed inside its op
     load_mb_terms(c, node, in_, ds, out_);
   } else {
     const Vq tin = total_in(c, node);
