@@ -213,6 +213,32 @@ def main():
         except Exception:
             traffic = None
 
+    # ---------------- share of each kernel in a step (CUDA events around each phase) -------------
+    from wsi_b200.backend import capi as _c
+
+    def _phase_ms(flags, b=0, e=0, reps=5):
+        for _ in range(2):
+            runner.sched_range(W, b, e, flags)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(reps):
+            runner.sched_range(W, b, e, flags)
+        a1.record(stream)
+        torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / reps
+
+    n_sched = len(fm.sched_op)
+    phases = {
+        "wsi_surface_kernel (x3 classes)": _phase_ms(_c.RUN_SURFACES | _c.RUN_MASS_BALANCE) - _phase_ms(_c.RUN_MASS_BALANCE),
+        "wsi_step_kernel": _phase_ms(_c.RUN_SCHEDULE | _c.RUN_MASS_BALANCE, 0, n_sched) - _phase_ms(_c.RUN_MASS_BALANCE),
+        "wsi_mb_kernel + wsi_mb_finalize": _phase_ms(_c.RUN_MASS_BALANCE),
+        "wsi_record_kernel": _phase_ms(_c.RUN_RECORD),
+        "wsi_end_kernel": _phase_ms(_c.RUN_END_TIMESTEP),
+    }
+    empty = _phase_ms(0)
+    kernel_ms = {k: max(v - (0 if "step" in k or "surface" in k else empty), 0.0) for k, v in phases.items()}
+
     # ---------------- end to end through host buffers ------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -274,8 +300,11 @@ def main():
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_member_step": int(alg_bytes),
-                         "field_counts": {k: int(v) for k, v in parts.items()}, "kernel": "wsi_step_kernel",
-                         "avg_launch_ms": ms / K},
+                         "field_counts": {k: int(v) for k, v in parts.items()},
+                         "kernel": "one timestep = wsi_surface_kernel x3 + wsi_step_kernel + wsi_mb_kernel + "
+                                   "wsi_mb_finalize + wsi_record_kernel + wsi_end_kernel (dominant: wsi_step_kernel)",
+                         "avg_launch_ms": ms / K,
+                         "kernel_ms": {k: round(v, 4) for k, v in kernel_ms.items()}},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
