@@ -92,6 +92,22 @@ typedef struct WsiModelDesc {
   const int32_t* sched_op;   /* [n_sched] WSI_OP_* */
   const int32_t* sched_node; /* [n_sched] node slot */
 
+  /* ---- network engine (engine == 1): level-synchronous routing of a dendritic river network,
+   *      one thread per (node, replica); see wsi_b200/csrc/wsi_net.cuh ---- */
+  int32_t engine;            /* 0: replica engine (one thread per replica runs the schedule), 1: network */
+  int32_t n_net_levels;
+  int32_t n_net_calc;
+  int32_t n_net_final;
+  const int32_t* net_level_ptr;   /* [n_net_levels+1] CSR over net_level_node (upstream depth ascending) */
+  const int32_t* net_level_ptr_host; /* HOST copy of net_level_ptr (the launcher sizes one grid per level) */
+  const int32_t* net_level_node;  /* river node slots */
+  const int32_t* net_calc_node;   /* [n_net_calc] rivers whose calculate_discharge is scheduled */
+  const int32_t* net_final_node;  /* [n_net_final] gather-only nodes (Waste, rivers outside the order) */
+  const int32_t* net_path_ptr;    /* [n_nodes+1] incoming paths per receiving node */
+  const int32_t* net_path_sender; /* sender node of each path */
+  const int32_t* net_path_arc_ptr; /* CSR over net_path_arcs: arcs along each path (diagnostic) */
+  const int32_t* net_path_arcs;
+
   /* ---- SoA groups, fp64 [n_fields][n_obj*R] ---- */
   double* arc;
   double* land;
@@ -126,6 +142,10 @@ typedef struct WsiModelDesc {
 
 /* ABI version of the loaded library (== WSI_ABI_VERSION). */
 int wsi_version(void);
+
+/* sizeof(WsiModelDesc) the library was compiled with: a binding compares it with its own
+ * mirror of the struct before passing descriptors (catches a stale build). */
+int wsi_desc_size(void);
 
 /* Thread-local message for the last non-zero return. */
 const char* wsi_last_error(void);

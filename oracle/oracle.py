@@ -19,8 +19,9 @@ _LIB = None
 
 def build(force=False):
     """Compile the C restatement with the system gcc (oracle/Makefile)."""
-    src = os.path.join(_HERE, "wsi_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    inc = os.path.join(os.path.dirname(_HERE), "include")
+    deps = [os.path.join(_HERE, "wsi_oracle.c"), os.path.join(inc, "wsi_b200.h"), os.path.join(inc, "wsi_layout.h")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["make", "-C", _HERE, "-B", "-s"])
     return _SO
 
@@ -28,9 +29,11 @@ def build(force=False):
 def lib():
     global _LIB
     if _LIB is None:
-        if not os.path.exists(_SO):
-            build()
+        build()  # no-op when the library is newer than its sources
         _LIB = C.CDLL(_SO)
+        _LIB.wsi_oracle_desc_size.restype = C.c_int
+        if _LIB.wsi_oracle_desc_size() != C.sizeof(WsiModelDesc):
+            raise RuntimeError("libwsi_oracle.so was built against another WsiModelDesc layout; make -C oracle -B")
         _LIB.wsi_oracle_run.argtypes = [C.POINTER(WsiModelDesc), C.c_int64, C.c_int64, C.c_int]
         _LIB.wsi_oracle_run.restype = C.c_int
     return _LIB

@@ -411,12 +411,76 @@ def scenario_rivernet(T=420):
     save("rivernet", fm, ref, "synthetic river/sewer network with decays, splits and binding capacities")
 
 
+def scenario_rivertree(T=380):
+    """Dendritic river network (the network engine's case): catchments and rivers joined through
+    junctions (also chained and shared ones), a binding river-arc capacity, decays, a dry
+    headwater river and a Waste outlet."""
+    set_default_pollutants()
+    dates = [pd.Timestamp("2003-06-01") + pd.Timedelta(days=i) for i in range(T)]
+    rng = np.random.default_rng(20261101)
+    forcing = synthetic_forcing(dates, rng)
+    tdata = {k: v for k, v in forcing.items() if k[0] == "temperature"}
+
+    def catch_data(seed, q):
+        r = np.random.default_rng(seed)
+        d = {}
+        flow = q * (1 + 0.6 * np.sin(np.arange(T) / 25.0 + seed)) * r.lognormal(0, 0.4, T)
+        for t, date in enumerate(dates):
+            d[("flow", date)] = float(flow[t])
+            for p in constants.POLLUTANTS:
+                if p == "temperature":
+                    d[(p, date)] = forcing[("temperature", date)] + 0.5 * seed
+                elif p == "ph":
+                    d[(p, date)] = 7.0 + 0.05 * seed
+                elif p == "do":
+                    d[(p, date)] = 0.009
+                else:
+                    d[(p, date)] = float(r.uniform(1e-5, 2e-3))
+        return d
+
+    init = lambda v: {"volume": v, "do": 0.008, "org-phosphorus": v * 2e-5, "phosphate": v * 5e-5,  # noqa: E731
+                      "ammonia": v * 1e-4, "solids": v * 1e-3, "bod": v * 1e-3, "cod": v * 2e-3, "ph": 7.1,
+                      "temperature": 9.0, "nitrate": v * 2e-3, "nitrite": v * 1e-5, "org-nitrogen": v * 3e-4}
+    river = lambda name, length, width, vol, **kw: dict(  # noqa: E731
+        {"type_": "River", "name": name, "length": length, "width": width, "data_input_dict": tdata,
+         "initial_storage": init(vol) if vol else 0}, **kw)
+    nodes = [{"type_": "Catchment", "name": "c%d" % i, "data_input_dict": catch_data(i, q)}
+             for i, q in enumerate([3e4, 1e4, 2e4, 5e3, 8e3, 1.5e4, 4e3], start=1)]
+    nodes += [
+        river("r1", 6000, 10, 4e4), river("r2", 2500, 6, 8e3), river("r3", 9000, 15, 7e4, damp=0.15),
+        river("r4", 7000, 22, 9e4), river("r5", 3000, 7, 0),
+        river("r6", 11000, 30, 1.5e5, decays={"ammonia": {"constant": 0.03, "exponent": 1.01}}),
+        river("r7", 4000, 9, 2e4), river("r8", 3500, 8, 1e4,
+                                         decays={"bod": {"constant": 0.02, "exponent": 1.02},
+                                                 "nitrite": {"constant": 0.01, "exponent": 1.0}}),
+        river("r9", 1500, 4, 0),
+        {"type_": "Node", "name": "j1"}, {"type_": "Node", "name": "j2"}, {"type_": "Node", "name": "j3"},
+        {"type_": "Node", "name": "j4"},
+        {"type_": "Waste", "name": "outlet"},
+    ]
+    arcs = [
+        ("c1-r1", "c1", "r1", {}), ("c2-r2", "c2", "r2", {}), ("r1-j1", "r1", "j1", {}), ("r2-j1", "r2", "j1", {}),
+        ("j1-r3", "j1", "r3", {}), ("c3-r3", "c3", "r3", {}), ("r3-r4", "r3", "r4", {"capacity": 4.5e4}),
+        ("c4-j2", "c4", "j2", {}), ("j2-j3", "j2", "j3", {}), ("j3-r5", "j3", "r5", {}), ("r5-r4", "r5", "r4", {}),
+        ("r4-r6", "r4", "r6", {}), ("c5-r7", "c5", "r7", {"capacity": 9e3}), ("r7-r6", "r7", "r6", {}),
+        ("c6-r8", "c6", "r8", {}), ("r8-r6", "r8", "r6", {}), ("r9-r7", "r9", "r7", {}),
+        ("r6-j4", "r6", "j4", {}), ("c7-j4", "c7", "j4", {}), ("j4-outlet", "j4", "outlet", {}),
+    ]
+    m = Model()
+    m.add_nodes(nodes)
+    m.add_arcs([dict({"type_": "Arc", "name": a, "in_port": i, "out_port": o}, **kw) for a, i, o, kw in arcs])
+    fm = flatten_ref(m, dates)
+    ref = run_reference(m, dates)
+    save("rivertree", fm, ref, "dendritic river network with junction chains, binding capacities and decays")
+
+
 SCENARIOS = {
     "quickstart": scenario_quickstart,
     "quickstart_simple": scenario_quickstart_simple,
     "fixture3607": scenario_fixture3607,
     "config2": scenario_config2,
     "rivernet": scenario_rivernet,
+    "rivertree": scenario_rivertree,
 }
 
 if __name__ == "__main__":

@@ -50,7 +50,7 @@ def test_library_exports_every_declared_symbol():
     lib = C.CDLL(capi.library_path())
     syms = _declared_symbols()
     assert {"wsi_version", "wsi_last_error", "wsi_validate", "wsi_step", "wsi_run_steps", "wsi_sched_range",
-            "wsi_launch_count", "wsi_num_blocks"} <= set(syms)
+            "wsi_launch_count", "wsi_num_blocks", "wsi_desc_size"} <= set(syms)
     for s in syms:
         assert hasattr(lib, s), s
     assert capi.load_library().wsi_version() == capi.ABI_VERSION

@@ -7,13 +7,13 @@ from parity_util import compare_blocks, compare_mb, load_golden
 
 pytestmark = pytest.mark.gpu
 
-GOLDENS = ["quickstart", "quickstart_simple", "fixture3607", "config2", "rivernet"]
+GOLDENS = ["quickstart", "quickstart_simple", "fixture3607", "config2", "rivernet", "rivertree"]
 
 
-def _run_gpu(fm, ps, record_mb=True, chunks=1):
+def _run_gpu(fm, ps, record_mb=True, chunks=1, engine="replica"):
     from wsi_b200.backend.engine import GpuRunner
 
-    run = GpuRunner(fm, probes=ps.probes, rec_t0=0, rec_T=fm.T, record_mb=record_mb)
+    run = GpuRunner(fm, probes=ps.probes, rec_t0=0, rec_T=fm.T, record_mb=record_mb, engine=engine)
     edges = np.linspace(0, fm.T, chunks + 1).astype(int)
     for a, b in zip(edges[:-1], edges[1:]):
         run.run(int(a), int(b))
@@ -48,7 +48,7 @@ STATE_FIELDS = {
 }
 
 
-@pytest.mark.parametrize("name", ["config2", "rivernet"])
+@pytest.mark.parametrize("name", ["config2", "rivernet", "rivertree"])
 def test_final_state_matches_oracle(name):
     """Persistent state left in the SoA tensors after the run equals the oracle's (this is what
     scatter_back writes into the Python objects and what a follow-on run starts from)."""
@@ -197,3 +197,55 @@ def test_session_host_buffer_api_matches_device_run():
     got[fm.T - 1 if (fm.T - 1) % 2 == 1 else fm.T - 2] = rest[1].copy()
     for t in range(fm.T):
         assert np.array_equal(got[t], ref[t]), t
+
+
+# ---- network engine (level-synchronous routing, one thread per node) ---------------------------
+def test_network_engine_golden_parity_and_equals_replica_engine():
+    from wsi_b200.backend.probes import ProbeSet
+
+    fm, ref = load_golden("rivertree")
+    ps = ProbeSet(fm).add_standard()
+    net = _run_gpu(fm, ps, chunks=2, engine="network")
+    assert net.buffers.engine == 1
+    ok, reports = compare_blocks(ps.split(net.out_probe()), ref, fm)
+    ok2, rep = compare_mb(net.out_mb(), ref["mb"], fm)
+    assert ok and ok2, "\n".join(reports + [rep])
+    seq = _run_gpu(fm, ps, engine="replica")
+    assert np.array_equal(net.out_probe(), seq.out_probe())  # same arithmetic in another order of threads
+    assert np.array_equal(net.out_mb(), seq.out_mb())
+    assert np.array_equal(net.mb_count(), seq.mb_count())
+
+
+def test_network_engine_replicated_members():
+    """R > 1 on the network engine: members are independent columns of the flat (node, member) index."""
+    from wsi_b200.backend.probes import ProbeSet
+
+    fm, _ = load_golden("rivertree")
+    one = _run_gpu(fm, ProbeSet(fm).add_flows(), record_mb=False, engine="network")
+    fm5 = fm.replicate(5)
+    five = _run_gpu(fm5, ProbeSet(fm5).add_flows(), record_mb=False, engine="network")
+    for r in range(5):
+        assert np.array_equal(five.out_probe()[:, :, r], one.out_probe()[:, :, 0])
+    np.testing.assert_allclose(five.mb_sums(), 5 * one.mb_sums(), rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("N,T,binding", [(1500, 25, 0.05), (60000, 6, 0.01)])
+def test_network_engine_equals_oracle_on_dendritic_network(N, T, binding):
+    """SURVEY 8d config 4 at sizes the sequential oracle finishes in seconds."""
+    from oracle import oracle
+    from wsi_b200 import rivernet
+    from wsi_b200.backend.probes import ProbeSet
+
+    fm = rivernet.build_dendritic(N, T=T, binding_frac=binding, names=N < 10000)
+    ps = ProbeSet(fm).add_flows(range(0, N, max(1, N // 2000)))  # river arcs, thinned
+    run = _run_gpu(fm, ps, record_mb=False, engine="network")
+    ora = oracle.run(fm, probes=ps.probes)
+    scale = np.abs(ora.out_probe).max(axis=(0, 2), keepdims=True) + 1e-300
+    np.testing.assert_allclose(run.out_probe(), ora.out_probe, rtol=1e-9, atol=0)
+    assert np.max(np.abs(run.out_probe() - ora.out_probe) / scale) < 1e-9
+    np.testing.assert_allclose(run.mb_sums(), ora.mb_sums, rtol=1e-9, atol=1e-6)
+    assert np.array_equal(run.mb_count(), ora.mb_count)
+    tank = fm.plane("tank", "storage")
+    got, exp = run.groups()["tank"][tank:tank + fm.V], ora.groups["tank"][tank:tank + fm.V]
+    np.testing.assert_allclose(got, exp, rtol=1e-9, atol=1e-9)
+    assert not (run.node_flags() & ~np.uint32(1)).any()

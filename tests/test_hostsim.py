@@ -8,7 +8,7 @@ import pytest
 
 from parity_util import compare_blocks, compare_mb, load_golden
 
-GOLDENS = ["quickstart", "quickstart_simple", "fixture3607", "config2", "rivernet"]
+GOLDENS = ["quickstart", "quickstart_simple", "fixture3607", "config2", "rivernet", "rivertree"]
 
 
 @pytest.fixture(scope="module")
@@ -22,10 +22,10 @@ def hostsim():
     return lib
 
 
-def _run(lib, fm, probes, force_runtime=0, record_mb=True):
+def _run(lib, fm, probes, force_runtime=0, record_mb=True, engine="replica"):
     from wsi_b200.backend.capi import ModelBuffers
 
-    buf = ModelBuffers(fm, device="numpy", probes=probes, rec_t0=0, rec_T=fm.T, record_mb=record_mb)
+    buf = ModelBuffers(fm, device="numpy", probes=probes, rec_t0=0, rec_T=fm.T, record_mb=record_mb, engine=engine)
     assert lib.wsi_hostsim_run(C.byref(buf.desc), 0, fm.T, force_runtime) == 0
     return buf
 
@@ -67,3 +67,30 @@ def test_kernel_logic_equals_oracle_on_ensemble(hostsim):
     assert np.array_equal(buf.array("out_probe"), ora.out_probe)
     np.testing.assert_allclose(buf.array("mb_sums"), ora.mb_sums, rtol=1e-12, atol=1e-9)
     assert np.array_equal(buf.array("mb_count"), ora.mb_count)
+
+
+def test_network_engine_matches_reference_outputs(hostsim):
+    """Level-order routing (wsi_net.cuh) reproduces the reference's sequential, upstream-first
+    river routing bit for bit on a dendritic network."""
+    from wsi_b200.backend.probes import ProbeSet
+
+    fm, ref = load_golden("rivertree")
+    ps = ProbeSet(fm).add_standard()
+    buf = _run(hostsim, fm, ps.probes, engine="network")
+    assert buf.engine == 1 and buf.net["n_levels"] >= 4
+    ok, reports = compare_blocks(ps.split(buf.array("out_probe")), ref, fm)
+    ok2, rep = compare_mb(buf.array("out_mb"), ref["mb"], fm)
+    assert ok and ok2, "\n".join(reports + [rep])
+    seq = _run(hostsim, fm, ps.probes, engine="replica")
+    assert np.array_equal(buf.array("out_probe"), seq.array("out_probe"))
+    assert np.array_equal(buf.array("out_mb"), seq.array("out_mb"))
+
+
+def test_network_engine_rejects_non_dendritic_models():
+    from wsi_b200.backend import network
+    from wsi_b200.backend.capi import ModelBuffers
+
+    fm, _ = load_golden("rivernet")  # has Land, Sewer, a preference split ...
+    assert network.plan_network(fm) is None and network.why_not(fm)
+    with pytest.raises(ValueError):
+        ModelBuffers(fm, device="numpy", engine="network")

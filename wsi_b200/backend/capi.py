@@ -89,6 +89,19 @@ class WsiModelDesc(C.Structure):
         ("reserved1", C.c_int32),
         ("sched_op", _i32p),
         ("sched_node", _i32p),
+        ("engine", C.c_int32),
+        ("n_net_levels", C.c_int32),
+        ("n_net_calc", C.c_int32),
+        ("n_net_final", C.c_int32),
+        ("net_level_ptr", _i32p),
+        ("net_level_ptr_host", _i32p),
+        ("net_level_node", _i32p),
+        ("net_calc_node", _i32p),
+        ("net_final_node", _i32p),
+        ("net_path_ptr", _i32p),
+        ("net_path_sender", _i32p),
+        ("net_path_arc_ptr", _i32p),
+        ("net_path_arcs", _i32p),
         ("arc", _f64p),
         ("land", _f64p),
         ("surf", _f64p),
@@ -116,7 +129,9 @@ class WsiModelDesc(C.Structure):
     ]
 
 
-_INT_ARRAYS = [
+_NET_ARRAYS = ["net_level_ptr", "net_level_node", "net_calc_node", "net_final_node", "net_path_ptr",
+               "net_path_sender", "net_path_arc_ptr", "net_path_arcs"]
+_INT_ARRAYS = _NET_ARRAYS + [
     "surf_order", "end_kind", "end_obj", "mb_term_slot", "node_type", "node_gidx", "arc_in", "arc_out", "out_ptr", "out_arcs", "in_ptr", "in_arcs",
     "cand_ptr", "cand_arcs", "land_surf_ptr", "land_surf", "sched_op", "sched_node", "month_idx",
     "dayofyear", "doy_adj",
@@ -163,6 +178,9 @@ def load_library():
     lib.wsi_launch_count.restype = C.c_int64
     if lib.wsi_version() != ABI_VERSION:
         raise ExtensionMissingError("libwsi_b200.so ABI version mismatch; rebuild")
+    lib.wsi_desc_size.restype = C.c_int
+    if lib.wsi_desc_size() != C.sizeof(WsiModelDesc):
+        raise ExtensionMissingError("libwsi_b200.so was built against another WsiModelDesc layout; rebuild")
     _LIB = lib
     return lib
 
@@ -181,10 +199,20 @@ class ModelBuffers:
 
     def partial_rows(self):
         fm = self.fm
-        nb_obj = -(-fm.R // self.OBJ_BLOCK)
-        return (len(fm.node_names) + len(fm.arc_names)) * nb_obj
+        items = len(fm.node_names) + len(fm.arc_names)
+        if self.engine == 1:  # flat (item, replica) index
+            return -(-(items * fm.R) // self.OBJ_BLOCK)
+        return items * -(-fm.R // self.OBJ_BLOCK)
 
-    def __init__(self, fm, device="cuda", probes=(), rec_t0=0, rec_T=None, record_mb=False):
+    def __init__(self, fm, device="cuda", probes=(), rec_t0=0, rec_T=None, record_mb=False, engine="auto"):
+        from . import network
+
+        self.net = network.plan_network(fm) if engine in ("auto", "network") else None
+        if engine == "network" and self.net is None:
+            raise ValueError("model is not eligible for the network engine: " + network.why_not(fm))
+        if engine == "auto" and self.net is not None and fm.R * 8 > len(fm.node_names):
+            self.net = None  # plenty of replicas: the replica engine has the parallelism
+        self.engine = 1 if self.net is not None else 0
         # surface slots sorted by surface class (stable), for the per-class surface kernels
         types = fm.view("surf", "type")[0, :, 0].astype(np.int64) if fm.n_obj["surf"] else np.zeros(0, np.int64)
         order = np.argsort(types, kind="stable").astype(np.int32)
@@ -199,8 +227,10 @@ class ModelBuffers:
         slot = np.full(len(fm.node_type), -1, dtype=np.int32)
         slot[np.nonzero(fused)[0]] = np.arange(int(np.sum(fused)), dtype=np.int32)
         self.n_fused = int(np.sum(fused))
-        self._extra_int = {"surf_order": order if len(order) else np.zeros(1, np.int32), "mb_term_slot": slot,
-                           "end_kind": np.ascontiguousarray(it[:, 0]), "end_obj": np.ascontiguousarray(it[:, 1])}
+        net = self.net or network.empty_plan(len(fm.node_names))
+        self._extra_int = {k: np.ascontiguousarray(net[k], dtype=np.int32) for k in _NET_ARRAYS}
+        self._extra_int.update({"surf_order": order if len(order) else np.zeros(1, np.int32), "mb_term_slot": slot,
+                           "end_kind": np.ascontiguousarray(it[:, 0]), "end_obj": np.ascontiguousarray(it[:, 1])})
         self.surf_class_ptr = [int(np.searchsorted(types[order], k, side="left")) for k in range(4)] + [len(order)]
         self.fm = fm
         self.device = device
@@ -301,6 +331,11 @@ class ModelBuffers:
         for i, v in enumerate(self.surf_class_ptr):
             d.surf_class_ptr[i] = v
         d.n_end = self.n_end
+        net = self.net or {}
+        d.engine = self.engine
+        d.n_net_levels = int(len(net["net_level_ptr"]) - 1) if self.net else 0
+        d.n_net_calc = int(net.get("n_net_calc", 0))
+        d.n_net_final = int(net.get("n_net_final", 0))
         d.nq = fm.nq
         d.n_fseries = fm.node_forcing.shape[1]
         d.n_months = fm.surf_inputs.shape[0]
@@ -326,6 +361,8 @@ class ModelBuffers:
         for name in ("out_probe", "out_mb", "mb_partial", "mb_sums", "mb_terms"):
             setattr(d, name, C.cast(P(k[name]), _f64p))
         d.node_flags = C.cast(P(k["node_flags"]), _u32p)
+        self._level_ptr_host = np.ascontiguousarray(self._extra_int["net_level_ptr"], dtype=np.int32)
+        d.net_level_ptr_host = self._level_ptr_host.ctypes.data_as(_i32p)
         return d
 
     # ----------------------------------------------------------------- access

@@ -13,11 +13,14 @@ class GpuRunner:
 
     Parameters mirror what ``Model.run`` needs: which planes to record every step
     (``probes``), how many steps the record buffer covers (``rec_T``) and whether the
-    per-node mass-balance terms are kept (``record_mb``).
+    per-node mass-balance terms are kept (``record_mb``).  ``engine``: "replica" (one thread per
+    replica walks the orchestration schedule), "network" (level-synchronous routing of one large
+    dendritic river network, one thread per node) or "auto" (network when the model is eligible
+    and has few replicas per node).
     """
 
     def __init__(self, fm, probes=(), rec_t0=0, rec_T=None, record_mb=False, device="cuda:0",
-                 system_sums=True):
+                 system_sums=True, engine="auto"):
         import torch
 
         self.torch = torch
@@ -25,7 +28,7 @@ class GpuRunner:
         self.fm = fm
         self.device = torch.device(device)
         self.buffers = capi.ModelBuffers(fm, device=device, probes=probes, rec_t0=rec_t0, rec_T=rec_T,
-                                         record_mb=record_mb)
+                                         record_mb=record_mb, engine=engine)
         self.desc = self.buffers.desc
         if not system_sums:
             self.desc.mb_sums = C.cast(None, C.POINTER(C.c_double))

@@ -90,6 +90,7 @@ class FlatModel:
     dayofyear: np.ndarray
     doy_adj: np.ndarray
     dates: list = field(default_factory=list)
+    recipe: dict = None  # what a synthetic builder drew (tests); not part of the model
 
     # ------------------------------------------------------------------ basics
     @property

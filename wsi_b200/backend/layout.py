@@ -139,6 +139,7 @@ ARC = Group(
         S("preference"),
         S("flow_in"),  # per-step transient (arcs.py:64,152)
         Q("vqip_in"),  # per-step transient; vqip_out aliases it (arcs.py:155-156)
+        Q("pending"),  # network engine: what the arc's sender sent this step (read by the gather)
     ],
 )
 

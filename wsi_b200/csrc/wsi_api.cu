@@ -10,6 +10,10 @@
 //   wsi_mb_finalize       fixed-order reduction of the per-block partials -> mb_sums[t].
 //   wsi_record_kernel     one thread per (probe, replica): recording is a strided copy.
 //   wsi_end_kernel        one thread per (end_timestep item, replica).
+//   wsi_net_kernel / wsi_net_tail_kernel   network engine (desc.engine == 1): one thread per (river
+//                         node, replica), one launch per upstream-depth level; the narrow main-stem
+//                         levels in a single block.  Replaces wsi_step_kernel for one large
+//                         dendritic network; mb / record / end then use a flat (item, replica) index.
 //
 // The path is HBM-bound fp64 element-wise work: no tensor cores.  Grid sizing,
 // coalescing and the byte accounting are described in DESIGN.md.
@@ -48,6 +52,25 @@ constexpr int kBlock = 64;      // replicas per block of the per-replica schedul
 constexpr int kSurfBlock = 128; // surfaces per block of the surface kernels
 constexpr int kObjBlock = 128;  // replicas per block of the object-parallel kernels
 
+// Work-item decode of the object-parallel kernels.  Replica engine (FLAT = false): blockIdx.y is
+// the item and blockIdx.x tiles the replicas, so every block is homogeneous in item.  Network
+// engine (FLAT = true): one flat index over (item, replica) with the replica fastest, so a graph
+// with few replicas and a million nodes still fills the machine (and gridDim.y's 65535 limit
+// does not apply).
+template <bool FLAT>
+__device__ __forceinline__ bool decode_item(const WsiModelDesc& d, int n_items, int& item, int& r) {
+  if constexpr (FLAT) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    item = (int)(gid / (size_t)d.R);
+    r = (int)(gid % (size_t)d.R);
+    return item < n_items;
+  } else {
+    item = blockIdx.y;
+    r = blockIdx.x * blockDim.x + threadIdx.x;
+    return r < d.R;
+  }
+}
+
 // One thread per (surface slot, replica).  blockIdx.y selects the slot inside the surface
 // class being launched, so every block (and warp) is homogeneous in surface class and reads
 // 256 contiguous bytes per plane.
@@ -81,15 +104,15 @@ __global__ void __launch_bounds__(kBlock, WSI_STEP_MINB)
 // the system totals of model.py:1016-1036.  Block-reduced: violations via warp shuffle + one
 // atomic per warp; the (in, ds, out) lanes via warp shuffles, a fixed cross-warp sum, and one
 // row of mb_partial per block (summed in block order by wsi_mb_finalize: deterministic).
-template <class CFG>
+template <class CFG, bool FLAT>
 __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
-    wsi_mb_kernel(const int slot, const CFG cfg, const int t, const uint32_t flags) {
+    wsi_mb_kernel(const int slot, const CFG cfg, const int t, const uint32_t flags, const int n_items) {
   constexpr int V = CFG::P + 1;
   constexpr int kWarps = kObjBlock / 32;
   __shared__ double s_w[kWarps][3 * V];
   const WsiModelDesc& d = g_wsi_desc[slot];
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = r < d.R;
+  int item, r;
+  const bool active = decode_item<FLAT>(d, n_items, item, r);
   const bool want_sums = d.mb_sums != nullptr;
   Ctx<CFG> c = make_ctx(nullptr, slot, cfg, active ? r : 0, t, flags);
   using Vq = typename Ctx<CFG>::Vq;
@@ -97,7 +120,6 @@ __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
   term[0] = vq_zero<CFG::P>();
   term[1] = vq_zero<CFG::P>();
   term[2] = vq_zero<CFG::P>();
-  const int item = blockIdx.y;
   if (active) {
     if (item < d.n_nodes) {
       node_mass_balance(c, item, term[0], term[1], term[2]);
@@ -129,31 +151,67 @@ __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
       double acc = 0.0;
       if (p == 0 || bit(c.add, p))
         for (int w = 0; w < kWarps; w++) acc += s_w[w][threadIdx.x];
-      d.mb_partial[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 3 * V + threadIdx.x] = acc;
+      d.mb_partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 3 * V + threadIdx.x] = acc;
     }
   }
 }
 
 // One thread per (probe, replica): Model.run's recording (model.py:1063-1170) is a strided copy.
-template <class CFG>
+template <class CFG, bool FLAT>
 __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
     wsi_record_kernel(const int slot, const CFG cfg, const int t, const int row) {
   const WsiModelDesc& d = g_wsi_desc[slot];
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= d.R) return;
+  int item, r;
+  if (!decode_item<FLAT>(d, d.n_probe, item, r)) return;
   Ctx<CFG> c = make_ctx(nullptr, slot, cfg, r, t, 0u);
-  record_probe(c, row, (int)blockIdx.y);
+  record_probe(c, row, item);
 }
 
 // One thread per (end_timestep item, replica): arcs reset, DecayTank decay, QueueTank shift.
-template <class CFG>
+template <class CFG, bool FLAT>
 __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
     wsi_end_kernel(const int slot, const CFG cfg, const int t) {
   const WsiModelDesc& d = g_wsi_desc[slot];
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= d.R) return;
+  int item, r;
+  if (!decode_item<FLAT>(d, d.n_end, item, r)) return;
   Ctx<CFG> c = make_ctx(nullptr, slot, cfg, r, t, 0u);
-  end_item(c, d.end_kind[blockIdx.y], d.end_obj[blockIdx.y]);
+  end_item(c, d.end_kind[item], d.end_obj[item]);
+}
+
+// Network engine: one thread per (node of a work list, replica) -- River.calculate_discharge of
+// every river, one upstream-depth level of the routing, or the final deliveries (wsi_net.cuh).
+__device__ __forceinline__ const int32_t* net_list(const WsiModelDesc& d, int kind) {
+  return kind == kNetRiverCalc ? d.net_calc_node : kind == kNetLevel ? d.net_level_node : d.net_final_node;
+}
+template <class CFG>
+__global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
+    wsi_net_kernel(const int slot, const CFG cfg, const int t, const uint32_t flags, const int kind, const int begin,
+                   const int count) {
+  const WsiModelDesc& d = g_wsi_desc[slot];
+  int item, r;
+  if (!decode_item<true>(d, count, item, r)) return;
+  Ctx<CFG> c = make_ctx(nullptr, slot, cfg, r, t, flags);
+  net_item(c, kind, net_list(d, kind)[begin + item]);
+}
+// The narrow downstream end of the network (levels with at most kNetTail work items: the main
+// stem) and the final deliveries in ONE block, levels separated by __syncthreads() instead of
+// kernel boundaries -- a launch per level would cost more than the level's arithmetic.
+constexpr int kNetTail = 256;
+template <class CFG>
+__global__ void __launch_bounds__(kNetTail)
+    wsi_net_tail_kernel(const int slot, const CFG cfg, const int t, const uint32_t flags, const int level_begin) {
+  const WsiModelDesc& d = g_wsi_desc[slot];
+  for (int l = level_begin; l <= d.n_net_levels; l++) {
+    const bool fin = l == d.n_net_levels;
+    const int begin = fin ? 0 : d.net_level_ptr[l];
+    const int count = fin ? d.n_net_final : d.net_level_ptr[l + 1] - begin;
+    const int32_t* list = fin ? d.net_final_node : d.net_level_node;
+    for (size_t w = threadIdx.x; w < (size_t)count * d.R; w += kNetTail) {
+      Ctx<CFG> c = make_ctx(nullptr, slot, cfg, (int)(w % (size_t)d.R), t, flags);
+      net_item(c, fin ? kNetGatherOnly : kNetLevel, list[begin + (int)(w / (size_t)d.R)]);
+    }
+    __syncthreads();  // block-wide execution + memory barrier: level l is visible to level l+1
+  }
 }
 
 // Sum the mass-balance partial rows of one timestep: block j reduces column j of
@@ -199,7 +257,12 @@ bool is_default12(const WsiModelDesc* d) {
 
 int n_blocks(const WsiModelDesc* d) { return (d->R + kBlock - 1) / kBlock; }
 int n_obj_blocks(const WsiModelDesc* d) { return (d->R + kObjBlock - 1) / kObjBlock; }
-int n_partial_rows(const WsiModelDesc* d) { return (d->n_nodes + d->n_arcs) * n_obj_blocks(d); }
+int n_flat_blocks(const WsiModelDesc* d, int n_items) {
+  return (int)(((size_t)n_items * (size_t)d->R + kObjBlock - 1) / kObjBlock);
+}
+int n_partial_rows(const WsiModelDesc* d) {
+  return d->engine == 1 ? n_flat_blocks(d, d->n_nodes + d->n_arcs) : (d->n_nodes + d->n_arcs) * n_obj_blocks(d);
+}
 
 #define WSI_CHECK_LAUNCH(name)                                                                         \
   do {                                                                                                 \
@@ -232,34 +295,77 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
     if (!rc) rc = launch_surfaces<CFG, WSI_ST_GROWINGSURFACE>(d, slot, cfg, t, flags, s);
     if (rc) return rc;
   }
+  const bool net = d->engine == 1;
   if ((flags & WSI_RUN_SCHEDULE) && e > b) {
-    wsi_step_kernel<CFG><<<n_blocks(d), kBlock, 0, s>>>(slot, cfg, (int)t, b, e, flags);
-    WSI_CHECK_LAUNCH("wsi_step_kernel");
+    if (net) {
+      if (d->n_net_calc > 0) {
+        wsi_net_kernel<CFG><<<n_flat_blocks(d, d->n_net_calc), kObjBlock, 0, s>>>(slot, cfg, (int)t, flags,
+                                                                                  kNetRiverCalc, 0, d->n_net_calc);
+        WSI_CHECK_LAUNCH("wsi_net_kernel");
+      }
+      // wide levels: one launch each; from the first level after which everything is narrow,
+      // a single block walks the rest
+      const int32_t* lp = d->net_level_ptr_host;
+      int tail = d->n_net_levels;
+      while (tail > 0 && (size_t)(lp[tail] - lp[tail - 1]) * (size_t)d->R <= (size_t)kNetTail) tail--;
+      if ((size_t)d->n_net_final * (size_t)d->R > (size_t)kNetTail) tail = d->n_net_levels + 1;  // wide final list
+      for (int l = 0; l < tail && l < d->n_net_levels; l++) {
+        const int count = lp[l + 1] - lp[l];
+        if (count <= 0) continue;
+        wsi_net_kernel<CFG><<<n_flat_blocks(d, count), kObjBlock, 0, s>>>(slot, cfg, (int)t, flags, kNetLevel, lp[l],
+                                                                          count);
+        WSI_CHECK_LAUNCH("wsi_net_kernel");
+      }
+      if (tail <= d->n_net_levels) {
+        wsi_net_tail_kernel<CFG><<<1, kNetTail, 0, s>>>(slot, cfg, (int)t, flags, tail);
+        WSI_CHECK_LAUNCH("wsi_net_tail_kernel");
+      } else if (d->n_net_final > 0) {
+        wsi_net_kernel<CFG><<<n_flat_blocks(d, d->n_net_final), kObjBlock, 0, s>>>(slot, cfg, (int)t, flags,
+                                                                                   kNetGatherOnly, 0, d->n_net_final);
+        WSI_CHECK_LAUNCH("wsi_net_kernel");
+      }
+    } else {
+      wsi_step_kernel<CFG><<<n_blocks(d), kBlock, 0, s>>>(slot, cfg, (int)t, b, e, flags);
+      WSI_CHECK_LAUNCH("wsi_step_kernel");
+    }
   }
   if (want_mb) {
     const int items = d->n_nodes + (want_sums ? d->n_arcs : 0);
+    const int rows = net ? n_flat_blocks(d, items) : items * n_obj_blocks(d);
     if (items > 0) {
-      const dim3 grid(n_obj_blocks(d), items);
-      wsi_mb_kernel<CFG><<<grid, kObjBlock, 0, s>>>(slot, cfg, (int)t, flags);
+      if (net) {
+        wsi_mb_kernel<CFG, true><<<rows, kObjBlock, 0, s>>>(slot, cfg, (int)t, flags, items);
+      } else {
+        const dim3 grid(n_obj_blocks(d), items);
+        wsi_mb_kernel<CFG, false><<<grid, kObjBlock, 0, s>>>(slot, cfg, (int)t, flags, items);
+      }
       WSI_CHECK_LAUNCH("wsi_mb_kernel");
     }
     if (want_sums) {
       const int n = 3 * V;
-      wsi_mb_finalize<<<n, kFinBlock, 0, s>>>(d->mb_partial, d->mb_sums + (size_t)t * n, items * n_obj_blocks(d), n);
+      wsi_mb_finalize<<<n, kFinBlock, 0, s>>>(d->mb_partial, d->mb_sums + (size_t)t * n, rows, n);
       WSI_CHECK_LAUNCH("wsi_mb_finalize");
     }
   }
   if (flags & WSI_RUN_RECORD) {
     const int row = (int)t - d->rec_t0;
     if (d->n_probe > 0 && row >= 0 && row < d->rec_T) {
-      const dim3 grid(n_obj_blocks(d), d->n_probe);
-      wsi_record_kernel<CFG><<<grid, kObjBlock, 0, s>>>(slot, cfg, (int)t, row);
+      if (net) {
+        wsi_record_kernel<CFG, true><<<n_flat_blocks(d, d->n_probe), kObjBlock, 0, s>>>(slot, cfg, (int)t, row);
+      } else {
+        const dim3 grid(n_obj_blocks(d), d->n_probe);
+        wsi_record_kernel<CFG, false><<<grid, kObjBlock, 0, s>>>(slot, cfg, (int)t, row);
+      }
       WSI_CHECK_LAUNCH("wsi_record_kernel");
     }
   }
   if ((flags & WSI_RUN_END_TIMESTEP) && d->n_end > 0) {
-    const dim3 grid(n_obj_blocks(d), d->n_end);
-    wsi_end_kernel<CFG><<<grid, kObjBlock, 0, s>>>(slot, cfg, (int)t);
+    if (net) {
+      wsi_end_kernel<CFG, true><<<n_flat_blocks(d, d->n_end), kObjBlock, 0, s>>>(slot, cfg, (int)t);
+    } else {
+      const dim3 grid(n_obj_blocks(d), d->n_end);
+      wsi_end_kernel<CFG, false><<<grid, kObjBlock, 0, s>>>(slot, cfg, (int)t);
+    }
     WSI_CHECK_LAUNCH("wsi_end_kernel");
   }
   return WSI_OK;
@@ -292,6 +398,8 @@ extern "C" {
 
 int wsi_version(void) { return WSI_ABI_VERSION; }
 
+int wsi_desc_size(void) { return (int)sizeof(WsiModelDesc); }
+
 const char* wsi_last_error(void) { return g_err; }
 
 int wsi_validate(const WsiModelDesc* d) {
@@ -305,8 +413,14 @@ int wsi_validate(const WsiModelDesc* d) {
     return fail(WSI_ERR_BAD_DESC, "graph arrays missing%s");
   if (d->n_sched > 0 && (!d->sched_op || !d->sched_node)) return fail(WSI_ERR_BAD_DESC, "schedule missing%s");
   if (d->n_end > 0 && (!d->end_kind || !d->end_obj)) return fail(WSI_ERR_BAD_DESC, "end_timestep items missing%s");
-  if (d->n_probe > 65535 || d->n_end > 65535 || d->n_nodes + d->n_arcs > 65535)
-    return fail(WSI_ERR_UNSUPPORTED, "more than 65535 probes / nodes+arcs / end items per template%s");
+  if (d->engine != 0 && d->engine != 1) return fail(WSI_ERR_BAD_DESC, "unknown engine%s");
+  if (d->engine == 0 && (d->n_probe > 65535 || d->n_end > 65535 || d->n_nodes + d->n_arcs > 65535))
+    return fail(WSI_ERR_UNSUPPORTED,
+                "more than 65535 probes / nodes+arcs / end items per template need the network engine%s");
+  if (d->engine == 1 && (d->n_net_levels < 0 || !d->net_level_ptr || !d->net_level_ptr_host || !d->net_level_node ||
+                         !d->net_calc_node || !d->net_final_node || !d->net_path_ptr || !d->net_path_sender))
+    return fail(WSI_ERR_BAD_DESC, "network plan missing%s");
+  if (d->engine == 1 && d->n_surf > 0) return fail(WSI_ERR_UNSUPPORTED, "the network engine has no Land nodes%s");
   if (d->n_surf > 0 && (!d->surf_order || d->surf_class_ptr[0] != 0 || d->surf_class_ptr[4] != d->n_surf))
     return fail(WSI_ERR_BAD_DESC, "surface class order missing%s");
   if ((d->n_arcs > 0 && !d->arc) || (d->n_land > 0 && !d->land) || (d->n_surf > 0 && !d->surf) ||

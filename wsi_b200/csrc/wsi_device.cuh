@@ -656,3 +656,4 @@ WSI_HD double decay_total_of(PlaneFn plane, int f_n, int pol) {
 
 #include "wsi_land.cuh"
 #include "wsi_nodes.cuh"
+#include "wsi_net.cuh"

@@ -494,6 +494,9 @@ WSI_HD void run_op(C& c, int op, int node) {
   }
 }
 
+template <class C>
+WSI_HD void net_schedule(C& c);  // wsi_net.cuh
+
 // ---- the whole timestep of one replica --------------------------------------------------------
 // FUSED_SURFACES: this thread also runs the replica's surfaces (host build / tiny models);
 // the CUDA library runs them in wsi_surface_kernel instead and instantiates <false>.
@@ -504,8 +507,11 @@ WSI_HD void replica_step(C& c, int sched_begin, int sched_end) {
     if (c.run_flags & WSI_RUN_SURFACES)
       for (int u = 0; u < d.n_surf; u++) surface_phase<-1>(c, u);
   }
-  if (c.run_flags & WSI_RUN_SCHEDULE)
-    for (int k = sched_begin; k < sched_end; k++) run_op(c, d.sched_op[k], d.sched_node[k]);
+  if (c.run_flags & WSI_RUN_SCHEDULE) {
+    if (d.engine == 1) net_schedule(c);
+    else
+      for (int k = sched_begin; k < sched_end; k++) run_op(c, d.sched_op[k], d.sched_node[k]);
+  }
   if (c.run_flags & WSI_RUN_MASS_BALANCE) {
     if (c.mb_acc)
       for (int a = 0; a < d.n_arcs; a++) arc_system_totals(c, a);
