@@ -101,12 +101,22 @@ typedef struct WsiModelDesc {
   const int32_t* net_level_ptr;   /* [n_net_levels+1] CSR over net_level_node (upstream depth ascending) */
   const int32_t* net_level_ptr_host; /* HOST copy of net_level_ptr (the launcher sizes one grid per level) */
   const int32_t* net_level_node;  /* river node slots */
-  const int32_t* net_calc_node;   /* [n_net_calc] rivers whose calculate_discharge is scheduled */
+  const int32_t* net_calc_node;   /* [n_net_calc] the rivers (calculate_discharge + their catchments' route) */
   const int32_t* net_final_node;  /* [n_net_final] gather-only nodes (Waste, rivers outside the order) */
   const int32_t* net_path_ptr;    /* [n_nodes+1] incoming paths per receiving node */
+  const int32_t* net_path_split;  /* [n_nodes] first path of the node whose sender is a River: catchments
+                                     come first (they are routed before any river discharges) */
   const int32_t* net_path_sender; /* sender node of each path */
-  const int32_t* net_path_arc_ptr; /* CSR over net_path_arcs: arcs along each path (diagnostic) */
+  const int32_t* net_path_arc_ptr; /* CSR over net_path_arcs: arcs along each path */
   const int32_t* net_path_arcs;
+  const int32_t* net_item;   /* [n_level_items][8] per entry of net_level_node: node, tank slot, river slot,
+                                out-arc (-1: none), [begin, end) into net_rpath, 1 if the out-arc goes
+                                straight to a River / Waste, arc of the first river path */
+  int32_t* net_scratch;      /* [4] device scratch: level at which the fast tail kernel handed over */
+  int32_t* net_done;         /* [n_level_items] device scratch: t + 1 of the last step in which the fast tail
+                                kernel completed the item (the general kernel skips those when it resumes) */
+  const int32_t* net_rpath;  /* [.][4] river paths in delivery order: sender's arc, sender's tank slot,
+                                1 if the arc goes straight to the receiver, sender node */
 
   /* ---- SoA groups, fp64 [n_fields][n_obj*R] ---- */
   double* arc;

@@ -2,7 +2,7 @@
 """Correlate an ncu SASS profile with source lines (no GUI needed).
 
     ncu -i prof.ncu-rep --page source --csv -k regex:<kernel> > sass.csv
-    python tools/ncu_hotspots.py sass.csv wsi_b200/csrc/libwsi_b200.so <kernel-substring>
+    python tools/ncu_hotspots.py sass.csv wsi_b200/csrc/libwsi_b200.so <kernel-substring> [top] [mangled-section-substring]
 
 Uses `cuobjdump -xelf` + `nvdisasm --print-line-info-inline` for the offset -> file:line map and
 reports executed warp instructions and stall samples per source line and per device function.
@@ -11,6 +11,7 @@ import collections, csv, os, re, subprocess, sys, tempfile
 
 sass_csv, so, kname = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+sec_name = sys.argv[5] if len(sys.argv) > 5 else kname  # substring of the (mangled) .text section
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -24,7 +25,7 @@ fresh = True
 cur_func = None
 for line in dis.splitlines():
     if line.startswith("//--------------------- .text."):
-        in_sec = kname in line
+        in_sec = sec_name in line
         pend = None
         cur_func = "kernel"
         continue

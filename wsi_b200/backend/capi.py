@@ -99,9 +99,14 @@ class WsiModelDesc(C.Structure):
         ("net_calc_node", _i32p),
         ("net_final_node", _i32p),
         ("net_path_ptr", _i32p),
+        ("net_path_split", _i32p),
         ("net_path_sender", _i32p),
         ("net_path_arc_ptr", _i32p),
         ("net_path_arcs", _i32p),
+        ("net_item", _i32p),
+        ("net_scratch", _i32p),
+        ("net_done", _i32p),
+        ("net_rpath", _i32p),
         ("arc", _f64p),
         ("land", _f64p),
         ("surf", _f64p),
@@ -130,7 +135,7 @@ class WsiModelDesc(C.Structure):
 
 
 _NET_ARRAYS = ["net_level_ptr", "net_level_node", "net_calc_node", "net_final_node", "net_path_ptr",
-               "net_path_sender", "net_path_arc_ptr", "net_path_arcs"]
+               "net_path_split", "net_path_sender", "net_path_arc_ptr", "net_path_arcs", "net_item", "net_scratch", "net_done", "net_rpath"]
 _INT_ARRAYS = _NET_ARRAYS + [
     "surf_order", "end_kind", "end_obj", "mb_term_slot", "node_type", "node_gidx", "arc_in", "arc_out", "out_ptr", "out_arcs", "in_ptr", "in_arcs",
     "cand_ptr", "cand_arcs", "land_surf_ptr", "land_surf", "sched_op", "sched_node", "month_idx",
@@ -228,6 +233,7 @@ class ModelBuffers:
         slot[np.nonzero(fused)[0]] = np.arange(int(np.sum(fused)), dtype=np.int32)
         self.n_fused = int(np.sum(fused))
         net = self.net or network.empty_plan(len(fm.node_names))
+        net = dict(net, net_scratch=np.zeros(4, np.int32), net_done=np.zeros(max(len(net["net_item"]) // 8, 1) * fm.R, np.int32))
         self._extra_int = {k: np.ascontiguousarray(net[k], dtype=np.int32) for k in _NET_ARRAYS}
         self._extra_int.update({"surf_order": order if len(order) else np.zeros(1, np.int32), "mb_term_slot": slot,
                            "end_kind": np.ascontiguousarray(it[:, 0]), "end_obj": np.ascontiguousarray(it[:, 1])})

@@ -138,8 +138,10 @@ ARC = Group(
         S("capacity"),
         S("preference"),
         S("flow_in"),  # per-step transient (arcs.py:64,152)
+        S("pending_mode"),  # network engine: 0 = the sender already booked `pending` on the arc and
+        #                     the receiver only adds it to its tank; 1 = the receiver runs the whole push
         Q("vqip_in"),  # per-step transient; vqip_out aliases it (arcs.py:155-156)
-        Q("pending"),  # network engine: what the arc's sender sent this step (read by the gather)
+        Q("pending"),  # network engine: the release the arc's sender parked for its receiver
     ],
 )
 

@@ -18,8 +18,10 @@ MAX_JUNCTIONS = 2  # kJunctionDepth in wsi_device.cuh
 
 def empty_plan(n_nodes):
     z = np.zeros(1, dtype=np.int32)
-    return {"net_level_ptr": np.zeros(1, np.int32), "net_level_node": z, "net_calc_node": z, "net_final_node": z,
-            "net_path_ptr": np.zeros(n_nodes + 1, np.int32), "net_path_sender": z,
+    return {"net_item": np.zeros(8, np.int32), "net_rpath": np.zeros(4, np.int32),
+            "net_level_ptr": np.zeros(1, np.int32), "net_level_node": z, "net_calc_node": z, "net_final_node": z,
+            "net_path_ptr": np.zeros(n_nodes + 1, np.int32), "net_path_split": np.zeros(max(n_nodes, 1), np.int32),
+            "net_path_sender": z,
             "net_path_arc_ptr": np.zeros(1, np.int32), "net_path_arcs": z}
 
 
@@ -42,6 +44,9 @@ def why_not(fm):
         if t == L.NT["Node"]:
             if n_out[n] != 1:
                 return f"junction {fm.node_names[n]} has no outlet"
+    rivers = set(int(n) for n in np.nonzero(fm.node_type == L.NT["River"])[0])
+    if set(int(n) for o, n in zip(fm.sched_op, fm.sched_node) if int(o) == L.OP["RIVER_CALC"]) != rivers:
+        return "River.calculate_discharge is not scheduled for every river"
     # order of ops: every calculate_discharge / route entry must precede the discharge sweep
     ops = [int(o) for o in fm.sched_op if int(o) != L.OP["NOP"]]
     first_dist = next((i for i, o in enumerate(ops) if o == L.OP["RIVER_DISTRIBUTE"]), len(ops))
@@ -127,17 +132,36 @@ def plan_network(fm):
              if (fm.node_type[n] == L.NT["Waste"] or (fm.node_type[n] == L.NT["River"] and n not in distributes))
              and paths[n]]
     path_ptr = np.zeros(n_nodes + 1, dtype=np.int32)
+    path_split = np.zeros(max(n_nodes, 1), dtype=np.int32)
     path_sender, path_arc_ptr, path_arcs = [], [0], []
     for n in range(n_nodes):
+        path_split[n] = len(path_sender) + sum(1 for s, _ in paths[n] if fm.node_type[s] == L.NT["Catchment"])
         for s, arcs in paths[n]:  # already in push order: catchments (orchestration order), then rivers
             path_sender.append(s)
             path_arcs += arcs
             path_arc_ptr.append(len(path_arcs))
         path_ptr[n + 1] = len(path_sender)
+    # compact records in level order: what one river of a level needs, without index chasing
+    river_tank = fm.view("river", "tank")[0, :, 0].astype(np.int64) if fm.n_obj["river"] else np.zeros(0, np.int64)
+    n_out = np.diff(fm.out_ptr)
+    item_rec = np.zeros((max(len(level_node), 1), 8), dtype=np.int32)
+    rpath_rec = []
+    for i, n in enumerate(level_node):
+        g = int(fm.node_gidx[n])
+        begin = len(rpath_rec)
+        for k in range(int(path_split[n]), int(path_ptr[n + 1])):
+            s_ = path_sender[k]
+            rpath_rec.append((path_arcs[path_arc_ptr[k]], int(river_tank[fm.node_gidx[s_]]),
+                              1 if path_arc_ptr[k + 1] - path_arc_ptr[k] == 1 else 0, s_))
+        direct = 1 if n_out[n] == 1 and fm.node_type[fm.arc_out[out_arc[n]]] in (L.NT["River"], L.NT["Waste"]) else 0
+        item_rec[i] = (n, int(river_tank[g]), g, out_arc[n] if n_out[n] == 1 else -1, begin, len(rpath_rec), direct,
+                       rpath_rec[begin][0] if len(rpath_rec) > begin else 0)
     i32 = lambda x: np.array(x if len(x) else [0], dtype=np.int32)  # noqa: E731
     return {
+        "net_item": item_rec.reshape(-1), "net_rpath": np.array(rpath_rec or [(0, 0, 0, 0)], dtype=np.int32).reshape(-1),
         "net_level_ptr": level_ptr, "net_level_node": i32(level_node), "net_calc_node": i32(calc),
-        "net_final_node": i32(final), "net_path_ptr": path_ptr, "net_path_sender": i32(path_sender),
+        "net_final_node": i32(final), "net_path_ptr": path_ptr, "net_path_split": path_split,
+        "net_path_sender": i32(path_sender),
         "net_path_arc_ptr": np.array(path_arc_ptr, dtype=np.int32), "net_path_arcs": i32(path_arcs),
         "n_net_calc": len(calc), "n_net_final": len(final), "n_levels": n_levels,
     }

@@ -180,9 +180,6 @@ __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
 
 // Network engine: one thread per (node of a work list, replica) -- River.calculate_discharge of
 // every river, one upstream-depth level of the routing, or the final deliveries (wsi_net.cuh).
-__device__ __forceinline__ const int32_t* net_list(const WsiModelDesc& d, int kind) {
-  return kind == kNetRiverCalc ? d.net_calc_node : kind == kNetLevel ? d.net_level_node : d.net_final_node;
-}
 template <class CFG>
 __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
     wsi_net_kernel(const int slot, const CFG cfg, const int t, const uint32_t flags, const int kind, const int begin,
@@ -191,26 +188,158 @@ __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
   int item, r;
   if (!decode_item<true>(d, count, item, r)) return;
   Ctx<CFG> c = make_ctx(nullptr, slot, cfg, r, t, flags);
-  net_item(c, kind, net_list(d, kind)[begin + item]);
+  net_item(c, kind, begin + item);
 }
-// The narrow downstream end of the network (levels with at most kNetTail work items: the main
-// stem) and the final deliveries in ONE block, levels separated by __syncthreads() instead of
-// kernel boundaries -- a launch per level would cost more than the level's arithmetic.
-constexpr int kNetTail = 256;
+// Mid-width levels: a group of kLanes threads per (river, replica) (wsi_net.cuh, lane-parallel
+// form) -- fewer instructions on the critical path of the level than one thread per river.
+constexpr int kLaneBlock = 256;
+constexpr size_t kLaneLevelMax = 32768;  // (river, replica) items per level up to which lane groups are used
+template <class CFG>
+__global__ void __launch_bounds__(kLaneBlock)
+    wsi_net_lane_kernel(const int slot, const CFG cfg, const int t, const uint32_t flags, const int begin,
+                        const int count) {
+  const WsiModelDesc& d = g_wsi_desc[slot];
+  const size_t gid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
+  const int q = threadIdx.x % kLanes;
+  const unsigned gmask = 0xFFFFu << (threadIdx.x & 16);
+  const int item = (int)(gid / (size_t)d.R);
+  if (item >= count) return;  // whole groups leave together
+  using Cx = Ctx<CFG>;
+  Cx c = make_ctx(nullptr, slot, cfg, (int)(gid % (size_t)d.R), t, flags);
+  LaneItem<Cx> it = lane_item_load(c, net_rec_load(c, begin + item), q);
+  LaneOut<Cx> out;
+  const bool general = net_lanes_release(c, it, q, gmask, out);
+  if (!general) net_lanes_settle(c, it, q, gmask, out);
+  else if (q == 0) net_level_scalar(c, begin + item);
+}
+
+// The narrow downstream end of the network (levels with at most kTailGroups work items: the
+// main stem) in ONE block, levels separated by __syncthreads() instead of kernel boundaries -- a
+// launch per level would cost more than the level's arithmetic.  Half of the block's lane groups
+// are consumers, one per (river, replica); what does not depend on upstream rivers is loaded one
+// level (state) and two levels (indices) ahead, so that only pending -> sum -> pull -> pending
+// is on a level's critical path.  The other half run kTailAhead levels ahead and prefetch.
+// The kernel contains no calls: when a river needs the general push code it stops at that level
+// and wsi_net_tail_general (launched right behind it) takes over from there.
+#ifdef WSI_NET_DEBUG  // development aid: per-phase clock64() totals of the tail kernel's thread 0
+__device__ unsigned long long g_net_dbg[16];
+#define NET_DBG(i)                                        \
+  do {                                                    \
+    if (threadIdx.x == 0) {                               \
+      const long long now_ = clock64();                   \
+      g_net_dbg[i] += (unsigned long long)(now_ - dbg_t); \
+      dbg_t = now_;                                       \
+    }                                                     \
+  } while (0)
+#else
+#define NET_DBG(i)
+#endif
+constexpr int kNetTail = 512;
+constexpr int kTailGroups = kNetTail / kLanes / 2;
+constexpr int kTailAhead = 12;
 template <class CFG>
 __global__ void __launch_bounds__(kNetTail)
     wsi_net_tail_kernel(const int slot, const CFG cfg, const int t, const uint32_t flags, const int level_begin) {
+  __shared__ int s_general;
+  __shared__ uint64_t s_bar;
   const WsiModelDesc& d = g_wsi_desc[slot];
-  for (int l = level_begin; l <= d.n_net_levels; l++) {
-    const bool fin = l == d.n_net_levels;
-    const int begin = fin ? 0 : d.net_level_ptr[l];
-    const int count = fin ? d.n_net_final : d.net_level_ptr[l + 1] - begin;
-    const int32_t* list = fin ? d.net_final_node : d.net_level_node;
-    for (size_t w = threadIdx.x; w < (size_t)count * d.R; w += kNetTail) {
-      Ctx<CFG> c = make_ctx(nullptr, slot, cfg, (int)(w % (size_t)d.R), t, flags);
-      net_item(c, fin ? kNetGatherOnly : kNetLevel, list[begin + (int)(w / (size_t)d.R)]);
+  const int R = d.R;
+  const int grp = threadIdx.x / kLanes, q = threadIdx.x % kLanes;
+  const unsigned gmask = 0xFFFFu << (threadIdx.x & 16);
+  const bool prefetcher = grp >= kTailGroups;
+  const int wg = prefetcher ? grp - kTailGroups : grp;
+  const int r = wg % R, k = wg / R;  // a tail level has at most kTailGroups / R rivers
+  using Cx = Ctx<CFG>;
+  Cx c = make_ctx(nullptr, slot, cfg, r, t, flags);
+  const int L = d.n_net_levels;
+  const int32_t* __restrict__ lptr = d.net_level_ptr;
+  if (threadIdx.x == 0) {
+    s_general = 0;
+    mbar_init(&s_bar, kNetTail);
+  }
+  // consumer groups: unconditional look-ahead loads -- absent items read item 0, a select
+  // would have to wait for the loaded values
+  NetRec<Cx> rec2 = {};
+  LaneItem<Cx> item1 = {};
+  bool has1 = false, has2 = false;
+  int i1 = 0, i2 = 0;
+  if (!prefetcher) {
+    has1 = level_begin < L && k < lptr[level_begin + 1] - lptr[level_begin];
+    has2 = level_begin + 1 < L && k < lptr[level_begin + 2] - lptr[level_begin + 1];
+    i1 = has1 ? lptr[level_begin] + k : 0;
+    i2 = has2 ? lptr[level_begin + 1] + k : 0;
+    item1 = lane_item_load(c, net_rec_load(c, i1), q);
+    rec2 = net_rec_load(c, i2);
+  } else {
+    for (int l = level_begin; l < level_begin + kTailAhead && l < L; l++)
+      if (k < lptr[l + 1] - lptr[l]) net_prefetch_item(c, lptr[l] + k, q);
+  }
+  __syncthreads();
+#ifdef WSI_NET_DEBUG
+  long long dbg_t = clock64();
+#endif
+  int l = level_begin;
+  for (; l < L; l++) {
+    if (prefetcher) {
+      mbar_arrive(&s_bar);  // produces nothing anybody waits for: only paced by the wait below
+      const int lp = l + kTailAhead;
+      if (lp < L && k < lptr[lp + 1] - lptr[lp]) net_prefetch_item(c, lptr[lp] + k, q);
+    } else {
+      LaneItem<Cx> cur = item1;
+      const bool has = has1;
+      const int i0 = i1;
+      has1 = has2;
+      i1 = i2;
+      item1 = lane_item_load(c, rec2, q);
+      has2 = l + 2 < L && k < lptr[l + 3] - lptr[l + 2];
+      i2 = has2 ? lptr[l + 2] + k : 0;
+      rec2 = net_rec_load(c, i2);
+      NET_DBG(0);
+      LaneOut<Cx> out;
+      const bool general = has && net_lanes_release(c, cur, q, gmask, out);
+      if (general && q == 0) s_general = 1;
+      NET_DBG(1);
+      mbar_arrive(&s_bar);  // level l + 1 may start as soon as everybody's releases are parked
+      if (has && !general) {
+        net_lanes_settle(c, cur, q, gmask, out);
+        if (q == 0) d.net_done[(size_t)i0 * R + r] = t + 1;
+      }
+      NET_DBG(3);
     }
-    __syncthreads();  // block-wide execution + memory barrier: level l is visible to level l+1
+    mbar_wait(&s_bar, (uint32_t)(l - level_begin) & 1u);
+    NET_DBG(2);
+    if (s_general) break;  // rivers of level l that took the lane path are marked in net_done; a
+                           // general river has stored nothing and is done by wsi_net_tail_general
+  }
+  if (threadIdx.x == 0) {
+    d.net_scratch[0] = l;  // first level wsi_net_tail_general still has to do (L: none)
+    d.net_scratch[1] = s_general;
+  }
+}
+
+// General continuation of the tail: from the level the lane kernel stopped at to the end with
+// the scalar code (any push protocol case), then the final deliveries.  In the level it resumes
+// at, rivers the lane kernel completed (net_done == t + 1) are skipped.
+template <class CFG>
+__global__ void __launch_bounds__(kObjBlock)
+    wsi_net_tail_general(const int slot, const CFG cfg, const int t, const uint32_t flags) {
+  const WsiModelDesc& d = g_wsi_desc[slot];
+  const int R = d.R;
+  const int L = d.n_net_levels;
+  const int resume = d.net_scratch[0];
+  for (int l = resume; l < L; l++) {
+    const int begin = d.net_level_ptr[l], count = d.net_level_ptr[l + 1] - begin;
+    for (size_t w = threadIdx.x; w < (size_t)count * R; w += kObjBlock) {
+      const int i = begin + (int)(w / (size_t)R), r = (int)(w % (size_t)R);
+      if (l == resume && d.net_done[(size_t)i * R + r] == t + 1) continue;
+      Ctx<CFG> cl = make_ctx(nullptr, slot, cfg, r, t, flags);
+      net_item(cl, kNetLevel, i);
+    }
+    __syncthreads();
+  }
+  for (size_t w = threadIdx.x; w < (size_t)d.n_net_final * R; w += kObjBlock) {
+    Ctx<CFG> cf = make_ctx(nullptr, slot, cfg, (int)(w % (size_t)R), t, flags);
+    net_item(cf, kNetFinal, (int)(w / (size_t)R));
   }
 }
 
@@ -300,28 +429,38 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
     if (net) {
       if (d->n_net_calc > 0) {
         wsi_net_kernel<CFG><<<n_flat_blocks(d, d->n_net_calc), kObjBlock, 0, s>>>(slot, cfg, (int)t, flags,
-                                                                                  kNetRiverCalc, 0, d->n_net_calc);
+                                                                                  kNetPre, 0, d->n_net_calc);
         WSI_CHECK_LAUNCH("wsi_net_kernel");
       }
-      // wide levels: one launch each; from the first level after which everything is narrow,
-      // a single block walks the rest
+      // wide levels: one launch each, a thread per (river, replica) while the level is wide enough
+      // to fill the machine that way, lane groups below that; from the first level after which
+      // every level fits one block's lane groups, a single block walks the rest
       const int32_t* lp = d->net_level_ptr_host;
       int tail = d->n_net_levels;
-      while (tail > 0 && (size_t)(lp[tail] - lp[tail - 1]) * (size_t)d->R <= (size_t)kNetTail) tail--;
-      if ((size_t)d->n_net_final * (size_t)d->R > (size_t)kNetTail) tail = d->n_net_levels + 1;  // wide final list
+      while (tail > 0 && (size_t)(lp[tail] - lp[tail - 1]) * (size_t)d->R <= (size_t)kTailGroups) tail--;
+      if ((size_t)d->n_net_final * (size_t)d->R > (size_t)kObjBlock * 8) tail = d->n_net_levels + 1;  // wide final list
       for (int l = 0; l < tail && l < d->n_net_levels; l++) {
         const int count = lp[l + 1] - lp[l];
         if (count <= 0) continue;
-        wsi_net_kernel<CFG><<<n_flat_blocks(d, count), kObjBlock, 0, s>>>(slot, cfg, (int)t, flags, kNetLevel, lp[l],
-                                                                          count);
-        WSI_CHECK_LAUNCH("wsi_net_kernel");
+        const size_t work = (size_t)count * (size_t)d->R;
+        if (work > kLaneLevelMax) {
+          wsi_net_kernel<CFG><<<n_flat_blocks(d, count), kObjBlock, 0, s>>>(slot, cfg, (int)t, flags, kNetLevel,
+                                                                            lp[l], count);
+          WSI_CHECK_LAUNCH("wsi_net_kernel");
+        } else {
+          const int blocks = (int)((work * kLanes + kLaneBlock - 1) / kLaneBlock);
+          wsi_net_lane_kernel<CFG><<<blocks, kLaneBlock, 0, s>>>(slot, cfg, (int)t, flags, lp[l], count);
+          WSI_CHECK_LAUNCH("wsi_net_lane_kernel");
+        }
       }
       if (tail <= d->n_net_levels) {
         wsi_net_tail_kernel<CFG><<<1, kNetTail, 0, s>>>(slot, cfg, (int)t, flags, tail);
         WSI_CHECK_LAUNCH("wsi_net_tail_kernel");
+        wsi_net_tail_general<CFG><<<1, kObjBlock, 0, s>>>(slot, cfg, (int)t, flags);
+        WSI_CHECK_LAUNCH("wsi_net_tail_general");
       } else if (d->n_net_final > 0) {
         wsi_net_kernel<CFG><<<n_flat_blocks(d, d->n_net_final), kObjBlock, 0, s>>>(slot, cfg, (int)t, flags,
-                                                                                   kNetGatherOnly, 0, d->n_net_final);
+                                                                                   kNetFinal, 0, d->n_net_final);
         WSI_CHECK_LAUNCH("wsi_net_kernel");
       }
     } else {
@@ -418,7 +557,8 @@ int wsi_validate(const WsiModelDesc* d) {
     return fail(WSI_ERR_UNSUPPORTED,
                 "more than 65535 probes / nodes+arcs / end items per template need the network engine%s");
   if (d->engine == 1 && (d->n_net_levels < 0 || !d->net_level_ptr || !d->net_level_ptr_host || !d->net_level_node ||
-                         !d->net_calc_node || !d->net_final_node || !d->net_path_ptr || !d->net_path_sender))
+                         !d->net_calc_node || !d->net_final_node || !d->net_path_ptr || !d->net_path_sender ||
+                         !d->net_path_split || !d->net_path_arc_ptr || !d->net_path_arcs || !d->net_item || !d->net_rpath || !d->net_scratch || !d->net_done))
     return fail(WSI_ERR_BAD_DESC, "network plan missing%s");
   if (d->engine == 1 && d->n_surf > 0) return fail(WSI_ERR_UNSUPPORTED, "the network engine has no Land nodes%s");
   if (d->n_surf > 0 && (!d->surf_order || d->surf_class_ptr[0] != 0 || d->surf_class_ptr[4] != d->n_surf))
@@ -473,5 +613,12 @@ int wsi_run_steps(const WsiModelDesc* d, int64_t t0, int64_t t1, void* stream) {
 }
 
 int64_t wsi_launch_count(void) { return (int64_t)g_launches.load(); }
+
+#ifdef WSI_NET_DEBUG
+int wsi_net_debug(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out, g_net_dbg, sizeof(unsigned long long) * 16);
+}
+#endif
 
 }  // extern "C"

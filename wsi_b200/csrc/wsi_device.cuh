@@ -162,7 +162,7 @@ WSI_HD void tank_push_force(const C& c, double* st, size_t stride, const typenam
       for (int p = 1; p <= C::P; p++)
         if (!bit(c.add, p)) {
           const double num = v.x[p] * v.x[0] + st[(size_t)p * stride] * vol;
-          st[(size_t)p * stride] = num == 0.0 ? num : num / vol;
+          st[(size_t)p * stride] = div_z(num, vol);
         }
     }
     return;

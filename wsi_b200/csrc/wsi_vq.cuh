@@ -113,6 +113,15 @@ WSI_HD VQ<P> vq_zero() {  // empty_vqip core.py:32
 
 WSI_HD bool bit(uint32_t m, int p) { return (m >> p) & 1u; }
 
+// num / den for den > 0, returning a zero numerator as it is ((+-0)/x == +-0).  The fp64 division
+// sequence leaves its inline fast path for a zero numerator, and the compiler turns
+// `num == 0 ? num : num / den` into divide-then-select, so the divide itself is given a harmless
+// numerator instead.
+WSI_HD double div_z(double num, double den) {
+  const double q = (num == 0.0 ? 1.0 : num) / den;
+  return num == 0.0 ? num : q;
+}
+
 // sum_vqip core.py:83-116: volume and additive add, non-additive volume-weighted blend
 // (t2 term first), first operand survives when the total volume is zero.
 template <int P>
@@ -130,7 +139,7 @@ WSI_HD VQ<P> vq_sum(uint32_t add, const VQ<P>& a, const VQ<P>& b) {
       // 0/den is +-0 with the numerator's sign: return it directly -- a zero numerator would
       // send the fp64 division down its slow path
       const double num = b.x[p] * b.x[0] + a.x[p] * a.x[0];
-      t.x[p] = wet ? (num == 0.0 ? num : num / den) : a.x[p];
+      t.x[p] = wet ? div_z(num, den) : a.x[p];
     }
   }
   return t;
@@ -151,7 +160,7 @@ template <int P>
 WSI_HD VQ<P> vq_vchange(uint32_t add, const VQ<P>& a, double v) {
   VQ<P> t = a;
   if (a.x[0] > 0) {
-    const double ratio = v == 0.0 ? v : v / a.x[0];  // (+-0)/x is +-0; skip the slow division path
+    const double ratio = div_z(v, a.x[0]);
     t.x[0] = a.x[0] * ratio;
 #pragma unroll
     for (int p = 1; p <= P; p++)
@@ -162,7 +171,7 @@ WSI_HD VQ<P> vq_vchange(uint32_t add, const VQ<P>& a, double v) {
   return t;
 }
 // the volume lane of v_change_vqip alone
-WSI_HD double vol_vchange(double vol, double v) { return vol > 0 ? vol * (v == 0.0 ? v : v / vol) : v; }
+WSI_HD double vol_vchange(double vol, double v) { return vol > 0 ? vol * div_z(v, vol) : v; }
 
 // a VQIP that carries only a volume: v_change_vqip(empty_vqip(), v)
 template <int P>
