@@ -199,7 +199,7 @@ def check(lib, rc):
 class ModelBuffers:
     """Owns the buffers of one flattened model on a device and its C descriptor."""
 
-    STEP_BLOCK = 64   # replicas per block of wsi_step_kernel (kBlock in wsi_api.cu)
+    STEP_BLOCK = 256  # replicas per block of wsi_step_kernel (kBlock in wsi_api.cu)
     OBJ_BLOCK = 128   # replicas per block of the object-parallel kernels (kObjBlock)
 
     def partial_rows(self):

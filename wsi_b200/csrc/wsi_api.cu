@@ -43,12 +43,15 @@ int fail(int code, const char* fmt, const char* detail = "") {
 #define WSI_SURF_MINB 3
 #endif
 #ifndef WSI_STEP_MINB
-#define WSI_STEP_MINB 12
+#define WSI_STEP_MINB 3
 #endif
 #ifndef WSI_OBJ_MINB
 #define WSI_OBJ_MINB 6
 #endif
-constexpr int kBlock = 64;      // replicas per block of the per-replica schedule kernel
+#ifndef WSI_STEP_BLOCK
+#define WSI_STEP_BLOCK 256
+#endif
+constexpr int kBlock = WSI_STEP_BLOCK;  // replicas per block of the per-replica schedule kernel
 constexpr int kSurfBlock = 128; // surfaces per block of the surface kernels
 constexpr int kObjBlock = 128;  // replicas per block of the object-parallel kernels
 
@@ -95,9 +98,15 @@ __global__ void __launch_bounds__(kBlock, WSI_STEP_MINB)
                     const uint32_t flags) {
   const WsiModelDesc& d = g_wsi_desc[slot];
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= d.R) return;
-  Ctx<CFG> c = make_ctx(nullptr, slot, cfg, r, t, flags);
-  for (int k = sched_begin; k < sched_end; k++) run_op(c, d.sched_op[k], d.sched_node[k]);
+  const bool active = r < d.R;
+  Ctx<CFG> c = make_ctx(nullptr, slot, cfg, active ? r : 0, t, flags);
+  for (int k = sched_begin; k < sched_end; k++) {
+    if (active) run_op(c, d.sched_op[k], d.sched_node[k]);
+    // The kernel stalls on instruction fetch more than on anything else (ncu: no_instruction):
+    // a warp walks ~20k instructions of a ~1 MB kernel.  Re-aligning the block's 8 warps after
+    // every schedule entry keeps them in the same stretch of code.
+    __syncthreads();
+  }
 }
 
 // One thread per (node or arc, replica): WSIObj.mass_balance (core.py:370-429) of every node and

@@ -445,6 +445,8 @@ WSI_HDN typename C::Vq push_distributed(C& c, int node, const typename C::Vq& vq
       not_pushed_ = c.extract(not_pushed_, sent);
     }
     not_pushed = not_pushed_.x[0];
+    iter++;
+    if (!(not_pushed > c.FA)) break;  // the loop ends here: get_connected's result would go unused
     avail = 0.0;
     priority = 0.0;
 #pragma unroll 1
@@ -456,7 +458,6 @@ WSI_HDN typename C::Vq push_distributed(C& c, int node, const typename C::Vq& vq
       priority += a * pref;
       alloc[i] = a * pref;
     }
-    iter++;
   }
   if (iter == kMaxIter) c.flag(node, WSI_FLAG_MAXITER);
   return not_pushed_;

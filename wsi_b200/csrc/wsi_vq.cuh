@@ -114,11 +114,16 @@ WSI_HD VQ<P> vq_zero() {  // empty_vqip core.py:32
 WSI_HD bool bit(uint32_t m, int p) { return (m >> p) & 1u; }
 
 // num / den for den > 0, returning a zero numerator as it is ((+-0)/x == +-0).  The fp64 division
-// sequence leaves its inline fast path for a zero numerator, and the compiler turns
-// `num == 0 ? num : num / den` into divide-then-select, so the divide itself is given a harmless
-// numerator instead.
+// sequence leaves its inline fast path (for a ~150-instruction subroutine) when the quotient is
+// zero, and the compiler turns `num == 0 ? num : num / den` into divide-then-select, so the
+// divide itself is given a harmless numerator.  The empty asm keeps the optimiser from folding
+// that numerator back into `num`.
 WSI_HD double div_z(double num, double den) {
-  const double q = (num == 0.0 ? 1.0 : num) / den;
+  double n = num == 0.0 ? 1.0 : num;
+#if defined(__CUDA_ARCH__)
+  asm("" : "+d"(n));
+#endif
+  const double q = n / den;
   return num == 0.0 ? num : q;
 }
 
