@@ -246,12 +246,14 @@ __device__ unsigned long long g_net_dbg[16];
 constexpr int kNetTail = 512;
 constexpr int kTailGroups = kNetTail / kLanes / 2;
 constexpr int kTailAhead = 12;
+constexpr int kTailRounds = 4;  // (lane kernel, general kernel) pairs launched per step
 template <class CFG>
 __global__ void __launch_bounds__(kNetTail)
-    wsi_net_tail_kernel(const int slot, const CFG cfg, const int t, const uint32_t flags, const int level_begin) {
+    wsi_net_tail_kernel(const int slot, const CFG cfg, const int t, const uint32_t flags, const int level_begin_) {
   __shared__ int s_general;
   __shared__ uint64_t s_bar;
   const WsiModelDesc& d = g_wsi_desc[slot];
+  const int level_begin = level_begin_ >= 0 ? level_begin_ : d.net_scratch[0];  // < 0: resume
   const int R = d.R;
   const int grp = threadIdx.x / kLanes, q = threadIdx.x % kLanes;
   const unsigned gmask = 0xFFFFu << (threadIdx.x & 16);
@@ -320,23 +322,28 @@ __global__ void __launch_bounds__(kNetTail)
     if (s_general) break;  // rivers of level l that took the lane path are marked in net_done; a
                            // general river has stored nothing and is done by wsi_net_tail_general
   }
+  __syncthreads();  // everybody has read net_scratch[0] / s_general
   if (threadIdx.x == 0) {
-    d.net_scratch[0] = l;  // first level wsi_net_tail_general still has to do (L: none)
+    d.net_scratch[0] = l;  // first level still to do (L: none)
     d.net_scratch[1] = s_general;
   }
 }
 
-// General continuation of the tail: from the level the lane kernel stopped at to the end with
-// the scalar code (any push protocol case), then the final deliveries.  In the level it resumes
-// at, rivers the lane kernel completed (net_done == t + 1) are skipped.
+// General continuation of the tail with the scalar code (any push protocol case): `max_levels`
+// levels from the one the lane kernel stopped at (rivers it completed there, net_done == t + 1,
+// are skipped), then -- `finish` -- the final deliveries.  The launcher alternates the two kernels
+// a few times, so that a handful of general rivers per step do not push the whole main stem onto
+// the slow path; the last general launch runs to the end.
 template <class CFG>
 __global__ void __launch_bounds__(kObjBlock)
-    wsi_net_tail_general(const int slot, const CFG cfg, const int t, const uint32_t flags) {
+    wsi_net_tail_general(const int slot, const CFG cfg, const int t, const uint32_t flags, const int max_levels,
+                         const int finish) {
   const WsiModelDesc& d = g_wsi_desc[slot];
   const int R = d.R;
   const int L = d.n_net_levels;
   const int resume = d.net_scratch[0];
-  for (int l = resume; l < L; l++) {
+  const int stop = (L - resume > max_levels) ? resume + max_levels : L;
+  for (int l = resume; l < stop; l++) {
     const int begin = d.net_level_ptr[l], count = d.net_level_ptr[l + 1] - begin;
     for (size_t w = threadIdx.x; w < (size_t)count * R; w += kObjBlock) {
       const int i = begin + (int)(w / (size_t)R), r = (int)(w % (size_t)R);
@@ -346,6 +353,11 @@ __global__ void __launch_bounds__(kObjBlock)
     }
     __syncthreads();
   }
+  if (threadIdx.x == 0) {
+    d.net_scratch[0] = stop;
+    d.net_scratch[1] = 0;
+  }
+  if (!finish) return;
   for (size_t w = threadIdx.x; w < (size_t)d.n_net_final * R; w += kObjBlock) {
     Ctx<CFG> cf = make_ctx(nullptr, slot, cfg, (int)(w % (size_t)R), t, flags);
     net_item(cf, kNetFinal, (int)(w / (size_t)R));
@@ -463,10 +475,14 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
         }
       }
       if (tail <= d->n_net_levels) {
-        wsi_net_tail_kernel<CFG><<<1, kNetTail, 0, s>>>(slot, cfg, (int)t, flags, tail);
-        WSI_CHECK_LAUNCH("wsi_net_tail_kernel");
-        wsi_net_tail_general<CFG><<<1, kObjBlock, 0, s>>>(slot, cfg, (int)t, flags);
-        WSI_CHECK_LAUNCH("wsi_net_tail_general");
+        for (int k = 0; k < kTailRounds; k++) {
+          const bool last = k == kTailRounds - 1;
+          wsi_net_tail_kernel<CFG><<<1, kNetTail, 0, s>>>(slot, cfg, (int)t, flags, k == 0 ? tail : -1);
+          WSI_CHECK_LAUNCH("wsi_net_tail_kernel");
+          wsi_net_tail_general<CFG><<<1, kObjBlock, 0, s>>>(slot, cfg, (int)t, flags, last ? 0x7fffffff : 1,
+                                                           last ? 1 : 0);
+          WSI_CHECK_LAUNCH("wsi_net_tail_general");
+        }
       } else if (d->n_net_final > 0) {
         wsi_net_kernel<CFG><<<n_flat_blocks(d, d->n_net_final), kObjBlock, 0, s>>>(slot, cfg, (int)t, flags,
                                                                                    kNetFinal, 0, d->n_net_final);
