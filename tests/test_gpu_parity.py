@@ -7,7 +7,7 @@ from parity_util import compare_blocks, compare_mb, load_golden
 
 pytestmark = pytest.mark.gpu
 
-GOLDENS = ["quickstart", "quickstart_simple", "fixture3607", "config2", "rivernet", "rivertree"]
+GOLDENS = ["quickstart", "quickstart_simple", "fixture3607", "config2", "rivernet", "rivertree", "config3"]
 
 
 def _run_gpu(fm, ps, record_mb=True, chunks=1, engine="replica"):
@@ -48,7 +48,7 @@ STATE_FIELDS = {
 }
 
 
-@pytest.mark.parametrize("name", ["config2", "rivernet", "rivertree"])
+@pytest.mark.parametrize("name", ["config2", "rivernet", "rivertree", "config3"])
 def test_final_state_matches_oracle(name):
     """Persistent state left in the SoA tensors after the run equals the oracle's (this is what
     scatter_back writes into the Python objects and what a follow-on run starts from)."""
@@ -272,3 +272,23 @@ def test_network_engine_bitwise_equals_replica_engine_on_dendritic_network():
             a, b = a[keep], b[keep]
         assert np.array_equal(a, b), g
     np.testing.assert_allclose(net.mb_sums(), seq.mb_sums(), rtol=1e-13, atol=1e-9)  # other reduction order
+
+
+def test_config3_ensemble_equals_oracle():
+    """SURVEY 8d config 3 (Oxford land + river-side subset, 12 Oxford pollutants with only
+    temperature non-additive -> CfgRuntime<12>, junction chains three deep) as an ensemble."""
+    from oracle import oracle
+    from wsi_b200 import ensemble as E
+    from wsi_b200.backend.probes import ProbeSet
+
+    template, _ = load_golden("config3")
+    fm = E.build_config3(96, template)
+    ps = ProbeSet(fm).add_flows()
+    run = _run_gpu(fm, ps, record_mb=False)
+    ora = oracle.run(fm, probes=ps.probes)
+    scale = np.abs(ora.out_probe).max(axis=(0, 2), keepdims=True) + 1e-300
+    assert np.max(np.abs(run.out_probe() - ora.out_probe) / scale) < 1e-9
+    for r in range(2, 96):  # tiled members repeat the template's
+        assert np.array_equal(run.out_probe()[:, :, r], run.out_probe()[:, :, r % 2])
+    np.testing.assert_allclose(run.mb_sums(), ora.mb_sums, rtol=1e-9, atol=1e-3)
+    assert not run.node_flags().any()

@@ -308,8 +308,14 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
         raise UnsupportedModelError("POLLUTANTS must be the disjoint union of additive and non-additive")
     has_nitrate = "nitrate" in pollutants
     if has_nitrate:
+        # River.biochemical_processes (storage.py:727) and the GrowingSurface nutrient processes read
+        # the whole nutrient set once "nitrate" is modelled; other node classes never look at it
         needed = {"nitrite", "ammonia", "phosphate", "org-phosphorus", "org-nitrogen", "temperature"}
-        if not needed <= set(pollutants):
+        uses_nutrients = any(
+            _cls(n) == "River" or any(_cls(s) == "GrowingSurface" for s in getattr(n, "surfaces", []))
+            for n in model.nodes.values()
+        )
+        if uses_nutrients and not needed <= set(pollutants):
             raise UnsupportedModelError(f"'nitrate' modelled without {sorted(needed - set(pollutants))}")
     dates = list(dates)
     T = len(dates)

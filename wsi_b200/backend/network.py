@@ -13,7 +13,7 @@ import numpy as np
 
 from . import layout as L
 
-MAX_JUNCTIONS = 2  # kJunctionDepth in wsi_device.cuh
+MAX_JUNCTIONS = 3  # kJunctionDepth in wsi_device.cuh
 
 
 def empty_plan(n_nodes):

@@ -22,7 +22,7 @@ namespace wsi {
 constexpr double kUnbounded = 1e15;  // constants.UNBOUNDED_CAPACITY
 constexpr int kMaxIter = 5;          // constants.MAXITER
 constexpr int kMaxCand = 8;          // arcs one push_distributed call can split over
-constexpr int kJunctionDepth = 2;    // nested junction Nodes a push may traverse
+constexpr int kJunctionDepth = 3;    // nested junction Nodes a push may traverse (the Oxford demo chains 3)
 
 // The model descriptor lives in constant memory on the device (direct constant-bank loads with
 // immediate offsets from every function, inlined or not); wsi_api.cu copies it into a slot

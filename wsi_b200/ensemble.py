@@ -207,3 +207,13 @@ def algorithmic_bytes_per_replica_step(fm, n_recorded_planes):
     Q += 2 * len(fm.arc_names)
     O = n_recorded_planes
     return 8 * (2 * S + Q + F + O), dict(S=S, Q=Q, F=F, O=O)
+
+
+def build_config3(R, template):
+    """``R`` members of the Oxford catchment's land + river-side subset.
+
+    ``template`` is a flat model holding a few distinct members (the golden fixture
+    ``tests/golden/config3.npz`` generated from the reference's own Oxford data, which is not
+    shipped here); member ``i`` of the ensemble is template member ``i mod R0``.  Forcing and the
+    four catchment inflow series are shared by all members (broadcast loads)."""
+    return template.take_replicas(np.arange(int(R)) % template.R)
