@@ -98,11 +98,14 @@ typedef struct WsiModelDesc {
   int32_t n_net_levels;
   int32_t n_net_calc;
   int32_t n_net_final;
+  int32_t n_net_bnd;
+  int32_t reserved2;
   const int32_t* net_level_ptr;   /* [n_net_levels+1] CSR over net_level_node (upstream depth ascending) */
   const int32_t* net_level_ptr_host; /* HOST copy of net_level_ptr (the launcher sizes one grid per level) */
   const int32_t* net_level_node;  /* river node slots */
   const int32_t* net_calc_node;   /* [n_net_calc] the rivers (calculate_discharge + their catchments' route) */
   const int32_t* net_final_node;  /* [n_net_final] gather-only nodes (Waste, rivers outside the order) */
+  const int32_t* net_bnd_node;    /* [n_net_bnd] Boundary nodes (partitioned networks) */
   const int32_t* net_path_ptr;    /* [n_nodes+1] incoming paths per receiving node */
   const int32_t* net_path_split;  /* [n_nodes] first path of the node whose sender is a River: catchments
                                      come first (they are routed before any river discharges) */

@@ -292,3 +292,46 @@ def test_config3_ensemble_equals_oracle():
         assert np.array_equal(run.out_probe()[:, :, r], run.out_probe()[:, :, r % 2])
     np.testing.assert_allclose(run.mb_sums(), ora.mb_sums, rtol=1e-9, atol=1e-3)
     assert not run.node_flags().any()
+
+
+@pytest.mark.parametrize("chunk", [None, 3])
+def test_partitioned_network_is_bit_identical_on_gpu(chunk):
+    """upland shards + trunk (boundary series on the cut arcs) == the whole
+    network on one device, bit for bit -- also when every model runs on its own stream in chunks
+    of timesteps (shards ahead of the trunk)."""
+    from wsi_b200 import rivernet
+    from wsi_b200.backend import partition as P
+    from wsi_b200.backend.engine import GpuRunner
+    from wsi_b200.parallel import build_partition_runners, run_partitioned
+
+    N, T = 20000, 10
+    fm = rivernet.build_dendritic(N, T=T, binding_frac=0.01, names=False)
+    outlet = [int(a) for a in np.nonzero(fm.arc_out == 0)[0]]  # slot 0 is the outlet
+
+    def outlet_probes(sub):
+        if "nodes" in (sub.recipe or {}):  # a part: only the trunk still holds the outlet
+            nodes = list(sub.recipe["nodes"])
+            if 0 not in nodes:
+                return []
+            w = nodes.index(0)
+            return [p for a in np.nonzero(sub.arc_out == w)[0] for p in sub.probes_for_arc(int(a))]
+        return [p for a in outlet for p in sub.probes_for_arc(a)]
+
+    def make(sub, probes, T_):
+        return GpuRunner(sub, probes=probes, rec_t0=0, rec_T=T_, engine="network")
+
+    whole = make(fm, outlet_probes(fm), T)
+    whole.run(0, T)
+    whole.synchronize()
+    parts = P.partition_network(fm, 4)
+    runners = run_partitioned(parts, build_partition_runners(parts, make, T, extra_probes=outlet_probes), T,
+                              chunk=chunk)
+    assert np.array_equal(runners["trunk"].out_probe(), whole.out_probe())
+    o = fm.plane("tank", "storage")
+    ref = whole.groups()["tank"][o:o + fm.V]
+    got = np.full_like(ref, np.nan)
+    for sub, r in [(parts["shards"][k], r) for k, r in runners["shards"].items()] + [(parts["trunk"], runners["trunk"])]:
+        nodes = sub.recipe["nodes"]
+        rivers = nodes[fm.node_type[nodes] == 6] - 1  # river slots 1..N hold tanks 0..N-1
+        got[:, rivers] = r.groups()["tank"][o:o + fm.V][:, :len(rivers)]
+    assert np.array_equal(got, ref)

@@ -93,11 +93,14 @@ class WsiModelDesc(C.Structure):
         ("n_net_levels", C.c_int32),
         ("n_net_calc", C.c_int32),
         ("n_net_final", C.c_int32),
+        ("n_net_bnd", C.c_int32),
+        ("reserved2", C.c_int32),
         ("net_level_ptr", _i32p),
         ("net_level_ptr_host", _i32p),
         ("net_level_node", _i32p),
         ("net_calc_node", _i32p),
         ("net_final_node", _i32p),
+        ("net_bnd_node", _i32p),
         ("net_path_ptr", _i32p),
         ("net_path_split", _i32p),
         ("net_path_sender", _i32p),
@@ -134,7 +137,7 @@ class WsiModelDesc(C.Structure):
     ]
 
 
-_NET_ARRAYS = ["net_level_ptr", "net_level_node", "net_calc_node", "net_final_node", "net_path_ptr",
+_NET_ARRAYS = ["net_level_ptr", "net_level_node", "net_calc_node", "net_final_node", "net_bnd_node", "net_path_ptr",
                "net_path_split", "net_path_sender", "net_path_arc_ptr", "net_path_arcs", "net_item", "net_scratch", "net_done", "net_rpath"]
 _INT_ARRAYS = _NET_ARRAYS + [
     "surf_order", "end_kind", "end_obj", "mb_term_slot", "node_type", "node_gidx", "arc_in", "arc_out", "out_ptr", "out_arcs", "in_ptr", "in_arcs",
@@ -342,6 +345,7 @@ class ModelBuffers:
         d.n_net_levels = int(len(net["net_level_ptr"]) - 1) if self.net else 0
         d.n_net_calc = int(net.get("n_net_calc", 0))
         d.n_net_final = int(net.get("n_net_final", 0))
+        d.n_net_bnd = int(net.get("n_net_bnd", 0))
         d.nq = fm.nq
         d.n_fseries = fm.node_forcing.shape[1]
         d.n_months = fm.surf_inputs.shape[0]

@@ -60,6 +60,24 @@ class GpuRunner:
     def synchronize(self):
         self.torch.cuda.synchronize(self.device)
 
+    def set_catch_series(self, ids, values, t0=0):
+        """Overwrite the inflow series ``ids`` for timesteps ``t0 ..`` (catch_inputs[t0:t0+n, ids, :])
+        with ``values[n, len(ids), V]`` on the device (current stream) -- the boundary series of a
+        partitioned network's trunk."""
+        ci = self.buffers.array("catch_inputs")
+        key = tuple(ids)
+        if getattr(self, "_series_key", None) != key:
+            self._series_key = key
+            self._series_idx = self.torch.as_tensor(list(ids), dtype=self.torch.int64, device=ci.device)
+        values = self.torch.as_tensor(values, dtype=ci.dtype).to(ci.device)
+        ci[t0:t0 + values.shape[0]].index_copy_(1, self._series_idx, values)
+
+    def private_stream(self):
+        """A CUDA stream of this runner's own (models stepped concurrently, parallel.run_partitioned)."""
+        if getattr(self, "_stream_own", None) is None:
+            self._stream_own = self.torch.cuda.Stream(self.device)
+        return self._stream_own
+
     # ---- results ----
     def out_probe(self):
         return self.buffers.to_numpy("out_probe")

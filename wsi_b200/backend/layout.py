@@ -37,6 +37,8 @@ NODE_TYPES = [
     "River",
     "Reservoir",
     "Catchment",
+    "Boundary",  # not a reference class: the downstream end of a cut arc of a partitioned network --
+    #              releases a prescribed VQIP series (totals) where the upstream river used to discharge
 ]
 NT = {n: i for i, n in enumerate(NODE_TYPES)}
 
@@ -70,6 +72,7 @@ OPS = [
     "RIVER_DISTRIBUTE",  # River.distribute            storage.py:926
     "STORAGE_DISTRIBUTE",  # Storage.distribute          storage.py:120
     "NOP",  # e.g. Land.apply_irrigation without IrrigationSurface
+    "BOUNDARY_RELEASE",  # partitioned networks: stands where the cut-off river's distribute stood
 ]
 OP = {n: i for i, n in enumerate(OPS)}
 

@@ -20,6 +20,7 @@ def empty_plan(n_nodes):
     z = np.zeros(1, dtype=np.int32)
     return {"net_item": np.zeros(8, np.int32), "net_rpath": np.zeros(4, np.int32),
             "net_level_ptr": np.zeros(1, np.int32), "net_level_node": z, "net_calc_node": z, "net_final_node": z,
+            "net_bnd_node": z,
             "net_path_ptr": np.zeros(n_nodes + 1, np.int32), "net_path_split": np.zeros(max(n_nodes, 1), np.int32),
             "net_path_sender": z,
             "net_path_arc_ptr": np.zeros(1, np.int32), "net_path_arcs": z}
@@ -27,10 +28,11 @@ def empty_plan(n_nodes):
 
 def why_not(fm):
     """Reason the model cannot use the network engine ('' if it can)."""
-    ok_types = {L.NT["Node"], L.NT["Waste"], L.NT["River"], L.NT["Catchment"]}
+    ok_types = {L.NT["Node"], L.NT["Waste"], L.NT["River"], L.NT["Catchment"], L.NT["Boundary"]}
     if not set(int(t) for t in fm.node_type) <= ok_types:
         return "node types other than River / Node / Waste / Catchment"
-    ok_ops = {L.OP["RIVER_CALC"], L.OP["CATCHMENT_ROUTE"], L.OP["RIVER_DISTRIBUTE"], L.OP["NOP"]}
+    SWEEP = (L.OP["RIVER_DISTRIBUTE"], L.OP["BOUNDARY_RELEASE"])
+    ok_ops = {L.OP["RIVER_CALC"], L.OP["CATCHMENT_ROUTE"], L.OP["NOP"]} | set(SWEEP)
     if not set(int(o) for o in fm.sched_op) <= ok_ops:
         return "orchestration entries other than River.calculate_discharge / Catchment.route"
     n_out = np.diff(fm.out_ptr)
@@ -41,6 +43,9 @@ def why_not(fm):
             return f"node {fm.node_names[n]} has more than one out-arc"
         if t == L.NT["Catchment"] and n_out[n] != 1:
             return f"catchment {fm.node_names[n]} has no out-arc"
+        if t == L.NT["Boundary"] and (
+                n_out[n] != 1 or fm.node_type[fm.arc_out[fm.out_arcs[fm.out_ptr[n]]]] not in (L.NT["River"], L.NT["Waste"])):
+            return f"boundary {fm.node_names[n]} does not feed a River / Waste directly"
         if t == L.NT["Node"]:
             if n_out[n] != 1:
                 return f"junction {fm.node_names[n]} has no outlet"
@@ -49,8 +54,8 @@ def why_not(fm):
         return "River.calculate_discharge is not scheduled for every river"
     # order of ops: every calculate_discharge / route entry must precede the discharge sweep
     ops = [int(o) for o in fm.sched_op if int(o) != L.OP["NOP"]]
-    first_dist = next((i for i, o in enumerate(ops) if o == L.OP["RIVER_DISTRIBUTE"]), len(ops))
-    if any(o != L.OP["RIVER_DISTRIBUTE"] for o in ops[first_dist:]):
+    first_dist = next((i for i, o in enumerate(ops) if o in SWEEP), len(ops))
+    if any(o not in SWEEP for o in ops[first_dist:]):
         return "orchestration entries after the river discharge sweep"
     # a catchment route must not precede a calculate_discharge of the river it feeds differently
     # from the default order (all calculate_discharge first)
@@ -68,7 +73,9 @@ def plan_network(fm):
     out_arc = [int(fm.out_arcs[fm.out_ptr[n]]) if fm.out_ptr[n + 1] > fm.out_ptr[n] else -1 for n in range(n_nodes)]
     ops = [(int(o), int(n)) for o, n in zip(fm.sched_op, fm.sched_node)]
     calc = [n for o, n in ops if o == L.OP["RIVER_CALC"]]
-    senders = [n for o, n in ops if o == L.OP["CATCHMENT_ROUTE"]] + [n for o, n in ops if o == L.OP["RIVER_DISTRIBUTE"]]
+    sweep = (L.OP["RIVER_DISTRIBUTE"], L.OP["BOUNDARY_RELEASE"])  # boundary nodes stand in the sweep's order
+    senders = [n for o, n in ops if o == L.OP["CATCHMENT_ROUTE"]] + [n for o, n in ops if o in sweep]
+    boundary = [n for o, n in ops if o == L.OP["BOUNDARY_RELEASE"]]
     distributes = set(n for o, n in ops if o == L.OP["RIVER_DISTRIBUTE"])
     JUNCTION = L.NT["Node"]
     paths = [[] for _ in range(n_nodes)]  # receiver -> [(sender, [arcs])]
@@ -151,7 +158,8 @@ def plan_network(fm):
         begin = len(rpath_rec)
         for k in range(int(path_split[n]), int(path_ptr[n + 1])):
             s_ = path_sender[k]
-            rpath_rec.append((path_arcs[path_arc_ptr[k]], int(river_tank[fm.node_gidx[s_]]),
+            rpath_rec.append((path_arcs[path_arc_ptr[k]],
+                              int(river_tank[fm.node_gidx[s_]]) if fm.node_type[s_] == L.NT["River"] else 0,
                               1 if path_arc_ptr[k + 1] - path_arc_ptr[k] == 1 else 0, s_))
         direct = 1 if n_out[n] == 1 and fm.node_type[fm.arc_out[out_arc[n]]] in (L.NT["River"], L.NT["Waste"]) else 0
         item_rec[i] = (n, int(river_tank[g]), g, out_arc[n] if n_out[n] == 1 else -1, begin, len(rpath_rec), direct,
@@ -160,7 +168,8 @@ def plan_network(fm):
     return {
         "net_item": item_rec.reshape(-1), "net_rpath": np.array(rpath_rec or [(0, 0, 0, 0)], dtype=np.int32).reshape(-1),
         "net_level_ptr": level_ptr, "net_level_node": i32(level_node), "net_calc_node": i32(calc),
-        "net_final_node": i32(final), "net_path_ptr": path_ptr, "net_path_split": path_split,
+        "net_final_node": i32(final), "net_bnd_node": i32(boundary), "n_net_bnd": len(boundary),
+        "net_path_ptr": path_ptr, "net_path_split": path_split,
         "net_path_sender": i32(path_sender),
         "net_path_arc_ptr": np.array(path_arc_ptr, dtype=np.int32), "net_path_arcs": i32(path_arcs),
         "n_net_calc": len(calc), "n_net_final": len(final), "n_levels": n_levels,

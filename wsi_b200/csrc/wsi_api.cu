@@ -22,6 +22,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "wsi_device.cuh"
 
@@ -448,6 +449,11 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
   const bool net = d->engine == 1;
   if ((flags & WSI_RUN_SCHEDULE) && e > b) {
     if (net) {
+      if (d->n_net_bnd > 0) {
+        wsi_net_kernel<CFG><<<n_flat_blocks(d, d->n_net_bnd), kObjBlock, 0, s>>>(slot, cfg, (int)t, flags,
+                                                                                 kNetBoundary, 0, d->n_net_bnd);
+        WSI_CHECK_LAUNCH("wsi_net_kernel");
+      }
       if (d->n_net_calc > 0) {
         wsi_net_kernel<CFG><<<n_flat_blocks(d, d->n_net_calc), kObjBlock, 0, s>>>(slot, cfg, (int)t, flags,
                                                                                   kNetPre, 0, d->n_net_calc);
@@ -535,12 +541,35 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
   return WSI_OK;
 }
 
-// Copy the descriptor into a constant-memory slot, ordered on the launching stream.  Slots are
-// handed out round-robin per call so that models stepped concurrently on different streams do
-// not overwrite each other's descriptor (up to WSI_DESC_SLOTS in flight).
-std::atomic<unsigned> g_next_slot{0};
+// Copy the descriptor into a constant-memory slot, ordered on the launching stream.  A descriptor
+// (identified by its address: one per model) keeps its slot from call to call, so models stepped
+// concurrently on different streams -- the shards of a partitioned network -- never overwrite each
+// other's descriptor; calls for one model are ordered by its stream.  When more than
+// WSI_DESC_SLOTS models are alive the least recently used slot is recycled after a device
+// synchronisation.
+struct SlotEntry {
+  const void* key;
+  unsigned long long last_use;
+};
+SlotEntry g_slots[WSI_DESC_SLOTS];
+unsigned long long g_slot_clock = 0;
+std::mutex g_slot_mutex;
 int upload_desc(const WsiModelDesc* d, cudaStream_t s, int* slot) {
-  *slot = (int)(g_next_slot.fetch_add(1) % WSI_DESC_SLOTS);
+  {
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    int found = -1, lru = 0;
+    for (int i = 0; i < WSI_DESC_SLOTS; i++) {
+      if (g_slots[i].key == (const void*)d) found = i;
+      if (g_slots[i].last_use < g_slots[lru].last_use) lru = i;
+    }
+    if (found < 0) {
+      found = lru;
+      if (g_slots[lru].key != nullptr) cudaDeviceSynchronize();  // its last user may still be running
+      g_slots[lru].key = (const void*)d;
+    }
+    g_slots[found].last_use = ++g_slot_clock;
+    *slot = found;
+  }
   cudaError_t err = cudaMemcpyToSymbolAsync(g_wsi_desc, d, sizeof(WsiModelDesc), (size_t)*slot * sizeof(WsiModelDesc),
                                             cudaMemcpyHostToDevice, s);
   if (err != cudaSuccess) return fail(WSI_ERR_LAUNCH, "descriptor upload failed: %s", cudaGetErrorString(err));
@@ -582,7 +611,7 @@ int wsi_validate(const WsiModelDesc* d) {
     return fail(WSI_ERR_UNSUPPORTED,
                 "more than 65535 probes / nodes+arcs / end items per template need the network engine%s");
   if (d->engine == 1 && (d->n_net_levels < 0 || !d->net_level_ptr || !d->net_level_ptr_host || !d->net_level_node ||
-                         !d->net_calc_node || !d->net_final_node || !d->net_path_ptr || !d->net_path_sender ||
+                         !d->net_calc_node || !d->net_final_node || !d->net_bnd_node || !d->net_path_ptr || !d->net_path_sender ||
                          !d->net_path_split || !d->net_path_arc_ptr || !d->net_path_arcs || !d->net_item || !d->net_rpath || !d->net_scratch || !d->net_done))
     return fail(WSI_ERR_BAD_DESC, "network plan missing%s");
   if (d->engine == 1 && d->n_surf > 0) return fail(WSI_ERR_UNSUPPORTED, "the network engine has no Land nodes%s");

@@ -28,7 +28,7 @@ constexpr int kJunctionDepth = 3;    // nested junction Nodes a push may travers
 // immediate offsets from every function, inlined or not); wsi_api.cu copies it into a slot
 // before launching.  The host build (tests/hostsim) reads it through a pointer.
 #ifndef WSI_DESC_SLOTS
-#define WSI_DESC_SLOTS 8
+#define WSI_DESC_SLOTS 32
 #endif
 #if defined(__CUDACC__)
 __constant__ WsiModelDesc g_wsi_desc[WSI_DESC_SLOTS];

@@ -201,6 +201,7 @@ WSI_HD void net_final(C& c, int node) {
 constexpr int kNetPre = 0;    // every river: calculate_discharge + its catchments
 constexpr int kNetLevel = 1;  // the rivers of one level
 constexpr int kNetFinal = 2;  // receive-only nodes
+constexpr int kNetBoundary = 3;  // boundary nodes of a partitioned network: park the series value
 
 // `i` indexes net_calc_node (pre), net_level_node / net_item (level) or net_final_node (final)
 template <class C>
@@ -213,6 +214,7 @@ WSI_HD void net_item(C& c, int kind, int i) {
       net_level(c, it);
       break;
     }
+    case kNetBoundary: boundary_release(c, d.net_bnd_node[i], false); break;
     default: net_final(c, d.net_final_node[i]); break;
   }
 }
@@ -432,6 +434,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
 template <class C>
 WSI_HD void net_schedule(C& c) {
   const WsiModelDesc& d = c.D();
+  for (int i = 0; i < d.n_net_bnd; i++) net_item(c, kNetBoundary, i);
   for (int i = 0; i < d.n_net_calc; i++) net_item(c, kNetPre, i);
   for (int l = 0; l < d.n_net_levels; l++)
     for (int i = d.net_level_ptr[l]; i < d.net_level_ptr[l + 1]; i++) net_item(c, kNetLevel, i);

@@ -298,6 +298,40 @@ WSI_HD typename C::Vq catch_get_flow(const C& c, int g) {  // catchment.py:60-75
     if (bit(c.add, p)) v.x[p] *= v.x[0];
   return v;
 }
+// Boundary node of a partitioned network (backend/partition.py): the VQIP the cut-off upstream
+// river parked on the cut arc at this timestep, as totals; its series id is the node's group index.
+template <class C>
+WSI_HD typename C::Vq boundary_flow(const C& c, int node) {
+  const WsiModelDesc& d = c.D();
+  const double* row = d.catch_inputs + ((size_t)c.t * d.n_cseries + d.node_gidx[node]) * C::V;
+  typename C::Vq v;
+#pragma unroll
+  for (int p = 0; p <= C::P; p++) v.x[p] = row[p];
+  return v;
+}
+// Put the series value on the node's out-arc exactly as a river whose release is admitted in
+// full books it (wsi_net.cuh, pending_mode 0); `deliver`: also hand it to the receiving river
+// (the sequential engine; the network engine's receivers pick `pending` up themselves).
+template <class C>
+WSI_HD void boundary_release(C& c, int node, bool deliver) {
+  constexpr int V = C::V;
+  const WsiModelDesc& d = c.D();
+  const int a0 = d.out_arcs[d.out_ptr[node]];
+  const Obj A = c.arc_obj(a0);
+  const typename C::Vq v = boundary_flow(c, node);
+  c.stv(A(WSI_ARC_PENDING(V)), A.s, v);
+  *A(WSI_ARC_PENDING_MODE) = 0.0;
+  *A(WSI_ARC_FLOW_IN) = *A(WSI_ARC_FLOW_IN) + v.x[0];
+  c.stv(A(WSI_ARC_VQIP_IN(V)), A.s, c.sum(c.ldv(A(WSI_ARC_VQIP_IN(V)), A.s), v));
+  if (deliver) {
+    const int recv = d.arc_out[a0];
+    if (d.node_type[recv] == WSI_NT_RIVER) {
+      const int tk = (int)*c.river(WSI_RIVER_TANK, d.node_gidx[recv]);
+      tank_push_force(c, c.tank(WSI_TANK_STORAGE(V), tk), c.s_tank(), v);
+    }
+  }
+}
+
 // Catchment.route catchment.py:77-88; returns unrouted_water (needed by the mass balance)
 template <class C>
 WSI_HDN void catchment_route(C& c, int node) {
@@ -360,6 +394,11 @@ WSI_HD void node_mass_balance(C& c, int node, typename C::Vq& in_, typename C::V
     land_mass_balance_terms(c, node, in_, ds, out_);
   } else if (type == WSI_NT_CATCHMENT) {  // formed inside its op
     load_mb_terms(c, node, in_, ds, out_);
+  } else if (type == WSI_NT_BOUNDARY) {  // what it releases is what its arc carries
+    in_ = vq_zero<C::P>();
+    ds_add(c, in_, boundary_flow(c, node));
+    out_ = total_out(c, node);
+    ds = vq_zero<C::P>();
   } else {
     const Vq tin = total_in(c, node);
     in_ = tin;
@@ -490,6 +529,7 @@ WSI_HD void run_op(C& c, int op, int node) {
     case WSI_OP_CATCHMENT_ROUTE: catchment_route(c, node); break;
     case WSI_OP_RIVER_DISTRIBUTE: river_distribute(c, node); break;
     case WSI_OP_STORAGE_DISTRIBUTE: storage_distribute(c, node); break;
+    case WSI_OP_BOUNDARY_RELEASE: boundary_release(c, node, true); break;
     default: break;
   }
 }
