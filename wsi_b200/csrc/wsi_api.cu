@@ -19,6 +19,7 @@
 // coalescing and the byte accounting are described in DESIGN.md.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -61,6 +62,13 @@ constexpr int kObjBlock = 128;  // replicas per block of the object-parallel ker
 // engine (FLAT = true): one flat index over (item, replica) with the replica fastest, so a graph
 // with few replicas and a million nodes still fills the machine (and gridDim.y's 65535 limit
 // does not apply).
+// The timestep a kernel works on: its argument, or -- inside a captured CUDA graph, which is the
+// same for every step -- the device-side step counter (net_scratch[2], advanced by
+// wsi_advance_kernel at the end of each step).
+__device__ __forceinline__ int step_of(const WsiModelDesc& d, int t_arg) {
+  return t_arg >= 0 ? t_arg : d.net_scratch[2];
+}
+
 template <bool FLAT>
 __device__ __forceinline__ bool decode_item(const WsiModelDesc& d, int n_items, int& item, int& r) {
   if constexpr (FLAT) {
@@ -80,8 +88,9 @@ __device__ __forceinline__ bool decode_item(const WsiModelDesc& d, int n_items, 
 // 256 contiguous bytes per plane.
 template <class CFG, int TYPE>
 __global__ void __launch_bounds__(kSurfBlock, WSI_SURF_MINB)
-    wsi_surface_kernel(const int slot, const CFG cfg, const int t, const uint32_t flags) {
+    wsi_surface_kernel(const int slot, const CFG cfg, const int t_arg, const uint32_t flags) {
   const WsiModelDesc& d = g_wsi_desc[slot];
+  const int t = step_of(d, t_arg);
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= d.R) return;
   const int u = d.surf_order[d.surf_class_ptr[TYPE] + blockIdx.y];
@@ -95,9 +104,10 @@ __global__ void __launch_bounds__(kSurfBlock, WSI_SURF_MINB)
 // Routing is sequential inside a replica by construction.
 template <class CFG>
 __global__ void __launch_bounds__(kBlock, WSI_STEP_MINB)
-    wsi_step_kernel(const int slot, const CFG cfg, const int t, const int sched_begin, const int sched_end,
+    wsi_step_kernel(const int slot, const CFG cfg, const int t_arg, const int sched_begin, const int sched_end,
                     const uint32_t flags) {
   const WsiModelDesc& d = g_wsi_desc[slot];
+  const int t = step_of(d, t_arg);
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = r < d.R;
   Ctx<CFG> c = make_ctx(nullptr, slot, cfg, active ? r : 0, t, flags);
@@ -116,11 +126,12 @@ __global__ void __launch_bounds__(kBlock, WSI_STEP_MINB)
 // row of mb_partial per block (summed in block order by wsi_mb_finalize: deterministic).
 template <class CFG, bool FLAT>
 __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
-    wsi_mb_kernel(const int slot, const CFG cfg, const int t, const uint32_t flags, const int n_items) {
+    wsi_mb_kernel(const int slot, const CFG cfg, const int t_arg, const uint32_t flags, const int n_items) {
   constexpr int V = CFG::P + 1;
   constexpr int kWarps = kObjBlock / 32;
   __shared__ double s_w[kWarps][3 * V];
   const WsiModelDesc& d = g_wsi_desc[slot];
+  const int t = step_of(d, t_arg);
   int item, r;
   const bool active = decode_item<FLAT>(d, n_items, item, r);
   const bool want_sums = d.mb_sums != nullptr;
@@ -169,8 +180,11 @@ __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
 // One thread per (probe, replica): Model.run's recording (model.py:1063-1170) is a strided copy.
 template <class CFG, bool FLAT>
 __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
-    wsi_record_kernel(const int slot, const CFG cfg, const int t, const int row) {
+    wsi_record_kernel(const int slot, const CFG cfg, const int t_arg, const int row_arg) {
   const WsiModelDesc& d = g_wsi_desc[slot];
+  const int t = step_of(d, t_arg);
+  const int row = t_arg >= 0 ? row_arg : t - d.rec_t0;
+  if (row < 0 || row >= d.rec_T) return;
   int item, r;
   if (!decode_item<FLAT>(d, d.n_probe, item, r)) return;
   Ctx<CFG> c = make_ctx(nullptr, slot, cfg, r, t, 0u);
@@ -180,8 +194,9 @@ __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
 // One thread per (end_timestep item, replica): arcs reset, DecayTank decay, QueueTank shift.
 template <class CFG, bool FLAT>
 __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
-    wsi_end_kernel(const int slot, const CFG cfg, const int t) {
+    wsi_end_kernel(const int slot, const CFG cfg, const int t_arg) {
   const WsiModelDesc& d = g_wsi_desc[slot];
+  const int t = step_of(d, t_arg);
   int item, r;
   if (!decode_item<FLAT>(d, d.n_end, item, r)) return;
   Ctx<CFG> c = make_ctx(nullptr, slot, cfg, r, t, 0u);
@@ -192,9 +207,10 @@ __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
 // every river, one upstream-depth level of the routing, or the final deliveries (wsi_net.cuh).
 template <class CFG>
 __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
-    wsi_net_kernel(const int slot, const CFG cfg, const int t, const uint32_t flags, const int kind, const int begin,
+    wsi_net_kernel(const int slot, const CFG cfg, const int t_arg, const uint32_t flags, const int kind, const int begin,
                    const int count) {
   const WsiModelDesc& d = g_wsi_desc[slot];
+  const int t = step_of(d, t_arg);
   int item, r;
   if (!decode_item<true>(d, count, item, r)) return;
   Ctx<CFG> c = make_ctx(nullptr, slot, cfg, r, t, flags);
@@ -206,9 +222,10 @@ constexpr int kLaneBlock = 256;
 constexpr size_t kLaneLevelMax = 32768;  // (river, replica) items per level up to which lane groups are used
 template <class CFG>
 __global__ void __launch_bounds__(kLaneBlock)
-    wsi_net_lane_kernel(const int slot, const CFG cfg, const int t, const uint32_t flags, const int begin,
+    wsi_net_lane_kernel(const int slot, const CFG cfg, const int t_arg, const uint32_t flags, const int begin,
                         const int count) {
   const WsiModelDesc& d = g_wsi_desc[slot];
+  const int t = step_of(d, t_arg);
   const size_t gid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
   const int q = threadIdx.x % kLanes;
   const unsigned gmask = 0xFFFFu << (threadIdx.x & 16);
@@ -250,10 +267,11 @@ constexpr int kTailAhead = 12;
 constexpr int kTailRounds = 4;  // (lane kernel, general kernel) pairs launched per step
 template <class CFG>
 __global__ void __launch_bounds__(kNetTail)
-    wsi_net_tail_kernel(const int slot, const CFG cfg, const int t, const uint32_t flags, const int level_begin_) {
+    wsi_net_tail_kernel(const int slot, const CFG cfg, const int t_arg, const uint32_t flags, const int level_begin_) {
   __shared__ int s_general;
   __shared__ uint64_t s_bar;
   const WsiModelDesc& d = g_wsi_desc[slot];
+  const int t = step_of(d, t_arg);
   const int level_begin = level_begin_ >= 0 ? level_begin_ : d.net_scratch[0];  // < 0: resume
   const int R = d.R;
   const int grp = threadIdx.x / kLanes, q = threadIdx.x % kLanes;
@@ -337,9 +355,10 @@ __global__ void __launch_bounds__(kNetTail)
 // the slow path; the last general launch runs to the end.
 template <class CFG>
 __global__ void __launch_bounds__(kObjBlock)
-    wsi_net_tail_general(const int slot, const CFG cfg, const int t, const uint32_t flags, const int max_levels,
+    wsi_net_tail_general(const int slot, const CFG cfg, const int t_arg, const uint32_t flags, const int max_levels,
                          const int finish) {
   const WsiModelDesc& d = g_wsi_desc[slot];
+  const int t = step_of(d, t_arg);
   const int R = d.R;
   const int L = d.n_net_levels;
   const int resume = d.net_scratch[0];
@@ -365,12 +384,19 @@ __global__ void __launch_bounds__(kObjBlock)
   }
 }
 
+// Device-side step counter of the graph mode.
+__global__ void wsi_set_step_kernel(const int slot, const int t) { g_wsi_desc[slot].net_scratch[2] = t; }
+__global__ void wsi_advance_kernel(const int slot) { g_wsi_desc[slot].net_scratch[2] += 1; }
+
 // Sum the mass-balance partial rows of one timestep: block j reduces column j of
 // partial[n_rows][n] with a fixed strided pass + fixed shared-memory tree (deterministic).
 constexpr int kFinBlock = 256;
 __global__ void __launch_bounds__(kFinBlock)
-    wsi_mb_finalize(const double* __restrict__ partial, double* __restrict__ sums, int n_rows, int n) {
+    wsi_mb_finalize(const int slot, const int t_arg, int n_rows, int n) {
   __shared__ double s[kFinBlock];
+  const WsiModelDesc& d = g_wsi_desc[slot];
+  const double* __restrict__ partial = d.mb_partial;
+  double* __restrict__ sums = d.mb_sums + (size_t)step_of(d, t_arg) * n;
   const int j = blockIdx.x;
   double acc = 0.0;
   for (int b = threadIdx.x; b < n_rows; b += kFinBlock) acc += partial[(size_t)b * n + j];
@@ -513,13 +539,13 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
     }
     if (want_sums) {
       const int n = 3 * V;
-      wsi_mb_finalize<<<n, kFinBlock, 0, s>>>(d->mb_partial, d->mb_sums + (size_t)t * n, rows, n);
+      wsi_mb_finalize<<<n, kFinBlock, 0, s>>>(slot, (int)t, rows, n);
       WSI_CHECK_LAUNCH("wsi_mb_finalize");
     }
   }
   if (flags & WSI_RUN_RECORD) {
     const int row = (int)t - d->rec_t0;
-    if (d->n_probe > 0 && row >= 0 && row < d->rec_T) {
+    if (d->n_probe > 0 && (t < 0 || (row >= 0 && row < d->rec_T))) {
       if (net) {
         wsi_record_kernel<CFG, true><<<n_flat_blocks(d, d->n_probe), kObjBlock, 0, s>>>(slot, cfg, (int)t, row);
       } else {
@@ -583,6 +609,84 @@ int dispatch(const WsiModelDesc* d, int slot, int64_t t, int b, int e, uint32_t 
   if (d->P == 2) return launch(d, slot, runtime_cfg<2>(d), t, b, e, flags, s);
 #endif
   return fail(WSI_ERR_UNSUPPORTED, "no kernel instantiated for this number of pollutants%s");
+}
+
+// ---- CUDA graph of one timestep ------------------------------------------------------------------
+// A timestep of the network engine is hundreds of small dependent launches (one per level); issued
+// one by one they cost more host and launch latency than they compute.  wsi_run_steps therefore
+// captures ONE timestep -- launched with t = -1, i.e. "read the step from net_scratch[2]" -- into a
+// graph, instantiates it once per model and replays it for every step; wsi_advance_kernel at the
+// end of the graph moves the device-side step counter.  The graph is re-captured when anything in
+// the descriptor (or the level sizes) changes.
+bool graphs_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("WSI_B200_NO_GRAPH");
+    return !(e && e[0] && e[0] != '0');
+  }();
+  return on;
+}
+struct GraphEntry {
+  const void* key = nullptr;
+  unsigned long long hash = 0;
+  cudaGraphExec_t exec = nullptr;
+  long long launches = 0;
+};
+GraphEntry g_graphs[WSI_DESC_SLOTS];
+cudaStream_t g_capture_stream = nullptr;
+std::mutex g_graph_mutex;
+
+unsigned long long fnv(unsigned long long h, const void* p, size_t n) {
+  const unsigned char* b = (const unsigned char*)p;
+  for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+  return h;
+}
+
+int run_steps_graph(const WsiModelDesc* d, int slot, int64_t t0, int64_t t1, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(g_graph_mutex);
+  // everything a captured launch bakes in (grid sizes, kernel arguments); pointers and the record
+  // window are read from the descriptor in constant memory when the graph runs
+  const int32_t baked[] = {slot, d->P, (int32_t)d->additive_mask, d->idx[0], d->idx[1], d->idx[2], d->idx[3], d->idx[4],
+                           d->idx[5], d->idx[6], d->idx[7], d->R, d->n_nodes, d->n_arcs, d->n_surf, d->surf_class_ptr[0],
+                           d->surf_class_ptr[1], d->surf_class_ptr[2], d->surf_class_ptr[3], d->surf_class_ptr[4],
+                           d->n_probe, d->n_end, d->n_sched, d->engine, d->n_net_levels, d->n_net_calc, d->n_net_final,
+                           d->n_net_bnd, d->mb_sums ? 1 : 0};
+  unsigned long long h = fnv(1469598103934665603ull, baked, sizeof baked);
+  if (d->engine == 1) h = fnv(h, d->net_level_ptr_host, sizeof(int32_t) * (size_t)(d->n_net_levels + 1));
+  GraphEntry& g = g_graphs[slot];
+  if (g.key != (const void*)d || g.hash != h || !g.exec) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g = GraphEntry();
+    if (!g_capture_stream && cudaStreamCreateWithFlags(&g_capture_stream, cudaStreamNonBlocking) != cudaSuccess)
+      return fail(WSI_ERR_LAUNCH, "cannot create the capture stream%s");
+    const long long before = g_launches.load();
+    cudaError_t err = cudaStreamBeginCapture(g_capture_stream, cudaStreamCaptureModeThreadLocal);
+    if (err != cudaSuccess) return fail(WSI_ERR_LAUNCH, "graph capture failed: %s", cudaGetErrorString(err));
+    int rc = dispatch(d, slot, -1, 0, d->n_sched, WSI_RUN_ALL, g_capture_stream);
+    wsi_advance_kernel<<<1, 1, 0, g_capture_stream>>>(slot);
+    g_launches++;
+    cudaGraph_t graph = nullptr;
+    err = cudaStreamEndCapture(g_capture_stream, &graph);
+    g.launches = g_launches.load() - before;
+    g_launches -= g.launches;  // captured, not executed
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (err != cudaSuccess || !graph) return fail(WSI_ERR_LAUNCH, "graph capture failed: %s", cudaGetErrorString(err));
+    err = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (err != cudaSuccess) return fail(WSI_ERR_LAUNCH, "graph instantiation failed: %s", cudaGetErrorString(err));
+    g.key = (const void*)d;
+    g.hash = h;
+  }
+  wsi_set_step_kernel<<<1, 1, 0, stream>>>(slot, (int)t0);
+  WSI_CHECK_LAUNCH("wsi_set_step_kernel");
+  for (int64_t t = t0; t < t1; t++) {
+    cudaError_t err = cudaGraphLaunch(g.exec, stream);
+    if (err != cudaSuccess) return fail(WSI_ERR_LAUNCH, "graph launch failed: %s", cudaGetErrorString(err));
+    g_launches += g.launches;
+  }
+  return WSI_OK;
 }
 
 }  // namespace
@@ -659,6 +763,7 @@ int wsi_run_steps(const WsiModelDesc* d, int64_t t0, int64_t t1, void* stream) {
   int slot;
   rc = upload_desc(d, (cudaStream_t)stream, &slot);
   if (rc) return rc;
+  if (t1 - t0 >= 2 && d->net_scratch && graphs_enabled()) return run_steps_graph(d, slot, t0, t1, (cudaStream_t)stream);
   for (int64_t t = t0; t < t1; t++) {
     rc = dispatch(d, slot, t, 0, d->n_sched, WSI_RUN_ALL, (cudaStream_t)stream);
     if (rc) return rc;
