@@ -4,9 +4,12 @@
 Workload at N GPUs: the config-2 ensemble of SURVEY 8d / BASELINE.json configs[1] --
 ``--members`` (default 100 000) independent {Land(Impervious, Pervious, Growing) -> Sewer,
 Groundwater, junction Node -> Waste} catchments per GPU, default 12 pollutants, daily
-synthetic forcing from 2000-01-01.  A *step* is one model timestep of every member: one launch
-of the fused kernel (plus the tiny mass-balance finalize).  Members shard across ranks with no
-data-path collective (weak scaling); only the timing reduction uses NCCL.
+synthetic forcing from 2000-01-01.  A *step* is one model timestep of every member: the surface
+kernels, the schedule kernel, mass balance, recording and end_timestep, replayed
+as one CUDA graph per step.  Members shard across ranks with no data-path collective (weak
+scaling); only the timing reduction uses NCCL.  The other workloads have their own tools:
+tools/config3_profile.py (Oxford ensemble), tools/net_profile.py and
+tools/net_partition_profile.py (dendritic network, one GPU / partitioned over several).
 
     python bench.py --gpus 1 --steps 365 --warmup 5
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
@@ -229,6 +232,7 @@ def main():
         return a0.elapsed_time(a1) / reps
 
     n_sched = len(fm.sched_op)
+    runner.buffers.set_rec_window(W)  # timestep W must fall inside the record window for RUN_RECORD to launch
     phases = {
         "wsi_surface_kernel (x3 classes)": _phase_ms(_c.RUN_SURFACES | _c.RUN_MASS_BALANCE) - _phase_ms(_c.RUN_MASS_BALANCE),
         "wsi_step_kernel": _phase_ms(_c.RUN_SCHEDULE | _c.RUN_MASS_BALANCE, 0, n_sched) - _phase_ms(_c.RUN_MASS_BALANCE),
