@@ -5,7 +5,7 @@ depend on what lies below it: it can run any number of timesteps ahead.  The par
 network at direct, unbounded River -> River arcs:
 
 * every cut-off subtree becomes part of an upland **shard** (a self-contained flat model: the
-  cut arc now ends in a local Waste node, which -- like the river it replaces -- accepts
+  cut arc now ends in a Waste node of its own, which -- like the river it replaces -- accepts
   everything, so the arc's own capacity logic is unchanged);
 * the remaining downstream part is the **trunk**: the cut arcs stay in place (same slot order, so
   every receiver sums its in-arcs in the original order) but start at a ``Boundary`` node that
@@ -173,7 +173,8 @@ def _submodel(fm, sel, recv, out_arc, cut_roots_here, boundary_of, trunk):
     else:
         arcs = np.nonzero(sel[fm.arc_in])[0]
         cut = out_arc[cut_roots_here]
-    n_extra = len(cut) if trunk else 1
+    n_extra = len(cut)  # trunk: one Boundary node per cut arc; shard: one Waste sink per cut arc (a single
+    #                     sink would have one thread walk all of its in-arcs in the final delivery pass)
     n_nodes = len(keep) + n_extra
     node_type = np.empty(n_nodes, dtype=np.int64)
     node_type[:len(keep)] = fm.node_type[keep]
@@ -185,7 +186,7 @@ def _submodel(fm, sel, recv, out_arc, cut_roots_here, boundary_of, trunk):
     if trunk:
         a_in[cut_pos] = len(keep) + np.arange(len(cut))
     else:
-        a_out[cut_pos] = len(keep)
+        a_out[cut_pos] = len(keep) + np.arange(len(cut))
     # groups: keep object order
     g_old = fm.node_gidx
     rivers = keep[fm.node_type[keep] == river]
@@ -222,7 +223,7 @@ def _submodel(fm, sel, recv, out_arc, cut_roots_here, boundary_of, trunk):
             sched.append((o, int(new_id[n])))
         elif trunk and o == L.OP["RIVER_DISTRIBUTE"] and n in bnode:
             sched.append((L.OP["BOUNDARY_RELEASE"], bnode[n]))
-    extra = ["boundary:%s" % fm.arc_names[int(a)] for a in cut] if trunk else ["cut_sink"]
+    extra = [("boundary:%s" if trunk else "cut_sink:%s") % fm.arc_names[int(a)] for a in cut]
     names = ([fm.node_names[int(i)] for i in keep] + extra, [fm.arc_names[int(a)] for a in arcs])
     sub = _extract(fm, keep, arcs, a_in, a_out, node_type, gidx, groups, sched, names, catch_inputs)
     sub.recipe = {"nodes": keep, "arcs": arcs, "cut_arcs_local": cut_pos, "cut_arcs": np.asarray(cut)}
