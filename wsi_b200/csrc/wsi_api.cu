@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(kBlock, WSI_STEP_MINB)
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = r < d.R;
   Ctx<CFG> c = make_ctx(nullptr, slot, cfg, active ? r : 0, t, flags);
+  c.block_sync = (blockIdx.x + 1) * blockDim.x <= (unsigned)d.R;  // full block: all threads walk the schedule
   for (int k = sched_begin; k < sched_end; k++) {
     if (active) run_op(c, d.sched_op[k], d.sched_node[k]);
     // The kernel stalls on instruction fetch more than on anything else (ncu: no_instruction):

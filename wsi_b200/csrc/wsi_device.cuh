@@ -34,6 +34,17 @@ constexpr int kJunctionDepth = 3;    // nested junction Nodes a push may travers
 __constant__ WsiModelDesc g_wsi_desc[WSI_DESC_SLOTS];
 #endif
 
+// Re-align the warps of a block inside a long schedule entry (instruction-cache locality, see
+// wsi_step_kernel); only at points every thread of the block reaches.
+#if defined(__CUDA_ARCH__)
+#define WSI_BLOCK_ALIGN(c)                \
+  do {                                    \
+    if ((c).block_sync) __syncthreads();  \
+  } while (0)
+#else
+#define WSI_BLOCK_ALIGN(c)
+#endif
+
 // One object's column in a group tensor: plane k lives at p[k * s]
 struct Obj {
   double* p;
@@ -56,6 +67,7 @@ struct Ctx {
   uint32_t add;
   double FA;
   uint32_t run_flags;
+  bool block_sync;  // device: every thread of the block walks the same schedule -> WSI_BLOCK_ALIGN may sync
   int viol;        // mass-balance violations found for this replica this step
   double* mb_acc;  // [3*V] per-thread system-total accumulators (stride mb_stride) or null
   int mb_stride;

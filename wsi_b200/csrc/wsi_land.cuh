@@ -741,8 +741,10 @@ WSI_HDN void land_phase(C& c, int node) {
   for (int i = s0; i < s1; i++) {
     const int u = d.land_surf[i];
     if ((int)*c.surf(WSI_SURF_TYPE, u) == WSI_ST_IMPERVIOUSSURFACE) land_impervious_push(c, node, u);
+    WSI_BLOCK_ALIGN(c);  // (surface types are the template's: the branch is uniform in the block)
   }
 
+  WSI_BLOCK_ALIGN(c);
   // percolation tank -> Groundwater (land.py:207-215)
   {
     double* tp = c.land(WSI_LAND_PERCOLATION(V), L);
@@ -757,6 +759,7 @@ WSI_HDN void land_phase(C& c, int node) {
     const Vq reply = push_distributed<kJunctionDepth>(c, node, percolation, WSI_FILTER_GROUNDWATER);
     if (reply.x[0] > c.FA) tank_push_force(c, tp, sl, reply);
   }
+  WSI_BLOCK_ALIGN(c);
   // surface + subsurface runoff -> River / junction Node (land.py:217-244)
   {
     double* t_surf = c.land(WSI_LAND_SURFACE_RUNOFF(V), L);
@@ -774,6 +777,7 @@ WSI_HDN void land_phase(C& c, int node) {
       v_surf = total_runoff.x[0];
       c.stv(t_surf, sl, T);
     }
+    WSI_BLOCK_ALIGN(c);
     {
       Vq T = c.ldv(t_sub, sl);
       if (want_mb) c.stv_add(parked + (size_t)V * c.R, c.R, T);
@@ -786,6 +790,7 @@ WSI_HDN void land_phase(C& c, int node) {
       c.stv(t_sub, sl, T);
       total_runoff = c.sum(total_runoff, subsurface_runoff);
     }
+    WSI_BLOCK_ALIGN(c);
     if (total_runoff.x[0] > 0) {
       const double v_total = total_runoff.x[0];
       const Vq reply = push_distributed<kJunctionDepth>(c, node, total_runoff, WSI_FILTER_RIVER_NODE);

@@ -577,6 +577,7 @@ WSI_HD Ctx<CFG> make_ctx(const WsiModelDesc* host_d, int slot, const CFG& cfg, i
   c.FA = c.D().float_accuracy;
   c.run_flags = flags;
   c.viol = 0;
+  c.block_sync = false;
   c.mb_acc = nullptr;
   c.mb_stride = 1;
   return c;
