@@ -657,7 +657,7 @@ WSI_HD void surface_phase(C& c, int u) {
 // ResidenceTank.pull_outflow tanks.py:387-400 on a register-resident tank
 template <class C>
 WSI_HD typename C::Vq residence_pull(const C& c, typename C::Vq& s, double residence_time) {
-  const double outflow = vol_vchange(s.x[0], s.x[0] / residence_time);
+  const double outflow = vol_vchange(s.x[0], div_z(s.x[0], residence_time));  // residence_time > 0
   return vq_pull(c, s, outflow);
 }
 
