@@ -294,11 +294,11 @@ def test_config3_ensemble_equals_oracle():
     assert not run.node_flags().any()
 
 
-@pytest.mark.parametrize("chunk", [None, 3])
-def test_partitioned_network_is_bit_identical_on_gpu(chunk):
-    """upland shards + trunk (boundary series on the cut arcs) == the whole
-    network on one device, bit for bit -- also when every model runs on its own stream in chunks
-    of timesteps (shards ahead of the trunk)."""
+@pytest.mark.parametrize("segments,chunk", [(1, None), (1, 3), (3, 2)])
+def test_partitioned_network_is_bit_identical_on_gpu(segments, chunk):
+    """upland shards + trunk segments (boundary series on the cut arcs) == the
+    whole network on one device, bit for bit -- also when every part runs on its own stream in
+    chunks of timesteps (shards ahead of the trunk, the trunk's segments as a pipeline)."""
     from wsi_b200 import rivernet
     from wsi_b200.backend import partition as P
     from wsi_b200.backend.engine import GpuRunner
@@ -306,16 +306,16 @@ def test_partitioned_network_is_bit_identical_on_gpu(chunk):
 
     N, T = 20000, 10
     fm = rivernet.build_dendritic(N, T=T, binding_frac=0.01, names=False)
-    outlet = [int(a) for a in np.nonzero(fm.arc_out == 0)[0]]  # slot 0 is the outlet
 
     def outlet_probes(sub):
-        if "nodes" in (sub.recipe or {}):  # a part: only the trunk still holds the outlet
-            nodes = list(sub.recipe["nodes"])
-            if 0 not in nodes:
-                return []
+        nodes = list(sub.recipe["nodes"]) if "nodes" in (sub.recipe or {}) else None
+        if nodes is None:
+            w = 0  # slot 0 is the outlet
+        elif 0 in nodes:
             w = nodes.index(0)
-            return [p for a in np.nonzero(sub.arc_out == w)[0] for p in sub.probes_for_arc(int(a))]
-        return [p for a in outlet for p in sub.probes_for_arc(a)]
+        else:
+            return []
+        return [p for a in np.nonzero(sub.arc_out == w)[0] for p in sub.probes_for_arc(int(a))]
 
     def make(sub, probes, T_):
         return GpuRunner(sub, probes=probes, rec_t0=0, rec_T=T_, engine="network")
@@ -323,15 +323,48 @@ def test_partitioned_network_is_bit_identical_on_gpu(chunk):
     whole = make(fm, outlet_probes(fm), T)
     whole.run(0, T)
     whole.synchronize()
-    parts = P.partition_network(fm, 4)
+    parts = P.partition_network(fm, 4, stem_segments=segments)
+    subs = parts["parts"]
     runners = run_partitioned(parts, build_partition_runners(parts, make, T, extra_probes=outlet_probes), T,
                               chunk=chunk)
-    assert np.array_equal(runners["trunk"].out_probe(), whole.out_probe())
+    assert np.array_equal(runners[len(subs) - 1].out_probe(), whole.out_probe())
     o = fm.plane("tank", "storage")
     ref = whole.groups()["tank"][o:o + fm.V]
     got = np.full_like(ref, np.nan)
-    for sub, r in [(parts["shards"][k], r) for k, r in runners["shards"].items()] + [(parts["trunk"], runners["trunk"])]:
-        nodes = sub.recipe["nodes"]
+    for k, r in runners.items():
+        nodes = subs[k].recipe["nodes"]
         rivers = nodes[fm.node_type[nodes] == 6] - 1  # river slots 1..N hold tanks 0..N-1
         got[:, rivers] = r.groups()["tank"][o:o + fm.V][:, :len(rivers)]
     assert np.array_equal(got, ref)
+
+
+def test_cluster_tail_kernel_bitwise(monkeypatch):
+    """WSI_B200_CLUSTER=1: the mid-width levels run in one thread-block cluster launch (hardware
+    cluster barrier between levels) -- same bits as the default path.  Runs in a subprocess because
+    the switch is read once per process."""
+    import subprocess
+    import sys
+
+    code = (
+        "import numpy as np, sys; sys.path.insert(0, 'tests');"
+        "from wsi_b200 import rivernet; from wsi_b200.backend.engine import GpuRunner;"
+        "from wsi_b200.backend.probes import ProbeSet;"
+        "fm = rivernet.build_dendritic(30000, T=6, binding_frac=0.01, names=False);"
+        "ps = ProbeSet(fm).add_flows(range(0, 30000, 15));"
+        "r = GpuRunner(fm, probes=ps.probes, rec_t0=0, rec_T=6, engine='network'); r.run(0, 6); r.synchronize();"
+        "np.save(sys.argv[1], r.out_probe()); print(r.launch_count())"
+    )
+    import os
+    import tempfile
+
+    outs, launches = [], []
+    for flag in ("0", "1"):
+        path = os.path.join(tempfile.mkdtemp(), "o.npy")
+        env = dict(os.environ, WSI_B200_CLUSTER=flag)
+        res = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True,
+                             cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        outs.append(np.load(path))
+        launches.append(int(res.stdout.strip().splitlines()[-1]))
+    assert np.array_equal(outs[0], outs[1])
+    assert launches[1] < launches[0]  # fewer, fatter launches

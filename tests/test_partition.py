@@ -63,8 +63,8 @@ def outlet_probes(fm):
     return [p for a in arcs for p in fm.probes_for_arc(a)]
 
 
-@pytest.mark.parametrize("n_parts", [1, 3])
-def test_partitioned_run_is_bit_identical(n_parts):
+@pytest.mark.parametrize("n_parts,segments,chunk", [(1, 1, None), (3, 1, None), (3, 3, 7), (2, 4, None)])
+def test_partitioned_run_is_bit_identical(n_parts, segments, chunk):
     from wsi_b200.parallel import build_partition_runners, run_partitioned
 
     N, T = 900, 20
@@ -74,20 +74,23 @@ def test_partitioned_run_is_bit_identical(n_parts):
     ref = np.zeros((fm.V, len(fm.node_type)))
     river_tanks(fm, whole, ref, np.arange(len(fm.node_type)))
 
-    parts = P.partition_network(fm, n_parts)
-    sizes = [len(s.recipe["nodes"]) for s in parts["shards"]]
-    assert sum(sizes) + len(parts["trunk"].recipe["nodes"]) == len(fm.node_type)
-    assert min(sizes) > 0.5 * max(sizes) and len(parts["trunk"].recipe["nodes"]) < 0.4 * len(fm.node_type)
-    out = run_partitioned(parts, build_partition_runners(parts, HostsimRunner, T, extra_probes=outlet_probes), T)
+    parts = P.partition_network(fm, n_parts, stem_segments=segments)
+    subs = parts["parts"]
+    assert len(subs) == n_parts + segments
+    sizes = [len(s.recipe["nodes"]) for s in subs]
+    assert sum(sizes) == len(fm.node_type)
+    assert min(sizes[:n_parts]) > 0.5 * max(sizes[:n_parts]) and sum(sizes[n_parts:]) < 0.4 * len(fm.node_type)
+    out = run_partitioned(parts, build_partition_runners(parts, HostsimRunner, T, extra_probes=outlet_probes), T,
+                          chunk=chunk)
     got = np.zeros_like(ref)
-    for k, r in out["shards"].items():
-        river_tanks(parts["shards"][k], r, got, parts["shards"][k].recipe["nodes"])
-    river_tanks(parts["trunk"], out["trunk"], got, parts["trunk"].recipe["nodes"])
+    for k, r in out.items():
+        river_tanks(subs[k], r, got, subs[k].recipe["nodes"])
     assert np.array_equal(got, ref)
-    assert np.array_equal(out["trunk"].out_probe(), whole.out_probe())  # outlet VQIP, every step
+    last = out[len(subs) - 1]  # the segment holding the outlet
+    n_cut = len(subs[-1].recipe["cut_out"]) * fm.V
+    assert np.array_equal(last.out_probe()[:, n_cut:], whole.out_probe())  # outlet VQIP, every step
     assert not whole.buf.array("mb_count").any()
-    assert not out["trunk"].buf.array("mb_count").any()
-    assert all(not r.buf.array("mb_count").any() for r in out["shards"].values())
+    assert all(not r.buf.array("mb_count").any() for r in out.values())
 
 
 def _worker(rank, world, port, q):
@@ -99,11 +102,11 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     N, T = 400, 8
     fm = rivernet.build_dendritic(N, T=T)
-    parts = P.partition_network(fm, 4)
+    parts = P.partition_network(fm, 4, stem_segments=2)
     runners = build_partition_runners(parts, HostsimRunner, T, rank=rank, world=world, extra_probes=outlet_probes)
-    out = run_partitioned(parts, runners, T, rank=rank, world=world)
+    out = run_partitioned(parts, runners, T, rank=rank, world=world, chunk=4)
     if rank == 0:
-        q.put(np.asarray(out["trunk"].out_probe()).copy())
+        q.put(np.asarray(out[len(parts["parts"]) - 1].out_probe()).copy())
     dist.barrier()
     dist.destroy_process_group()
 

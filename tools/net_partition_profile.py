@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """one dendritic network partitioned by subtree over the GPUs of a box.
 
-    python tools/net_partition_profile.py [N] [T] [parts]              # one GPU, shards one after another
+    python tools/net_partition_profile.py [N] [T] [parts] [segments]   # one GPU, every part on its own stream
     python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 --master-port P \
         tools/net_partition_profile.py [N] [T] [parts]                  # shard k on rank k % G, trunk on rank 0
 
@@ -27,6 +27,7 @@ T = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 rank = int(os.environ.get("RANK", 0))
 world = int(os.environ.get("WORLD_SIZE", 1))
 n_parts = int(sys.argv[3]) if len(sys.argv) > 3 else max(world, 4)
+n_seg = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
 if world > 1:
     dist.init_process_group("nccl")
@@ -66,14 +67,13 @@ if rank == 0:
     del whole
     torch.cuda.empty_cache()
 t0 = time.time()
-parts = P.partition_network(fm, n_parts)
+parts = P.partition_network(fm, n_parts, stem_segments=n_seg)
 res["partition_s"] = round(time.time() - t0, 1)
-res["shard_nodes"] = [len(s.recipe["nodes"]) for s in parts["shards"]]
-res["trunk_nodes"] = len(parts["trunk"].recipe["nodes"])
-res["cut_arcs"] = len(parts["boundary_of"])
+res["segments"] = n_seg
+res["part_nodes"] = [len(s.recipe["nodes"]) for s in parts["parts"]]
+res["cut_arcs"] = len(parts["links"])
 runners = build_partition_runners(parts, make, T, rank=rank, world=world)
-res["levels"] = {"shards": [r.buffers.net["n_levels"] for r in runners["shards"].values()],
-                 "trunk": runners["trunk"].buffers.net["n_levels"] if runners["trunk"] else None}
+res["levels"] = {k: r.buffers.net["n_levels"] for k, r in runners.items()}
 CHUNK = int(os.environ.get("WSI_CHUNK", 8))
 dt = timed(lambda: run_partitioned(parts, runners, T, rank=rank, world=world, chunk=CHUNK or None))
 res["chunk"] = CHUNK

@@ -10,7 +10,10 @@ network at direct, unbounded River -> River arcs:
 * the remaining downstream part is the **trunk**: the cut arcs stay in place (same slot order, so
   every receiver sums its in-arcs in the original order) but start at a ``Boundary`` node that
   releases, at the cut-off river's position in the discharge sweep, the VQIP series that river
-  parked on the arc (``pending``: its release, recorded every step by the upland shard).
+  parked on the arc (``pending``: its release, recorded every step by the upland shard);
+* the trunk's main stem -- a chain of thousands of dependent levels, the floor of a timestep --
+  can itself be cut into **segments**: segment j works on timestep t while segment j + 1, just
+  upstream, is already on a later chunk of timesteps (a pipeline along the river).
 
 Because the receiver adds exactly the VQIP the original river released, in the original order,
 the partitioned run is bit-identical to the unpartitioned one (tests/test_partition.py).
@@ -156,37 +159,35 @@ def _cols(fm, group, objs):
     return np.ascontiguousarray(arr.reshape(arr.shape[0], n, fm.R)[:, objs, :].reshape(arr.shape[0], -1))
 
 
-def _submodel(fm, sel, recv, out_arc, cut_roots_here, boundary_of, trunk):
-    """Flat model of the nodes ``sel`` (bool mask).
+def _submodel(fm, sel):
+    """Flat model of the nodes ``sel`` (bool mask) of ``fm``.
 
-    Upland shard (``trunk`` False): the out-arcs of ``cut_roots_here`` are retargeted to a new
-    Waste node.  Trunk: arcs whose sender was cut off keep their slot and start at a new Boundary
-    node; ``boundary_of[arc] = series id``."""
+    Arcs leaving the part (sender inside, receiver outside) are retargeted to a new Waste sink each;
+    arcs entering it keep their slot (receivers still sum their in-arcs in the original order) and
+    start at a new Boundary node each, which stands in the discharge sweep where the cut-off river
+    stood and releases series ``n_series + k`` of the part's ``catch_inputs`` (filled by the driver)."""
     river, catch = L.NT["River"], L.NT["Catchment"]
     n_all = len(fm.node_type)
     keep = np.nonzero(sel)[0]
+    if np.any(~np.isin(fm.node_type[keep], [river, catch, L.NT["Waste"], L.NT["Node"]])):
+        raise ValueError("partitioning supports River / Catchment / junction / Waste nodes")
     new_id = np.full(n_all, -1, dtype=np.int64)
     new_id[keep] = np.arange(len(keep))
-    if trunk:
-        arcs = np.nonzero(sel[fm.arc_out])[0]  # every arc that ends in the trunk, original order
-        cut = arcs[~sel[fm.arc_in[arcs]]]
-    else:
-        arcs = np.nonzero(sel[fm.arc_in])[0]
-        cut = out_arc[cut_roots_here]
-    n_extra = len(cut)  # trunk: one Boundary node per cut arc; shard: one Waste sink per cut arc (a single
-    #                     sink would have one thread walk all of its in-arcs in the final delivery pass)
-    n_nodes = len(keep) + n_extra
+    inside_in, inside_out = sel[fm.arc_in], sel[fm.arc_out]
+    arcs = np.nonzero(inside_in | inside_out)[0]  # original order
+    cut_out = np.nonzero(inside_in[arcs] & ~inside_out[arcs])[0]  # positions in `arcs`
+    cut_in = np.nonzero(~inside_in[arcs] & inside_out[arcs])[0]
+    n_nodes = len(keep) + len(cut_out) + len(cut_in)
     node_type = np.empty(n_nodes, dtype=np.int64)
     node_type[:len(keep)] = fm.node_type[keep]
-    node_type[len(keep):] = L.NT["Boundary"] if trunk else L.NT["Waste"]
+    sink0 = len(keep)
+    bnd0 = sink0 + len(cut_out)
+    node_type[sink0:bnd0] = L.NT["Waste"]
+    node_type[bnd0:] = L.NT["Boundary"]
     a_in = new_id[fm.arc_in[arcs]]
     a_out = new_id[fm.arc_out[arcs]]
-    pos = {int(a): i for i, a in enumerate(arcs)}
-    cut_pos = np.array([pos[int(a)] for a in cut], dtype=np.int64)
-    if trunk:
-        a_in[cut_pos] = len(keep) + np.arange(len(cut))
-    else:
-        a_out[cut_pos] = len(keep) + np.arange(len(cut))
+    a_out[cut_out] = sink0 + np.arange(len(cut_out))
+    a_in[cut_in] = bnd0 + np.arange(len(cut_in))
     # groups: keep object order
     g_old = fm.node_gidx
     rivers = keep[fm.node_type[keep] == river]
@@ -204,62 +205,106 @@ def _submodel(fm, sel, recv, out_arc, cut_roots_here, boundary_of, trunk):
     gidx = np.zeros(n_nodes, dtype=np.int64)
     gidx[new_id[rivers]] = np.arange(len(rivers))
     gidx[new_id[catchs]] = np.arange(len(catchs))
-    if np.any(~np.isin(fm.node_type[keep], [river, catch, L.NT["Waste"], L.NT["Node"]])):
-        raise ValueError("partitioning supports River / Catchment / junction / Waste nodes")
-    catch_inputs = None
-    if trunk:
-        n_series = fm.catch_inputs.shape[1]
-        gidx[len(keep):] = n_series + np.arange(len(cut))  # series filled in by the driver
-        catch_inputs = np.concatenate([fm.catch_inputs, np.zeros((fm.T, len(cut), fm.V))], axis=1)
-        for k, a in enumerate(cut):
-            boundary_of[int(a)] = n_series + k
-    # schedule: ops of kept nodes in order; in the trunk a cut-off river's distribute becomes the
-    # boundary node's release at the same position
-    bnode = {int(fm.arc_in[a]): len(keep) + k for k, a in enumerate(cut)} if trunk else {}
+    n_series = fm.catch_inputs.shape[1]
+    gidx[bnd0:] = n_series + np.arange(len(cut_in))
+    catch_inputs = fm.catch_inputs
+    if len(cut_in):
+        catch_inputs = np.concatenate([fm.catch_inputs, np.zeros((fm.T, len(cut_in), fm.V))], axis=1)
+    # schedule: ops of kept nodes in order; a cut-off river's distribute becomes the release of the
+    # boundary node that took its place on the arc, at the same position of the sweep
+    bnode = {int(fm.arc_in[arcs[q]]): bnd0 + k for k, q in enumerate(cut_in)}
     sched = []
     for o, n in zip(fm.sched_op, fm.sched_node):
         o, n = int(o), int(n)
         if sel[n]:
             sched.append((o, int(new_id[n])))
-        elif trunk and o == L.OP["RIVER_DISTRIBUTE"] and n in bnode:
+        elif o == L.OP["RIVER_DISTRIBUTE"] and n in bnode:
             sched.append((L.OP["BOUNDARY_RELEASE"], bnode[n]))
-    extra = [("boundary:%s" if trunk else "cut_sink:%s") % fm.arc_names[int(a)] for a in cut]
+    extra = ["cut_sink:%s" % fm.arc_names[int(arcs[q])] for q in cut_out]
+    extra += ["boundary:%s" % fm.arc_names[int(arcs[q])] for q in cut_in]
     names = ([fm.node_names[int(i)] for i in keep] + extra, [fm.arc_names[int(a)] for a in arcs])
     sub = _extract(fm, keep, arcs, a_in, a_out, node_type, gidx, groups, sched, names, catch_inputs)
-    sub.recipe = {"nodes": keep, "arcs": arcs, "cut_arcs_local": cut_pos, "cut_arcs": np.asarray(cut)}
+    sub.recipe = {"nodes": keep, "arcs": arcs,
+                  "cut_out_local": cut_out, "cut_out": arcs[cut_out],  # arcs whose release this part records
+                  "cut_in": arcs[cut_in], "cut_in_series": n_series + np.arange(len(cut_in))}
     return sub
 
 
-def partition_network(fm, n_parts, granularity=4):
-    """Split ``fm`` into ``n_parts`` upland shards and a trunk.
+def _stem_segments(fm, part, recv, out_arc, k):
+    """Split the trunk (``part == -1``) into ``k`` segments along its main stem: returns seg[node]
+    (0 = the segment holding the outlet, k - 1 the most upstream) for trunk nodes, -1 elsewhere."""
+    n = len(recv)
+    river = L.NT["River"]
+    trunk = part == -1
+    seg = np.full(n, -1, dtype=np.int64)
+    order = _downstream_first(recv)
+    if k <= 1:
+        seg[trunk] = 0
+        return seg
+    height = np.zeros(n, dtype=np.int64)  # longest chain of trunk rivers upstream of (and including) v
+    best = np.full(n, -1, dtype=np.int64)
+    for v in order[::-1]:
+        if not trunk[v] or fm.node_type[v] != river:
+            continue
+        height[v] += 1
+        r = recv[v]
+        if r >= 0 and trunk[r] and fm.node_type[r] == river and height[v] > height[r]:
+            height[r] = height[v]
+            best[r] = v
+    roots = [v for v in order if trunk[v] and fm.node_type[v] == river and (recv[v] < 0 or fm.node_type[recv[v]] != river)]
+    if not roots:
+        seg[trunk] = 0
+        return seg
+    v = max(roots, key=lambda x: height[x])
+    stem = []
+    while v >= 0:
+        stem.append(int(v))
+        v = best[v]
+    cap = fm.view("arc", "capacity")[0].min(axis=1)
+    cuts = {}
+    for j in range(1, k):
+        i = round(j * len(stem) / k)
+        while i < len(stem) and not (cap[out_arc[stem[i]]] >= UNBOUNDED):
+            i += 1  # the cut arc must be unbounded
+        if 0 < i < len(stem) and stem[i] not in cuts:
+            cuts[stem[i]] = len(cuts) + 1
+    for v in order:
+        if not trunk[v]:
+            continue
+        if int(v) in cuts:
+            seg[v] = cuts[int(v)]
+        else:
+            r = recv[v]
+            seg[v] = seg[r] if (r >= 0 and trunk[r]) else 0
+    return seg
 
-    Returns ``{"shards": [FlatModel], "trunk": FlatModel, "boundary_of": {cut arc: series id in
-    trunk.catch_inputs}, "part": per-node part id}``.  Every shard's ``recipe`` maps its nodes /
-    arcs back to ``fm`` and lists its cut arcs (whose ``pending`` planes are the boundary series).
-    """
+
+def partition_network(fm, n_parts, granularity=4, stem_segments=1):
+    """Split ``fm`` into ``n_parts`` upland shards and a trunk of ``stem_segments`` segments.
+
+    Returns ``{"parts": [FlatModel], "n_upland": n_parts, "links": [(producer, consumer, k, series)],
+    "part": per-node part index}``.  Parts are ordered so that a part only feeds parts after it:
+    upland shards first, then the trunk's segments from the most upstream to the one holding the
+    outlet.  ``links``: cut-out arc ``k`` of ``producer`` (its ``recipe["cut_out"][k]``, recorded by
+    ``cut_probes``) is boundary series ``series`` of ``consumer``."""
     if fm.n_obj["land"] or fm.n_obj["sewer"]:
         raise ValueError("partitioning supports River / Catchment / junction / Waste nodes")
     part, roots, recv, out_arc = assign_parts(fm, n_parts, granularity)
-    boundary_of = {}
-    trunk = _submodel(fm, part == -1, recv, out_arc, None, boundary_of, trunk=True)
-    shards = []
-    for k in range(n_parts):
-        roots_k = roots[part[roots] == k]
-        shards.append(_submodel(fm, part == k, recv, out_arc, roots_k, None, trunk=False))
-    return {"shards": shards, "trunk": trunk, "boundary_of": boundary_of, "part": part}
+    seg = _stem_segments(fm, part, recv, out_arc, stem_segments)
+    n_seg = int(seg.max()) + 1
+    index = np.where(part >= 0, part, n_parts + (n_seg - 1 - seg))  # upstream segments first
+    parts = [_submodel(fm, index == k) for k in range(n_parts + n_seg)]
+    series_of = [{int(a): int(sid) for a, sid in zip(p.recipe["cut_in"], p.recipe["cut_in_series"])} for p in parts]
+    links = []
+    for pi, p in enumerate(parts):
+        for k, a in enumerate(p.recipe["cut_out"]):
+            q = int(index[fm.arc_out[a]])
+            assert q > pi, "a part may only feed parts after it"
+            links.append((pi, q, k, series_of[q][int(a)]))
+    return {"parts": parts, "n_upland": n_parts, "links": links, "part": index}
 
 
-def cut_probes(shard):
-    """Probes recording the release parked on every cut arc of an upland shard (V planes each)."""
-    o = shard.plane("arc", "pending")
-    return [(L.GROUP_ID["arc"], o + p, int(a)) for a in shard.recipe["cut_arcs_local"] for p in range(shard.V)]
-
-
-def fill_boundary_series(trunk, boundary_of, shard, out_probe, t0=0):
-    """Write a shard's recorded cut-arc releases ``out_probe[T', n_cut*V, R]`` (R == 1) into the
-    trunk's boundary series for timesteps ``t0 .. t0 + T' - 1``."""
-    V = trunk.V
-    cuts = shard.recipe["cut_arcs"]
-    rec = np.asarray(out_probe)[:, :, 0].reshape(out_probe.shape[0], len(cuts), V)
-    for k, a in enumerate(cuts):
-        trunk.catch_inputs[t0:t0 + rec.shape[0], boundary_of[int(a)], :] = rec[:, k, :]
+def cut_probes(sub):
+    """Probes recording the release parked on every cut-out arc of a part (V planes each)."""
+    o = sub.plane("arc", "pending")
+    return [(L.GROUP_ID["arc"], o + p, int(a)) for a in sub.recipe["cut_out_local"] for p in range(sub.V)]

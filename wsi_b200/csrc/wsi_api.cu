@@ -265,28 +265,49 @@ __device__ unsigned long long g_net_dbg[16];
 constexpr int kNetTail = 512;
 constexpr int kTailGroups = kNetTail / kLanes / 2;
 constexpr int kTailAhead = 12;
-constexpr int kTailRounds = 4;  // (lane kernel, general kernel) pairs launched per step
-template <class CFG>
+constexpr int kTailRounds = 3;     // (lane kernel, general kernel) pairs launched per step and range
+constexpr int kClusterCtas = 8;    // CTAs of the cluster variant (portable maximum)
+constexpr int kClusterMax = kClusterCtas * kTailGroups;  // rivers per level it takes in one round
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
+
+// CLUSTER = false: one block, levels [begin, end) separated by a split-phase mbarrier (the main
+// stem: <= kTailGroups rivers per level).  CLUSTER = true: a thread-block cluster of kClusterCtas
+// such blocks, levels separated by the hardware cluster barrier (release / acquire at cluster
+// scope) -- the mid-width levels (<= kClusterMax rivers), which would otherwise be one launch
+// each.  Wider levels than a round takes are handled in further rounds (correct, just slower).
+template <class CFG, bool CLUSTER>
 __global__ void __launch_bounds__(kNetTail)
-    wsi_net_tail_kernel(const int slot, const CFG cfg, const int t_arg, const uint32_t flags, const int level_begin_) {
+    wsi_net_tail_kernel(const int slot, const CFG cfg, const int t_arg, const uint32_t flags, const int level_begin_,
+                        const int level_end_) {
   __shared__ int s_general;
   __shared__ uint64_t s_bar;
   const WsiModelDesc& d = g_wsi_desc[slot];
   const int t = step_of(d, t_arg);
-  const int level_begin = level_begin_ >= 0 ? level_begin_ : d.net_scratch[0];  // < 0: resume
+  const int L = level_end_ >= 0 ? level_end_ : d.n_net_levels;
+  const int level_begin = level_begin_ >= 0 ? level_begin_ : min(d.net_scratch[0], L);  // < 0: resume
   const int R = d.R;
+  const int cta = CLUSTER ? (int)cluster_ctarank() : 0;
+  const int stride = (CLUSTER ? kClusterCtas : 1) * kTailGroups;  // (river, replica) items per round
   const int grp = threadIdx.x / kLanes, q = threadIdx.x % kLanes;
   const unsigned gmask = 0xFFFFu << (threadIdx.x & 16);
   const bool prefetcher = grp >= kTailGroups;
-  const int wg = prefetcher ? grp - kTailGroups : grp;
-  const int r = wg % R, k = wg / R;  // a tail level has at most kTailGroups / R rivers
+  const int w0 = cta * kTailGroups + (prefetcher ? grp - kTailGroups : grp);  // this group's item in round 0
+  const int r = w0 % R, k = w0 / R;
   using Cx = Ctx<CFG>;
   Cx c = make_ctx(nullptr, slot, cfg, r, t, flags);
-  const int L = d.n_net_levels;
   const int32_t* __restrict__ lptr = d.net_level_ptr;
+  volatile int* g_general = d.net_scratch + 3;  // the cluster's "a river needs the general code" flag
   if (threadIdx.x == 0) {
     s_general = 0;
-    mbar_init(&s_bar, kNetTail);
+    if (!CLUSTER) mbar_init(&s_bar, kNetTail);
+    if (CLUSTER && cta == 0) *g_general = 0;
   }
   // consumer groups: unconditional look-ahead loads -- absent items read item 0, a select
   // would have to wait for the loaded values
@@ -306,13 +327,19 @@ __global__ void __launch_bounds__(kNetTail)
       if (k < lptr[l + 1] - lptr[l]) net_prefetch_item(c, lptr[l] + k, q);
   }
   __syncthreads();
+  if (CLUSTER) {  // the flag reset above is visible to the whole cluster before anybody may set it
+    cluster_arrive();
+    cluster_wait();
+  }
 #ifdef WSI_NET_DEBUG
   long long dbg_t = clock64();
 #endif
   int l = level_begin;
-  for (; l < L; l++) {
+  bool stop = false;
+  for (; l < L && !stop; l++) {
     if (prefetcher) {
-      mbar_arrive(&s_bar);  // produces nothing anybody waits for: only paced by the wait below
+      if (CLUSTER) cluster_arrive();
+      else mbar_arrive(&s_bar);  // produces nothing anybody waits for: only paced by the wait below
       const int lp = l + kTailAhead;
       if (lp < L && k < lptr[lp + 1] - lptr[lp]) net_prefetch_item(c, lptr[lp] + k, q);
     } else {
@@ -327,25 +354,47 @@ __global__ void __launch_bounds__(kNetTail)
       rec2 = net_rec_load(c, i2);
       NET_DBG(0);
       LaneOut<Cx> out;
-      const bool general = has && net_lanes_release(c, cur, q, gmask, out);
-      if (general && q == 0) s_general = 1;
+      const bool general0 = has && net_lanes_release(c, cur, q, gmask, out);
+      bool general = general0;
+      // further rounds of a level wider than one round takes (rare; no look-ahead for them)
+      const int count = (lptr[l + 1] - lptr[l]) * R;
+      for (int w = w0 + stride; w < count; w += stride) {
+        Cx cw = make_ctx(nullptr, slot, cfg, w % R, t, flags);
+        const int iw = lptr[l] + w / R;
+        LaneItem<Cx> itw = lane_item_load(cw, net_rec_load(cw, iw), q);
+        LaneOut<Cx> ow;
+        if (net_lanes_release(cw, itw, q, gmask, ow)) {
+          general = true;
+        } else {
+          net_lanes_settle(cw, itw, q, gmask, ow);
+          if (q == 0) d.net_done[(size_t)iw * R + (w % R)] = t + 1;
+        }
+      }
+      if (general && q == 0) {
+        if (CLUSTER) *g_general = 1;
+        else s_general = 1;
+      }
       NET_DBG(1);
-      mbar_arrive(&s_bar);  // level l + 1 may start as soon as everybody's releases are parked
-      if (has && !general) {
+      if (CLUSTER) cluster_arrive();
+      else mbar_arrive(&s_bar);  // level l + 1 may start as soon as everybody's releases are parked
+      if (has && !general0) {
         net_lanes_settle(c, cur, q, gmask, out);
         if (q == 0) d.net_done[(size_t)i0 * R + r] = t + 1;
       }
       NET_DBG(3);
     }
-    mbar_wait(&s_bar, (uint32_t)(l - level_begin) & 1u);
+    if (CLUSTER) cluster_wait();
+    else mbar_wait(&s_bar, (uint32_t)(l - level_begin) & 1u);
     NET_DBG(2);
-    if (s_general) break;  // rivers of level l that took the lane path are marked in net_done; a
-                           // general river has stored nothing and is done by wsi_net_tail_general
+    stop = CLUSTER ? (*g_general != 0) : (s_general != 0);
+    // rivers of level l that took the lane path are marked in net_done; a general river has
+    // stored nothing and is done by wsi_net_tail_general
   }
+  if (stop) l--;  // level l (now l - 1 after the loop's increment) is the one to resume at
   __syncthreads();  // everybody has read net_scratch[0] / s_general
-  if (threadIdx.x == 0) {
-    d.net_scratch[0] = l;  // first level still to do (L: none)
-    d.net_scratch[1] = s_general;
+  if (threadIdx.x == 0 && cta == 0) {
+    d.net_scratch[0] = l;  // first level still to do (the range's end: none)
+    d.net_scratch[1] = stop ? 1 : 0;
   }
 }
 
@@ -362,6 +411,7 @@ __global__ void __launch_bounds__(kObjBlock)
   const int t = step_of(d, t_arg);
   const int R = d.R;
   const int L = d.n_net_levels;
+  if (!finish && d.net_scratch[1] == 0) return;  // the lane kernel got through its range
   const int resume = d.net_scratch[0];
   const int stop = (L - resume > max_levels) ? resume + max_levels : L;
   for (int l = resume; l < stop; l++) {
@@ -449,6 +499,16 @@ int n_partial_rows(const WsiModelDesc* d) {
     if (err_ != cudaSuccess) return fail(WSI_ERR_LAUNCH, name " launch failed: %s", cudaGetErrorString(err_)); \
   } while (0)
 
+// The cluster variant of the tail kernel (mid-width levels in one launch of a thread-block cluster)
+// is correct and tested but measured no faster than one lane-kernel launch per level inside the
+// CUDA graph (N = 1e6: 10.2 vs 10.0 ms per step), so it is opt-in: WSI_B200_CLUSTER=1.
+bool cluster_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("WSI_B200_CLUSTER");
+    return e && e[0] && e[0] != '0';
+  }();
+  return on;
+}
 template <class CFG, int TYPE>
 int launch_surfaces(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, uint32_t flags, cudaStream_t s) {
   const int n = d->surf_class_ptr[TYPE + 1] - d->surf_class_ptr[TYPE];
@@ -486,14 +546,20 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
                                                                                   kNetPre, 0, d->n_net_calc);
         WSI_CHECK_LAUNCH("wsi_net_kernel");
       }
-      // wide levels: one launch each, a thread per (river, replica) while the level is wide enough
-      // to fill the machine that way, lane groups below that; from the first level after which
-      // every level fits one block's lane groups, a single block walks the rest
+      // wide levels: one launch each -- a thread per (river, replica) while the level fills the
+      // machine that way, lane groups below that; then ONE cluster launch for the levels that fit a
+      // round of the cluster kernel, then ONE block for the levels that fit a round of the tail
+      // kernel (the main stem).  Each of the two alternates with the general kernel a few times.
       const int32_t* lp = d->net_level_ptr_host;
-      int tail = d->n_net_levels;
-      while (tail > 0 && (size_t)(lp[tail] - lp[tail - 1]) * (size_t)d->R <= (size_t)kTailGroups) tail--;
-      if ((size_t)d->n_net_final * (size_t)d->R > (size_t)kObjBlock * 8) tail = d->n_net_levels + 1;  // wide final list
-      for (int l = 0; l < tail && l < d->n_net_levels; l++) {
+      const int L = d->n_net_levels;
+      auto first_after_which_all_fit = [&](size_t limit) {
+        int l = L;
+        while (l > 0 && (size_t)(lp[l] - lp[l - 1]) * (size_t)d->R <= limit) l--;
+        return l;
+      };
+      const int tail = first_after_which_all_fit((size_t)kTailGroups);
+      const int mid = cluster_enabled() ? first_after_which_all_fit((size_t)kClusterMax) : tail;
+      for (int l = 0; l < mid; l++) {
         const int count = lp[l + 1] - lp[l];
         if (count <= 0) continue;
         const size_t work = (size_t)count * (size_t)d->R;
@@ -507,19 +573,36 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
           WSI_CHECK_LAUNCH("wsi_net_lane_kernel");
         }
       }
-      if (tail <= d->n_net_levels) {
+      bool started = false;  // has a lane kernel of this step already written net_scratch[0]?
+      if (mid < tail) {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(kClusterCtas);
+        lc.blockDim = dim3(kNetTail);
+        lc.stream = s;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = kClusterCtas;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        lc.attrs = &attr;
+        lc.numAttrs = 1;
         for (int k = 0; k < kTailRounds; k++) {
-          const bool last = k == kTailRounds - 1;
-          wsi_net_tail_kernel<CFG><<<1, kNetTail, 0, s>>>(slot, cfg, (int)t, flags, k == 0 ? tail : -1);
-          WSI_CHECK_LAUNCH("wsi_net_tail_kernel");
-          wsi_net_tail_general<CFG><<<1, kObjBlock, 0, s>>>(slot, cfg, (int)t, flags, last ? 0x7fffffff : 1,
-                                                           last ? 1 : 0);
+          cudaError_t err = cudaLaunchKernelEx(&lc, wsi_net_tail_kernel<CFG, true>, slot, cfg, (int)t, flags,
+                                               started ? -1 : mid, tail);
+          if (err != cudaSuccess) return fail(WSI_ERR_LAUNCH, "cluster launch failed: %s", cudaGetErrorString(err));
+          WSI_CHECK_LAUNCH("wsi_net_tail_kernel<cluster>");
+          started = true;
+          wsi_net_tail_general<CFG><<<1, kObjBlock, 0, s>>>(slot, cfg, (int)t, flags, 1, 0);
           WSI_CHECK_LAUNCH("wsi_net_tail_general");
         }
-      } else if (d->n_net_final > 0) {
-        wsi_net_kernel<CFG><<<n_flat_blocks(d, d->n_net_final), kObjBlock, 0, s>>>(slot, cfg, (int)t, flags,
-                                                                                   kNetFinal, 0, d->n_net_final);
-        WSI_CHECK_LAUNCH("wsi_net_kernel");
+      }
+      for (int k = 0; k < kTailRounds; k++) {
+        const bool last = k == kTailRounds - 1;
+        wsi_net_tail_kernel<CFG, false><<<1, kNetTail, 0, s>>>(slot, cfg, (int)t, flags, started ? -1 : tail, -1);
+        WSI_CHECK_LAUNCH("wsi_net_tail_kernel");
+        started = true;
+        wsi_net_tail_general<CFG><<<1, kObjBlock, 0, s>>>(slot, cfg, (int)t, flags, last ? 0x7fffffff : 1, last ? 1 : 0);
+        WSI_CHECK_LAUNCH("wsi_net_tail_general");
       }
     } else {
       wsi_step_kernel<CFG><<<n_blocks(d), kBlock, 0, s>>>(slot, cfg, (int)t, b, e, flags);
@@ -577,8 +660,10 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
 struct SlotEntry {
   const void* key;
   unsigned long long last_use;
+  bool uploaded;
 };
 SlotEntry g_slots[WSI_DESC_SLOTS];
+WsiModelDesc g_slot_image[WSI_DESC_SLOTS];  // what each slot holds (uploads of an unchanged descriptor are skipped)
 unsigned long long g_slot_clock = 0;
 std::mutex g_slot_mutex;
 int upload_desc(const WsiModelDesc* d, cudaStream_t s, int* slot) {
@@ -593,9 +678,18 @@ int upload_desc(const WsiModelDesc* d, cudaStream_t s, int* slot) {
       found = lru;
       if (g_slots[lru].key != nullptr) cudaDeviceSynchronize();  // its last user may still be running
       g_slots[lru].key = (const void*)d;
+      g_slots[lru].uploaded = false;
     }
     g_slots[found].last_use = ++g_slot_clock;
     *slot = found;
+    // A copy to a __constant__ symbol is ordered against every kernel that may read the bank; a
+    // model that is stepped in chunks re-sends the same bytes each time, so compare first.  (The
+    // image is only trusted for the stream-ordered case: same model, same stream, which is the rule.)
+    if (g_slots[found].key == (const void*)d && memcmp(&g_slot_image[found], d, sizeof(WsiModelDesc)) == 0 &&
+        g_slots[found].uploaded)
+      return WSI_OK;
+    memcpy(&g_slot_image[found], d, sizeof(WsiModelDesc));
+    g_slots[found].uploaded = true;
   }
   cudaError_t err = cudaMemcpyToSymbolAsync(g_wsi_desc, d, sizeof(WsiModelDesc), (size_t)*slot * sizeof(WsiModelDesc),
                                             cudaMemcpyHostToDevice, s);

@@ -64,98 +64,102 @@ def gather_outputs(local, group=None):
 
 
 # ---- one network partitioned across ranks ---------------------------------
+def _owner(parts, k, world):
+    """Upland shard k runs on rank k % world; the trunk's segments stay together on rank 0."""
+    return k % world if k < parts["n_upland"] else 0
+
+
 def build_partition_runners(parts, make_runner, T, rank=0, world=1, extra_probes=None):
-    """Runners of the upland shards owned by ``rank`` (shard ``k`` belongs to rank ``k % world``)
-    and, on rank 0, of the trunk.  ``make_runner(fm, probes, T)`` returns an object with
+    """Runners of the parts owned by ``rank``.  ``make_runner(fm, probes, T)`` returns an object with
     ``run(t0, t1)``, ``synchronize()``, ``out_probe()`` (``[T, n_probe, R]`` array or tensor) and
-    ``set_catch_series(ids, values[T, len(ids), V])`` -- ``GpuRunner`` with the network engine in
+    ``set_catch_series(ids, values[n, len(ids), V], t0)`` -- ``GpuRunner`` with the network engine in
     production, a host build of the kernel logic in the CPU tests.  ``extra_probes(fm)`` may add
     probes after the cut-arc ones."""
     from .backend import partition as P
 
     runners = {}
-    for k, shard in enumerate(parts["shards"]):
-        if k % world == rank:
-            probes = P.cut_probes(shard) + (list(extra_probes(shard)) if extra_probes else [])
-            runners[k] = make_runner(shard, probes, T)
-    trunk = None
-    if rank == 0:
-        trunk = make_runner(parts["trunk"], list(extra_probes(parts["trunk"])) if extra_probes else [], T)
-    return {"shards": runners, "trunk": trunk}
+    for k, sub in enumerate(parts["parts"]):
+        if _owner(parts, k, world) == rank:
+            probes = P.cut_probes(sub) + (list(extra_probes(sub)) if extra_probes else [])
+            runners[k] = make_runner(sub, probes, T)
+    return runners
 
 
 def run_partitioned(parts, runners, T, rank=0, world=1, group=None, chunk=None):
     """Run a partitioned network (``backend.partition.partition_network``) for timesteps 0..T-1.
 
-    Upland shards need nothing from each other or from the trunk, so they run ahead.  The
-    releases they parked on their cut arcs every step (``[T, n_cut * V]`` doubles per shard) are
-    broadcast from their owners -- the scheme's only communication -- written into the trunk's
-    boundary series, and rank 0 runs the trunk.
+    Parts only feed parts after them (upland shards -> trunk segments, upstream segment ->
+    downstream segment), through the releases their rivers parked on the cut arcs every step
+    (``V`` doubles per cut arc and step).  Upland shards on other ranks broadcast theirs -- the
+    scheme's only communication.
 
-    With GPU runners and ``chunk`` set, every model runs on its own CUDA stream in chunks of
-    ``chunk`` timesteps: the shards of a rank overlap each other (each of them alone is bound by
-    the latency of its chain of levels, not by the machine), and the trunk works on chunk ``c``
-    while the shards are already on chunk ``c + 1``."""
+    With GPU runners and ``chunk`` set, every part runs on its own CUDA stream in chunks of
+    ``chunk`` timesteps, each chunk waiting only for the same chunk of its producers: the parts
+    of a rank overlap (each alone is bound by the latency of its chain of levels, not by the
+    machine) and the trunk's segments form a pipeline along the river."""
     import torch
     import torch.distributed as dist
 
-    shards, boundary_of = parts["shards"], parts["boundary_of"]
+    subs, links, n_up = parts["parts"], parts["links"], parts["n_upland"]
     distributed = world > 1 and dist.is_available() and dist.is_initialized()
-    mine = runners["shards"]
-    trunk = runners["trunk"] if rank == 0 else None
-    n_cut = {k: len(s.recipe["cut_arcs"]) for k, s in enumerate(shards)}
-    ids = {k: [boundary_of[int(a)] for a in s.recipe["cut_arcs"]] for k, s in enumerate(shards)}
-    gpu = chunk is not None and all(hasattr(r, "private_stream") for r in list(mine.values()) + ([trunk] if trunk else []))
-    if not gpu:
-        for r in mine.values():
-            r.run(0, T)
-        series = {}
-        for k, r in mine.items():
-            r.synchronize()
-            series[k] = torch.as_tensor(r.out_probe())[:T, :n_cut[k] * shards[k].V, :]
-        if distributed:
-            nccl = dist.get_backend(group) == "nccl"
-            device = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
-            for k, shard in enumerate(shards):
-                buf = (series[k].to(device).contiguous() if k in series
-                       else torch.zeros((T, n_cut[k] * shard.V, shard.R), dtype=torch.float64, device=device))
-                dist.broadcast(buf, src=k % world, group=group)
-                series[k] = buf
-        if trunk is not None:
-            for k, shard in enumerate(shards):
-                if n_cut[k]:
-                    trunk.set_catch_series(ids[k], series[k][:, :, 0].reshape(T, n_cut[k], shard.V))
-            trunk.run(0, T)
-            trunk.synchronize()
-        return runners
+    V = subs[0].V
+    n_out = [len(s.recipe["cut_out"]) for s in subs]
+    feeds = {}  # consumer -> producer -> (cut-out positions in the producer, series ids in the consumer)
+    for pi, q, k, sid in links:
+        ks, sids = feeds.setdefault(q, {}).setdefault(pi, ([], []))
+        ks.append(k)
+        sids.append(sid)
+    gpu = chunk is not None and all(hasattr(r, "private_stream") for r in runners.values())
+    device = torch.device("cuda", torch.cuda.current_device()) if gpu or (
+        distributed and dist.get_backend(group) == "nccl") else torch.device("cpu")
 
-    # ---- pipelined: one stream per model, chunks of timesteps ----
-    device = torch.device("cuda", torch.cuda.current_device())
-    link = trunk.private_stream() if trunk is not None else torch.cuda.Stream(device)
-    for c0 in range(0, T, chunk):
-        c1 = min(T, c0 + chunk)
-        done = {}
-        for k, r in mine.items():
-            st = r.private_stream()
-            r.run(c0, c1, stream=st)
-            done[k] = torch.cuda.Event()
-            done[k].record(st)
-        with torch.cuda.stream(link):
-            for k, shard in enumerate(shards):
-                if n_cut[k] == 0:
-                    continue
-                n = n_cut[k] * shard.V
-                if k in mine:
-                    link.wait_event(done[k])
-                    buf = mine[k].buffers.array("out_probe")[c0:c1, :n, :]
+    def produced(pi, c0, c1, local):
+        """[c1 - c0, n_out, V] releases of part pi (a view of its record buffer, or a receive buffer)."""
+        if local:
+            r = runners[pi]
+            buf = r.buffers.array("out_probe") if gpu else torch.as_tensor(r.out_probe())
+            return buf[c0:c1, :n_out[pi] * V, 0].reshape(c1 - c0, n_out[pi], V)
+        return torch.empty((c1 - c0, n_out[pi], V), dtype=torch.float64, device=device)
+
+    def feed(q, series, c0):
+        for pi, (ks, sids) in feeds.get(q, {}).items():
+            runners[q].set_catch_series(sids, series[pi][:, ks, :], t0=c0)
+
+    for c0 in range(0, T, chunk or T):
+        c1 = min(T, c0 + (chunk or T))
+        done, series = {}, {}
+        for k in range(len(subs)):
+            mine = k in runners
+            if mine:
+                r = runners[k]
+                if gpu:
+                    st = r.private_stream()
+                    for pi in feeds.get(k, {}):
+                        if pi in done:
+                            st.wait_event(done[pi])
+                    with torch.cuda.stream(st):
+                        feed(k, series, c0)
+                    r.run(c0, c1, stream=st)
+                    done[k] = torch.cuda.Event()
+                    done[k].record(st)
                 else:
-                    buf = torch.empty((c1 - c0, n, shard.R), dtype=torch.float64, device=device)
-                if distributed:
-                    buf = buf.contiguous()
-                    dist.broadcast(buf, src=k % world, group=group)
-                if trunk is not None:
-                    trunk.set_catch_series(ids[k], buf[:, :, 0].reshape(c1 - c0, n_cut[k], shard.V), t0=c0)
-            if trunk is not None:
-                trunk.run(c0, c1, stream=link)
-    torch.cuda.synchronize(device)
+                    feed(k, series, c0)
+                    r.run(c0, c1)
+                    r.synchronize()
+            if n_out[k] == 0:
+                continue
+            remote_consumer = distributed and k < n_up  # upland releases go to rank 0's trunk
+            if mine or remote_consumer:
+                if gpu and mine and remote_consumer:
+                    torch.cuda.current_stream().wait_event(done[k])
+                buf = produced(k, c0, c1, mine)
+                if remote_consumer:
+                    buf = buf.to(device).contiguous()
+                    dist.broadcast(buf, src=_owner(parts, k, world), group=group)
+                    if gpu and rank == 0:
+                        done[k] = torch.cuda.Event()
+                        done[k].record(torch.cuda.current_stream())
+                series[k] = buf
+    if gpu:
+        torch.cuda.synchronize(device)
     return runners
