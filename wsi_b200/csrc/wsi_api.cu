@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
     for (int k = 0; k < 3; k++) {
 #pragma unroll
       for (int p = 0; p < V; p++) {
-        if (p != 0 && !bit(c.add, p)) continue;
+        if (p != 0 && !bit(c.addm(), p)) continue;
         double x = active ? term[k].x[p] : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
     if (threadIdx.x < 3 * V) {
       const int p = threadIdx.x % V;
       double acc = 0.0;
-      if (p == 0 || bit(c.add, p))
+      if (p == 0 || bit(c.addm(), p))
         for (int w = 0; w < kWarps; w++) acc += s_w[w][threadIdx.x];
       d.mb_partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 3 * V + threadIdx.x] = acc;
     }

@@ -64,13 +64,17 @@ struct Ctx {
   size_t R;
   int r;
   int t;
-  uint32_t add;
   double FA;
   uint32_t run_flags;
   bool block_sync;  // device: every thread of the block walks the same schedule -> WSI_BLOCK_ALIGN may sync
   int viol;        // mass-balance violations found for this replica this step
   double* mb_acc;  // [3*V] per-thread system-total accumulators (stride mb_stride) or null
   int mb_stride;
+
+  // additive-pollutant mask: a compile-time constant for the default pollutant set -- also inside
+  // the noinline functions, where a copy kept in the context would be a run-time value (twelve
+  // run-time bit tests in every VQIP operation)
+  WSI_HD uint32_t addm() const { return cfg.add_mask(); }
 
   WSI_HD const WsiModelDesc& D() const {
 #if defined(__CUDA_ARCH__)
@@ -117,13 +121,13 @@ struct Ctx {
   WSI_HD Vq ldv_add(const double* p, size_t stride) const {
     Vq v;
 #pragma unroll
-    for (int i = 0; i < V; i++) v.x[i] = (i == 0 || bit(add, i)) ? p[(size_t)i * stride] : 0.0;
+    for (int i = 0; i < V; i++) v.x[i] = (i == 0 || bit(addm(), i)) ? p[(size_t)i * stride] : 0.0;
     return v;
   }
   WSI_HD void stv_add(double* p, size_t stride, const Vq& v) const {
 #pragma unroll
     for (int i = 0; i < V; i++)
-      if (i == 0 || bit(add, i)) p[(size_t)i * stride] = v.x[i];
+      if (i == 0 || bit(addm(), i)) p[(size_t)i * stride] = v.x[i];
   }
   WSI_HD void flag(int node, uint32_t f) const { D().node_flags[(size_t)node * R + r] |= f; }
 
@@ -136,9 +140,9 @@ struct Ctx {
   }
 
   // ---- algebra shorthands ----
-  WSI_HD Vq sum(const Vq& a, const Vq& b) const { return vq_sum<P>(add, a, b); }
-  WSI_HD Vq extract(const Vq& a, const Vq& b) const { return vq_extract<P>(add, a, b); }
-  WSI_HD Vq vchange(const Vq& a, double v) const { return vq_vchange<P>(add, a, v); }
+  WSI_HD Vq sum(const Vq& a, const Vq& b) const { return vq_sum<P>(addm(), a, b); }
+  WSI_HD Vq extract(const Vq& a, const Vq& b) const { return vq_extract<P>(addm(), a, b); }
+  WSI_HD Vq vchange(const Vq& a, double v) const { return vq_vchange<P>(addm(), a, v); }
 };
 
 // =========================================================================================
@@ -158,7 +162,7 @@ WSI_HD bool vq_is_empty(const C& c, const typename C::Vq& v) {
   bool z = v.x[0] == 0.0;
 #pragma unroll
   for (int p = 1; p <= C::P; p++)
-    if (bit(c.add, p)) z = z && v.x[p] == 0.0;
+    if (bit(c.addm(), p)) z = z && v.x[p] == 0.0;
   return z;
 }
 
@@ -172,7 +176,7 @@ WSI_HD void tank_push_force(const C& c, double* st, size_t stride, const typenam
     if (vol > 0) {
 #pragma unroll
       for (int p = 1; p <= C::P; p++)
-        if (!bit(c.add, p)) {
+        if (!bit(c.addm(), p)) {
           const double num = v.x[p] * v.x[0] + st[(size_t)p * stride] * vol;
           st[(size_t)p * stride] = div_z(num, vol);
         }
@@ -219,7 +223,7 @@ template <class C>
 WSI_HD void vq_pull_pollutants(const C& c, typename C::Vq& s, typename C::Vq& req) {
 #pragma unroll
   for (int p = 1; p <= C::P; p++)
-    if (bit(c.add, p)) req.x[p] = pymin(s.x[p], req.x[p]);
+    if (bit(c.addm(), p)) req.x[p] = pymin(s.x[p], req.x[p]);
   req.x[0] = pymin(s.x[0], req.x[0]);
   s = c.extract(s, req);
 }
@@ -251,7 +255,7 @@ WSI_HD void sewer_update_queue(C& c, int w) {  // AltQueueArc.update_queue arcs.
   else {
 #pragma unroll
     for (int p = 1; p <= C::P; p++)
-      if (!bit(c.add, p)) q0[(size_t)p * s] = 0.0;
+      if (!bit(c.addm(), p)) q0[(size_t)p * s] = 0.0;
   }
 }
 // QueueTank.push_storage(vqip, time) tanks.py:513-539 through AltQueueArc (arcs.py:360-407).
@@ -518,7 +522,7 @@ WSI_HD void mb_check(C& c, int node, const typename C::Vq& in_, const typename C
   int viol = 0;
 #pragma unroll
   for (int p = 0; p <= C::P; p++) {
-    if (p != 0 && !bit(c.add, p)) continue;
+    if (p != 0 && !bit(c.addm(), p)) continue;
     const double a = in_.x[p], o = out_.x[p], dd = ds_.x[p];
     const double largest = pymax(pymax(a, o), dd);
     // core.py:404-419: |in/m - ds/m - out/m| > FLOAT_ACCURACY with m = 10**int(log10(largest))
@@ -550,7 +554,7 @@ WSI_HD void mb_check(C& c, int node, const typename C::Vq& in_, const typename C
   if (c.mb_acc) {
 #pragma unroll
     for (int p = 0; p <= C::P; p++) {
-      if (p != 0 && !bit(c.add, p)) continue;
+      if (p != 0 && !bit(c.addm(), p)) continue;
       c.mb_acc[(0 * V + p) * c.mb_stride] += in_.x[p];
       c.mb_acc[(1 * V + p) * c.mb_stride] += ds_.x[p];
       c.mb_acc[(2 * V + p) * c.mb_stride] += out_.x[p];
@@ -618,7 +622,7 @@ template <class C>
 WSI_HD void ds_add(const C& c, typename C::Vq& acc, const typename C::Vq& v) {
 #pragma unroll
   for (int p = 0; p <= C::P; p++)
-    if (p == 0 || bit(c.add, p)) acc.x[p] += v.x[p];
+    if (p == 0 || bit(c.addm(), p)) acc.x[p] += v.x[p];
 }
 
 // =========================================================================================
@@ -640,7 +644,7 @@ WSI_HD void decay_end_timestep(const C& c, typename C::Vq& st, PlaneFn plane, in
     *plane(f_n + 1 + 4 * WSI_MAX_DECAY + i) = x;  // storage_[pol] (tanks.py:445)
     vset<C::P>(st, pol, x - diff);
     // total_decayed = sum_vqip(empty, diff): only additive lanes accumulate (core.py:491)
-    *plane(f_n + 1 + 3 * WSI_MAX_DECAY + i) = bit(c.add, pol) ? 0.0 + diff : 0.0;
+    *plane(f_n + 1 + 3 * WSI_MAX_DECAY + i) = bit(c.addm(), pol) ? 0.0 + diff : 0.0;
   }
 }
 // total_decayed as a VQIP (zero volume)

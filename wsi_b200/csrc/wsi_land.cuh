@@ -13,7 +13,7 @@ template <class C>
 WSI_HD void mb_acc(const C& c, typename C::Vq& acc, const typename C::Vq& v) {
 #pragma unroll
   for (int p = 0; p <= C::P; p++)
-    if (p == 0 || bit(c.add, p)) acc.x[p] += v.x[p];
+    if (p == 0 || bit(c.addm(), p)) acc.x[p] += v.x[p];
 }
 
 // NutrientStore.extract nutrient_pool.py:542-556
@@ -205,7 +205,7 @@ WSI_HD void surface_phase(C& c, int u) {
     pol.x[0] = 0.0;
     const double* lp = S(WSI_SURF_LOAD(V));
 #pragma unroll
-    for (int p = 1; p <= P; p++) pol.x[p] = bit(c.add, p) ? lp[(size_t)p * ss] * area : lp[(size_t)p * ss];
+    for (int p = 1; p <= P; p++) pol.x[p] = bit(c.addm(), p) ? lp[(size_t)p * ss] * area : lp[(size_t)p * ss];
     st = c.sum(st, pol);
     mb_acc(c, mb_in, pol);
   }
@@ -626,7 +626,7 @@ WSI_HD void surface_phase(C& c, int u) {
       // decay_ds tanks.py:449-457: (storage - storage_) + total_decayed
       Vq dsv;
 #pragma unroll
-      for (int p = 0; p <= P; p++) dsv.x[p] = (p == 0 || bit(c.add, p)) ? st.x[p] - old.x[p] : 0.0;
+      for (int p = 0; p <= P; p++) dsv.x[p] = (p == 0 || bit(c.addm(), p)) ? st.x[p] - old.x[p] : 0.0;
       dsv = c.sum(dsv, decay_total<C>(c, S, WSI_SURF_N_DECAY));
       c.stv_add(S(WSI_SURF_MB_DS(V)), ss, dsv);
     }
@@ -701,7 +701,7 @@ WSI_HD void land_mass_balance_terms(const C& c, int node, typename C::Vq& in_, t
       const Vq old = c.ldv_add(S(WSI_SURF_MB_DS(V)), ss);
       Vq dsv;
 #pragma unroll
-      for (int p = 0; p <= P; p++) dsv.x[p] = (p == 0 || bit(c.add, p)) ? st.x[p] - old.x[p] : 0.0;
+      for (int p = 0; p <= P; p++) dsv.x[p] = (p == 0 || bit(c.addm(), p)) ? st.x[p] - old.x[p] : 0.0;
       dsv = c.sum(dsv, decay_total<C>(c, S, WSI_SURF_N_DECAY));
       ds_add(c, ds, dsv);
     } else {
@@ -717,7 +717,7 @@ WSI_HD void land_mass_balance_terms(const C& c, int node, typename C::Vq& in_, t
     const Vq ini = c.ldv_add(parked + (size_t)k * V * c.R, c.R);
 #pragma unroll
     for (int p = 0; p <= P; p++)
-      if (p == 0 || bit(c.add, p)) ds.x[p] += fin.x[p] - ini.x[p];
+      if (p == 0 || bit(c.addm(), p)) ds.x[p] += fin.x[p] - ini.x[p];
   }
 }
 

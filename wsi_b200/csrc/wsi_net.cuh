@@ -162,7 +162,7 @@ WSI_HD void net_level(C& c, NetItem<C>& it) {
     if (T.x[0] > 0) {  // tank.push_storage(empty reply, force=True)
 #pragma unroll
       for (int q = 1; q <= C::P; q++)
-        if (!bit(c.add, q)) {
+        if (!bit(c.addm(), q)) {
           const double num = 0.0 * 0.0 + T.x[q] * T.x[0];
           T.x[q] = div_z(num, T.x[0]);
         }
@@ -327,7 +327,7 @@ __device__ __forceinline__ bool net_lanes_release(C& c, const LaneItem<C>& it, i
   const NetRec<C>& rec = it.rec;
   const size_t s_a = c.s_arc();
   const bool live = q < V;
-  const bool blend = q != 0 && live && !bit(c.add, q);  // non-additive lane
+  const bool blend = q != 0 && live && !bit(c.addm(), q);  // non-additive lane
   const int np = rec.pe - rec.pb;
   // all loads first, then the folds (which are a dependent chain through the tank)
   double vq[kLanePaths], md[kLanePaths];
@@ -389,7 +389,7 @@ __device__ __forceinline__ void net_lanes_settle(C& c, const LaneItem<C>& it, in
   constexpr int V = C::V;
   const NetRec<C>& rec = it.rec;
   const bool live = q < V;
-  const bool blend = q != 0 && live && !bit(c.add, q);
+  const bool blend = q != 0 && live && !bit(c.addm(), q);
   double Tq = out.Tq;
   if (out.booked) {
     const Obj A = c.arc_obj(rec.out_arc);

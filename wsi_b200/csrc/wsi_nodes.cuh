@@ -230,7 +230,7 @@ WSI_HDN void sewer_discharge(C& c, int node) {  // sewer.py:201-239
   reply.x[0] = pymin(reply.x[0], active.x[0]);
 #pragma unroll
   for (int p = 1; p <= C::P; p++)
-    if (bit(c.add, p)) reply.x[p] = pymin(reply.x[p], active.x[p]);
+    if (bit(c.addm(), p)) reply.x[p] = pymin(reply.x[p], active.x[p]);
   active = c.extract(active, reply);
   Vq storage = c.extract(c.ldv(st, s), reply);
   // pull_ponded tanks.py:78-100 -> QueueTank.pull_storage tanks.py:541-564
@@ -295,7 +295,7 @@ WSI_HD typename C::Vq catch_get_flow(const C& c, int g) {  // catchment.py:60-75
   for (int p = 0; p <= C::P; p++) v.x[p] = row[p];
 #pragma unroll
   for (int p = 1; p <= C::P; p++)
-    if (bit(c.add, p)) v.x[p] *= v.x[0];
+    if (bit(c.addm(), p)) v.x[p] *= v.x[0];
   return v;
 }
 // Boundary node of a partitioned network (backend/partition.py): the VQIP the cut-off upstream
@@ -362,7 +362,7 @@ WSI_HD typename C::Vq tank_ds(const C& c, int tk) {  // tanks.py:70-76 / 449-457
   const Vq st_ = c.ldv_add(c.tank(WSI_TANK_STORAGE_LAG(V), tk), c.s_tank());
   Vq dsv;
 #pragma unroll
-  for (int p = 0; p <= C::P; p++) dsv.x[p] = (p == 0 || bit(c.add, p)) ? st.x[p] - st_.x[p] : 0.0;
+  for (int p = 0; p <= C::P; p++) dsv.x[p] = (p == 0 || bit(c.addm(), p)) ? st.x[p] - st_.x[p] : 0.0;
   if (*c.tank(WSI_TANK_IS_DECAY, tk) != 0.0) {
     const Obj Tk = c.tank_obj(tk);
     dsv = c.sum(dsv, decay_total<C>(c, Tk, WSI_TANK_N_DECAY));
@@ -377,7 +377,7 @@ WSI_HD void arc_system_totals(C& c, int a) {
   const typename C::Vq v = c.ldv_add(c.arc(WSI_ARC_VQIP_IN(C::V), a), c.s_arc());
 #pragma unroll
   for (int p = 0; p <= C::P; p++)
-    if (p == 0 || bit(c.add, p)) {
+    if (p == 0 || bit(c.addm(), p)) {
       c.mb_acc[(0 * C::V + p) * c.mb_stride] += v.x[p];
       c.mb_acc[(2 * C::V + p) * c.mb_stride] += v.x[p];
     }
@@ -413,7 +413,7 @@ WSI_HD void node_mass_balance(C& c, int node, typename C::Vq& in_, typename C::V
         const Vq st_ = c.ldv_add(c.sewer(WSI_SEWER_STORAGE_LAG(V), g), c.s_sewer());
 #pragma unroll
         for (int p = 0; p <= C::P; p++)
-          if (p == 0 || bit(c.add, p)) ds.x[p] += st.x[p] - st_.x[p];
+          if (p == 0 || bit(c.addm(), p)) ds.x[p] += st.x[p] - st_.x[p];
         break;
       }
       case WSI_NT_GROUNDWATER:
@@ -573,7 +573,6 @@ WSI_HD Ctx<CFG> make_ctx(const WsiModelDesc* host_d, int slot, const CFG& cfg, i
   c.R = (size_t)c.D().R;
   c.r = r;
   c.t = t;
-  c.add = cfg.add_mask();
   c.FA = c.D().float_accuracy;
   c.run_flags = flags;
   c.viol = 0;
