@@ -460,6 +460,20 @@ __global__ void __launch_bounds__(kFinBlock)
   if (threadIdx.x == 0) sums[j] = s[0];
 }
 
+template <class CFGR>
+CFGR runtime_cfg_as(const WsiModelDesc* d) {
+  CFGR c;
+  c.mask = d->additive_mask;
+  c.i_no3 = d->idx[0];
+  c.i_no2 = d->idx[1];
+  c.i_nh4 = d->idx[2];
+  c.i_po4 = d->idx[3];
+  c.i_orgp = d->idx[4];
+  c.i_orgn = d->idx[5];
+  c.i_solids = d->idx[6];
+  c.i_temp = d->idx[7];
+  return c;
+}
 template <int P>
 CfgRuntime<P> runtime_cfg(const WsiModelDesc* d) {
   CfgRuntime<P> c;
@@ -475,6 +489,7 @@ CfgRuntime<P> runtime_cfg(const WsiModelDesc* d) {
   return c;
 }
 
+constexpr uint32_t kOxfordMask = 0x1FFCu;
 bool is_default12(const WsiModelDesc* d) {
   static const int def_idx[8] = {10, 11, 4, 3, 2, 12, 5, 9};
   if (d->P != 12 || d->additive_mask != 0x1CFCu) return false;
@@ -700,6 +715,8 @@ int upload_desc(const WsiModelDesc* d, cudaStream_t s, int* slot) {
 int dispatch(const WsiModelDesc* d, int slot, int64_t t, int b, int e, uint32_t flags, cudaStream_t s) {
   if (is_default12(d)) return launch(d, slot, CfgDefault12(), t, b, e, flags, s);
 #ifndef WSI_ONLY_DEFAULT12  // development builds instantiate a single configuration
+  if (d->P == 12 && d->additive_mask == kOxfordMask)  // every pollutant additive but plane 1
+    return launch(d, slot, runtime_cfg_as<CfgStaticMask<12, kOxfordMask>>(d), t, b, e, flags, s);
   if (d->P == 12) return launch(d, slot, runtime_cfg<12>(d), t, b, e, flags, s);
   if (d->P == 2) return launch(d, slot, runtime_cfg<2>(d), t, b, e, flags, s);
 #endif

@@ -67,6 +67,14 @@ struct CfgRuntime {
   WSI_HD int temp() const { return i_temp; }
 };
 
+// Run-time named planes but a compile-time additive mask: the mask is what every VQIP operation
+// branches on, so fixing it specialises the hot code; instantiated for the Oxford demo's pollutant
+// set (12 pollutants, temperature the only non-additive one: mask 0x1FFC minus its bit).
+template <int P_, uint32_t MASK>
+struct CfgStaticMask : CfgRuntime<P_> {
+  WSI_HD uint32_t add_mask() const { return MASK; }
+};
+
 // --- lane access by (possibly run-time) plane index -------------------------------------
 // With a compile-time index the unrolled select chain folds to a single register.
 template <int P>
