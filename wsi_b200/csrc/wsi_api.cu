@@ -56,6 +56,7 @@ int fail(int code, const char* fmt, const char* detail = "") {
 constexpr int kBlock = WSI_STEP_BLOCK;  // replicas per block of the per-replica schedule kernel
 constexpr int kSurfBlock = 128; // surfaces per block of the surface kernels
 constexpr int kObjBlock = 128;  // replicas per block of the object-parallel kernels
+constexpr size_t kDescSmem = sizeof(WsiModelDesc);  // dynamic shared memory: the staged descriptor
 
 // Work-item decode of the object-parallel kernels.  Replica engine (FLAT = false): blockIdx.y is
 // the item and blockIdx.x tiles the replicas, so every block is homogeneous in item.  Network
@@ -106,11 +107,12 @@ template <class CFG>
 __global__ void __launch_bounds__(kBlock, WSI_STEP_MINB)
     wsi_step_kernel(const int slot, const CFG cfg, const int t_arg, const int sched_begin, const int sched_end,
                     const uint32_t flags) {
+  wsi_stage_desc(slot);
   const WsiModelDesc& d = g_wsi_desc[slot];
   const int t = step_of(d, t_arg);
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = r < d.R;
-  Ctx<CFG> c = make_ctx(nullptr, slot, cfg, active ? r : 0, t, flags);
+  Ctx<CFG, true> c = make_ctx<true>(nullptr, slot, cfg, active ? r : 0, t, flags);
   c.block_sync = (blockIdx.x + 1) * blockDim.x <= (unsigned)d.R;  // full block: all threads walk the schedule
   for (int k = sched_begin; k < sched_end; k++) {
     if (active) run_op(c, d.sched_op[k], d.sched_node[k]);
@@ -620,7 +622,7 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
         WSI_CHECK_LAUNCH("wsi_net_tail_general");
       }
     } else {
-      wsi_step_kernel<CFG><<<n_blocks(d), kBlock, 0, s>>>(slot, cfg, (int)t, b, e, flags);
+      wsi_step_kernel<CFG><<<n_blocks(d), kBlock, kDescSmem, s>>>(slot, cfg, (int)t, b, e, flags);
       WSI_CHECK_LAUNCH("wsi_step_kernel");
     }
   }

@@ -32,6 +32,18 @@ constexpr int kJunctionDepth = 3;    // nested junction Nodes a push may travers
 #endif
 #if defined(__CUDACC__)
 __constant__ WsiModelDesc g_wsi_desc[WSI_DESC_SLOTS];
+// The schedule kernel stages its descriptor at the start of its dynamic shared memory
+// (wsi_stage_desc): its device functions then read it with immediate-offset shared loads, whereas
+// a constant-bank access indexed by the run-time slot needs a uniform-register move per access
+// (9 % of that kernel's instructions).  Small kernels with many blocks keep the constant slot --
+// there the 640-byte copy per block costs more than it saves (measured).
+extern __shared__ __align__(16) unsigned char wsi_smem[];
+__device__ __forceinline__ void wsi_stage_desc(int slot) {
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&g_wsi_desc[slot]);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(wsi_smem);
+  for (int i = threadIdx.x; i < (int)(sizeof(WsiModelDesc) / 4); i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+}
 #endif
 
 // Re-align the warps of a block inside a long schedule entry (instruction-cache locality, see
@@ -52,7 +64,9 @@ struct Obj {
   WSI_HD double* operator()(int plane) const { return p + (size_t)plane * s; }
 };
 
-template <class CFG>
+// SMEM: the kernel staged its descriptor in shared memory (wsi_stage_desc) and device functions
+// read it from there; otherwise from the constant-memory slot.
+template <class CFG, bool SMEM = false>
 struct Ctx {
   static constexpr int P = CFG::P;
   static constexpr int V = P + 1;
@@ -78,7 +92,8 @@ struct Ctx {
 
   WSI_HD const WsiModelDesc& D() const {
 #if defined(__CUDA_ARCH__)
-    return g_wsi_desc[slot];
+    if constexpr (SMEM) return *reinterpret_cast<const WsiModelDesc*>(wsi_smem);
+    else return g_wsi_desc[slot];
 #else
     return *host_d;
 #endif

@@ -564,9 +564,9 @@ WSI_HD void replica_step(C& c, int sched_begin, int sched_end) {
   if (c.run_flags & WSI_RUN_END_TIMESTEP) end_timestep(c);
 }
 
-template <class CFG>
-WSI_HD Ctx<CFG> make_ctx(const WsiModelDesc* host_d, int slot, const CFG& cfg, int r, int t, uint32_t flags) {
-  Ctx<CFG> c;
+template <bool SMEM = false, class CFG>
+WSI_HD Ctx<CFG, SMEM> make_ctx(const WsiModelDesc* host_d, int slot, const CFG& cfg, int r, int t, uint32_t flags) {
+  Ctx<CFG, SMEM> c;
   c.host_d = host_d;
   c.slot = slot;
   c.cfg = cfg;
