@@ -9,12 +9,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 SO = os.path.join(CSRC, "libwsi_b200.so")
-SOURCES = ["wsi_api.cu"]
+# one translation unit per pollutant configuration (compiled in parallel) + the host API
+SOURCES = ["wsi_api.cu", "wsi_cfg_default12.cu", "wsi_cfg_oxford12.cu", "wsi_cfg_runtime12.cu", "wsi_cfg_runtime2.cu"]
 HEADERS = [
     os.path.join(CSRC, "wsi_vq.cuh"),
     os.path.join(CSRC, "wsi_device.cuh"),
     os.path.join(CSRC, "wsi_land.cuh"),
     os.path.join(CSRC, "wsi_nodes.cuh"),
+    os.path.join(CSRC, "wsi_net.cuh"),
+    os.path.join(CSRC, "wsi_kernels.cuh"),
+    os.path.join(CSRC, "wsi_host.h"),
     os.path.join(ROOT, "include", "wsi_b200.h"),
     os.path.join(ROOT, "include", "wsi_layout.h"),
 ]
@@ -29,7 +33,6 @@ NVCC_FLAGS = [
     # keep their explicit fma)
     "-fmad=false",
     "-Xcompiler", "-fPIC",
-    "-shared",
 ]
 
 
@@ -48,12 +51,28 @@ def is_current():
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build_extension(force=False, verbose=False):
-    """Compile libwsi_b200.so (cross-compiles without a GPU)."""
+def build_extension(force=False, verbose=False, only_default12=False):
+    """Compile libwsi_b200.so (cross-compiles without a GPU): the translation units in parallel,
+    then one link.  ``only_default12``: development build with the default pollutant set only."""
     if not force and is_current():
         return SO
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + SOURCES
-    subprocess.check_call(cmd, cwd=CSRC)
+    from concurrent.futures import ThreadPoolExecutor
+
+    nvcc = nvcc_path()
+    objdir = os.path.join(CSRC, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    sources = SOURCES[:2] if only_default12 else SOURCES
+    extra = ["-DWSI_ONLY_DEFAULT12"] if only_default12 else []
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        subprocess.check_call(cmd, cwd=CSRC)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(sources)) as pool:
+        objs = list(pool.map(compile_one, sources))
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO] + objs, cwd=CSRC)
     return SO
 
 

@@ -1,0 +1,5 @@
+// Configuration unit "runtime12" of libwsi_b200.so: the kernels of wsi_kernels.cuh instantiated for one
+// pollutant configuration (see wsi_host.h).
+#include "wsi_kernels.cuh"
+
+WSI_DEFINE_CONFIG_UNIT(runtime12, runtime_cfg<12>(d))

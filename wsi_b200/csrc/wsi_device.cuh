@@ -31,7 +31,7 @@ constexpr int kJunctionDepth = 3;    // nested junction Nodes a push may travers
 #define WSI_DESC_SLOTS 32
 #endif
 #if defined(__CUDACC__)
-__constant__ WsiModelDesc g_wsi_desc[WSI_DESC_SLOTS];
+static __constant__ WsiModelDesc g_wsi_desc[WSI_DESC_SLOTS];  // one copy per configuration unit
 // The schedule kernel stages its descriptor at the start of its dynamic shared memory
 // (wsi_stage_desc): its device functions then read it with immediate-offset shared loads, whereas
 // a constant-bank access indexed by the run-time slot needs a uniform-register move per access
@@ -255,7 +255,7 @@ WSI_HD typename C::Vq arc_send_push_request(C& c, int a, const typename C::Vq& v
 template <int D, class C>
 WSI_HD typename C::Vq node_push_set(C& c, int node, const typename C::Vq& vqip);
 template <int D, class C>
-WSI_HDN typename C::Vq push_distributed(C& c, int node, const typename C::Vq& vqip, int filter);
+WSI_HD typename C::Vq push_distributed(C& c, int node, const typename C::Vq& vqip, int filter);
 
 // sewer QueueTank helpers -------------------------------------------------------------------
 template <class C>
@@ -429,7 +429,20 @@ WSI_HD typename C::Vq arc_send_push_request(C& c, int a, const typename C::Vq& v
 
 // Node.push_distributed nodes.py:409-478
 template <int D, class C>
-WSI_HDN typename C::Vq push_distributed(C& c, int node, const typename C::Vq& vqip, int filter) {
+WSI_HD typename C::Vq push_distributed_body(C& c, int node, const typename C::Vq& vqip, int filter);
+template <int D, class C>
+WSI_HDN typename C::Vq push_distributed_call(C& c, int node, const typename C::Vq& vqip, int filter) {
+  return push_distributed_body<D>(c, node, vqip, filter);
+}
+// The top level (a schedule entry pushing) is inlined into its caller; the nested levels (junction
+// Nodes forwarding) are calls, which bounds the code size.
+template <int D, class C>
+WSI_HD typename C::Vq push_distributed(C& c, int node, const typename C::Vq& vqip, int filter) {
+  if constexpr (D == kJunctionDepth) return push_distributed_body<D>(c, node, vqip, filter);
+  else return push_distributed_call<D>(c, node, vqip, filter);
+}
+template <int D, class C>
+WSI_HD typename C::Vq push_distributed_body(C& c, int node, const typename C::Vq& vqip, int filter) {
   using Vq = typename C::Vq;
   const WsiModelDesc& d = c.D();
   const int cb = d.cand_ptr[node * WSI_NF + filter];
@@ -513,7 +526,7 @@ WSI_HD double pow10i(int k) {  // 0 <= k <= 22
   if (k & 16) p *= 1e16;
   return p;
 }
-WSI_HDN double magnitude10(double x) {
+inline WSI_HDN double magnitude10(double x) {
   if (!(x > 1e-22 && x < 1e22)) return pow(10.0, (double)(int)log10(x));
   int e2;
   (void)frexp(x, &e2);  // x = m * 2^e2, m in [0.5, 1)

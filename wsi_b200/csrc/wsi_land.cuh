@@ -664,7 +664,7 @@ WSI_HD typename C::Vq residence_pull(const C& c, typename C::Vq& s, double resid
 // push_to_sewers land.py:699-721, second half: the ponded runoff left by surface_phase goes to
 // the Sewers and whatever they do not take is forced back into the surface tank.
 template <class C>
-WSI_HDN void land_impervious_push(C& c, int node, int u) {
+WSI_HD void land_impervious_push(C& c, int node, int u) {
   using Vq = typename C::Vq;
   constexpr int V = C::V;
   const Obj S = c.surf_obj(u);
@@ -726,7 +726,7 @@ WSI_HD void land_mass_balance_terms(const C& c, int node, typename C::Vq& in_, t
 // surface order, so every sum is the reference's -- which lets each ResidenceTank be loaded and
 // stored once and keeps nothing large alive across the calls into the push protocol.
 template <class C>
-WSI_HDN void land_phase(C& c, int node) {
+WSI_HD void land_phase(C& c, int node) {
   using Vq = typename C::Vq;
   constexpr int V = C::V;
   const WsiModelDesc& d = c.D();

@@ -8,7 +8,7 @@ namespace wsi {
 
 // ---- Groundwater / Storage / Reservoir ----------------------------------------------------
 template <class C>
-WSI_HDN void gw_infiltrate(C& c, int node) {  // storage.py:231-245
+WSI_HD void gw_infiltrate(C& c, int node) {  // storage.py:231-245
   constexpr int V = C::V;
   const int g = c.D().node_gidx[node];
   double* st = c.tank(WSI_TANK_STORAGE(V), g);
@@ -20,7 +20,7 @@ WSI_HDN void gw_infiltrate(C& c, int node) {  // storage.py:231-245
   tank_push_force(c, st, c.s_tank(), retained);
 }
 template <class C>
-WSI_HDN void gw_distribute(C& c, int node) {  // storage.py:222-229
+WSI_HD void gw_distribute(C& c, int node) {  // storage.py:222-229
   constexpr int V = C::V;
   const int g = c.D().node_gidx[node];
   double* st = c.tank(WSI_TANK_STORAGE(V), g);
@@ -213,7 +213,7 @@ WSI_HDN void river_distribute(C& c, int node) {  // storage.py:926-936
 
 // ---- Sewer --------------------------------------------------------------------------------
 template <class C>
-WSI_HDN void sewer_discharge(C& c, int node) {  // sewer.py:201-239
+WSI_HD void sewer_discharge(C& c, int node) {  // sewer.py:201-239
   using Vq = typename C::Vq;
   constexpr int V = C::V;
   const int w = c.D().node_gidx[node];
