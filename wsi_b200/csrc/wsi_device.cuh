@@ -434,11 +434,12 @@ template <int D, class C>
 WSI_HDN typename C::Vq push_distributed_call(C& c, int node, const typename C::Vq& vqip, int filter) {
   return push_distributed_body<D>(c, node, vqip, filter);
 }
-// The top level (a schedule entry pushing) is inlined into its caller; the nested levels (junction
-// Nodes forwarding) are calls, which bounds the code size.
+// The top two levels (a schedule entry pushing, and the junction Node it usually pushes into) are
+// inlined into the caller; deeper junction levels are calls, which bounds the code size.  (Measured
+// on config 2: all calls 0.358 ms, one level inlined 0.322, two 0.297, three 0.298.)
 template <int D, class C>
 WSI_HD typename C::Vq push_distributed(C& c, int node, const typename C::Vq& vqip, int filter) {
-  if constexpr (D == kJunctionDepth) return push_distributed_body<D>(c, node, vqip, filter);
+  if constexpr (D >= kJunctionDepth - 1) return push_distributed_body<D>(c, node, vqip, filter);
   else return push_distributed_call<D>(c, node, vqip, filter);
 }
 template <int D, class C>
