@@ -68,6 +68,7 @@ struct Obj {
 // read it from there; otherwise from the constant-memory slot.
 template <class CFG, bool SMEM = false>
 struct Ctx {
+  static constexpr bool kInlinePush = SMEM;  // the schedule kernel's context (see push_distributed)
   static constexpr int P = CFG::P;
   static constexpr int V = P + 1;
   using Vq = VQ<P>;
@@ -435,11 +436,13 @@ WSI_HDN typename C::Vq push_distributed_call(C& c, int node, const typename C::V
   return push_distributed_body<D>(c, node, vqip, filter);
 }
 // The top two levels (a schedule entry pushing, and the junction Node it usually pushes into) are
-// inlined into the caller; deeper junction levels are calls, which bounds the code size.  (Measured
+// inlined into the caller -- in the schedule kernel (Ctx<CFG, true>), where pushes are the bulk of
+// the work; elsewhere, and for deeper junction levels, they are calls, which bounds code size and
+// compile time.  (Measured
 // on config 2: all calls 0.358 ms, one level inlined 0.322, two 0.297, three 0.298.)
 template <int D, class C>
 WSI_HD typename C::Vq push_distributed(C& c, int node, const typename C::Vq& vqip, int filter) {
-  if constexpr (D >= kJunctionDepth - 1) return push_distributed_body<D>(c, node, vqip, filter);
+  if constexpr (C::kInlinePush && D >= kJunctionDepth - 1) return push_distributed_body<D>(c, node, vqip, filter);
   else return push_distributed_call<D>(c, node, vqip, filter);
 }
 template <int D, class C>
