@@ -18,6 +18,7 @@ HEADERS = [
     os.path.join(CSRC, "wsi_nodes.cuh"),
     os.path.join(CSRC, "wsi_net.cuh"),
     os.path.join(CSRC, "wsi_kernels.cuh"),
+    os.path.join(CSRC, "wsi_warp.cuh"),
     os.path.join(CSRC, "wsi_host.h"),
     os.path.join(ROOT, "include", "wsi_b200.h"),
     os.path.join(ROOT, "include", "wsi_layout.h"),

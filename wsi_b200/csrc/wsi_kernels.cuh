@@ -26,6 +26,7 @@
 
 #include "wsi_host.h"
 #include "wsi_device.cuh"
+#include "wsi_warp.cuh"
 
 using namespace wsi;
 using namespace wsi_host;
@@ -147,14 +148,12 @@ __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
+      double a[16];
 #pragma unroll
-      for (int p = 0; p < V; p++) {
-        if (p != 0 && !bit(c.addm(), p)) continue;
-        double x = active ? term[k].x[p] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        if (lane == 0) s_w[warp][k * V + p] = x;
-      }
+      for (int p = 0; p < 16; p++) a[p] = (p < V && active && (p == 0 || bit(c.addm(), p))) ? term[k].x[p < V ? p : 0] : 0.0;
+      int p_mine;
+      const double x = warp_sum_16(a, lane, p_mine);
+      if ((lane & 1) == 0 && p_mine < V && (p_mine == 0 || bit(c.addm(), p_mine))) s_w[warp][k * V + p_mine] = x;
     }
     __syncthreads();
     if (threadIdx.x < 3 * V) {
