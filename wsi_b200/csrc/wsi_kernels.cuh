@@ -44,6 +44,9 @@ namespace {
 #ifndef WSI_OBJ_MINB
 #define WSI_OBJ_MINB 6
 #endif
+#ifndef WSI_MB_MINB  // mass balance / record / end_timestep: streaming kernels
+#define WSI_MB_MINB 5  // 96 registers: 6 (80) spills more, 4 (128) starves the end_timestep copy (gpurun sweep, round 1)
+#endif
 constexpr size_t kDescSmem = sizeof(WsiModelDesc);  // dynamic shared memory: the staged descriptor
 
 // Work-item decode of the object-parallel kernels.  Replica engine (FLAT = false): blockIdx.y is
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(kBlock, WSI_STEP_MINB)
 // atomic per warp; the (in, ds, out) lanes via warp shuffles, a fixed cross-warp sum, and one
 // row of mb_partial per block (summed in block order by wsi_mb_finalize: deterministic).
 template <class CFG, bool FLAT>
-__global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
+__global__ void __launch_bounds__(kObjBlock, WSI_MB_MINB)
     wsi_mb_kernel(const int slot, const CFG cfg, const int t_arg, const uint32_t flags, const int n_items) {
   constexpr int V = CFG::P + 1;
   constexpr int kWarps = kObjBlock / 32;
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
 
 // One thread per (probe, replica): Model.run's recording (model.py:1063-1170) is a strided copy.
 template <class CFG, bool FLAT>
-__global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
+__global__ void __launch_bounds__(kObjBlock, WSI_MB_MINB)
     wsi_record_kernel(const int slot, const CFG cfg, const int t_arg, const int row_arg) {
   const WsiModelDesc& d = g_wsi_desc[slot];
   const int t = step_of(d, t_arg);
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
 
 // One thread per (end_timestep item, replica): arcs reset, DecayTank decay, QueueTank shift.
 template <class CFG, bool FLAT>
-__global__ void __launch_bounds__(kObjBlock, WSI_OBJ_MINB)
+__global__ void __launch_bounds__(kObjBlock, WSI_MB_MINB)
     wsi_end_kernel(const int slot, const CFG cfg, const int t_arg) {
   const WsiModelDesc& d = g_wsi_desc[slot];
   const int t = step_of(d, t_arg);
