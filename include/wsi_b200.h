@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WSI_ABI_VERSION 1
+#define WSI_ABI_VERSION 2
 
 /* error classes returned by every entry point (0 == success) */
 #define WSI_OK 0
@@ -151,6 +151,13 @@ typedef struct WsiModelDesc {
   double* mb_sums;            /* [T][3][V] system totals sys_in, sys_ds, sys_out */
   int32_t* mb_count;          /* [T] number of (node, component) violations */
   uint32_t* node_flags;       /* [n_nodes*R] sticky WSI_FLAG_* */
+
+  /* ---- simple chains (ABI 2): arc_chain[arc_chain_ptr[a] .. arc_chain_ptr[a+1]) lists arc `a` followed by
+   *      the arcs a push down `a` travels through junction Nodes that forward to exactly one arc
+   *      (nodes.py:62-66, 424-438); empty when a junction on the way splits, dead-ends, or the chain is
+   *      longer than the kernels unroll.  NULL: every push takes the general recursive code. ---- */
+  const int32_t* arc_chain_ptr; /* [n_arcs+1] */
+  const int32_t* arc_chain;
 } WsiModelDesc;
 
 /* ABI version of the loaded library (== WSI_ABI_VERSION). */

@@ -17,7 +17,7 @@ import numpy as np
 
 from . import layout as L
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 RUN_SCHEDULE = 1
 RUN_MASS_BALANCE = 2
@@ -134,13 +134,15 @@ class WsiModelDesc(C.Structure):
         ("mb_sums", _f64p),
         ("mb_count", _i32p),
         ("node_flags", _u32p),
+        ("arc_chain_ptr", _i32p),
+        ("arc_chain", _i32p),
     ]
 
 
 _NET_ARRAYS = ["net_level_ptr", "net_level_node", "net_calc_node", "net_final_node", "net_bnd_node", "net_path_ptr",
                "net_path_split", "net_path_sender", "net_path_arc_ptr", "net_path_arcs", "net_item", "net_scratch", "net_done", "net_rpath"]
 _INT_ARRAYS = _NET_ARRAYS + [
-    "surf_order", "end_kind", "end_obj", "mb_term_slot", "node_type", "node_gidx", "arc_in", "arc_out", "out_ptr", "out_arcs", "in_ptr", "in_arcs",
+    "arc_chain_ptr", "arc_chain", "surf_order", "end_kind", "end_obj", "mb_term_slot", "node_type", "node_gidx", "arc_in", "arc_out", "out_ptr", "out_arcs", "in_ptr", "in_arcs",
     "cand_ptr", "cand_arcs", "land_surf_ptr", "land_surf", "sched_op", "sched_node", "month_idx",
     "dayofyear", "doy_adj",
 ]
@@ -150,6 +152,8 @@ _GROUP_FIELD = {"arc": "arc", "land": "land", "surf": "surf", "tank": "tank", "r
 
 _LIB = None
 _LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "libwsi_b200.so")
+if os.environ.get("WSI_B200_LIB"):  # development: a variant build of the same library (tools/build_variants.py)
+    _LIB_PATH = os.path.abspath(os.environ["WSI_B200_LIB"])
 
 
 class ExtensionMissingError(RuntimeError):
@@ -199,6 +203,38 @@ def check(lib, rc):
         raise RuntimeError(f"wsi_b200 error {rc}: {msg.decode() if msg else ''}")
 
 
+MAX_CHAIN = 4  # kMaxChain in csrc/wsi_device.cuh: arcs a push may travel (kJunctionDepth junction Nodes)
+
+
+def simple_chains(fm):
+    """CSR ``(ptr, arcs)``: for every arc the arcs a push down it travels while each receiving node is
+    a junction ``Node`` that forwards to exactly one arc (``nodes.py:62-66``: ``push_distributed`` with
+    ``of_type = [Node, River, Waste, Reservoir]``; one out-arc and that arc eligible).  Empty when a
+    junction on the way splits or dead-ends or the chain is longer than ``MAX_CHAIN`` -- such pushes run
+    the general recursive code."""
+    n_arcs = len(fm.arc_names)
+    nrwr = L.FI["NRWR"]
+    ptr = np.zeros(n_arcs + 1, dtype=np.int32)
+    flat = []
+    for a in range(n_arcs):
+        arcs = [a]
+        node = int(fm.arc_out[a])
+        ok = True
+        while int(fm.node_type[node]) == L.NT["Node"]:
+            n_out = int(fm.out_ptr[node + 1] - fm.out_ptr[node])
+            cb, ce = int(fm.cand_ptr[node * L.NF + nrwr]), int(fm.cand_ptr[node * L.NF + nrwr + 1])
+            if n_out != 1 or ce - cb != 1 or len(arcs) >= MAX_CHAIN:
+                ok = False
+                break
+            nxt = int(fm.out_arcs[fm.out_ptr[node]])
+            arcs.append(nxt)
+            node = int(fm.arc_out[nxt])
+        if ok:
+            flat.extend(arcs)
+        ptr[a + 1] = len(flat)
+    return ptr, np.array(flat or [0], dtype=np.int32)
+
+
 class ModelBuffers:
     """Owns the buffers of one flattened model on a device and its C descriptor."""
 
@@ -238,6 +274,8 @@ class ModelBuffers:
         net = self.net or network.empty_plan(len(fm.node_names))
         net = dict(net, net_scratch=np.zeros(4, np.int32), net_done=np.zeros(max(len(net["net_item"]) // 8, 1) * fm.R, np.int32))
         self._extra_int = {k: np.ascontiguousarray(net[k], dtype=np.int32) for k in _NET_ARRAYS}
+        chain_ptr, chain = simple_chains(fm)
+        self._extra_int.update({"arc_chain_ptr": chain_ptr, "arc_chain": chain})
         self._extra_int.update({"surf_order": order if len(order) else np.zeros(1, np.int32), "mb_term_slot": slot,
                            "end_kind": np.ascontiguousarray(it[:, 0]), "end_obj": np.ascontiguousarray(it[:, 1])})
         self.surf_class_ptr = [int(np.searchsorted(types[order], k, side="left")) for k in range(4)] + [len(order)]

@@ -52,18 +52,19 @@ def is_current():
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build_extension(force=False, verbose=False, only_default12=False):
+def build_extension(force=False, verbose=False, only_default12=False, defines=(), out=None):
     """Compile libwsi_b200.so (cross-compiles without a GPU): the translation units in parallel,
     then one link.  ``only_default12``: development build with the default pollutant set only."""
-    if not force and is_current():
+    if out is None and not force and is_current():
         return SO
     from concurrent.futures import ThreadPoolExecutor
 
     nvcc = nvcc_path()
-    objdir = os.path.join(CSRC, "_obj")
+    objdir = os.path.join(CSRC, "_obj" if out is None else "_obj_" + os.path.basename(out))
     os.makedirs(objdir, exist_ok=True)
     sources = SOURCES[:2] if only_default12 else SOURCES
-    extra = ["-DWSI_ONLY_DEFAULT12"] if only_default12 else []
+    extra = (["-DWSI_ONLY_DEFAULT12"] if only_default12 else []) + ["-D" + x for x in defines]
+    so = SO if out is None else out
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
@@ -73,8 +74,8 @@ def build_extension(force=False, verbose=False, only_default12=False):
 
     with ThreadPoolExecutor(max_workers=len(sources)) as pool:
         objs = list(pool.map(compile_one, sources))
-    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO] + objs, cwd=CSRC)
-    return SO
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", so] + objs, cwd=CSRC)
+    return so
 
 
 if __name__ == "__main__":

@@ -48,7 +48,7 @@ __device__ __forceinline__ void wsi_stage_desc(int slot) {
 
 // Re-align the warps of a block inside a long schedule entry (instruction-cache locality, see
 // wsi_step_kernel); only at points every thread of the block reaches.
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(WSI_NO_ALIGN)
 #define WSI_BLOCK_ALIGN(c)                \
   do {                                    \
     if ((c).block_sync) __syncthreads();  \
@@ -428,34 +428,30 @@ WSI_HD typename C::Vq arc_send_push_request(C& c, int a, const typename C::Vq& v
   return reply;
 }
 
-// Node.push_distributed nodes.py:409-478
+// Node.push_distributed nodes.py:409-478 -- general form (any number of candidate arcs, junctions
+// that split): recursive through the junction Nodes, one call per level.  The schedule kernel only
+// comes here when a push is NOT a simple chain (push_out below); it is kept out of line so that
+// its VQIP temporaries and candidate tables cost stack only when it actually runs.
 template <int D, class C>
 WSI_HD typename C::Vq push_distributed_body(C& c, int node, const typename C::Vq& vqip, int filter);
 template <int D, class C>
 WSI_HDN typename C::Vq push_distributed_call(C& c, int node, const typename C::Vq& vqip, int filter) {
   return push_distributed_body<D>(c, node, vqip, filter);
 }
-// The top two levels (a schedule entry pushing, and the junction Node it usually pushes into) are
-// inlined into the caller -- in the schedule kernel (Ctx<CFG, true>), where pushes are the bulk of
-// the work; elsewhere, and for deeper junction levels, they are calls, which bounds code size and
-// compile time.  (Measured
-// on config 2: all calls 0.358 ms, one level inlined 0.322, two 0.297, three 0.298.)
 template <int D, class C>
 WSI_HD typename C::Vq push_distributed(C& c, int node, const typename C::Vq& vqip, int filter) {
-  if constexpr (C::kInlinePush && D >= kJunctionDepth - 1) return push_distributed_body<D>(c, node, vqip, filter);
-  else return push_distributed_call<D>(c, node, vqip, filter);
+  return push_distributed_call<D>(c, node, vqip, filter);
 }
 template <int D, class C>
 WSI_HD typename C::Vq push_distributed_body(C& c, int node, const typename C::Vq& vqip, int filter) {
   using Vq = typename C::Vq;
   const WsiModelDesc& d = c.D();
   const int cb = d.cand_ptr[node * WSI_NF + filter];
-  int nc = d.cand_ptr[node * WSI_NF + filter + 1] - cb;
+  const int nc = d.cand_ptr[node * WSI_NF + filter + 1] - cb;  // <= kMaxCand (refused by the flattener otherwise)
   const int* cand = d.cand_arcs + cb;
   const int n_out = d.out_ptr[node + 1] - d.out_ptr[node];
   const bool single = n_out == 1;  // nodes.py:424-438: one out-arc -> send everything down it
   if (single && nc <= 0) return vqip;
-  if (nc > kMaxCand) nc = kMaxCand;
   double not_pushed = vqip.x[0];
   Vq not_pushed_ = vqip;
   double alloc[kMaxCand], cap_[kMaxCand];
@@ -509,6 +505,329 @@ WSI_HD typename C::Vq push_distributed_body(C& c, int node, const typename C::Vq
   }
   if (iter == kMaxIter) c.flag(node, WSI_FLAG_MAXITER);
   return not_pushed_;
+}
+
+// =========================================================================================
+// Simple chains: the push protocol without recursion
+//
+// Almost every push of a real model travels down a *simple chain*: an arc, then zero or more
+// junction `Node`s that each forward to exactly one arc, then a node that stores or swallows
+// the water.  The host lists the arcs of the chain that starts at every arc (arc_chain_ptr /
+// arc_chain; empty when a junction on the way splits or the chain is longer than kMaxChain).
+// For such a chain the recursion arc.send_push_request -> node.push_set -> push_distributed ->
+// arc.send_push_request ... (arcs.py:112-158, nodes.py:62-66, 409-438) unrolls into three
+// passes over at most kMaxChain arcs -- the excess the chain offers (volumes only, bottom up),
+// the request each arc admits (top down), the receiver's push_set and the arcs' bookkeeping
+// (bottom up) -- with exactly the arithmetic of the recursive form, no calls and nothing
+// indexed at run time, so every VQIP stays in registers.  When an arc on the way does not admit
+// the whole request the general recursive code runs instead (nothing has been changed yet).
+// =========================================================================================
+constexpr int kMaxChain = kJunctionDepth + 1;
+
+#if !defined(__CUDA_ARCH__) && defined(WSI_HOST_STATS)  // development aid (host build): which path a send takes
+static long long g_send_stats[8];
+#define WSI_STAT(i) (g_send_stats[i]++)
+#else
+#define WSI_STAT(i)
+#endif
+
+// vol_vchange(x, min(p, x)): the request x clamped by a pipe's remaining room p.  When p >= x
+// this is x * (x / x) == x exactly, so the division is only evaluated when the pipe binds.
+WSI_HD double clamp_to(double x, double p) { return p < x ? vol_vchange(x, p) : x; }
+
+template <class C>
+WSI_HD int chain_of(const C& c, int a, const int*& arcs) {
+  const WsiModelDesc& d = c.D();
+  if (!d.arc_chain_ptr) return 0;
+  const int b = d.arc_chain_ptr[a];
+  arcs = d.arc_chain + b;
+  return d.arc_chain_ptr[a + 1] - b;
+}
+
+// What a chain can take: pipe[k] = capacity - flow_in of its k-th arc and E[k] =
+// Arc.get_excess("push") of that arc without a request (arcs.py:230-257 with vqip None; a
+// junction's push_check without a request is the excess of its only arc, nodes.py:480-508).
+template <class C>
+WSI_HD void chain_excess(C& c, const int* arcs, int n, double (&pipe)[kMaxChain], double (&E)[kMaxChain]) {
+  double u = node_push_check_vol<0>(c, c.D().arc_out[arcs[n - 1]], false, 0.0);
+#pragma unroll
+  for (int k = kMaxChain - 1; k >= 0; k--) {
+    pipe[k] = 0.0;
+    E[k] = 0.0;
+    if (k < n) {
+      pipe[k] = *c.arc(WSI_ARC_CAPACITY, arcs[k]) - *c.arc(WSI_ARC_FLOW_IN, arcs[k]);
+      u = clamp_to(u, pipe[k]);
+      E[k] = u;
+      u = 0.0 + u;  // the junction above sums its candidates' excesses from zero
+    }
+  }
+}
+
+template <class C>
+WSI_HD void arc_book(C& c, int a, const typename C::Vq& sent) {  // arcs.py:152-156
+  double* fi = c.arc(WSI_ARC_FLOW_IN, a);
+  *fi = *fi + sent.x[0];
+  double* vi = c.arc(WSI_ARC_VQIP_IN(C::V), a);
+  c.stv(vi, c.s_arc(), c.sum(c.ldv(vi, c.s_arc()), sent));
+}
+
+template <class C>
+WSI_HDN typename C::Vq arc_send_general_call(C c, int a, typename C::Vq vqip, int* viol) {
+  const typename C::Vq r = arc_send_push_request<kJunctionDepth>(c, a, vqip);
+  *viol = c.viol;
+  return r;
+}
+template <class C>
+WSI_HDN typename C::Vq push_general_call(C c, int node, typename C::Vq vqip, int filter, int* viol) {
+  const typename C::Vq r = push_distributed_body<kJunctionDepth>(c, node, vqip, filter);
+  *viol = c.viol;
+  return r;
+}
+
+// Arc.send_push_request(vqip) on arc `a` (== arc_send_push_request<kJunctionDepth>).  Returns true
+// when the reply is empty (zero volume and zero additive lanes; `reply` is then all zeros -- the
+// non-additive lanes of an empty VQIP never reach a result, they are only ever multiplied by its
+// zero volume).
+// An empty request (zero volume, zero additive lanes) travelling down arcs[k0 .. n) to node X: on
+// every arc not_pushed = v_change_vqip(vqip, 0) is the request itself, what travels on is empty
+// again, and so is every reply.  What is left of sum_vqip with an empty operand is the re-blend
+// of the non-additive lanes, (x_p * 0 + s_p * vol) / vol: of the receiver's store (push_set_river
+// storage.py:711-721, Tank.push_storage tanks.py:160-205, QueueTank.push_storage below
+// FLOAT_ACCURACY tanks.py:513-539) and of every arc's vqip_in (arcs.py:152-156); Waste takes
+// nothing.
+template <class C>
+WSI_HD void chain_push_empty(C& c, const int* arcs, int k0, int n, int X) {
+  constexpr int V = C::V;
+  const WsiModelDesc& d = c.D();
+  const typename C::Vq none = vq_zero<C::P>();
+  const int g = d.node_gidx[X];
+  switch (d.node_type[X]) {
+    case WSI_NT_RIVER:
+      tank_push_force(c, c.tank(WSI_TANK_STORAGE(V), (int)*c.river(WSI_RIVER_TANK, g)), c.s_tank(), none);
+      break;
+    case WSI_NT_GROUNDWATER:
+    case WSI_NT_STORAGE:
+    case WSI_NT_RESERVOIR:
+      tank_push_force(c, c.tank(WSI_TANK_STORAGE(V), g), c.s_tank(), none);
+      break;
+    case WSI_NT_SEWER:
+      tank_push_force(c, c.sewer(WSI_SEWER_STORAGE(V), g), c.s_sewer(), none);
+      break;
+    case WSI_NT_WASTE:
+      break;
+    default:
+      c.flag(X, WSI_FLAG_DENY);
+      break;
+  }
+#pragma unroll 1
+  for (int k = k0; k < n; k++) tank_push_force(c, c.arc(WSI_ARC_VQIP_IN(V), arcs[k]), c.s_arc(), none);
+}
+
+template <class C>
+WSI_HD bool arc_send(C& c, int a, const typename C::Vq& vqip, typename C::Vq& reply) {
+  using Vq = typename C::Vq;
+  const int* arcs = nullptr;
+  const int n = chain_of(c, a, arcs);
+  const double v0 = vqip.x[0];
+  if (n > 0) {
+    double pipe[kMaxChain], E[kMaxChain];
+    chain_excess(c, arcs, n, pipe, E);
+    const WsiModelDesc& d = c.D();
+    const int X = d.arc_out[arcs[n - 1]];
+    // Top-down: what every arc admits of the request (the receiver itself, or a junction handing
+    // the question down -- check_basic nodes.py:480-508: min(excess of its arc, request)).  The
+    // request is unchanged on its way down while all of it is admitted; `j` is the first arc that
+    // does not admit everything (arcs.py:126-133), below it travels w = vqip - not_pushed.
+    int j = -1;
+    bool ok = true, room = true, below_empty = false;
+    double cv = v0, ratio = 0.0;
+#pragma unroll
+    for (int k = 0; k < kMaxChain; k++) {
+      if (k < n) {
+        double ne;
+        if (k == n - 1) {
+          ne = node_push_check_vol<0>(c, X, true, cv);
+        } else {
+          const double below = E[k + 1 < kMaxChain ? k + 1 : 0];
+          ne = clamp_to(below, cv);
+        }
+        const double excess_in = clamp_to(ne, pipe[k]);
+        room = room && excess_in >= 0.0;
+        if (!below_empty && pymax(cv - excess_in, 0.0) != 0.0) {
+          if (j >= 0 || !(cv > 0)) {
+            ok = false;  // a second arc binds: general code
+          } else {
+            j = k;
+            ratio = div_z(pymax(cv - excess_in, 0.0), cv);  // v_change_vqip(vqip, not_pushed volume)
+            cv = cv - cv * ratio;
+            if (!(cv > 0)) {  // nothing admitted: what travels on is empty iff the ratio is exactly 1
+              below_empty = true;
+              ok = ok && ratio == 1.0 && cv == 0.0;
+            }
+          }
+        }
+      }
+    }
+    if (j < 0 && v0 > 0) {
+      WSI_STAT(0);
+      reply = node_push_set<0>(c, X, vqip);
+      if (vq_is_empty(c, reply)) {
+#pragma unroll 1
+        for (int k = 0; k < n; k++) arc_book(c, arcs[k], vqip);
+        reply = vq_zero<C::P>();
+        return true;
+      }
+      // the receiver handed something back: every arc on the way books what stayed below it
+      // and adds its own (empty) not_pushed to the reply, deepest arc first (arcs.py:140-150)
+      const Vq not_pushed = c.vchange(vqip, 0.0);
+#pragma unroll 1
+      for (int k = n - 1; k >= 0; k--) {
+        const Vq sent = c.extract(vqip, reply);
+        reply = c.sum(reply, not_pushed);
+        arc_book(c, arcs[k], sent);
+      }
+      return false;
+    }
+    if (j < 0 && room && vq_is_empty(c, vqip)) {  // a dry store's release
+      WSI_STAT(1);
+      chain_push_empty(c, arcs, 0, n, X);
+      reply = vq_zero<C::P>();
+      return true;
+    }
+    if (j >= 0 && ok && room && v0 > 0) {
+      // Arc j admits only part of the request: not_pushed_j = v_change_vqip(vqip, np_j), and
+      // w = vqip - not_pushed_j travels on (fully admitted below, or empty when nothing fits).
+      WSI_STAT(7);
+      Vq w;
+      w.x[0] = cv;
+#pragma unroll
+      for (int p = 1; p <= C::P; p++) w.x[p] = bit(c.addm(), p) ? vqip.x[p] - vqip.x[p] * ratio : vqip.x[p];
+      if (below_empty) {
+        chain_push_empty(c, arcs, j + 1, n, X);
+        reply = vq_zero<C::P>();
+      } else {
+        reply = node_push_set<0>(c, X, w);
+        const bool rempty = vq_is_empty(c, reply);
+        const Vq np_w = c.vchange(w, 0.0);
+#pragma unroll 1
+        for (int k = n - 1; k > j; k--) {
+          if (rempty) {
+            arc_book(c, arcs[k], w);
+          } else {
+            const Vq sent = c.extract(w, reply);
+            reply = c.sum(reply, np_w);
+            arc_book(c, arcs[k], sent);
+          }
+        }
+      }
+      {
+        Vq np_j;  // v_change_vqip(vqip, np_j): the same ratio as above
+        np_j.x[0] = v0 * ratio;
+#pragma unroll
+        for (int p = 1; p <= C::P; p++) np_j.x[p] = bit(c.addm(), p) ? vqip.x[p] * ratio : vqip.x[p];
+        const Vq sent = c.extract(w, reply);
+        reply = c.sum(reply, np_j);
+        arc_book(c, arcs[j], sent);
+      }
+      const Vq np_0 = c.vchange(vqip, 0.0);
+#pragma unroll 1
+      for (int k = j - 1; k >= 0; k--) {
+        const Vq sent = c.extract(vqip, reply);
+        reply = c.sum(reply, np_0);
+        arc_book(c, arcs[k], sent);
+      }
+      return false;
+    }
+  }
+  WSI_STAT(2);
+  if (n <= 0) WSI_STAT(3);
+  else if (v0 > 0) WSI_STAT(4);       // several arcs bind
+  else if (v0 == 0) WSI_STAT(5);      // zero volume, not empty (or no room)
+  else WSI_STAT(6);
+  int viol = 0;
+  reply = arc_send_general_call<C>(c, a, vqip, &viol);
+  c.viol = viol;
+  return false;
+}
+
+// Arc.get_excess("push")["volume"] without a request, arcs.py:230-257
+template <class C>
+WSI_HD double arc_excess_free(C& c, int a) {
+  const int* arcs = nullptr;
+  const int n = chain_of(c, a, arcs);
+  if (n > 0) {
+    double pipe[kMaxChain], E[kMaxChain];
+    chain_excess(c, arcs, n, pipe, E);
+    return E[0];
+  }
+  return arc_excess_vol<kJunctionDepth>(c, a, false, 0.0);
+}
+
+// Node.push_distributed nodes.py:409-478 as the schedule entries call it; returns true when the
+// reply is empty (`reply` all zeros).  One candidate arc (or one out-arc) is handled here with
+// scalars; several candidates go to the general form.
+template <class C>
+WSI_HD bool push_out(C& c, int node, const typename C::Vq& vqip, int filter, typename C::Vq& reply) {
+  using Vq = typename C::Vq;
+  const WsiModelDesc& d = c.D();
+  const int cb = d.cand_ptr[node * WSI_NF + filter];
+  const int nc = d.cand_ptr[node * WSI_NF + filter + 1] - cb;
+  const int n_out = d.out_ptr[node + 1] - d.out_ptr[node];
+  const bool single = n_out == 1;  // nodes.py:424-438
+  if (nc <= 0) {  // nobody to push to (single: nodes.py:436-438; else the loop never runs)
+    reply = vqip;
+    return false;
+  }
+  if (!single && nc > 1) {
+    int viol = 0;
+    reply = push_general_call<C>(c, node, vqip, filter, &viol);
+    c.viol = viol;
+    return false;
+  }
+  const int arc = single ? d.out_arcs[d.out_ptr[node]] : d.cand_arcs[cb];
+  double avail = 0.0, priority = 1.0, alloc = 1.0, pref = 1.0;
+  double not_pushed = vqip.x[0];
+  if (!single) {  // get_connected nodes.py:271-317 for the one candidate
+    double a = arc_excess_free(c, arc);
+    if (a < c.FA) a = 0.0;
+    pref = *c.arc(WSI_ARC_PREFERENCE, arc);
+    avail = 0.0 + a;
+    priority = 0.0 + a * pref;
+    alloc = a * pref;
+    if (not_pushed > avail) {
+      priority = avail;
+      alloc = a;
+    }
+  }
+  reply = vqip;  // not_pushed_
+  int iter = 0;
+#pragma unroll 1
+  while (single || (not_pushed > c.FA && avail > c.FA && iter < kMaxIter)) {
+    const double amount = pymin(avail, not_pushed);
+    const Vq to_send = single ? vqip : c.vchange(reply, amount * alloc / priority);
+    Vq back;
+    const bool empty = arc_send(c, arc, to_send, back);
+    if (single) {
+      reply = back;
+      return empty;
+    }
+    if (empty) {
+      reply = c.extract(reply, to_send);  // sent == to_send
+    } else {
+      const Vq sent = c.extract(to_send, back);
+      reply = c.extract(reply, sent);
+    }
+    not_pushed = reply.x[0];
+    iter++;
+    if (!(not_pushed > c.FA)) break;
+    double a = arc_excess_free(c, arc);
+    if (a < c.FA) a = 0.0;
+    avail = 0.0 + a;
+    priority = 0.0 + a * pref;
+    alloc = a * pref;
+  }
+  if (iter == kMaxIter) c.flag(node, WSI_FLAG_MAXITER);
+  return false;
 }
 
 // =========================================================================================

@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(kBlock, WSI_STEP_MINB)
     // The kernel stalls on instruction fetch more than on anything else (ncu: no_instruction):
     // a warp walks ~20k instructions of a ~1 MB kernel.  Re-aligning the block's 8 warps after
     // every schedule entry keeps them in the same stretch of code.
+#ifndef WSI_NO_OPSYNC
     __syncthreads();
+#endif
   }
 }
 

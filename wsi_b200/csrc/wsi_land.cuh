@@ -661,19 +661,6 @@ WSI_HD typename C::Vq residence_pull(const C& c, typename C::Vq& s, double resid
   return vq_pull(c, s, outflow);
 }
 
-// push_to_sewers land.py:699-721, second half: the ponded runoff left by surface_phase goes to
-// the Sewers and whatever they do not take is forced back into the surface tank.
-template <class C>
-WSI_HD void land_impervious_push(C& c, int node, int u) {
-  using Vq = typename C::Vq;
-  constexpr int V = C::V;
-  const Obj S = c.surf_obj(u);
-  const size_t ss = c.s_surf();
-  const Vq runoff = c.ldv(S(WSI_SURF_FLOW_A(V)), ss);
-  const Vq reply = push_distributed<kJunctionDepth>(c, node, runoff, WSI_FILTER_SEWER);
-  tank_push_force(c, S(WSI_SURF_STORAGE(V)), ss, reply);
-}
-
 // Mass-balance terms of a Land node (core.py:370-429 with land.py:113,158-162), assembled by
 // the mass-balance pass from what is in memory after Land.run: the surfaces' shares (scratch planes), the out-arcs,
 // and the three ResidenceTanks whose storage_ land_phase parked in the node's mb_terms row.
@@ -721,12 +708,27 @@ WSI_HD void land_mass_balance_terms(const C& c, int node, typename C::Vq& in_, t
   }
 }
 
-// Land.run land.py:200-244 after its surfaces have run (surface_phase).  The surfaces' route()
-// pushes (land.py:1046-1058) are applied tank by tank -- each tank still receives them in
-// surface order, so every sum is the reference's -- which lets each ResidenceTank be loaded and
-// stored once and keeps nothing large alive across the calls into the push protocol.
+// Land.run land.py:200-244 after its surfaces have run (surface_phase), as sub-steps of the
+// schedule entry (run_op, wsi_nodes.cuh): one per surface -- an ImperviousSurface's ponded runoff
+// goes to the Sewers (push_to_sewers land.py:699-721, second half) -- then the percolation tank,
+// then the two runoff tanks.  Every sub-step prepares at most one push (land_pre) and consumes its
+// reply (land_post).  The surfaces' route() pushes (land.py:1046-1058) are applied tank by tank --
+// each tank still receives them in surface order, so every sum is the reference's -- which lets
+// each ResidenceTank be loaded and stored once.
+struct OpAux {
+  double x0, x1, x2;
+  int i;
+};
+
 template <class C>
-WSI_HD void land_phase(C& c, int node) {
+WSI_HD int land_substeps(const C& c, int node) {
+  const WsiModelDesc& d = c.D();
+  const int L = d.node_gidx[node];
+  return d.land_surf_ptr[L + 1] - d.land_surf_ptr[L] + 2;
+}
+
+template <class C>
+WSI_HD bool land_pre(C& c, int node, int sub, typename C::Vq& v, int& filter, OpAux& aux) {
   using Vq = typename C::Vq;
   constexpr int V = C::V;
   const WsiModelDesc& d = c.D();
@@ -736,17 +738,15 @@ WSI_HD void land_phase(C& c, int node) {
   const bool want_mb = (c.run_flags & WSI_RUN_MASS_BALANCE) != 0;
   const int s0 = d.land_surf_ptr[L], s1 = d.land_surf_ptr[L + 1];
   double* parked = d.mb_terms + (size_t)d.mb_term_slot[node] * 3 * V * c.R + c.r;
-
-  // impervious surfaces -> Sewers (independent of the Land's own tanks)
-  for (int i = s0; i < s1; i++) {
-    const int u = d.land_surf[i];
-    if ((int)*c.surf(WSI_SURF_TYPE, u) == WSI_ST_IMPERVIOUSSURFACE) land_impervious_push(c, node, u);
-    WSI_BLOCK_ALIGN(c);  // (surface types are the template's: the branch is uniform in the block)
+  if (sub < s1 - s0) {  // impervious surfaces -> Sewers (independent of the Land's own tanks)
+    const int u = d.land_surf[s0 + sub];
+    if ((int)*c.surf(WSI_SURF_TYPE, u) != WSI_ST_IMPERVIOUSSURFACE) return false;
+    v = c.ldv(c.surf(WSI_SURF_FLOW_A(V), u), ss);
+    filter = WSI_FILTER_SEWER;
+    aux.i = u;
+    return true;
   }
-
-  WSI_BLOCK_ALIGN(c);
-  // percolation tank -> Groundwater (land.py:207-215)
-  {
+  if (sub == s1 - s0) {  // percolation tank -> Groundwater (land.py:207-215)
     double* tp = c.land(WSI_LAND_PERCOLATION(V), L);
     Vq T = c.ldv(tp, sl);
     if (want_mb) c.stv_add(parked + (size_t)2 * V * c.R, c.R, T);  // storage_ for the mass balance
@@ -754,53 +754,60 @@ WSI_HD void land_phase(C& c, int node) {
       const Obj S = c.surf_obj(d.land_surf[i]);
       if ((int)*S(WSI_SURF_TYPE) >= WSI_ST_PERVIOUSSURFACE) T = c.sum(T, c.ldv(S(WSI_SURF_FLOW_C(V)), ss));
     }
-    const Vq percolation = residence_pull(c, T, *c.land(WSI_LAND_RES_PERCOLATION, L));
+    v = residence_pull(c, T, *c.land(WSI_LAND_RES_PERCOLATION, L));
     c.stv(tp, sl, T);
-    const Vq reply = push_distributed<kJunctionDepth>(c, node, percolation, WSI_FILTER_GROUNDWATER);
-    if (reply.x[0] > c.FA) tank_push_force(c, tp, sl, reply);
+    filter = WSI_FILTER_GROUNDWATER;
+    return true;
   }
-  WSI_BLOCK_ALIGN(c);
   // surface + subsurface runoff -> River / junction Node (land.py:217-244)
+  double* t_surf = c.land(WSI_LAND_SURFACE_RUNOFF(V), L);
+  double* t_sub = c.land(WSI_LAND_SUBSURFACE_RUNOFF(V), L);
   {
-    double* t_surf = c.land(WSI_LAND_SURFACE_RUNOFF(V), L);
-    double* t_sub = c.land(WSI_LAND_SUBSURFACE_RUNOFF(V), L);
-    Vq total_runoff;
-    double v_surf, v_sub;
-    {
-      Vq T = c.ldv(t_surf, sl);
-      if (want_mb) c.stv_add(parked, c.R, T);
-      for (int i = s0; i < s1; i++) {
-        const Obj S = c.surf_obj(d.land_surf[i]);
-        if ((int)*S(WSI_SURF_TYPE) >= WSI_ST_PERVIOUSSURFACE) T = c.sum(T, c.ldv(S(WSI_SURF_FLOW_A(V)), ss));
-      }
-      total_runoff = residence_pull(c, T, *c.land(WSI_LAND_RES_SURFACE, L));
-      v_surf = total_runoff.x[0];
-      c.stv(t_surf, sl, T);
+    Vq T = c.ldv(t_surf, sl);
+    if (want_mb) c.stv_add(parked, c.R, T);
+    for (int i = s0; i < s1; i++) {
+      const Obj S = c.surf_obj(d.land_surf[i]);
+      if ((int)*S(WSI_SURF_TYPE) >= WSI_ST_PERVIOUSSURFACE) T = c.sum(T, c.ldv(S(WSI_SURF_FLOW_A(V)), ss));
     }
-    WSI_BLOCK_ALIGN(c);
-    {
-      Vq T = c.ldv(t_sub, sl);
-      if (want_mb) c.stv_add(parked + (size_t)V * c.R, c.R, T);
-      for (int i = s0; i < s1; i++) {
-        const Obj S = c.surf_obj(d.land_surf[i]);
-        if ((int)*S(WSI_SURF_TYPE) >= WSI_ST_PERVIOUSSURFACE) T = c.sum(T, c.ldv(S(WSI_SURF_FLOW_B(V)), ss));
-      }
-      const Vq subsurface_runoff = residence_pull(c, T, *c.land(WSI_LAND_RES_SUBSURFACE, L));
-      v_sub = subsurface_runoff.x[0];
-      c.stv(t_sub, sl, T);
-      total_runoff = c.sum(total_runoff, subsurface_runoff);
+    v = residence_pull(c, T, *c.land(WSI_LAND_RES_SURFACE, L));
+    aux.x0 = v.x[0];
+    c.stv(t_surf, sl, T);
+  }
+  {
+    Vq T = c.ldv(t_sub, sl);
+    if (want_mb) c.stv_add(parked + (size_t)V * c.R, c.R, T);
+    for (int i = s0; i < s1; i++) {
+      const Obj S = c.surf_obj(d.land_surf[i]);
+      if ((int)*S(WSI_SURF_TYPE) >= WSI_ST_PERVIOUSSURFACE) T = c.sum(T, c.ldv(S(WSI_SURF_FLOW_B(V)), ss));
     }
-    WSI_BLOCK_ALIGN(c);
-    if (total_runoff.x[0] > 0) {
-      const double v_total = total_runoff.x[0];
-      const Vq reply = push_distributed<kJunctionDepth>(c, node, total_runoff, WSI_FILTER_RIVER_NODE);
-      if (reply.x[0] > 0) {
-        const Vq rs = c.vchange(reply, reply.x[0] * v_surf / v_total);
-        const Vq rss = c.vchange(reply, reply.x[0] * v_sub / v_total);
-        if (rs.x[0] > 0) tank_push_force(c, t_surf, sl, rs);
-        if (rss.x[0] > 0) tank_push_force(c, t_sub, sl, rss);
-      }
-    }
+    const Vq subsurface_runoff = residence_pull(c, T, *c.land(WSI_LAND_RES_SUBSURFACE, L));
+    aux.x1 = subsurface_runoff.x[0];
+    c.stv(t_sub, sl, T);
+    v = c.sum(v, subsurface_runoff);
+  }
+  aux.x2 = v.x[0];
+  filter = WSI_FILTER_RIVER_NODE;
+  return v.x[0] > 0;
+}
+
+template <class C>
+WSI_HD void land_post(C& c, int node, int sub, const typename C::Vq& reply, const OpAux& aux) {
+  using Vq = typename C::Vq;
+  constexpr int V = C::V;
+  const WsiModelDesc& d = c.D();
+  const int L = d.node_gidx[node];
+  const size_t sl = c.s_land();
+  const int ns = d.land_surf_ptr[L + 1] - d.land_surf_ptr[L];
+  if (sub < ns) {  // whatever the Sewers do not take is forced back into the surface tank
+    tank_push_force(c, c.surf(WSI_SURF_STORAGE(V), aux.i), c.s_surf(), reply);
+  } else if (sub == ns) {
+    if (reply.x[0] > c.FA) tank_push_force(c, c.land(WSI_LAND_PERCOLATION(V), L), sl, reply);
+  } else if (reply.x[0] > 0) {
+    const double v_total = aux.x2;
+    const Vq rs = c.vchange(reply, reply.x[0] * aux.x0 / v_total);
+    const Vq rss = c.vchange(reply, reply.x[0] * aux.x1 / v_total);
+    if (rs.x[0] > 0) tank_push_force(c, c.land(WSI_LAND_SURFACE_RUNOFF(V), L), sl, rs);
+    if (rss.x[0] > 0) tank_push_force(c, c.land(WSI_LAND_SUBSURFACE_RUNOFF(V), L), sl, rss);
   }
 }
 

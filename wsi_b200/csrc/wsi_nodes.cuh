@@ -7,41 +7,38 @@
 namespace wsi {
 
 // ---- Groundwater / Storage / Reservoir ----------------------------------------------------
+// A schedule entry that pushes is split in two: *_pre pulls what it wants to send out of its tank
+// (returning false when there is nothing to push), the push itself is the one instance in run_op,
+// and tank_post forces whatever comes back into the tank again.
 template <class C>
-WSI_HD void gw_infiltrate(C& c, int node) {  // storage.py:231-245
+WSI_HD void gw_infiltrate_pre(C& c, int node, typename C::Vq& v) {  // storage.py:231-245
   constexpr int V = C::V;
   const int g = c.D().node_gidx[node];
   double* st = c.tank(WSI_TANK_STORAGE(V), g);
   double avail = st[0];
   avail = pymax(avail - *c.tank(WSI_TANK_CAPACITY, g) * *c.tank(WSI_TANK_INFILTRATION_THRESHOLD, g), 0.0);
   avail = pow(avail * *c.tank(WSI_TANK_INFILTRATION_PCT, g), 0.5);
-  typename C::Vq to_send = tank_pull(c, st, c.s_tank(), avail);
-  typename C::Vq retained = push_distributed<kJunctionDepth>(c, node, to_send, WSI_FILTER_SEWER);
-  tank_push_force(c, st, c.s_tank(), retained);
+  v = tank_pull(c, st, c.s_tank(), avail);
 }
 template <class C>
-WSI_HD void gw_distribute(C& c, int node) {  // storage.py:222-229
+WSI_HD void gw_distribute_pre(C& c, int node, typename C::Vq& v) {  // storage.py:222-229
   constexpr int V = C::V;
   const int g = c.D().node_gidx[node];
   double* st = c.tank(WSI_TANK_STORAGE(V), g);
   const double avail = st[0] / *c.tank(WSI_TANK_RESIDENCE_TIME, g);
-  typename C::Vq to_send = tank_pull(c, st, c.s_tank(), avail);
-  typename C::Vq retained = push_distributed<kJunctionDepth>(c, node, to_send, WSI_FILTER_NRW);
-  tank_push_force(c, st, c.s_tank(), retained);
+  v = tank_pull(c, st, c.s_tank(), avail);
 }
 template <class C>
-WSI_HDN void storage_distribute(C& c, int node) {  // storage.py:120-127
+WSI_HD void storage_distribute_pre(C& c, int node, typename C::Vq& v) {  // storage.py:120-127
   constexpr int V = C::V;
   const int g = c.D().node_gidx[node];
   double* st = c.tank(WSI_TANK_STORAGE(V), g);
-  typename C::Vq storage = tank_pull(c, st, c.s_tank(), st[0]);
-  typename C::Vq retained = push_distributed<kJunctionDepth>(c, node, storage, WSI_FILTER_ALL);
-  tank_push_force(c, st, c.s_tank(), retained);
+  v = tank_pull(c, st, c.s_tank(), st[0]);
 }
 // Reservoir.make_abstractions storage.py:983-989 with no in-arcs: pull_distributed returns
 // an empty VQIP (nodes.py:376-407), which is then pushed (twice) into the tank.
 template <class C>
-WSI_HDN void reservoir_abstract(C& c, int node) {
+WSI_HD void reservoir_abstract(C& c, int node) {
   constexpr int V = C::V;
   const int g = c.D().node_gidx[node];
   double* st = c.tank(WSI_TANK_STORAGE(V), g);
@@ -70,7 +67,7 @@ WSI_HD double ring_sum(const double* ring, size_t stride, int cap, int head, int
 
 // River.calculate_discharge -> biochemical_processes storage.py:738-898, 917-924
 template <class C>
-WSI_HDN void river_calc(C& c, int node) {
+WSI_HD void river_calc(C& c, int node) {
   using Vq = typename C::Vq;
   constexpr int P = C::P;
   constexpr int V = C::V;
@@ -201,29 +198,31 @@ WSI_HDN void river_calc(C& c, int node) {
 }
 
 template <class C>
-WSI_HDN void river_distribute(C& c, int node) {  // storage.py:926-936
+WSI_HD void river_distribute_pre(C& c, int node, typename C::Vq& v) {  // storage.py:926-936
   constexpr int V = C::V;
   const int g = c.D().node_gidx[node];
   const int tk = (int)*c.river(WSI_RIVER_TANK, g);
   double* st = c.tank(WSI_TANK_STORAGE(V), tk);
-  typename C::Vq outflow = tank_pull(c, st, c.s_tank(), st[0] * *c.river(WSI_RIVER_RIVERRC, g));
-  typename C::Vq reply = push_distributed<kJunctionDepth>(c, node, outflow, WSI_FILTER_NRW);
-  tank_push_force(c, st, c.s_tank(), reply);
+  v = tank_pull(c, st, c.s_tank(), st[0] * *c.river(WSI_RIVER_RIVERRC, g));
 }
 
 // ---- Sewer --------------------------------------------------------------------------------
 template <class C>
-WSI_HD void sewer_discharge(C& c, int node) {  // sewer.py:201-239
+WSI_HD void sewer_discharge_pre(C& c, int node, typename C::Vq& v) {  // sewer.py:201-239, up to the push
+  constexpr int V = C::V;
+  const int w = c.D().node_gidx[node];
+  sewer_update_queue(c, w);
+  v = c.ldv(c.sewer(WSI_SEWER_ACTIVE_STORAGE(V), w), c.s_sewer());
+}
+template <class C>
+WSI_HD void sewer_discharge_post(C& c, int node, const typename C::Vq& remaining) {
   using Vq = typename C::Vq;
   constexpr int V = C::V;
   const int w = c.D().node_gidx[node];
   const size_t s = c.s_sewer();
-  sewer_update_queue(c, w);
   double* act = c.sewer(WSI_SEWER_ACTIVE_STORAGE(V), w);
   double* st = c.sewer(WSI_SEWER_STORAGE(V), w);
   Vq active = c.ldv(act, s);
-  Vq remaining = push_distributed<kJunctionDepth>(c, node, active, WSI_FILTER_ALL);
-  active = c.ldv(act, s);
   Vq sent = c.extract(active, remaining);
   // pull_storage_exact tanks.py:566-586
   Vq reply = sent;
@@ -332,21 +331,23 @@ WSI_HD void boundary_release(C& c, int node, bool deliver) {
   }
 }
 
-// Catchment.route catchment.py:77-88; returns unrouted_water (needed by the mass balance)
+// Catchment.route catchment.py:77-88: what is still to be routed, and -- after the push -- the
+// mass-balance terms, which need unrouted_water (the reply)
 template <class C>
-WSI_HDN void catchment_route(C& c, int node) {
-  using Vq = typename C::Vq;
+WSI_HD void catchment_route_pre(C& c, int node, typename C::Vq& v) {
   const WsiModelDesc& d = c.D();
   const int g = d.node_gidx[node];
-  Vq avail = catch_get_flow(c, g);
+  v = catch_get_flow(c, g);
   for (int i = d.out_ptr[node]; i < d.out_ptr[node + 1]; i++)  // get_avail catchment.py:90-104
-    avail = c.vchange(avail, avail.x[0] - *c.arc(WSI_ARC_VQIP_IN(C::V), d.out_arcs[i]));
-  const Vq flow = avail;
-  Vq reply = push_distributed<kJunctionDepth>(c, node, flow, WSI_FILTER_NRW);
+    v = c.vchange(v, v.x[0] - *c.arc(WSI_ARC_VQIP_IN(C::V), d.out_arcs[i]));
+}
+template <class C>
+WSI_HD void catchment_route_post(C& c, int node, const typename C::Vq& reply) {
+  using Vq = typename C::Vq;
   if (c.run_flags & WSI_RUN_MASS_BALANCE) {
     // in = total_in + get_flow(); out = total_out + unrouted_water (catchment.py:55-56)
     Vq in_ = total_in(c, node);
-    ds_add(c, in_, catch_get_flow(c, g));
+    ds_add(c, in_, catch_get_flow(c, c.D().node_gidx[node]));
     Vq out_ = total_out(c, node);
     ds_add(c, out_, reply);
     store_mb_terms(c, node, in_, vq_zero<C::P>(), out_);
@@ -516,22 +517,77 @@ WSI_HD void record(const C& c) {
   for (int k = 0; k < d.n_probe; k++) record_probe(c, row, k);
 }
 
+// Out-of-line ops receive a COPY of the context: a context whose address is handed to a function
+// that is not inlined would have to live in local memory for the whole kernel.
+template <class C>
+WSI_HDN void river_calc_call(C c, int node) {
+  river_calc(c, node);
+}
+template <class C>
+WSI_HDN void reservoir_abstract_call(C c, int node) {
+  reservoir_abstract(c, node);
+}
+
 // ---- one schedule entry -----------------------------------------------------------------------
+// An entry runs as one or more sub-steps (Land.run: one per surface, then its tanks); each sub-step
+// prepares at most one push_distributed call, and the push itself exists ONCE in the kernel (all
+// entries share it), which keeps the schedule kernel's code and its live registers small: between
+// a sub-step's two halves only the VQIP being pushed (then the reply) and three scalars are alive.
 template <class C>
 WSI_HD void run_op(C& c, int op, int node) {
-  switch (op) {
-    case WSI_OP_LAND_RUN: land_phase(c, node); break;
-    case WSI_OP_GW_INFILTRATE: gw_infiltrate(c, node); break;
-    case WSI_OP_SEWER_DISCHARGE: sewer_discharge(c, node); break;
-    case WSI_OP_GW_DISTRIBUTE: gw_distribute(c, node); break;
-    case WSI_OP_RIVER_CALC: river_calc(c, node); break;
-    case WSI_OP_RESERVOIR_ABSTRACT: reservoir_abstract(c, node); break;
-    case WSI_OP_CATCHMENT_ROUTE: catchment_route(c, node); break;
-    case WSI_OP_RIVER_DISTRIBUTE: river_distribute(c, node); break;
-    case WSI_OP_STORAGE_DISTRIBUTE: storage_distribute(c, node); break;
-    case WSI_OP_BOUNDARY_RELEASE: boundary_release(c, node, true); break;
-    default: break;
+  using Vq = typename C::Vq;
+  constexpr int V = C::V;
+  const int n_sub = op == WSI_OP_LAND_RUN ? land_substeps(c, node) : 1;
+#pragma unroll 1
+  for (int sub = 0; sub < n_sub; sub++) {
+    Vq v;
+    OpAux aux = {0.0, 0.0, 0.0, 0};
+    int filter = WSI_FILTER_ALL;
+    bool push = true;
+    switch (op) {
+      case WSI_OP_LAND_RUN: push = land_pre(c, node, sub, v, filter, aux); break;
+      case WSI_OP_GW_INFILTRATE: gw_infiltrate_pre(c, node, v); filter = WSI_FILTER_SEWER; break;
+      case WSI_OP_SEWER_DISCHARGE: sewer_discharge_pre(c, node, v); filter = WSI_FILTER_ALL; break;
+      case WSI_OP_GW_DISTRIBUTE: gw_distribute_pre(c, node, v); filter = WSI_FILTER_NRW; break;
+      case WSI_OP_RIVER_CALC: river_calc_call(c, node); push = false; break;
+      case WSI_OP_RESERVOIR_ABSTRACT: reservoir_abstract_call(c, node); push = false; break;
+      case WSI_OP_CATCHMENT_ROUTE: catchment_route_pre(c, node, v); filter = WSI_FILTER_NRW; break;
+      case WSI_OP_RIVER_DISTRIBUTE: river_distribute_pre(c, node, v); filter = WSI_FILTER_NRW; break;
+      case WSI_OP_STORAGE_DISTRIBUTE: storage_distribute_pre(c, node, v); filter = WSI_FILTER_ALL; break;
+      case WSI_OP_BOUNDARY_RELEASE: boundary_release(c, node, true); push = false; break;
+      default: push = false; break;
+    }
+    WSI_BLOCK_ALIGN(c);
+    Vq reply;
+    if (push) (void)push_out(c, node, v, filter, reply);
+    else reply = vq_zero<C::P>();
+    WSI_BLOCK_ALIGN(c);
+    if (!push) continue;
+    switch (op) {
+      case WSI_OP_LAND_RUN: land_post(c, node, sub, reply, aux); break;
+      case WSI_OP_SEWER_DISCHARGE: sewer_discharge_post(c, node, reply); break;
+      case WSI_OP_CATCHMENT_ROUTE: catchment_route_post(c, node, reply); break;
+      case WSI_OP_GW_INFILTRATE:
+      case WSI_OP_GW_DISTRIBUTE:
+      case WSI_OP_STORAGE_DISTRIBUTE:  // retained water goes back into the tank (storage.py:127,229,245)
+        tank_push_force(c, c.tank(WSI_TANK_STORAGE(V), c.D().node_gidx[node]), c.s_tank(), reply);
+        break;
+      case WSI_OP_RIVER_DISTRIBUTE:  // storage.py:934-936
+        tank_push_force(c, c.tank(WSI_TANK_STORAGE(V), (int)*c.river(WSI_RIVER_TANK, c.D().node_gidx[node])),
+                        c.s_tank(), reply);
+        break;
+      default: break;
+    }
   }
+}
+// out-of-line entry points of single ops for the network engine's scalar fall-backs (wsi_net.cuh)
+template <class C>
+WSI_HDN void catchment_route(C& c, int node) {
+  run_op(c, WSI_OP_CATCHMENT_ROUTE, node);
+}
+template <class C>
+WSI_HDN void river_distribute(C& c, int node) {
+  run_op(c, WSI_OP_RIVER_DISTRIBUTE, node);
 }
 
 template <class C>
