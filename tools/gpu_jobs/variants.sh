@@ -10,7 +10,7 @@ for so in wsi_b200/csrc/variants/libwsi_*.so; do
 import json
 try:
     d=json.load(open("gpurun_out/${tag}_${name}.json"))
-    print("${name}", "ms/step %.4f" % d["ms_per_step"], "frac %.4f" % d["roofline"]["frac"], {k.split()[0]: v for k, v in d["roofline"]["kernel_ms"].items()})
+    print("${name}", "ms/step %.4f" % d["ms_per_step"], "frac %.4f" % d["roofline"]["frac"], [round(v, 4) for v in d["roofline"]["kernel_ms"].values()])
 except Exception as e:
     print("${name}", "FAILED", e)
 PY

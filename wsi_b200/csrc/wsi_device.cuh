@@ -149,10 +149,10 @@ struct Ctx {
 
   // ---- forcing ----
   WSI_HD double forcing(int fid, int col) const {
-    return D().node_forcing[((size_t)t * D().n_fseries + fid) * 3 + col];
+    return ldp(D().node_forcing + ((size_t)t * D().n_fseries + fid) * 3 + col);
   }
   WSI_HD double dep(int dep_id, int col) const {
-    return D().surf_inputs[((size_t)D().month_idx[t] * D().n_dep_series + dep_id) * WSI_N_DEP + col];
+    return ldp(D().surf_inputs + ((size_t)D().month_idx[t] * D().n_dep_series + dep_id) * WSI_N_DEP + col);
   }
 
   // ---- algebra shorthands ----
@@ -866,6 +866,24 @@ inline WSI_HDN double magnitude10(double x) {
   return 1.0 / pow10i(j);
 }
 
+// one lane of WSIObj.mass_balance's test, core.py:404-419: |in/m - ds/m - out/m| > FLOAT_ACCURACY
+// with m = 10**int(log10(largest)) (m = 1 when largest <= FLOAT_ACCURACY).  m lies in (x/10, x] for
+// x >= 1 and in [x, 10x) below 1, so most lanes are decided from those bounds; the exact power of
+// ten (and the three divisions) are only evaluated when the residual is within 1 % of a possible
+// threshold.
+template <class C>
+WSI_HD bool mb_lane_bad(const C& c, double a, double dd, double o) {
+  const double largest = pymax(pymax(a, o), dd);
+  const double resid = fabs(a - dd - o);
+  if (!(largest > c.FA)) return resid > c.FA;
+  const double m_lo = largest >= 1.0 ? largest * 0.1 : largest;
+  const double m_hi = largest >= 1.0 ? largest : largest * 10.0;
+  if (c.FA >= 1e-12 && resid < 0.99 * c.FA * m_lo) return false;
+  if (c.FA >= 1e-12 && resid > 1.01 * c.FA * m_hi) return true;
+  const double magnitude = magnitude10(largest);
+  return fabs(a / magnitude - dd / magnitude - o / magnitude) > c.FA;
+}
+
 template <class C>
 WSI_HD void mb_check(C& c, int node, const typename C::Vq& in_, const typename C::Vq& ds_,
                      const typename C::Vq& out_) {
@@ -874,29 +892,7 @@ WSI_HD void mb_check(C& c, int node, const typename C::Vq& in_, const typename C
 #pragma unroll
   for (int p = 0; p <= C::P; p++) {
     if (p != 0 && !bit(c.addm(), p)) continue;
-    const double a = in_.x[p], o = out_.x[p], dd = ds_.x[p];
-    const double largest = pymax(pymax(a, o), dd);
-    // core.py:404-419: |in/m - ds/m - out/m| > FLOAT_ACCURACY with m = 10**int(log10(largest))
-    // (m = 1 when largest <= FLOAT_ACCURACY).  m lies in (x/10, x] for x >= 1 and in [x, 10x)
-    // below 1, so most lanes are decided from those bounds; the exact power of ten (and the
-    // three divisions) are only evaluated when the residual is within 1 % of a possible threshold.
-    const double resid = fabs(a - dd - o);
-    bool bad;
-    if (!(largest > c.FA)) {
-      bad = resid > c.FA;
-    } else {
-      const double m_lo = largest >= 1.0 ? largest * 0.1 : largest;
-      const double m_hi = largest >= 1.0 ? largest : largest * 10.0;
-      if (c.FA >= 1e-12 && resid < 0.99 * c.FA * m_lo) {
-        bad = false;
-      } else if (c.FA >= 1e-12 && resid > 1.01 * c.FA * m_hi) {
-        bad = true;
-      } else {
-        const double magnitude = magnitude10(largest);
-        bad = fabs(a / magnitude - dd / magnitude - o / magnitude) > c.FA;
-      }
-    }
-    if (bad) viol++;
+    if (mb_lane_bad(c, in_.x[p], ds_.x[p], out_.x[p])) viol++;
   }
   if (viol) {
     c.flag(node, WSI_FLAG_MASS_BALANCE);

@@ -25,7 +25,10 @@ int fail(int code, const char* fmt, const char* detail = "");
 bool cluster_enabled();
 
 constexpr int kBlock = WSI_STEP_BLOCK;  // replicas per block of the per-replica schedule kernel
-constexpr int kSurfBlock = 128;         // surfaces per block of the surface kernels
+#ifndef WSI_SURF_BLOCK
+#define WSI_SURF_BLOCK 128
+#endif
+constexpr int kSurfBlock = WSI_SURF_BLOCK;         // surfaces per block of the surface kernels
 constexpr int kObjBlock = 128;          // replicas per block of the object-parallel kernels
 
 inline int n_blocks(const WsiModelDesc* d) { return (d->R + kBlock - 1) / kBlock; }

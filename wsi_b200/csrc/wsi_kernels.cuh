@@ -36,7 +36,7 @@ namespace {
 // Minimum resident blocks per SM requested from ptxas (caps registers per thread): the kernels
 // are latency-bound, so occupancy matters more than avoiding a few spills.
 #ifndef WSI_SURF_MINB
-#define WSI_SURF_MINB 3
+#define WSI_SURF_MINB 6  // 80 registers: the merged launch prefers threads in flight (gpurun sweep r2j/r2k: 3 -> 0.134, 4 -> 0.128, 5 -> 0.138, 6 -> 0.119, 7 -> 0.123, 8 -> 0.133 ms)
 #endif
 #ifndef WSI_STEP_MINB
 #define WSI_STEP_MINB 3
@@ -47,7 +47,8 @@ namespace {
 #ifndef WSI_MB_MINB  // mass balance / record / end_timestep: streaming kernels
 #define WSI_MB_MINB 5  // 96 registers: 6 (80) spills more, 4 (128) starves the end_timestep copy (gpurun sweep, round 1)
 #endif
-constexpr size_t kDescSmem = sizeof(WsiModelDesc);  // dynamic shared memory: the staged descriptor
+constexpr size_t kDescSmem = sizeof(WsiModelDesc);
+constexpr int kFusedTailMaxR = 4096;  // replicas up to which the schedule kernel runs mb / record / end itself  // dynamic shared memory: the staged descriptor
 
 // Work-item decode of the object-parallel kernels.  Replica engine (FLAT = false): blockIdx.y is
 // the item and blockIdx.x tiles the replicas, so every block is homogeneous in item.  Network
@@ -90,14 +91,66 @@ __global__ void __launch_bounds__(kSurfBlock, WSI_SURF_MINB)
   surface_phase<TYPE>(c, u);
 }
 
+// All surface classes in ONE launch: blockIdx.y walks surf_order backwards, so the blocks of the
+// heaviest class (GrowingSurface, last in the order) are scheduled first and the light classes fill
+// the tail of the launch; every block is still homogeneous in class.
+template <class CFG>
+__global__ void __launch_bounds__(kSurfBlock, WSI_SURF_MINB)
+    wsi_surfaces_kernel(const int slot, const CFG cfg, const int t_arg, const uint32_t flags) {
+  const WsiModelDesc& d = g_wsi_desc[slot];
+  const int t = step_of(d, t_arg);
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= d.R) return;
+  const int k = (int)gridDim.y - 1 - (int)blockIdx.y;
+  const int u = d.surf_order[k];
+  Ctx<CFG> c = make_ctx(nullptr, slot, cfg, r, t, flags);
+  if (k >= d.surf_class_ptr[WSI_ST_GROWINGSURFACE]) surface_phase<WSI_ST_GROWINGSURFACE>(c, u);
+  else if (k >= d.surf_class_ptr[WSI_ST_PERVIOUSSURFACE]) surface_phase<WSI_ST_PERVIOUSSURFACE>(c, u);
+  else if (k >= d.surf_class_ptr[WSI_ST_IMPERVIOUSSURFACE]) surface_phase<WSI_ST_IMPERVIOUSSURFACE>(c, u);
+  else surface_phase<WSI_ST_SURFACE>(c, u);
+}
+
 // One thread per replica: the orchestration schedule (Land.run after its surfaces, Groundwater,
 // Sewer, River, Catchment ops and river routing, in the reference's order).  Land / Catchment
 // form their mass-balance terms here (everything is still at hand) and leave them in mb_terms.
 // Routing is sequential inside a replica by construction.
+// Block-level sink of the schedule kernel's fused mass balance: violations via one atomic per warp,
+// the replica's system-total contributions via a butterfly over the warp (every lane ends with the
+// same sum, fixed order) into one shared-memory row per warp.
+template <int V>
+struct MbBlockSink {
+  double (*s_w)[3 * V];
+  int viol;
+  template <class C>
+  __device__ __forceinline__ void take(C& c, int lane, int v, double a, double b, double o) {
+    viol += v;
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, k);
+      b += __shfl_xor_sync(0xffffffffu, b, k);
+      o += __shfl_xor_sync(0xffffffffu, o, k);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      double* row = s_w[threadIdx.x >> 5];
+      row[0 * V + lane] = a;
+      row[1 * V + lane] = b;
+      row[2 * V + lane] = o;
+    }
+  }
+};
+
+// One thread per replica: the orchestration schedule (Land.run after its surfaces, Groundwater,
+// Sewer, River, Catchment ops and river routing, in the reference's order), then -- fused tail --
+// the replica's mass balances (lane by lane, wsi_nodes.cuh), recording and end_timestep: the
+// thread reads back what it has just written (L1 / L2) instead of three more kernels re-streaming
+// the state from HBM.  Routing is sequential inside a replica by construction.
 template <class CFG>
 __global__ void __launch_bounds__(kBlock, WSI_STEP_MINB)
     wsi_step_kernel(const int slot, const CFG cfg, const int t_arg, const int sched_begin, const int sched_end,
-                    const uint32_t flags) {
+                    const uint32_t flags, const int row_arg, const int fused) {
+  constexpr int V = CFG::P + 1;
+  constexpr int kWarps = kBlock / 32;
+  __shared__ double s_w[kWarps][3 * V];
   wsi_stage_desc(slot);
   const WsiModelDesc& d = g_wsi_desc[slot];
   const int t = step_of(d, t_arg);
@@ -105,15 +158,45 @@ __global__ void __launch_bounds__(kBlock, WSI_STEP_MINB)
   const bool active = r < d.R;
   Ctx<CFG, true> c = make_ctx<true>(nullptr, slot, cfg, active ? r : 0, t, flags);
   c.block_sync = (blockIdx.x + 1) * blockDim.x <= (unsigned)d.R;  // full block: all threads walk the schedule
-  for (int k = sched_begin; k < sched_end; k++) {
-    if (active) run_op(c, d.sched_op[k], d.sched_node[k]);
-    // The kernel stalls on instruction fetch more than on anything else (ncu: no_instruction):
-    // a warp walks ~20k instructions of a ~1 MB kernel.  Re-aligning the block's 8 warps after
-    // every schedule entry keeps them in the same stretch of code.
+  if (flags & WSI_RUN_SCHEDULE) {
+    for (int k = sched_begin; k < sched_end; k++) {
+      if (active) run_op(c, d.sched_op[k], d.sched_node[k]);
+      // The kernel stalls on instruction fetch more than on anything else (ncu: no_instruction):
+      // a warp walks ~14k instructions.  Re-aligning the block's 8 warps after every schedule
+      // entry keeps them in the same stretch of code.
 #ifndef WSI_NO_OPSYNC
-    __syncthreads();
+      __syncthreads();
 #endif
+    }
   }
+  if (!fused) return;  // the object-parallel kernels run the other phases
+  if (flags & WSI_RUN_MASS_BALANCE) {
+    const bool want_sums = d.mb_sums != nullptr;
+    MbBlockSink<V> sink = {s_w, 0};
+    replica_mb_lanes<0>(c, active, want_sums, sink);
+    int v = sink.viol;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0 && d.mb_count) atomicAdd(&d.mb_count[t], v);
+    if (want_sums) {
+      __syncthreads();
+      if (threadIdx.x < 3 * V) {
+        const int p = threadIdx.x % V;
+        double acc = 0.0;
+        if (p == 0 || bit(c.addm(), p))
+          for (int w = 0; w < kWarps; w++) acc += s_w[w][threadIdx.x];
+        d.mb_partial[(size_t)blockIdx.x * 3 * V + threadIdx.x] = acc;
+      }
+    }
+  }
+  if (!active) return;
+  if (flags & WSI_RUN_RECORD) {
+    const int row = t_arg >= 0 ? row_arg : t - d.rec_t0;
+    if (row >= 0 && row < d.rec_T)
+      for (int k = 0; k < d.n_probe; k++) record_probe(c, row, k);
+  }
+  if (flags & WSI_RUN_END_TIMESTEP)
+    for (int i = 0; i < d.n_end; i++) end_item(c, d.end_kind[i], d.end_obj[i]);
 }
 
 // One thread per (node or arc, replica): WSIObj.mass_balance (core.py:370-429) of every node and
@@ -506,6 +589,13 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
   constexpr int V = CFG::P + 1;
   const bool want_mb = (flags & WSI_RUN_MASS_BALANCE) != 0;
   const bool want_sums = want_mb && d->mb_sums != nullptr;
+#ifndef WSI_SURF_SPLIT
+  if ((flags & WSI_RUN_SURFACES) && d->n_surf > 0 && d->n_surf <= 65535) {
+    const dim3 grid((d->R + kSurfBlock - 1) / kSurfBlock, d->n_surf);
+    wsi_surfaces_kernel<CFG><<<grid, kSurfBlock, 0, s>>>(slot, cfg, (int)t, flags);
+    WSI_CHECK_LAUNCH("wsi_surfaces_kernel");
+  } else
+#endif
   if (flags & WSI_RUN_SURFACES) {
     int rc = launch_surfaces<CFG, WSI_ST_SURFACE>(d, slot, cfg, t, flags, s);
     if (!rc) rc = launch_surfaces<CFG, WSI_ST_IMPERVIOUSSURFACE>(d, slot, cfg, t, flags, s);
@@ -585,8 +675,22 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
         WSI_CHECK_LAUNCH("wsi_net_tail_general");
       }
     } else {
-      wsi_step_kernel<CFG><<<n_blocks(d), kBlock, kDescSmem, s>>>(slot, cfg, (int)t, b, e, flags);
+      // Small ensembles are launch-latency bound: the schedule kernel then also runs the other
+      // phases asked for (fused tail, one thread per replica).  Large ones have the threads to hide
+      // the tail's dependent loads only when it runs one thread per (object, replica): measured on
+      // config 2 at R = 1e5, fused 0.228 ms vs 0.13 ms for the three object-parallel kernels.
+      const bool fused = d->R <= kFusedTailMaxR;
+      wsi_step_kernel<CFG><<<n_blocks(d), kBlock, kDescSmem, s>>>(slot, cfg, (int)t, b, e, flags, (int)t - d->rec_t0,
+                                                                    fused ? 1 : 0);
       WSI_CHECK_LAUNCH("wsi_step_kernel");
+      if (fused) {
+        if (want_sums) {
+          const int n = 3 * V;
+          wsi_mb_finalize<<<n, kFinBlock, 0, s>>>(slot, (int)t, n_blocks(d), n);
+          WSI_CHECK_LAUNCH("wsi_mb_finalize");
+        }
+        return WSI_OK;
+      }
     }
   }
   if (want_mb) {

@@ -44,12 +44,12 @@ WSI_HD void temp_soil_process(const Pools& pl, const double par0, const double p
 // xp/yp are table planes (stride `st` doubles apart)
 WSI_HD double quick_interp(double x, const double* xp, const double* yp, size_t st, int n) {
   int i = 0;
-  while (i < n && xp[(size_t)i * st] < x) i++;
+  while (i < n && ldp(xp + (size_t)i * st) < x) i++;
   int il = i - 1;
   if (il < 0) il += n;
   if (i >= n) i = n - 1;  // the reference raises IndexError here
-  const double x_left = xp[(size_t)il * st], x_right = xp[(size_t)i * st];
-  const double y_left = yp[(size_t)il * st], y_right = yp[(size_t)i * st];
+  const double x_left = ldp(xp + (size_t)il * st), x_right = ldp(xp + (size_t)i * st);
+  const double y_left = ldp(yp + (size_t)il * st), y_right = ldp(yp + (size_t)i * st);
   return y_left + (y_right - y_left) * (x - x_left) / (x_right - x_left);
 }
 
@@ -84,14 +84,14 @@ WSI_HD void surface_phase(C& c, int u) {
   constexpr int V = C::V;
   const size_t ss = c.s_surf();
   const Obj S = c.surf_obj(u);
-  const int type = TYPE >= 0 ? TYPE : (int)*S(WSI_SURF_TYPE);
-  const int L = (int)*S(WSI_SURF_LAND);
+  const int type = TYPE >= 0 ? TYPE : (int)ldp(S(WSI_SURF_TYPE));
+  const int L = (int)ldp(S(WSI_SURF_LAND));
   const Obj Lo = c.land_obj(L);
   const int fid = (int)*Lo(WSI_LAND_FORCING_ID);
   const double precip = c.forcing(fid, 0), et0 = c.forcing(fid, 1), temperature = c.forcing(fid, 2);
   const bool want_ds = (c.run_flags & WSI_RUN_MASS_BALANCE) != 0;
   Vq mb_in = vq_zero<P>(), mb_out = vq_zero<P>();
-  const double area = *S(WSI_SURF_AREA);
+  const double area = ldp(S(WSI_SURF_AREA));
   double* stp = S(WSI_SURF_STORAGE(V));
   Vq st = c.ldv(stp, ss);
   const auto& cfg = c.cfg;
@@ -122,7 +122,7 @@ WSI_HD void surface_phase(C& c, int u) {
     pl.smdf = 0.0;
   }
   double et0_coef = *S(WSI_SURF_ET0_COEFFICIENT);
-  double days_after_sow = 0.0, crop_cover = 0.0, ground_cover = 0.0;
+  double days_after_sow = 0.0, crop_cover = 0.0, ground_cover = 0.0, crop_factor_out = 0.0;
 
   // ---- inflows --------------------------------------------------------------------------
   if (growing) {  // calc_crop_cover land.py:1514-1572
@@ -132,9 +132,9 @@ WSI_HD void surface_phase(C& c, int u) {
     crop_cover = *S(WSI_SURF_CROP_COVER);
     ground_cover = *S(WSI_SURF_GROUND_COVER);
     if (days_after_sow < 0) {
-      if (dayofyear == *S(WSI_SURF_SOWING_DAY)) days_after_sow = 0.0;
+      if (dayofyear == ldp(S(WSI_SURF_SOWING_DAY))) days_after_sow = 0.0;
     } else {
-      if (dayofyear == *S(WSI_SURF_HARVEST_DAY)) {
+      if (dayofyear == ldp(S(WSI_SURF_HARVEST_DAY))) {
         days_after_sow = -1.0;
         crop_cover = 0.0;
         ground_cover = 0.0;
@@ -143,30 +143,26 @@ WSI_HD void surface_phase(C& c, int u) {
       }
     }
     const double crop_factor = quick_interp(doy, S(WSI_SURF_STAGE_DATES), S(WSI_SURF_STAGE_VALS), ss,
-                                            (int)*S(WSI_SURF_N_STAGE));
+                                            (int)ldp(S(WSI_SURF_N_STAGE)));
     if (days_after_sow > 0) {
       crop_cover = quick_interp(doy, S(WSI_SURF_HS_CALENDAR), S(WSI_SURF_CROP_COVER_STAGES), ss, 5);
       ground_cover = quick_interp(doy, S(WSI_SURF_HS_CALENDAR), S(WSI_SURF_GROUND_COVER_STAGES), ss, 5);
     }
-    const double fc_m = *S(WSI_SURF_FIELD_CAPACITY_M);
+    const double fc_m = ldp(S(WSI_SURF_FIELD_CAPACITY_M));
     const double rzd = pymax(fc_m - st.x[0] / area, 0.0);
     double stress;
-    if (rzd < *S(WSI_SURF_READILY_AVAILABLE_WATER)) {
+    if (rzd < ldp(S(WSI_SURF_READILY_AVAILABLE_WATER))) {
       stress = 1.0;
     } else {
-      const double taw = *S(WSI_SURF_TOTAL_AVAILABLE_WATER);
-      stress = pymax(0.0, (taw - rzd) / ((1 - *S(WSI_SURF_ET_DEPLETION_FACTOR)) * taw));
+      const double taw = ldp(S(WSI_SURF_TOTAL_AVAILABLE_WATER));
+      stress = pymax(0.0, (taw - rzd) / ((1 - ldp(S(WSI_SURF_ET_DEPLETION_FACTOR))) * taw));
     }
     et0_coef = stress * crop_factor;
-    *S(WSI_SURF_DAYS_AFTER_SOW) = days_after_sow;
-    *S(WSI_SURF_CROP_COVER) = crop_cover;
-    *S(WSI_SURF_GROUND_COVER) = ground_cover;
-    *S(WSI_SURF_CROP_FACTOR) = crop_factor;
-    *S(WSI_SURF_ET0_COEFFICIENT) = et0_coef;
+    crop_factor_out = crop_factor;
   }
 
-  const int dep_id = (int)*S(WSI_SURF_DEP_ID);
-  if (*S(WSI_SURF_HAS_DEP) != 0.0) {
+  const int dep_id = (int)ldp(S(WSI_SURF_DEP_ID));
+  if (ldp(S(WSI_SURF_HAS_DEP)) != 0.0) {
     // atmospheric_deposition / precipitation_deposition land.py:528-581 (dry, then wet)
 #pragma unroll
     for (int wet = 0; wet < 2; wet++) {
@@ -182,8 +178,8 @@ WSI_HD void surface_phase(C& c, int u) {
         const double depN = noy + nhx, depP = srp;
         double inN, inP;
         if (!wet) {  // allocate_dry_deposition nutrient_pool.py:226-248
-          const double f_di = *S(WSI_SURF_FRAC_DRY_N_TO_DIS_INORG);
-          pl.fast[0] += depN * *S(WSI_SURF_FRAC_DRY_N_TO_FAST);
+          const double f_di = ldp(S(WSI_SURF_FRAC_DRY_N_TO_DIS_INORG));
+          pl.fast[0] += depN * ldp(S(WSI_SURF_FRAC_DRY_N_TO_FAST));
           pl.dis_inorg[0] += depN * f_di;
           pl.ads_inorg[1] += depP;
           inN = depN * f_di;
@@ -200,12 +196,12 @@ WSI_HD void surface_phase(C& c, int u) {
       mb_acc(c, mb_in, v);
     }
   }
-  if (*S(WSI_SURF_HAS_LOAD) != 0.0) {  // simple_deposition land.py:505-526
+  if (ldp(S(WSI_SURF_HAS_LOAD)) != 0.0) {  // simple_deposition land.py:505-526
     Vq pol;
     pol.x[0] = 0.0;
     const double* lp = S(WSI_SURF_LOAD(V));
 #pragma unroll
-    for (int p = 1; p <= P; p++) pol.x[p] = bit(c.addm(), p) ? lp[(size_t)p * ss] * area : lp[(size_t)p * ss];
+    for (int p = 1; p <= P; p++) pol.x[p] = bit(c.addm(), p) ? ldp(lp + (size_t)p * ss) * area : ldp(lp + (size_t)p * ss);
     st = c.sum(st, pol);
     mb_acc(c, mb_in, pol);
   }
@@ -215,7 +211,7 @@ WSI_HD void surface_phase(C& c, int u) {
 
   if (type == WSI_ST_IMPERVIOUSSURFACE) {
     // precipitation_evaporation land.py:645-697
-    const double evaporation_depth = et0 * *S(WSI_SURF_ET0_TO_E);
+    const double evaporation_depth = et0 * ldp(S(WSI_SURF_ET0_TO_E));
     double total_evaporation;
     if (precip < evaporation_depth) {
       double e = (evaporation_depth - precip) * area;
@@ -234,27 +230,27 @@ WSI_HD void surface_phase(C& c, int u) {
     mb_out.x[0] += out_evap;
     // push_to_sewers land.py:699-721, first half: pull_ponded.  The push to the Sewers and
     // forcing the reply back into this tank happen in land_phase (the sewer is shared state).
-    const double ponded = pymax(st.x[0] - *S(WSI_SURF_CAPACITY), 0.0);
+    const double ponded = pymax(st.x[0] - ldp(S(WSI_SURF_CAPACITY)), 0.0);
     ie = vq_pull(c, st, ponded);
   } else if (type >= WSI_ST_PERVIOUSSURFACE) {
     // ihacres land.py:913-1044
-    const double depth = *S(WSI_SURF_DEPTH);
-    const double capacity = *S(WSI_SURF_CAPACITY);
-    const double fc_m = *S(WSI_SURF_FIELD_CAPACITY_M);
-    const double wp_m = *S(WSI_SURF_WILTING_POINT_M);
+    const double depth = ldp(S(WSI_SURF_DEPTH));
+    const double capacity = ldp(S(WSI_SURF_CAPACITY));
+    const double fc_m = ldp(S(WSI_SURF_FIELD_CAPACITY_M));
+    const double wp_m = ldp(S(WSI_SURF_WILTING_POINT_M));
     const double evaporation_depth = et0 * et0_coef;  // get_climate land.py:903-911
-    const double inf_cap = *S(WSI_SURF_INFILTRATION_CAPACITY);
+    const double inf_cap = ldp(S(WSI_SURF_INFILTRATION_CAPACITY));
     const double infiltrated = pymin(precip, inf_cap);
     double infiltration_excess = pymax(precip - infiltrated, 0.0);
     const double cmd = tank_excess_vol(capacity, st.x[0], false, 0.0) / area;  // get_cmd land.py:886
     double evaporation = evaporation_depth * pymin(1.0, exp(2 * (1 - cmd / (depth - wp_m))));
     const double outflow =
-        infiltrated * (1 - pymin(1.0, pow(cmd / (depth - fc_m), *S(WSI_SURF_IHACRES_P))));
+        infiltrated * (1 - pymin(1.0, pow(cmd / (depth - fc_m), ldp(S(WSI_SURF_IHACRES_P)))));
     evaporation = pymin(evaporation, precip + st.x[0] / area);
-    const double surf_coef = *S(WSI_SURF_SURFACE_COEFFICIENT);
+    const double surf_coef = ldp(S(WSI_SURF_SURFACE_COEFFICIENT));
     const double surface = outflow * surf_coef * area;
-    const double percolation = outflow * (1 - surf_coef) * *S(WSI_SURF_PERCOLATION_COEFFICIENT) * area;
-    const double subsurface_flow = outflow * (1 - surf_coef) * *S(WSI_SURF_SUBSURFACE_COEFFICIENT) * area;
+    const double percolation = outflow * (1 - surf_coef) * ldp(S(WSI_SURF_PERCOLATION_COEFFICIENT)) * area;
+    const double subsurface_flow = outflow * (1 - surf_coef) * ldp(S(WSI_SURF_SUBSURFACE_COEFFICIENT)) * area;
     const double tank_recharge = (infiltrated - evaporation - outflow) * area;
     infiltration_excess *= area;
     infiltration_excess += surface;
@@ -342,11 +338,11 @@ WSI_HD void surface_phase(C& c, int u) {
           inN = depN;
           inP = depP;
         } else {  // allocate_manure nutrient_pool.py:267-290
-          const double fN = *S(WSI_SURF_FRAC_MANURE_TO_DIS_INORG), fP = *S(WSI_SURF_FRAC_MANURE_TO_DIS_INORG + 1);
+          const double fN = ldp(S(WSI_SURF_FRAC_MANURE_TO_DIS_INORG)), fP = ldp(S(WSI_SURF_FRAC_MANURE_TO_DIS_INORG + 1));
           pl.dis_inorg[0] += depN * fN;
           pl.dis_inorg[1] += depP * fP;
-          pl.fast[0] += depN * *S(WSI_SURF_FRAC_MANURE_TO_FAST);
-          pl.fast[1] += depP * *S(WSI_SURF_FRAC_MANURE_TO_FAST + 1);
+          pl.fast[0] += depN * ldp(S(WSI_SURF_FRAC_MANURE_TO_FAST));
+          pl.fast[1] += depP * ldp(S(WSI_SURF_FRAC_MANURE_TO_FAST + 1));
           inN = depN * fN;
           inP = depP * fP;
         }
@@ -358,15 +354,15 @@ WSI_HD void surface_phase(C& c, int u) {
 
     // ---- processes ----------------------------------------------------------------------
     if (cfg.temp() >= 0) {  // calculate_soil_temperature land.py:1060-1079
-      const double w_prev = *S(WSI_SURF_SOIL_TEMP_W_PREV), w_air = *S(WSI_SURF_SOIL_TEMP_W_AIR),
-                   w_deep = *S(WSI_SURF_SOIL_TEMP_W_DEEP);
+      const double w_prev = ldp(S(WSI_SURF_SOIL_TEMP_W_PREV)), w_air = ldp(S(WSI_SURF_SOIL_TEMP_W_AIR)),
+                   w_deep = ldp(S(WSI_SURF_SOIL_TEMP_W_DEEP));
       const double au = vget<P>(st, cfg.temp()) * w_prev;
       const double air = temperature * w_air;
       const double total_weight = w_air + w_deep + w_prev;
-      vset<P>(st, cfg.temp(), (au + air + *S(WSI_SURF_SOIL_TEMP_DEEP) * w_deep) / total_weight);
+      vset<P>(st, cfg.temp(), (au + air + ldp(S(WSI_SURF_SOIL_TEMP_DEEP)) * w_deep) / total_weight);
     }
     if (nutrients) {
-      const double rooting_depth = *S(WSI_SURF_ROOTING_DEPTH);
+      const double rooting_depth = ldp(S(WSI_SURF_ROOTING_DEPTH));
       const double soilT = vget<P>(st, cfg.temp());
       // calc_temperature_dependence_factor land.py:1813-1831
       if (soilT > 5)
@@ -378,16 +374,16 @@ WSI_HD void surface_phase(C& c, int u) {
       // calc_soil_moisture_dependence_factor land.py:1833-1856
       {
         const double smc = st.x[0] / area;
-        const double satact = *S(WSI_SURF_SATACT);
+        const double satact = ldp(S(WSI_SURF_SATACT));
         if (smc >= fc_m) {
           pl.smdf = satact;
         } else if (smc <= wp_m) {
           pl.smdf = 0.0;
         } else {
-          const double thetapow = *S(WSI_SURF_THETAPOW);
-          double fc_comp = pow((fc_m - smc) / (*S(WSI_SURF_THETAUPP) * rooting_depth), thetapow);
+          const double thetapow = ldp(S(WSI_SURF_THETAPOW));
+          double fc_comp = pow((fc_m - smc) / (ldp(S(WSI_SURF_THETAUPP)) * rooting_depth), thetapow);
           fc_comp = (1 - satact) * fc_comp + satact;
-          const double wp_comp = pow((smc - wp_m) / (*S(WSI_SURF_THETALOW) * rooting_depth), thetapow);
+          const double wp_comp = pow((smc - wp_m) / (ldp(S(WSI_SURF_THETALOW)) * rooting_depth), thetapow);
           pl.smdf = pymin(pymin(1.0, wp_comp), fc_comp);
         }
       }
@@ -397,17 +393,17 @@ WSI_HD void surface_phase(C& c, int u) {
         if (sno3 + snh4 == 0) c.flag((int)*Lo(WSI_LAND_NODE), WSI_FLAG_NAN);
         const double nitrate_proportion = sno3 / (sno3 + snh4);
         double inc_di[2] = {0.0, 0.0}, inc_do[2] = {0.0, 0.0}, amount[2];
-        temp_soil_process(pl, *S(WSI_SURF_DEGRHPAR), *S(WSI_SURF_DEGRHPAR + 1), pl.humus, pl.fast, amount);
-        temp_soil_process(pl, *S(WSI_SURF_DISHPAR), *S(WSI_SURF_DISHPAR + 1), pl.humus, pl.dis_org, amount);
+        temp_soil_process(pl, ldp(S(WSI_SURF_DEGRHPAR)), ldp(S(WSI_SURF_DEGRHPAR + 1)), pl.humus, pl.fast, amount);
+        temp_soil_process(pl, ldp(S(WSI_SURF_DISHPAR)), ldp(S(WSI_SURF_DISHPAR + 1)), pl.humus, pl.dis_org, amount);
         inc_do[0] = inc_do[0] + amount[0];
         inc_do[1] = inc_do[1] + amount[1];
-        temp_soil_process(pl, *S(WSI_SURF_MINFPAR), *S(WSI_SURF_MINFPAR + 1), pl.fast, pl.dis_inorg, amount);
+        temp_soil_process(pl, ldp(S(WSI_SURF_MINFPAR)), ldp(S(WSI_SURF_MINFPAR + 1)), pl.fast, pl.dis_inorg, amount);
         inc_di[0] = inc_di[0] + amount[0];
         inc_di[1] = inc_di[1] + amount[1];
-        temp_soil_process(pl, *S(WSI_SURF_DISFPAR), *S(WSI_SURF_DISFPAR + 1), pl.fast, pl.dis_org, amount);
+        temp_soil_process(pl, ldp(S(WSI_SURF_DISFPAR)), ldp(S(WSI_SURF_DISFPAR + 1)), pl.fast, pl.dis_org, amount);
         inc_do[0] = inc_do[0] + amount[0];
         inc_do[1] = inc_do[1] + amount[1];
-        temp_soil_process(pl, *S(WSI_SURF_IMMOBDPAR), *S(WSI_SURF_IMMOBDPAR + 1), pl.dis_inorg, pl.fast, amount);
+        temp_soil_process(pl, ldp(S(WSI_SURF_IMMOBDPAR)), ldp(S(WSI_SURF_IMMOBDPAR + 1)), pl.dis_inorg, pl.fast, amount);
         inc_di[0] = inc_di[0] - amount[0];
         inc_di[1] = inc_di[1] - amount[1];
         Vq in_ = vq_zero<P>(), out_ = vq_zero<P>();
@@ -439,16 +435,16 @@ WSI_HD void surface_phase(C& c, int u) {
       if (days_after_sow > 0) {
         double das = days_after_sow;
         double temp_func = 1.0;
-        if (*S(WSI_SURF_AUTUMN_SOW) != 0.0) {
+        if (ldp(S(WSI_SURF_AUTUMN_SOW)) != 0.0) {
           temp_func = pymax(0.0, pymin(1.0, (vget<P>(st, cfg.temp()) - 5) / 20));
           das -= 25;
         }
-        const double u1 = *S(WSI_SURF_UPTAKE1), u2 = *S(WSI_SURF_UPTAKE2), u3 = *S(WSI_SURF_UPTAKE3);
+        const double u1 = ldp(S(WSI_SURF_UPTAKE1)), u2 = ldp(S(WSI_SURF_UPTAKE2)), u3 = ldp(S(WSI_SURF_UPTAKE3));
         const double uptake_par = (u1 - u2) * exp(-u3 * das);
         double N_common = 0.0;
         if (uptake_par + u2 > 0) N_common = u1 * u2 * u3 * uptake_par / ((u2 + uptake_par) * (u2 + uptake_par));
         N_common *= temp_func * 1e-3 * area;  // G_M2_TO_KG_M2
-        const double P_common = N_common * *S(WSI_SURF_UPTAKE_PNRATIO);
+        const double P_common = N_common * ldp(S(WSI_SURF_UPTAKE_PNRATIO));
         const double frac = pymax(0.0, st.x[0] - wp_m * area) / st.x[0];
         const double N_max = frac * pl.dis_inorg[0];
         const double P_max = frac * pl.dis_inorg[1];
@@ -470,12 +466,12 @@ WSI_HD void surface_phase(C& c, int u) {
               8.95 + 8.44 * log10(precipitation_depth *
                                   (0.257 + sin(2 * 3.141592653589793 * ((dayofyear - 70) / 365)) * 0.09) * 2);
           rainfall_energy *= precipitation_depth;
-          mobilised_rain = rainfall_energy * (1 - crop_cover) * *S(WSI_SURF_ERODIBILITY);
+          mobilised_rain = rainfall_energy * (1 - crop_cover) * ldp(S(WSI_SURF_ERODIBILITY));
         }
         if (ie.x[0] > 0) {
-          mobilised_flow = pow(ie.x[0] / area * 1e3 * 365, *S(WSI_SURF_SREROEXP));
-          mobilised_flow *= (1 - ground_cover) * (1 / (0.5 * *S(WSI_SURF_COHESION))) *
-                            sin(*S(WSI_SURF_SLOPE) / 100) / 365;
+          mobilised_flow = pow(ie.x[0] / area * 1e3 * 365, ldp(S(WSI_SURF_SREROEXP)));
+          mobilised_flow *= (1 - ground_cover) * (1 / (0.5 * ldp(S(WSI_SURF_COHESION)))) *
+                            sin(ldp(S(WSI_SURF_SLOPE)) / 100) / 365;
         }
         const double total_flows = ie.x[0] + sf.x[0] + pc.x[0];
         const double erodingflow = total_flows / area * 1e3;
@@ -491,11 +487,11 @@ WSI_HD void surface_phase(C& c, int u) {
           active = false;  // early return land.py:1996-1997
         if (active) {
           const double erodableP = (pl.ads_inorg[1] + pl.humus[1]) / area * 1e6;  // KG_M2_TO_KG_KM2
-          const double bulk_density = *S(WSI_SURF_BULK_DENSITY);
+          const double bulk_density = ldp(S(WSI_SURF_BULK_DENSITY));
           double erodedP = erodedsed * (erodableP / (rooting_depth * 1e-3 * bulk_density * 1e9)) * enrichment;
           erodedP *= area * 1e-6;
           erodedsed *= area * 1e-6;
-          const double srfilt = *S(WSI_SURF_SRFILT), macrofilt = *S(WSI_SURF_MACROFILT);
+          const double srfilt = ldp(S(WSI_SURF_SRFILT)), macrofilt = ldp(S(WSI_SURF_MACROFILT));
           const double surface_erodedP = srfilt * ie.x[0] / total_flows * erodedP;
           const double surface_erodedsed = srfilt * ie.x[0] / total_flows * erodedsed;
           const double subsurface_erodedP = macrofilt * sf.x[0] / total_flows * erodedP;
@@ -529,16 +525,16 @@ WSI_HD void surface_phase(C& c, int u) {
       {
         const double smc = st.x[0] / area;
         double dep_f = -1.0;
-        const double limpar = *S(WSI_SURF_LIMPAR);
+        const double limpar = ldp(S(WSI_SURF_LIMPAR));
         if (smc > fc_m)
           dep_f = 1.0;
         else if (smc / fc_m > limpar)
-          dep_f = pow(((smc / fc_m) - limpar) / (1 - limpar), *S(WSI_SURF_EXPPAR));
+          dep_f = pow(((smc / fc_m) - limpar) / (1 - limpar), ldp(S(WSI_SURF_EXPPAR)));
         if (dep_f >= 0) {
           double din_conc = pl.dis_inorg[0] / st.x[0];
           din_conc *= 1e3;  // KG_M3_TO_MG_L
-          const double hs = din_conc / (din_conc + *S(WSI_SURF_HSATINS));
-          const double denitrified = pl.dis_inorg[0] * hs * dep_f * pl.tdf * *S(WSI_SURF_DENPAR);
+          const double hs = din_conc / (din_conc + ldp(S(WSI_SURF_HSATINS)));
+          const double denitrified = pl.dis_inorg[0] * hs * dep_f * pl.tdf * ldp(S(WSI_SURF_DENPAR));
           const double got = pool_extract(pl.dis_inorg[0], denitrified);
           Vq out_ = vq_zero<P>();
           vset<P>(out_, cfg.no3(), got);
@@ -548,11 +544,11 @@ WSI_HD void surface_phase(C& c, int u) {
       }
       // adsorption land.py:2154-2265 (Freundlich isotherm, Newton-Raphson)
       {
-        const double bulk_density = *S(WSI_SURF_BULK_DENSITY);
+        const double bulk_density = ldp(S(WSI_SURF_BULK_DENSITY));
         double ad_de_P_pool = pl.ads_inorg[1] + pl.dis_inorg[1];
         ad_de_P_pool /= area * 1e-6;
         if (ad_de_P_pool != 0) {
-          const double kfr = *S(WSI_SURF_KFR), nfr = *S(WSI_SURF_NFR);
+          const double kfr = ldp(S(WSI_SURF_KFR)), nfr = ldp(S(WSI_SURF_NFR));
           const double smc_mm = st.x[0] / area * 1e3;
           const double conc_sol = pl.ads_inorg[1] * 1e6 / (bulk_density * rooting_depth * area);
           const double coeff = kfr * bulk_density * rooting_depth;
@@ -561,8 +557,8 @@ WSI_HD void surface_phase(C& c, int u) {
             const double xn_1 = ad_de_P_pool / (smc_mm + coeff);
             ad_P_equi_conc = kfr * xn_1;
           } else {
-            const double limit = *S(WSI_SURF_ADSORPTION_NR_LIMIT);
-            const int maxiter = (int)*S(WSI_SURF_ADSORPTION_NR_MAXITER);
+            const double limit = ldp(S(WSI_SURF_ADSORPTION_NR_LIMIT));
+            const int maxiter = (int)ldp(S(WSI_SURF_ADSORPTION_NR_MAXITER));
             const double x0 = exp((log(conc_sol) - log(kfr)) / nfr);
             double fxn = x0 * smc_mm + coeff * pow(x0, nfr) - ad_de_P_pool;
             double xn = x0, xn_1 = x0;
@@ -580,7 +576,7 @@ WSI_HD void surface_phase(C& c, int u) {
             ad_P_equi_conc = kfr * pow(xn_1, nfr);
           }
           if (fabs(ad_P_equi_conc - conc_sol) > 1e-6) {
-            const double adsdes = (ad_P_equi_conc - conc_sol) * (1 - exp(-*S(WSI_SURF_KADSDES)));
+            const double adsdes = (ad_P_equi_conc - conc_sol) * (1 - exp(-ldp(S(WSI_SURF_KADSDES))));
             double req = adsdes * bulk_density * rooting_depth * (area * 1e-6);
             if (req > 0) {
               const double adsorbed = pool_extract(pl.dis_inorg[1], req);
@@ -635,6 +631,11 @@ WSI_HD void surface_phase(C& c, int u) {
   }
   c.stv(stp, ss, st);
   if (growing) {
+    *S(WSI_SURF_DAYS_AFTER_SOW) = days_after_sow;  // crop calendar state (calc_crop_cover)
+    *S(WSI_SURF_CROP_COVER) = crop_cover;
+    *S(WSI_SURF_GROUND_COVER) = ground_cover;
+    *S(WSI_SURF_CROP_FACTOR) = crop_factor_out;
+    *S(WSI_SURF_ET0_COEFFICIENT) = et0_coef;
 #pragma unroll
     for (int k = 0; k < 2; k++) {
       *S(WSI_SURF_POOL_FAST + k) = pl.fast[k];

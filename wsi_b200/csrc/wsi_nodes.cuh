@@ -435,6 +435,157 @@ WSI_HD void node_mass_balance(C& c, int node, typename C::Vq& in_, typename C::V
   mb_check(c, node, in_, ds, out_);
 }
 
+// ---- the same mass balance, one VQIP lane at a time --------------------------------------------
+// The schedule kernel checks every node of its replica after the schedule (fused tail): formed lane
+// by lane, a node's (in, ds, out) are three scalars, so the whole pass needs a handful of
+// registers.  Every lane value is built with the additions of node_mass_balance in the same order
+// (bit-identical terms).  LANE is a compile-time lane (0 volume, else an additive pollutant).
+template <int LANE, class C>
+WSI_HD double arcs_lane_sum(const C& c, const int* ptr, const int* list, int node) {
+  double v = 0.0;
+  for (int i = ptr[node]; i < ptr[node + 1]; i++) v += *c.arc(WSI_ARC_VQIP_IN(C::V) + LANE, list[i]);
+  return v;
+}
+template <int LANE, class C>
+WSI_HD double tank_ds_lane(const C& c, int tk) {  // tank_ds
+  constexpr int V = C::V;
+  double dsv = *c.tank(WSI_TANK_STORAGE(V) + LANE, tk) - *c.tank(WSI_TANK_STORAGE_LAG(V) + LANE, tk);
+  if (*c.tank(WSI_TANK_IS_DECAY, tk) != 0.0) dsv = dsv + decay_total_of(c.tank_obj(tk), WSI_TANK_N_DECAY, LANE);
+  return dsv;
+}
+template <int LANE, class C>
+WSI_HD void node_mb_lane(const C& c, int node, double& in_, double& ds, double& out_) {
+  constexpr int V = C::V;
+  const WsiModelDesc& d = c.D();
+  const int g = d.node_gidx[node];
+  const int type = d.node_type[node];
+  if (type == WSI_NT_LAND) {  // land_mass_balance_terms
+    const size_t ss = c.s_surf();
+    in_ = arcs_lane_sum<LANE>(c, d.in_ptr, d.in_arcs, node);
+    out_ = arcs_lane_sum<LANE>(c, d.out_ptr, d.out_arcs, node);
+    ds = 0.0;
+    for (int i = d.land_surf_ptr[g]; i < d.land_surf_ptr[g + 1]; i++) {
+      const Obj S = c.surf_obj(d.land_surf[i]);
+      in_ += *S(WSI_SURF_MB_IN(V) + LANE);
+      out_ += *S(WSI_SURF_MB_OUT(V) + LANE);
+    }
+    for (int i = d.land_surf_ptr[g]; i < d.land_surf_ptr[g + 1]; i++) {
+      const Obj S = c.surf_obj(d.land_surf[i]);
+      if ((int)*S(WSI_SURF_TYPE) == WSI_ST_IMPERVIOUSSURFACE) {
+        double dsv = *S(WSI_SURF_STORAGE(V) + LANE) - *S(WSI_SURF_MB_DS(V) + LANE);
+        dsv = dsv + decay_total_of(S, WSI_SURF_N_DECAY, LANE);
+        ds += dsv;
+      } else {
+        ds += *S(WSI_SURF_MB_DS(V) + LANE);
+      }
+    }
+    const double* parked = d.mb_terms + (size_t)d.mb_term_slot[node] * 3 * V * c.R + c.r;
+    ds += *c.land(WSI_LAND_SURFACE_RUNOFF(V) + LANE, g) - parked[(size_t)(0 * V + LANE) * c.R];
+    ds += *c.land(WSI_LAND_SUBSURFACE_RUNOFF(V) + LANE, g) - parked[(size_t)(1 * V + LANE) * c.R];
+    ds += *c.land(WSI_LAND_PERCOLATION(V) + LANE, g) - parked[(size_t)(2 * V + LANE) * c.R];
+    (void)ss;
+  } else if (type == WSI_NT_CATCHMENT) {  // formed inside its op
+    const double* p = d.mb_terms + (size_t)d.mb_term_slot[node] * 3 * V * c.R + c.r;
+    in_ = p[(size_t)(0 * V + LANE) * c.R];
+    ds = p[(size_t)(1 * V + LANE) * c.R];
+    out_ = p[(size_t)(2 * V + LANE) * c.R];
+  } else if (type == WSI_NT_BOUNDARY) {
+    in_ = 0.0 + d.catch_inputs[((size_t)c.t * d.n_cseries + g) * V + LANE];
+    out_ = arcs_lane_sum<LANE>(c, d.out_ptr, d.out_arcs, node);
+    ds = 0.0;
+  } else {
+    const double tin = arcs_lane_sum<LANE>(c, d.in_ptr, d.in_arcs, node);
+    in_ = tin;
+    out_ = arcs_lane_sum<LANE>(c, d.out_ptr, d.out_arcs, node);
+    ds = 0.0;
+    switch (type) {
+      case WSI_NT_WASTE:
+        out_ += tin;
+        break;
+      case WSI_NT_SEWER:
+        ds += *c.sewer(WSI_SEWER_STORAGE(V) + LANE, g) - *c.sewer(WSI_SEWER_STORAGE_LAG(V) + LANE, g);
+        break;
+      case WSI_NT_GROUNDWATER:
+      case WSI_NT_STORAGE:
+      case WSI_NT_RESERVOIR:
+        ds += tank_ds_lane<LANE>(c, g);
+        break;
+      case WSI_NT_RIVER:
+        in_ += *c.river(WSI_RIVER_BIO_IN(V) + LANE, g);
+        out_ += *c.river(WSI_RIVER_BIO_OUT(V) + LANE, g);
+        ds += tank_ds_lane<LANE>(c, (int)*c.river(WSI_RIVER_TANK, g));
+        break;
+      default:
+        break;
+    }
+  }
+}
+// One lane of every node of the replica: violations (flagged on the node) and this replica's
+// contribution to the system totals of model.py:1016-1036 (nodes and -- `with_arcs` -- arcs).
+template <int LANE, class C>
+WSI_HD int replica_mb_lane(C& c, bool with_arcs, double& sys_in, double& sys_ds, double& sys_out) {
+  constexpr int V = C::V;
+  const WsiModelDesc& d = c.D();
+  const int row = c.t - d.rec_t0;
+  const bool rec = d.record_mb && row >= 0 && row < d.rec_T;
+  int viol = 0;
+  sys_in = 0.0;
+  sys_ds = 0.0;
+  sys_out = 0.0;
+  if (with_arcs)
+    for (int a = 0; a < d.n_arcs; a++) {
+      const double v = *c.arc(WSI_ARC_VQIP_IN(V) + LANE, a);
+      sys_in += v;
+      sys_out += v;
+    }
+  for (int node = 0; node < d.n_nodes; node++) {
+    double in_, ds, out_;
+    node_mb_lane<LANE>(c, node, in_, ds, out_);
+    if (mb_lane_bad(c, in_, ds, out_)) {
+      viol++;
+      c.flag(node, WSI_FLAG_MASS_BALANCE);
+    }
+    sys_in += in_;
+    sys_ds += ds;
+    sys_out += out_;
+    if (rec) {
+      double* o = d.out_mb + ((size_t)row * d.n_nodes + node) * 3 * V * c.R + c.r;
+      o[(size_t)(0 * V + LANE) * c.R] = in_;
+      o[(size_t)(1 * V + LANE) * c.R] = ds;
+      o[(size_t)(2 * V + LANE) * c.R] = out_;
+    }
+  }
+  return viol;
+}
+
+// all mass-balance lanes (volume + additive pollutants), each handed to `sink.take(c, lane, violations,
+// sys_in, sys_ds, sys_out)`; `active` is false for the padding threads of a block, which still take
+// part in the sink's reductions
+template <int LANE, class C, class SINK>
+WSI_HD void replica_mb_lanes(C& c, bool active, bool with_arcs, SINK& sink) {
+  if constexpr (LANE <= C::P) {
+    if (LANE == 0 || bit(c.addm(), LANE)) {
+      double a = 0.0, b = 0.0, o = 0.0;
+      int viol = 0;
+      if (active) viol = replica_mb_lane<LANE>(c, with_arcs, a, b, o);
+      sink.take(c, LANE, viol, a, b, o);
+    }
+    replica_mb_lanes<LANE + 1>(c, active, with_arcs, sink);
+  }
+}
+// host build: into the caller's accumulators
+struct MbHostSink {
+  template <class C>
+  WSI_HD void take(C& c, int lane, int viol, double a, double b, double o) {
+    c.viol += viol;
+    if (c.mb_acc) {
+      c.mb_acc[(0 * C::V + lane) * c.mb_stride] += a;
+      c.mb_acc[(1 * C::V + lane) * c.mb_stride] += b;
+      c.mb_acc[(2 * C::V + lane) * c.mb_stride] += o;
+    }
+  }
+};
+
 // ---- end_timestep (model.py:1172-1176) ------------------------------------------------------
 template <class C>
 WSI_HD void store_end_timestep(C& c, int tk) {  // tanks.py:348-351 / 442-447
@@ -609,12 +760,8 @@ WSI_HD void replica_step(C& c, int sched_begin, int sched_end) {
       for (int k = sched_begin; k < sched_end; k++) run_op(c, d.sched_op[k], d.sched_node[k]);
   }
   if (c.run_flags & WSI_RUN_MASS_BALANCE) {
-    if (c.mb_acc)
-      for (int a = 0; a < d.n_arcs; a++) arc_system_totals(c, a);
-    for (int n = 0; n < d.n_nodes; n++) {
-      typename C::Vq a, b, o;
-      node_mass_balance(c, n, a, b, o);
-    }
+    MbHostSink sink;
+    replica_mb_lanes<0>(c, true, c.mb_acc != nullptr, sink);
   }
   if (c.run_flags & WSI_RUN_RECORD) record(c);
   if (c.run_flags & WSI_RUN_END_TIMESTEP) end_timestep(c);

@@ -194,6 +194,17 @@ WSI_HD VQ<P> vq_volume(double v) {
   return t;
 }
 
+// A parameter plane (never written by a kernel): read through the non-coherent path, which lets
+// the compiler move the load across the kernel's stores -- every plane of a group hangs off the same
+// base pointer, so it cannot prove that for an ordinary load.
+WSI_HD double ldp(const double* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
 // min(a, b) with Python semantics (`a if a <= b`... `min(a, b)` returns a unless b < a)
 WSI_HD double pymin(double a, double b) { return b < a ? b : a; }
 WSI_HD double pymax(double a, double b) { return b > a ? b : a; }
