@@ -113,23 +113,50 @@ def cpu_port_throughput(members, steps, threads=0):
     return members * steps * NODES_PER_MEMBER / dt, cores, dt
 
 
+def reference_throughput(steps, warmup):
+    """The UNMODIFIED reference (baseline/_ref, see baseline/install_ref.sh) through its own
+    Model.run, one process per host core over disjoint catchments; None when it is not installed."""
+    from baseline import reference_arm as RA
+
+    if not RA.available():
+        return None
+    per_core = max(4, int(round(1100.0 / max(steps + warmup, 1))))  # ~1.5 s of Model.run per process
+    r = RA.run(steps=steps, warmup=warmup, members_per_core=per_core)
+    r["sample"] = (f"{r['members']} catchments ({per_core} per core) x {steps} timed steps (+{warmup} warm-up) of the "
+                   f"config-2 ensemble through wsimod Model.run (baseline/_ref), one process per core, "
+                   f"{r['timed_s']:.1f} s; one core alone: {r['single_core']:.0f} node-timesteps/s")
+    return r
+
+
 def run_reference(args, rank, world):
-    """CPU arm: the reference's algorithm (C oracle port; the Python reference cannot travel
-    to the GPU box) on all host threads, same workload definition, bounded sample per step."""
+    """CPU arm: the reference's own Model.run on all host cores (baseline/_ref), same workload
+    definition, bounded sample per step.  Falls back to the C oracle port (kind "port") only when
+    the reference is not installed."""
     if rank != 0:
         return
     steps = max(args.steps, 1)
-    members = args.cpu_members
-    cpu_port_throughput(min(members, 256), min(steps, 30))  # warm-up (page in, build)
-    value, cores, dt = cpu_port_throughput(members, steps)
-    sample = f"{members} members x {steps} steps of the config-2 ensemble (oracle/wsi_oracle.c, OpenMP over members)"
+    ref = reference_throughput(steps, max(args.warmup, 0))
+    cpu_port_throughput(min(args.cpu_members, 256), min(steps, 30))  # warm-up (page in, build)
+    port, port_cores, port_dt = cpu_port_throughput(args.cpu_members, steps)
+    if ref is not None:
+        value, cores, dt, kind, sample = ref["value"], ref["cores"], ref["timed_s"], "reference", ref["sample"]
+        members = ref["members"]
+    else:
+        value, cores, dt, kind = port, port_cores, port_dt, "port"
+        members = args.cpu_members
+        sample = f"{members} members x {steps} steps of the config-2 ensemble (oracle/wsi_oracle.c, OpenMP over members)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "node-timesteps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config2: independent Land(Impervious,Pervious,Growing)+Sewer+Groundwater+Node+Waste catchments, "
-                               "12 pollutants, daily synthetic forcing", "members_sampled": members},
-        "cpu_baseline": {"value": value, "unit": "node-timesteps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": "config2 (BASELINE.json configs[1]): independent Land(Impervious,Pervious,Growing)+Sewer+"
+                               "Groundwater+Node+Waste catchments, 12 pollutants, daily synthetic forcing from 2000-01-01",
+                   "members_sampled": members, "nodes_per_member": NODES_PER_MEMBER},
+        "cpu_baseline": {"value": value, "unit": "node-timesteps/s", "cores": cores, "kind": kind, "sample": sample,
+                         "single_core": ref["single_core"] if ref else None,
+                         "port": {"value": port, "cores": port_cores, "kind": "port",
+                                  "sample": f"{args.cpu_members} members x {steps} steps, oracle/wsi_oracle.c (C restatement, "
+                                            "OpenMP over members) -- ~100x the reference per core, for scale"}},
         "e2e": {"value": value, "unit": "node-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -282,10 +309,15 @@ def main():
         cpu_port_throughput(256, 30)
         steps_cpu = min(K, 365)
         v, cores, dt = cpu_port_throughput(args.cpu_members, steps_cpu)
-        cpu = {"value": v, "unit": "node-timesteps/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_members} members x {steps_cpu} steps of the same ensemble, oracle/wsi_oracle.c "
-                         f"(C restatement of the reference, OpenMP over members), {dt:.1f} s; the Python reference "
-                         "itself runs 2.1k-3.8k node-timesteps/s per core (BASELINE.md)"}
+        port = {"value": v, "unit": "node-timesteps/s", "cores": cores, "kind": "port",
+                "sample": f"{args.cpu_members} members x {steps_cpu} steps of the same ensemble, oracle/wsi_oracle.c "
+                          f"(C restatement of the reference, OpenMP over members), {dt:.1f} s"}
+        ref = reference_throughput(min(K, 40), 5)
+        if ref is not None:
+            cpu = {"value": ref["value"], "unit": "node-timesteps/s", "cores": ref["cores"], "kind": "reference",
+                   "sample": ref["sample"], "single_core": ref["single_core"], "port": port}
+        else:
+            cpu = port
 
     if rank == 0:
         line = {

@@ -115,7 +115,8 @@ typedef struct WsiModelDesc {
   const int32_t* net_item;   /* [n_level_items][8] per entry of net_level_node: node, tank slot, river slot,
                                 out-arc (-1: none), [begin, end) into net_rpath, 1 if the out-arc goes
                                 straight to a River / Waste, arc of the first river path */
-  int32_t* net_scratch;      /* [4] device scratch: level at which the fast tail kernel handed over */
+  int32_t* net_scratch;      /* [8] device scratch: [0] level at which the fast tail kernel handed over, [1] stop
+                                flag, [2] device-side step counter, [3..4] cluster "general" flags by level parity */
   int32_t* net_done;         /* [n_level_items] device scratch: t + 1 of the last step in which the fast tail
                                 kernel completed the item (the general kernel skips those when it resumes) */
   const int32_t* net_rpath;  /* [.][4] river paths in delivery order: sender's arc, sender's tank slot,

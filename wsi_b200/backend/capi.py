@@ -272,7 +272,7 @@ class ModelBuffers:
         slot[np.nonzero(fused)[0]] = np.arange(int(np.sum(fused)), dtype=np.int32)
         self.n_fused = int(np.sum(fused))
         net = self.net or network.empty_plan(len(fm.node_names))
-        net = dict(net, net_scratch=np.zeros(4, np.int32), net_done=np.zeros(max(len(net["net_item"]) // 8, 1) * fm.R, np.int32))
+        net = dict(net, net_scratch=np.zeros(8, np.int32), net_done=np.zeros(max(len(net["net_item"]) // 8, 1) * fm.R, np.int32))
         self._extra_int = {k: np.ascontiguousarray(net[k], dtype=np.int32) for k in _NET_ARRAYS}
         chain_ptr, chain = simple_chains(fm)
         self._extra_int.update({"arc_chain_ptr": chain_ptr, "arc_chain": chain})

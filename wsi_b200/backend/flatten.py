@@ -368,6 +368,13 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
                 for ty in types:
                     lst += [arc_index[k] for k in n.out_arcs_type.get(ty, {}).keys()]
                 cand_lists.append(lst)
+    for n_i, n in enumerate(nodes):
+        longest = max(len(l) for l in cand_lists[n_i * L.NF : (n_i + 1) * L.NF])
+        if longest > L.MAX_CAND:
+            # the kernels split a push over at most MAX_CAND arcs (nodes.py:440-473 has no limit)
+            raise UnsupportedModelError(
+                f"node {n.name!r} has {longest} eligible out-arcs for one push; the kernels support {L.MAX_CAND}"
+            )
     cand_ptr, cand_arcs = csr(cand_lists)
 
     # ---- forcing series ------------------------------------------------------

@@ -24,7 +24,7 @@ MAX_STAGE = 16  # crop_factor_stages table length (fixture uses 9)
 LAG_T = 21  # River.max_temp_lag + 1 (storage.py:560,753)
 LAG_TP = 366  # River.max_phosphorus_lag + 1 (storage.py:563,758)
 MAXP = 16  # compile-time bound on pollutants
-MAX_ITEMS = 8  # (unused placeholder for future per-node tables)
+MAX_CAND = 8  # candidate out-arcs one push_distributed call may split over (kMaxCand in csrc/wsi_device.cuh)
 
 # node types (Node.__class__.__name__ in the reference)
 NODE_TYPES = [
@@ -383,6 +383,7 @@ def c_header() -> str:
         ("WSI_LAG_T", LAG_T),
         ("WSI_LAG_TP", LAG_TP),
         ("WSI_MAXP", MAXP),
+        ("WSI_MAX_CAND", MAX_CAND),
         ("WSI_NF", NF),
         ("WSI_N_DEP", N_DEP),
     ):

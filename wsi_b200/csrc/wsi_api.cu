@@ -76,39 +76,57 @@ struct SlotEntry {
   unsigned long long last_use;
   bool uploaded;
 };
-SlotEntry g_slots[WSI_DESC_SLOTS];
-WsiModelDesc g_slot_image[WSI_DESC_SLOTS];  // what each slot holds (uploads of an unchanged descriptor are skipped)
-unsigned long long g_slot_clock = 0;
+struct GraphEntry {
+  const void* key = nullptr;
+  unsigned long long hash = 0;
+  cudaGraphExec_t exec = nullptr;
+  long long launches = 0;
+};
+// Constant memory, streams and graphs belong to a device: everything the library remembers between
+// calls is kept per device (one process may drive several GPUs, one host thread each).
+constexpr int kMaxDevices = 16;
+struct DeviceState {
+  SlotEntry slots[WSI_DESC_SLOTS] = {};
+  WsiModelDesc image[WSI_DESC_SLOTS] = {};  // what each slot holds (uploads of an unchanged descriptor are skipped)
+  unsigned long long clock = 0;
+  GraphEntry graphs[WSI_DESC_SLOTS];
+  cudaStream_t capture_stream = nullptr;
+};
+DeviceState g_dev[kMaxDevices];
 std::mutex g_slot_mutex;
+DeviceState* device_state() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  return &g_dev[dev];
+}
 int upload_desc(const WsiModelDesc* d, cudaStream_t s, int* slot) {
-  {
-    std::lock_guard<std::mutex> lock(g_slot_mutex);
-    int found = -1, lru = 0;
-    for (int i = 0; i < WSI_DESC_SLOTS; i++) {
-      if (g_slots[i].key == (const void*)d) found = i;
-      if (g_slots[i].last_use < g_slots[lru].last_use) lru = i;
-    }
-    if (found < 0) {
-      found = lru;
-      if (g_slots[lru].key != nullptr) cudaDeviceSynchronize();  // its last user may still be running
-      g_slots[lru].key = (const void*)d;
-      g_slots[lru].uploaded = false;
-    }
-    g_slots[found].last_use = ++g_slot_clock;
-    *slot = found;
-    // A copy to a __constant__ symbol is ordered against every kernel that may read the bank; a
-    // model that is stepped in chunks re-sends the same bytes each time, so compare first.  (The
-    // image is only trusted for the stream-ordered case: same model, same stream, which is the rule.)
-    if (g_slots[found].key == (const void*)d && memcmp(&g_slot_image[found], d, sizeof(WsiModelDesc)) == 0 &&
-        g_slots[found].uploaded)
-      return WSI_OK;
-    memcpy(&g_slot_image[found], d, sizeof(WsiModelDesc));
-    g_slots[found].uploaded = true;
-  }
   const ConfigUnit* u = unit_of(d);
   if (!u) return fail(WSI_ERR_UNSUPPORTED, "no kernel instantiated for this number of pollutants%s");
+  DeviceState* ds = device_state();
+  if (!ds) return fail(WSI_ERR_LAUNCH, "no current CUDA device (or more than 16 devices)%s");
+  std::lock_guard<std::mutex> lock(g_slot_mutex);
+  int found = -1, lru = 0;
+  for (int i = 0; i < WSI_DESC_SLOTS; i++) {
+    if (ds->slots[i].key == (const void*)d) found = i;
+    if (ds->slots[i].last_use < ds->slots[lru].last_use) lru = i;
+  }
+  if (found < 0) {
+    found = lru;
+    if (ds->slots[lru].key != nullptr) cudaDeviceSynchronize();  // its last user may still be running
+    ds->slots[lru].key = (const void*)d;
+    ds->slots[lru].uploaded = false;
+  }
+  ds->slots[found].last_use = ++ds->clock;
+  *slot = found;
+  // A copy to a __constant__ symbol is ordered against every kernel that may read the bank; a
+  // model that is stepped in chunks re-sends the same bytes each time, so compare first.  (The
+  // image is only trusted for the stream-ordered case: same model, same stream, which is the rule.)
+  if (ds->slots[found].uploaded && memcmp(&ds->image[found], d, sizeof(WsiModelDesc)) == 0) return WSI_OK;
+  ds->slots[found].uploaded = false;
   cudaError_t err = u->upload(d, *slot, s);
   if (err != cudaSuccess) return fail(WSI_ERR_LAUNCH, "descriptor upload failed: %s", cudaGetErrorString(err));
+  memcpy(&ds->image[found], d, sizeof(WsiModelDesc));  // committed only once the copy is enqueued
+  ds->slots[found].uploaded = true;
   return WSI_OK;
 }
 
@@ -132,14 +150,6 @@ bool graphs_enabled() {
   }();
   return on;
 }
-struct GraphEntry {
-  const void* key = nullptr;
-  unsigned long long hash = 0;
-  cudaGraphExec_t exec = nullptr;
-  long long launches = 0;
-};
-GraphEntry g_graphs[WSI_DESC_SLOTS];
-cudaStream_t g_capture_stream = nullptr;
 std::mutex g_graph_mutex;
 
 unsigned long long fnv(unsigned long long h, const void* p, size_t n) {
@@ -159,7 +169,10 @@ int run_steps_graph(const WsiModelDesc* d, int slot, int64_t t0, int64_t t1, cud
                            d->n_net_bnd, d->mb_sums ? 1 : 0};
   unsigned long long h = fnv(1469598103934665603ull, baked, sizeof baked);
   if (d->engine == 1) h = fnv(h, d->net_level_ptr_host, sizeof(int32_t) * (size_t)(d->n_net_levels + 1));
-  GraphEntry& g = g_graphs[slot];
+  DeviceState* ds = device_state();
+  if (!ds) return fail(WSI_ERR_LAUNCH, "no current CUDA device (or more than 16 devices)%s");
+  GraphEntry& g = ds->graphs[slot];
+  cudaStream_t& g_capture_stream = ds->capture_stream;
   if (g.key != (const void*)d || g.hash != h || !g.exec) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
     g = GraphEntry();
@@ -171,6 +184,7 @@ int run_steps_graph(const WsiModelDesc* d, int slot, int64_t t0, int64_t t1, cud
     int rc = dispatch(d, slot, -1, 0, d->n_sched, WSI_RUN_ALL, g_capture_stream);
     unit_of(d)->advance(slot, g_capture_stream);
     g_launches++;
+    if (!rc && cudaGetLastError() != cudaSuccess) rc = fail(WSI_ERR_LAUNCH, "wsi_advance_kernel launch failed%s");
     cudaGraph_t graph = nullptr;
     err = cudaStreamEndCapture(g_capture_stream, &graph);
     g.launches = g_launches.load() - before;

@@ -21,7 +21,7 @@ namespace wsi {
 
 constexpr double kUnbounded = 1e15;  // constants.UNBOUNDED_CAPACITY
 constexpr int kMaxIter = 5;          // constants.MAXITER
-constexpr int kMaxCand = 8;          // arcs one push_distributed call can split over
+constexpr int kMaxCand = WSI_MAX_CAND;  // arcs one push_distributed call can split over (the flattener refuses more)
 constexpr int kJunctionDepth = 3;    // nested junction Nodes a push may traverse (the Oxford demo chains 3)
 
 // The model descriptor lives in constant memory on the device (direct constant-bank loads with
@@ -180,6 +180,16 @@ WSI_HD bool vq_is_empty(const C& c, const typename C::Vq& v) {
   for (int p = 1; p <= C::P; p++)
     if (bit(c.addm(), p)) z = z && v.x[p] == 0.0;
   return z;
+}
+
+// compare_vqip core.py:354-368: every lane within FLOAT_ACCURACY
+template <class C>
+WSI_HD bool vq_compare(const C& c, const typename C::Vq& a, const typename C::Vq& b) {
+  bool same = true;
+#pragma unroll
+  for (int p = 0; p <= C::P; p++)
+    if (fabs(a.x[p] - b.x[p]) > c.FA) same = false;
+  return same;
 }
 
 // Tank.push_storage(force=True) tanks.py:189-192: storage = sum_vqip(storage, v).  When v is

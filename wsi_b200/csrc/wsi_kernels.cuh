@@ -362,7 +362,7 @@ template <class CFG, bool CLUSTER>
 __global__ void __launch_bounds__(kNetTail)
     wsi_net_tail_kernel(const int slot, const CFG cfg, const int t_arg, const uint32_t flags, const int level_begin_,
                         const int level_end_) {
-  __shared__ int s_general;
+  __shared__ int s_general[2];  // "a river of this level needs the general code", by level parity (see below)
   __shared__ uint64_t s_bar;
   const WsiModelDesc& d = g_wsi_desc[slot];
   const int t = step_of(d, t_arg);
@@ -379,11 +379,21 @@ __global__ void __launch_bounds__(kNetTail)
   using Cx = Ctx<CFG>;
   Cx c = make_ctx(nullptr, slot, cfg, r, t, flags);
   const int32_t* __restrict__ lptr = d.net_level_ptr;
-  volatile int* g_general = d.net_scratch + 3;  // the cluster's "a river needs the general code" flag
+  // The flag of level l is written before a group arrives at the level's barrier and read right
+  // after the wait.  A group may already be in level l + 1 (and set ITS flag) while a lagging group
+  // has not read level l's flag yet, so the two levels must not share a word: the flag is indexed
+  // by level parity.  Two words suffice -- nobody enters level l + 2 before everybody has arrived
+  // at level l + 1, i.e. has read level l's flag -- and a set flag ends the sweep, so no word is
+  // ever cleared inside the loop.
+  volatile int* g_general = d.net_scratch + 3;  // [2] the cluster's flags (net_scratch[3], [4])
   if (threadIdx.x == 0) {
-    s_general = 0;
+    s_general[0] = 0;
+    s_general[1] = 0;
     if (!CLUSTER) mbar_init(&s_bar, kNetTail);
-    if (CLUSTER && cta == 0) *g_general = 0;
+    if (CLUSTER && cta == 0) {
+      g_general[0] = 0;
+      g_general[1] = 0;
+    }
   }
   // consumer groups: unconditional look-ahead loads -- absent items read item 0, a select
   // would have to wait for the loaded values
@@ -447,8 +457,8 @@ __global__ void __launch_bounds__(kNetTail)
         }
       }
       if (general && q == 0) {
-        if (CLUSTER) *g_general = 1;
-        else s_general = 1;
+        if (CLUSTER) g_general[l & 1] = 1;
+        else s_general[l & 1] = 1;
       }
       NET_DBG(1);
       if (CLUSTER) cluster_arrive();
@@ -462,7 +472,7 @@ __global__ void __launch_bounds__(kNetTail)
     if (CLUSTER) cluster_wait();
     else mbar_wait(&s_bar, (uint32_t)(l - level_begin) & 1u);
     NET_DBG(2);
-    stop = CLUSTER ? (*g_general != 0) : (s_general != 0);
+    stop = CLUSTER ? (g_general[l & 1] != 0) : (s_general[l & 1] != 0);
     // rivers of level l that took the lane path are marked in net_done; a general river has
     // stored nothing and is done by wsi_net_tail_general
   }

@@ -428,6 +428,10 @@ WSI_HD void surface_phase(C& c, int u) {
           vset<P>(out_, cfg.orgp(), -inc_do[1]);
         st = c.sum(st, in_);
         vq_pull_pollutants(c, st, out_);  // clips out_ in place (tanks.py:261-262)
+        // land.py:1806-1808 "nutrient pool not tracking soil tank": pull_pollutants hands its
+        // (clipped) argument back, so the reference compares the request with itself -- the
+        // advisory can only fire on a NaN-free difference, i.e. never; kept as the status bit
+        if (!vq_compare(c, out_, out_)) c.flag((int)*Lo(WSI_LAND_NODE), WSI_FLAG_POOL_MISMATCH);
         mb_acc(c, mb_in, in_);
         mb_acc(c, mb_out, out_);
       }

@@ -44,13 +44,13 @@ def synthetic_forcing_arrays(dates, n_series, seed=20261019):
     return np.ascontiguousarray(np.stack([precipitation, et0, temperature], axis=2))
 
 
-def config2_template_model(dates, forcing_col):
-    """{Land(Impervious, Pervious, Growing) -> Sewer, Groundwater, junction Node -> Waste}
-    built through the drop-in ``Model`` API.  ``forcing_col`` is ``[T, 3]``."""
-    from .orchestration.model import Model
-
-    constants.set_default_pollutants()
-    constants.FLOAT_ACCURACY = 1e-11
+def config2_spec(dates, forcing_col, scale=1.0, area_scale=1.0):
+    """Node and arc specifications (the ``add_nodes`` / ``add_arcs`` dictionaries of
+    ``orchestration/model.py:642-778``) of one config-2 catchment, {Land(Impervious, Pervious,
+    Growing) -> Sewer, Groundwater, junction Node -> Waste}.  ``forcing_col`` is ``[T, 3]``.
+    The same dictionaries build the member with this package's ``Model`` and with the reference's
+    (bench.py's reference arm, baseline/reference_arm.py); ``scale`` / ``area_scale`` perturb an
+    object-level member the way tests/golden/make_golden.py does."""
     forcing = {}
     for t, d in enumerate(dates):
         forcing[("precipitation", d)] = float(forcing_col[t, 0])
@@ -62,7 +62,7 @@ def config2_template_model(dates, forcing_col):
         if not months or months[-1] != m:
             months.append(m)
     monthly = {(var, m): 1e-7 for var in L.DEP_COLS for m in months}  # kg/m2 as in land_demo.py
-    a_imp, a_perv, a_grow = 2.0e4, 5.0e4, 2.0e5
+    a_imp, a_perv, a_grow = 2.0e4 * area_scale, 5.0e4 * area_scale, 2.0e5 * area_scale
     vol = a_grow * 1.25 * 0.4 * 0.9
     init = {"do": 0.01, "org-phosphorus": vol * 1e-4, "phosphate": vol * 1e-4, "ammonia": vol * 5e-5,
             "solids": vol * 1e-2, "bod": vol * 1e-3, "cod": vol * 2e-2, "ph": 7.0, "temperature": 11.0,
@@ -72,24 +72,37 @@ def config2_template_model(dates, forcing_col):
     grow = dict(GROWING_TEMPLATE)
     grow.update(type_="GrowingSurface", surface="crop", area=a_grow, pollutant_load={}, initial_storage=init,
                 initial_soil_storage=soil, data_input_dict=monthly,
-                decays={"ammonia": {"constant": 0.1, "exponent": 1.005},
-                        "nitrite": {"constant": 0.05, "exponent": 1.005}})
-    imp = {"type_": "ImperviousSurface", "surface": "urban", "area": a_imp, "pore_depth": 0.004,
+                decays={"ammonia": {"constant": 0.1 * scale, "exponent": 1.005},
+                        "nitrite": {"constant": 0.05 * scale, "exponent": 1.005}},
+                infiltration_capacity=0.06 * scale)
+    imp = {"type_": "ImperviousSurface", "surface": "urban", "area": a_imp, "pore_depth": 0.004 * scale,
            "pollutant_load": {"phosphate": 1e-10, "solids": 1e-5, "bod": 1e-5, "ammonia": 1e-9, "temperature": 13.0,
                               "do": 0.005, "ph": 7.5}}
     perv = {"type_": "PerviousSurface", "surface": "rural", "area": a_perv, "depth": 0.5,
             "pollutant_load": {"phosphate": 1e-7}, "initial_storage": a_perv * 0.5 * 0.4 * 0.5,
             "infiltration_capacity": 0.05}
     land = {"type_": "Land", "name": "land", "data_input_dict": forcing, "surfaces": [imp, perv, grow],
-            "surface_residence_time": 2.0, "subsurface_residence_time": 10.0, "percolation_residence_time": 30.0}
-    sewer = {"type_": "Sewer", "name": "sewer", "capacity": a_imp * 0.01}
+            "surface_residence_time": 2.0 * scale, "subsurface_residence_time": 10.0,
+            "percolation_residence_time": 30.0 / scale}
+    sewer = {"type_": "Sewer", "name": "sewer", "capacity": a_imp * 0.01 * scale}
     gw = {"type_": "Groundwater", "name": "gw", "area": a_perv + a_grow, "capacity": (a_perv + a_grow) * 0.5,
-          "residence_time": 100.0, "initial_storage": (a_perv + a_grow) * 0.01}
+          "residence_time": 100.0 * scale, "initial_storage": (a_perv + a_grow) * 0.01}
     arcs = [("land-sewer", "land", "sewer"), ("land-gw", "land", "gw"), ("land-river", "land", "river"),
             ("sewer-river", "sewer", "river"), ("gw-river", "gw", "river"), ("river-outlet", "river", "outlet")]
+    nodes = [sewer, land, gw, {"type_": "Node", "name": "river"}, {"type_": "Waste", "name": "outlet"}]
+    return nodes, [{"type_": "Arc", "name": a, "in_port": i, "out_port": o} for a, i, o in arcs]
+
+
+def config2_template_model(dates, forcing_col):
+    """The config-2 catchment built through the drop-in ``Model`` API."""
+    from .orchestration.model import Model
+
+    constants.set_default_pollutants()
+    constants.FLOAT_ACCURACY = 1e-11
+    nodes, arcs = config2_spec(dates, forcing_col)
     m = Model()
-    m.add_nodes([sewer, land, gw, {"type_": "Node", "name": "river"}, {"type_": "Waste", "name": "outlet"}])
-    m.add_arcs([{"type_": "Arc", "name": a, "in_port": i, "out_port": o} for a, i, o in arcs])
+    m.add_nodes(nodes)
+    m.add_arcs(arcs)
     m.dates = dates
     return m
 
