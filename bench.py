@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--impl", default="wsi_b200", choices=["wsi_b200", "reference"])
     ap.add_argument("--members", type=int, default=100_000, help="ensemble members per GPU")
     ap.add_argument("--cpu-members", type=int, default=2048, help="members in the bounded CPU sample")
+    ap.add_argument("--members3", type=int, default=125_000, help="config-3 ensemble members per GPU (secondary block)")
+    ap.add_argument("--rivers4", type=int, default=1_000_000, help="config-4 network rivers (secondary block)")
+    ap.add_argument("--secondary", default="config3,config4", help="secondary workloads to add to the line ('' = none)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -163,6 +166,153 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def _timed_max(ms, world, device):
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return ms
+
+
+def bench_config3(args, rank, world, device, K, W, peak):
+    """SURVEY 8d config 3 / BASELINE.json configs[2]: the parameter ensemble of the Oxford catchment's
+    land + river-side nodes, ``--members3`` distinct members per GPU (members are independent: weak
+    scaling, no data-path collective).  Outputs as the spec asks: per-member objective reductions on
+    the device (running sum -> mean, and maximum, of the outlet's flow and every pollutant) and the
+    full outlet series of 16 members only."""
+    import torch
+    import torch.distributed as dist
+
+    from wsi_b200 import ensemble as E
+    from wsi_b200.backend.engine import GpuRunner
+    from wsi_b200.backend.flatten import FlatModel
+    from wsi_b200.backend.probes import ProbeSet
+
+    path = os.path.join(ROOT, "tests", "golden", "config3.npz")
+    template = FlatModel.from_npz_dict(dict(np.load(path, allow_pickle=False)))
+    R = args.members3
+    factors = E.config3_factors(world * R)[rank * R:(rank + 1) * R]
+    fm = E.build_config3(R, template, factors=factors)
+    n_nodes = len(fm.node_names)
+    outlet = [fm.arc_names.index("mixer_to_waste")]
+    ps = ProbeSet(fm).add_flows(outlet)
+    REC = 8
+    run = GpuRunner(fm, probes=ps.probes, rec_t0=0, rec_T=REC, device=device, engine="replica",
+                    reduce_probes=ps.probes, rec_members=(0, 16))
+    stream = torch.cuda.current_stream()
+
+    def steps(t0, t1):
+        t = t0
+        while t < t1:
+            n = min(REC, t1 - t)
+            run.buffers.set_rec_window(t)
+            run.run(t, t + n)
+            t += n
+
+    K = min(K, (fm.T - W - 8) // 2)  # the device-timed and the end-to-end stretch both fit the 1456-day series
+    steps(0, W)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    steps(W, W + K)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = _timed_max(e0.elapsed_time(e1), world, device)
+    # end to end: every step the forcing rows come from pinned host memory and the step's violation
+    # count goes back; the reductions and the 16 series are read once the steps are done
+    cin, nf = run.buffers.array("catch_inputs"), run.buffers.array("node_forcing")
+    h_cin, h_nf = torch.from_numpy(fm.catch_inputs).pin_memory(), torch.from_numpy(fm.node_forcing).pin_memory()
+    cnt = run.buffers.array("mb_count")
+    h_cnt = torch.zeros(fm.T, dtype=torch.int32).pin_memory()
+    d_red = run.buffers.array("red_out")
+    h_red = torch.empty(d_red.shape, dtype=torch.float64).pin_memory()
+    d_ser = run.buffers.array("out_probe")  # [REC, 13, 16]: the 16 members whose series are kept
+    h_ser = torch.empty((K + REC,) + tuple(d_ser.shape[1:]), dtype=torch.float64).pin_memory()
+    rows = 0
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_start = time.perf_counter()
+    t = W + K
+    while t < W + 2 * K:
+        n = min(REC, W + 2 * K - t)
+        cin[t:t + n].copy_(h_cin[t:t + n], non_blocking=True)
+        nf[t:t + n].copy_(h_nf[t:t + n], non_blocking=True)
+        run.buffers.set_rec_window(t)
+        run.run(t, t + n)
+        h_cnt[t:t + n].copy_(cnt[t:t + n], non_blocking=True)
+        h_ser[rows:rows + n].copy_(d_ser[:n], non_blocking=True)  # stream-ordered before the ring is reused
+        rows += n
+        t += n
+    h_red.copy_(d_red, non_blocking=True)
+    torch.cuda.synchronize()
+    red = h_red
+    e2e_s = time.perf_counter() - t_start
+    e2e_s = _timed_max(e2e_s, world, device)
+    alg, parts = E.algorithmic_bytes_per_replica_step(fm, 0)
+    alg += 8 * 2 * 2 * len(ps.probes)  # the running sum and maximum of every reduced plane: read + written
+    value = world * R * n_nodes * K / (ms * 1e-3)
+    h2d = (fm.catch_inputs[0].size + fm.node_forcing[0].size) * 8
+    d2h = 4 + h_ser[0].numel() * 8 + red.numel() * 8 / K
+    return {
+        "workload": "config3 (BASELINE.json configs[2]): parameter ensemble of the Oxford catchment's land + river-side "
+                    "nodes, 12 Oxford pollutants, members = Oxford parameters x log-uniform(0.8, 1.25)",
+        "members_per_gpu": R, "nodes_per_member": n_nodes, "steps": K, "ms_per_step": ms / K,
+        "value": value, "unit": "node-timesteps/s",
+        "roofline": {"bound": "hbm", "achieved": alg * R / (ms * 1e-3 / K) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg * R / (ms * 1e-3 / K) / 1e9 / peak, "algorithmic_bytes_per_member_step": int(alg)},
+        "e2e": {"value": world * R * n_nodes * K / e2e_s, "unit": "node-timesteps/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h),
+                "outputs": "per-member sum and maximum of the outlet VQIP (13 planes) reduced on the device, read "
+                           "once at the end; full outlet series of 16 members; violation count every step"},
+        "mass_balance_violations": int(run.mb_count()[:W + 2 * K].sum()),
+        "objective_checksum": float(np.nansum(red[0].numpy())),
+    }
+
+
+def bench_config4(args, device, K, W, peak):
+    """SURVEY 8d config 4 / BASELINE.json configs[3] on ONE GPU (rank 0): a dendritic network of
+    ``--rivers4`` River nodes (decays on a tenth of them) with a Catchment source each, level-synchronous
+    routing by the network engine; node-timesteps count rivers + catchments + the outlet."""
+    import torch
+
+    from wsi_b200 import rivernet
+    from wsi_b200.backend.engine import GpuRunner
+    from wsi_b200.backend.probes import ProbeSet
+
+    N = args.rivers4
+    T = W + K + 2
+    t0 = time.perf_counter()
+    fm = rivernet.build_dendritic(N, T=T, names=False)
+    ps = ProbeSet(fm).add_flows([0])
+    run = GpuRunner(fm, probes=ps.probes, rec_t0=0, rec_T=T, device=device, engine="network")
+    host_s = time.perf_counter() - t0
+    stream = torch.cuda.current_stream()
+    run.run(0, W)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    run.run(W, W + K)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    nodes = len(fm.node_names)
+    alg = rivernet.algorithmic_bytes_per_river_step(fm, 0)
+    return {
+        "workload": "config4 (BASELINE.json configs[3]): dendritic river network, level-synchronous routing, one GPU",
+        "rivers": N, "nodes": nodes, "levels": int(run.buffers.net["n_levels"]), "steps": K, "ms_per_step": ms / K,
+        "value": nodes * K / (ms * 1e-3), "unit": "node-timesteps/s", "n_gpus_used": 1,
+        "roofline": {"bound": "hbm", "achieved": alg * N / (ms * 1e-3 / K) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg * N / (ms * 1e-3 / K) / 1e9 / peak, "algorithmic_bytes_per_river_step": int(alg)},
+        "mass_balance_violations": int(run.mb_count()[:W + K].sum()), "host_build_plan_s": round(host_s, 1),
+    }
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -235,11 +385,15 @@ def main():
     value = world * R * NODES_PER_MEMBER * K / (ms * 1e-3)
     peak, peak_src = measured_peak_hbm()
     achieved = alg_bytes * R / (ms * 1e-3 / K) / 1e9  # GB/s per GPU
-    traffic = None
+    # DRAM bytes of one whole timestep (every kernel of the step, summed) from the committed ncu
+    # capture of this workload (tools/ncu_summary.py writes profiles/traffic.json)
+    traffic, traffic_by_kernel = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("dram_bytes_per_step")
+            traffic_by_kernel = tj.get("kernels")
         except Exception:
             traffic = None
 
@@ -319,6 +473,25 @@ def main():
         else:
             cpu = port
 
+    # ---------------- the other named workloads (BASELINE.json configs[2], configs[3]) -------------
+    secondary = {}
+    want = [x for x in args.secondary.split(",") if x]
+    del runner
+    torch.cuda.empty_cache()
+    if "config3" in want:
+        try:
+            secondary["config3"] = bench_config3(args, rank, world, device, min(K, 60), W, peak)
+        except Exception as exc:  # a secondary block never takes the headline line down with it
+            secondary["config3"] = {"error": repr(exc)[:300]}
+        torch.cuda.empty_cache()
+    if "config4" in want and rank == 0:
+        try:
+            secondary["config4"] = bench_config4(args, device, min(K, 20), W, peak)
+        except Exception as exc:
+            secondary["config4"] = {"error": repr(exc)[:300]}
+    if world > 1:
+        dist.barrier()
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "node-timesteps/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -335,13 +508,14 @@ def main():
                 "status_flags_beyond_advisories": bad,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_member_step": int(alg_bytes),
+                         "traffic": traffic, "traffic_by_kernel": traffic_by_kernel, "peak_source": peak_src, "algorithmic_bytes_per_member_step": int(alg_bytes),
                          "field_counts": {k: int(v) for k, v in parts.items()},
                          "kernel": "one timestep = wsi_surface_kernel x3 + wsi_step_kernel + wsi_mb_kernel + "
                                    "wsi_mb_finalize + wsi_record_kernel + wsi_end_kernel (dominant: wsi_step_kernel)",
                          "avg_launch_ms": ms / K,
                          "kernel_ms": {k: round(v, 4) for k, v in kernel_ms.items()}},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "secondary": secondary,
         }
         print(json.dumps(line))
     if world > 1:

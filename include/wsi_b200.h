@@ -159,6 +159,18 @@ typedef struct WsiModelDesc {
    *      longer than the kernels unroll.  NULL: every push takes the general recursive code. ---- */
   const int32_t* arc_chain_ptr; /* [n_arcs+1] */
   const int32_t* arc_chain;
+
+  /* ---- reduced outputs and member window (ABI 2): what an ensemble run brings home without streaming
+   *      every member's series (objectives of model.py:1177-1197 evaluated on the device) ---- */
+  int32_t n_red;      /* planes reduced over time instead of recorded as series */
+  int32_t rec_r0;     /* out_probe holds the members [rec_r0, rec_r0 + rec_R) only ... */
+  int32_t rec_R;      /* ... rec_R == 0: every member (out_probe is [rec_T][n_probe][R]) */
+  int32_t reserved3;
+  const int32_t* red_group; /* [n_red] like probe_group / probe_plane / probe_obj */
+  const int32_t* red_plane;
+  const int32_t* red_obj;
+  double* red_out;    /* [2][n_red][R]: running sum and running maximum over the timesteps stepped so far
+                         (caller-initialised: 0 and -inf) */
 } WsiModelDesc;
 
 /* ABI version of the loaded library (== WSI_ABI_VERSION). */

@@ -474,18 +474,7 @@ def scenario_rivertree(T=380):
     save("rivertree", fm, ref, "dendritic river network with junction chains, binding capacities and decays")
 
 
-def scenario_config3(R=2):
-    """SURVEY 8d config 3: the Oxford catchment's land + river-side nodes (Land{Pervious 2e7 m2,
-    Impervious 1e7 m2}, Groundwater, the junction Nodes, Waste, the 4 Catchment inflows as
-    prescribed sources) on the demo's own time series (1456 days, the 12 Oxford pollutants,
-    temperature the only non-additive one), R members with parameters x log-uniform(0.8, 1.25)."""
-    from wsimod.nodes.catchment import Catchment
-    from wsimod.nodes.land import Land
-    from wsimod.nodes.nodes import Node
-    from wsimod.nodes.storage import Groundwater
-    from wsimod.nodes.waste import Waste
-    from wsimod.arcs.arcs import Arc
-
+def _config3_setup():
     df = pd.read_csv(os.path.join(REF, "docs/demo/data/processed/timeseries_data.csv"))
     df.loc[df.variable == "flow", "value"] *= constants.M3_S_TO_M3_DT
     df.loc[df.variable == "precipitation", "value"] *= constants.MM_TO_M
@@ -497,41 +486,88 @@ def scenario_config3(R=2):
     constants.NON_ADDITIVE_POLLUTANTS = ["temperature"]
     constants.ADDITIVE_POLLUTANTS = [p for p in pol if p != "temperature"]
     constants.FLOAT_ACCURACY = 1e-8
+    return did, dates
+
+
+def _config3_member(did, f):
+    """One member of SURVEY 8d config 3 with the six parameter factors ``f`` (pervious area, field
+    capacity, depth, impervious area, groundwater area, groundwater residence time)."""
+    from wsimod.nodes.catchment import Catchment
+    from wsimod.nodes.land import Land
+    from wsimod.nodes.nodes import Node
+    from wsimod.nodes.storage import Groundwater
+    from wsimod.nodes.waste import Waste
+    from wsimod.arcs.arcs import Arc
+
     deposition = {"boron": 100e-10, "calcium": 70e-7, "chloride": 60e-10, "fluoride": 0.2e-7, "magnesium": 6e-7,
                   "nitrate": 2e-9, "nitrogen": 4e-7, "potassium": 7e-7, "silicon": 7e-9, "sodium": 30e-9,
                   "sulphate": 70e-7}
-    rng = np.random.default_rng(20261020)
+    nodes = [Waste(name="thames_above_abingdon")]
+    nodes += [Catchment(name=c, data_input_dict=did[c]) for c in ("evenlode", "thames", "ray", "cherwell")]
+    nodes.append(Land(name="oxford_land", data_input_dict=did["oxford_land"], surfaces=[
+        {"type_": "PerviousSurface", "area": 2e7 * f[0], "pollutant_load": dict(deposition), "surface": "rural",
+         "field_capacity": 0.3 * f[1], "depth": 0.5 * f[2], "initial_storage": 2e7 * f[0] * 0.4 * 0.5 * f[2]},
+        {"type_": "ImperviousSurface", "area": 1e7 * f[3], "pollutant_load": dict(deposition),
+         "surface": "urban", "initial_storage": 5e6 * f[3]}]))
+    nodes.append(Groundwater(capacity=3.2e9, area=3.2e8 * f[4], name="gw", residence_time=20 * f[5]))
+    nodes += [Node(name=n) for n in ("farmoor_abstraction", "evenlode_thames", "cherwell_ray",
+                                     "cherwell_thames", "thames_mixer")]
+    by = {n.name: n for n in nodes}
+    arcs = [Arc(in_port=by[i], out_port=by[o], name=a) for a, i, o in [
+        ("evenlode_to_thames", "evenlode", "evenlode_thames"), ("thames_to_thames", "thames", "evenlode_thames"),
+        ("ray_to_cherwell", "ray", "cherwell_ray"), ("cherwell_to_cherwell", "cherwell", "cherwell_ray"),
+        ("thames_to_farmoor", "evenlode_thames", "farmoor_abstraction"),
+        ("farmoor_to_mixer", "farmoor_abstraction", "thames_mixer"),
+        ("cherwell_to_mixer", "cherwell_ray", "thames_mixer"), ("land_to_gw", "oxford_land", "gw"),
+        ("land_to_mixer", "oxford_land", "thames_mixer"), ("gw_to_mixer", "gw", "thames_mixer"),
+        ("mixer_to_waste", "thames_mixer", "thames_above_abingdon")]]
+    m = Model()
+    m.add_instantiated_nodes(nodes)
+    m.add_instantiated_arcs(arcs)
+    return m
+
+
+def scenario_config3(R=2):
+    """SURVEY 8d config 3: the Oxford catchment's land + river-side nodes (Land{Pervious 2e7 m2,
+    Impervious 1e7 m2}, Groundwater, the junction Nodes, Waste, the 4 Catchment inflows as
+    prescribed sources) on the demo's own time series (1456 days, the 12 Oxford pollutants,
+    temperature the only non-additive one), R members with parameters x log-uniform(0.8, 1.25)."""
+    from wsi_b200.ensemble import config3_factors
+
+    did, dates = _config3_setup()
+    factors = config3_factors(R)
     fms, refs = [], []
     for member in range(R):
-        f = np.exp(rng.uniform(np.log(0.8), np.log(1.25), 6)) if member else np.ones(6)
-        nodes = [Waste(name="thames_above_abingdon")]
-        nodes += [Catchment(name=c, data_input_dict=did[c]) for c in ("evenlode", "thames", "ray", "cherwell")]
-        nodes.append(Land(name="oxford_land", data_input_dict=did["oxford_land"], surfaces=[
-            {"type_": "PerviousSurface", "area": 2e7 * f[0], "pollutant_load": dict(deposition), "surface": "rural",
-             "field_capacity": 0.3 * f[1], "depth": 0.5 * f[2], "initial_storage": 2e7 * f[0] * 0.4 * 0.5 * f[2]},
-            {"type_": "ImperviousSurface", "area": 1e7 * f[3], "pollutant_load": dict(deposition),
-             "surface": "urban", "initial_storage": 5e6 * f[3]}]))
-        nodes.append(Groundwater(capacity=3.2e9, area=3.2e8 * f[4], name="gw", residence_time=20 * f[5]))
-        nodes += [Node(name=n) for n in ("farmoor_abstraction", "evenlode_thames", "cherwell_ray",
-                                         "cherwell_thames", "thames_mixer")]
-        by = {n.name: n for n in nodes}
-        arcs = [Arc(in_port=by[i], out_port=by[o], name=a) for a, i, o in [
-            ("evenlode_to_thames", "evenlode", "evenlode_thames"), ("thames_to_thames", "thames", "evenlode_thames"),
-            ("ray_to_cherwell", "ray", "cherwell_ray"), ("cherwell_to_cherwell", "cherwell", "cherwell_ray"),
-            ("thames_to_farmoor", "evenlode_thames", "farmoor_abstraction"),
-            ("farmoor_to_mixer", "farmoor_abstraction", "thames_mixer"),
-            ("cherwell_to_mixer", "cherwell_ray", "thames_mixer"), ("land_to_gw", "oxford_land", "gw"),
-            ("land_to_mixer", "oxford_land", "thames_mixer"), ("gw_to_mixer", "gw", "thames_mixer"),
-            ("mixer_to_waste", "thames_mixer", "thames_above_abingdon")]]
-        m = Model()
-        m.add_instantiated_nodes(nodes)
-        m.add_instantiated_arcs(arcs)
+        m = _config3_member(did, factors[member])
         fms.append(flatten_ref(m, dates))
         refs.append(run_reference(m, dates))
     fm = merge_replicas(fms)
     ref = {k: np.stack([r[k] for r in refs], axis=-1) for k in refs[0] if k != "n_advisories"}
     ref["n_advisories"] = np.array([int(sum(r["n_advisories"][0] for r in refs))])
     save("config3", fm, ref, "SURVEY 8d config 3: Oxford land + river-side subset, %d members, %d days" % (R, len(dates)))
+    set_default_pollutants()
+
+
+def scenario_config3_members(R=16):
+    """The first 16 members of the config-3 ensemble (wsi_b200.ensemble.config3_factors), every one
+    built and run with the reference; to keep the fixture small only three arcs are stored: what the
+    Land sends to the groundwater and to the river, and the catchment outlet (which sums everything)."""
+    from wsi_b200.ensemble import config3_factors
+
+    did, dates = _config3_setup()
+    factors = config3_factors(R)
+    keep = ["land_to_gw", "land_to_mixer", "mixer_to_waste"]
+    fms, flows, adv = [], [], 0
+    for member in range(R):
+        m = _config3_member(did, factors[member])
+        fms.append(flatten_ref(m, dates))
+        r = run_reference(m, dates)
+        idx = [list(m.arcs.keys()).index(a) for a in keep]
+        flows.append(r["flows"][:, idx])
+        adv += int(r["n_advisories"][0])
+    fm = merge_replicas(fms)
+    ref = {"flows_kept": np.stack(flows, axis=-1), "kept_arcs": np.array(keep), "n_advisories": np.array([adv])}
+    save("config3_members16", fm, ref, "config 3: %d reference-built members, 3 arcs, %d days" % (R, len(dates)))
     set_default_pollutants()
 
 
@@ -543,6 +579,7 @@ SCENARIOS = {
     "rivernet": scenario_rivernet,
     "rivertree": scenario_rivertree,
     "config3": scenario_config3,
+    "config3_members16": scenario_config3_members,
 }
 
 if __name__ == "__main__":

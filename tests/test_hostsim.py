@@ -94,3 +94,27 @@ def test_network_engine_rejects_non_dendritic_models():
     assert network.plan_network(fm) is None and network.why_not(fm)
     with pytest.raises(ValueError):
         ModelBuffers(fm, device="numpy", engine="network")
+
+
+def test_reduced_outputs_and_member_window(hostsim):
+    """Objectives on the device: a reduced probe keeps the running sum and maximum of a plane per
+    member (model.py:1177-1197 needs no more of the series), and the series themselves are kept for
+    a window of members only -- both must equal what the full record gives."""
+    from wsi_b200 import ensemble as E
+    from wsi_b200.backend.capi import ModelBuffers
+    from wsi_b200.backend.probes import ProbeSet
+
+    fm = E.build_config2(R=24, T=60)
+    outlet = [fm.arc_names.index("river-outlet")]
+    ps = ProbeSet(fm).add_flows(outlet)
+    full = _run(hostsim, fm, ps.probes, record_mb=False).array("out_probe")  # [T, V, R]
+    buf = ModelBuffers(fm, device="numpy", probes=ps.probes, rec_t0=0, rec_T=fm.T, reduce_probes=ps.probes,
+                       rec_members=(5, 7), engine="replica")
+    assert hostsim.wsi_hostsim_run(C.byref(buf.desc), 0, fm.T, 0) == 0
+    assert np.array_equal(buf.array("out_probe"), full[:, :, 5:12])
+    red = buf.array("red_out")
+    assert np.array_equal(red[1], full.max(axis=0))
+    want = np.zeros_like(red[0])
+    for t in range(fm.T):  # the same left-to-right additions
+        want = want + full[t]
+    assert np.array_equal(red[0], want)

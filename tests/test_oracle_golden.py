@@ -40,6 +40,33 @@ def test_oracle_mass_balance_advisories_match_reference(name):
         assert int(run.mb_count.sum()) <= int(ref["n_advisories"][0])
 
 
+def _kept_flows(fm, ref, out_probe, ps):
+    idx = [fm.arc_names.index(str(a)) for a in ref["kept_arcs"]]
+    return ps.split(out_probe)["flows"][:, idx]
+
+
+def test_config3_ensemble_members_are_the_reference_built_members():
+    """wsi_b200.ensemble.build_config3 perturbs the flat planes of the Oxford member; its first 16
+    members must be the 16 members tests/golden/make_golden.py built object by object WITH THE
+    REFERENCE (same factors), and the oracle must reproduce the reference's flows on all of them."""
+    from oracle import oracle
+    from wsi_b200 import ensemble as E
+    from wsi_b200.backend.probes import ProbeSet
+
+    template, _ = load_golden("config3")
+    g16, ref = load_golden("config3_members16")
+    fm = E.build_config3(16, template)
+    for g in fm.groups:
+        if fm.groups[g].size:
+            np.testing.assert_allclose(fm.groups[g], g16.groups[g], rtol=1e-14, atol=0, err_msg=g)
+    f = E.config3_factors(16)
+    assert np.all(f[0] == 1.0) and len(np.unique(f[1:, 0])) == 15 and f[1:].min() >= 0.8 and f[1:].max() <= 1.25
+    ps = ProbeSet(g16).add_flows()
+    run = oracle.run(g16, probes=ps.probes, n_threads=4)
+    got = _kept_flows(g16, ref, run.out_probe, ps)
+    assert np.array_equal(got, ref["flows_kept"].reshape(got.shape))
+
+
 def test_oracle_chunked_run_equals_single_run():
     """State carried in the SoA tensors is complete: [0,T) == [0,a) + [a,T)."""
     from oracle import oracle

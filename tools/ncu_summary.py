@@ -30,10 +30,10 @@ for r in rows[2:]:
                  for i, x in enumerate(h) if 'issue_stalled' in x and 'per_issue_active' in x), reverse=True)
     print("\nStall cycles per issued instruction: " + ", ".join(f"{n} {v:.1f}" for v, n in st if v > 0.5) + "\n")
     traffic[short] = (float(r[h.index('dram__bytes_read.sum')]) + float(r[h.index('dram__bytes_write.sum')])) * 1e6
-step = [k for k in traffic if 'wsi_step_kernel' in k]
-if step:
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    json.dump({"dram_bytes_per_launch": int(traffic[step[0]]),
-               "source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum (tools/ncu_summary.py)",
-               "kernel": step[0], "all_kernels_bytes_per_launch": {k: int(v) for k, v in traffic.items()}},
-              open(os.path.join(root, "profiles", "traffic.json"), "w"), indent=1)
+# one entry per kernel of the captured timestep; the total is what bench.py reports as roofline.traffic
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+json.dump({"dram_bytes_per_step": int(sum(traffic.values())),
+           "source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of every kernel of ONE timestep "
+                     "(tools/ncu_summary.py; " + os.path.basename(rep) + ")",
+           "kernels": {k: int(v) for k, v in traffic.items()}},
+          open(os.path.join(root, "profiles", "traffic.json"), "w"), indent=1)

@@ -136,6 +136,14 @@ class WsiModelDesc(C.Structure):
         ("node_flags", _u32p),
         ("arc_chain_ptr", _i32p),
         ("arc_chain", _i32p),
+        ("n_red", C.c_int32),
+        ("rec_r0", C.c_int32),
+        ("rec_R", C.c_int32),
+        ("reserved3", C.c_int32),
+        ("red_group", _i32p),
+        ("red_plane", _i32p),
+        ("red_obj", _i32p),
+        ("red_out", _f64p),
     ]
 
 
@@ -248,7 +256,8 @@ class ModelBuffers:
             return -(-(items * fm.R) // self.OBJ_BLOCK)
         return items * -(-fm.R // self.OBJ_BLOCK)
 
-    def __init__(self, fm, device="cuda", probes=(), rec_t0=0, rec_T=None, record_mb=False, engine="auto"):
+    def __init__(self, fm, device="cuda", probes=(), rec_t0=0, rec_T=None, record_mb=False, engine="auto",
+                 reduce_probes=(), rec_members=None):
         from . import network
 
         self.net = network.plan_network(fm) if engine in ("auto", "network") else None
@@ -282,6 +291,13 @@ class ModelBuffers:
         self.fm = fm
         self.device = device
         self.probes = list(probes)
+        # planes reduced over time on the device (running sum / maximum per member) and the window of
+        # members whose full series are kept (None: all)
+        self.reduce_probes = list(reduce_probes)
+        self.rec_members = (0, 0) if rec_members is None else (int(rec_members[0]), int(rec_members[1]))
+        if self.rec_members[1] and not (0 <= self.rec_members[0] and sum(self.rec_members) <= fm.R):
+            raise ValueError("rec_members outside [0, R)")
+        self.rec_R = self.rec_members[1] or fm.R
         self.rec_t0 = int(rec_t0)
         self.rec_T = int(fm.T if rec_T is None else rec_T)
         self.record_mb = bool(record_mb)
@@ -308,7 +324,11 @@ class ModelBuffers:
         k["probe_plane"] = np.ascontiguousarray(pr[:, 1])
         k["probe_obj"] = np.ascontiguousarray(pr[:, 2])
         npb = max(len(self.probes), 1)
-        k["out_probe"] = np.zeros((self.rec_T, npb, fm.R), dtype=np.float64)
+        k["out_probe"] = np.zeros((self.rec_T, npb, self.rec_R), dtype=np.float64)
+        rd = np.array(self.reduce_probes or [(0, 0, 0)], dtype=np.int32).reshape(-1, 3)
+        k["red_group"], k["red_plane"], k["red_obj"] = (np.ascontiguousarray(rd[:, i]) for i in range(3))
+        k["red_out"] = np.zeros((2, max(len(self.reduce_probes), 1), fm.R), dtype=np.float64)
+        k["red_out"][1] = -np.inf
         k["out_mb"] = (
             np.zeros((self.rec_T, len(fm.node_names), 3, fm.V, fm.R), dtype=np.float64)
             if self.record_mb
@@ -345,7 +365,11 @@ class ModelBuffers:
         k["probe_plane"] = up(pr[:, 1], torch.int32)
         k["probe_obj"] = up(pr[:, 2], torch.int32)
         npb = max(len(self.probes), 1)
-        k["out_probe"] = torch.zeros((self.rec_T, npb, fm.R), dtype=torch.float64, device=dev)
+        k["out_probe"] = torch.zeros((self.rec_T, npb, self.rec_R), dtype=torch.float64, device=dev)
+        rd = np.array(self.reduce_probes or [(0, 0, 0)], dtype=np.int32).reshape(-1, 3)
+        k["red_group"], k["red_plane"], k["red_obj"] = (up(rd[:, i], torch.int32) for i in range(3))
+        k["red_out"] = torch.zeros((2, max(len(self.reduce_probes), 1), fm.R), dtype=torch.float64, device=dev)
+        k["red_out"][1] = float("-inf")
         k["out_mb"] = (
             torch.zeros((self.rec_T, len(fm.node_names), 3, fm.V, fm.R), dtype=torch.float64, device=dev)
             if self.record_mb
@@ -404,7 +428,10 @@ class ModelBuffers:
             setattr(d, name, C.cast(P(k[name]), _f64p))
         for g, fld in _GROUP_FIELD.items():
             setattr(d, fld, C.cast(P(k["group_" + g]), _f64p))
-        for name in ("probe_group", "probe_plane", "probe_obj", "mb_count"):
+        d.n_red = len(self.reduce_probes)
+        d.rec_r0, d.rec_R = self.rec_members
+        d.red_out = C.cast(P(k["red_out"]), _f64p)
+        for name in ("probe_group", "probe_plane", "probe_obj", "mb_count", "red_group", "red_plane", "red_obj"):
             setattr(d, name, C.cast(P(k[name]), _i32p))
         for name in ("out_probe", "out_mb", "mb_partial", "mb_sums", "mb_terms"):
             setattr(d, name, C.cast(P(k[name]), _f64p))

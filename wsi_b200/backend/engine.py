@@ -20,7 +20,7 @@ class GpuRunner:
     """
 
     def __init__(self, fm, probes=(), rec_t0=0, rec_T=None, record_mb=False, device="cuda:0",
-                 system_sums=True, engine="auto"):
+                 system_sums=True, engine="auto", reduce_probes=(), rec_members=None):
         import torch
 
         self.torch = torch
@@ -28,7 +28,8 @@ class GpuRunner:
         self.fm = fm
         self.device = torch.device(device)
         self.buffers = capi.ModelBuffers(fm, device=device, probes=probes, rec_t0=rec_t0, rec_T=rec_T,
-                                         record_mb=record_mb, engine=engine)
+                                         record_mb=record_mb, engine=engine, reduce_probes=reduce_probes,
+                                         rec_members=rec_members)
         self.desc = self.buffers.desc
         if not system_sums:
             self.desc.mb_sums = C.cast(None, C.POINTER(C.c_double))
@@ -81,6 +82,11 @@ class GpuRunner:
     # ---- results ----
     def out_probe(self):
         return self.buffers.to_numpy("out_probe")
+
+    def reduced(self):
+        """``(sum, max)`` over the timesteps stepped so far of every reduced probe, ``[n_red, R]`` each."""
+        a = self.buffers.to_numpy("red_out")
+        return a[0], a[1]
 
     def out_mb(self):
         return self.buffers.to_numpy("out_mb") if self.buffers.record_mb else None

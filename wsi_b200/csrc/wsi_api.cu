@@ -165,7 +165,7 @@ int run_steps_graph(const WsiModelDesc* d, int slot, int64_t t0, int64_t t1, cud
   const int32_t baked[] = {slot, d->P, (int32_t)d->additive_mask, d->idx[0], d->idx[1], d->idx[2], d->idx[3], d->idx[4],
                            d->idx[5], d->idx[6], d->idx[7], d->R, d->n_nodes, d->n_arcs, d->n_surf, d->surf_class_ptr[0],
                            d->surf_class_ptr[1], d->surf_class_ptr[2], d->surf_class_ptr[3], d->surf_class_ptr[4],
-                           d->n_probe, d->n_end, d->n_sched, d->engine, d->n_net_levels, d->n_net_calc, d->n_net_final,
+                           d->n_probe, d->n_red, d->n_end, d->n_sched, d->engine, d->n_net_levels, d->n_net_calc, d->n_net_final,
                            d->n_net_bnd, d->mb_sums ? 1 : 0};
   unsigned long long h = fnv(1469598103934665603ull, baked, sizeof baked);
   if (d->engine == 1) h = fnv(h, d->net_level_ptr_host, sizeof(int32_t) * (size_t)(d->n_net_levels + 1));
@@ -232,7 +232,7 @@ int wsi_validate(const WsiModelDesc* d) {
   if (d->n_sched > 0 && (!d->sched_op || !d->sched_node)) return fail(WSI_ERR_BAD_DESC, "schedule missing%s");
   if (d->n_end > 0 && (!d->end_kind || !d->end_obj)) return fail(WSI_ERR_BAD_DESC, "end_timestep items missing%s");
   if (d->engine != 0 && d->engine != 1) return fail(WSI_ERR_BAD_DESC, "unknown engine%s");
-  if (d->engine == 0 && (d->n_probe > 65535 || d->n_end > 65535 || d->n_nodes + d->n_arcs > 65535))
+  if (d->engine == 0 && (d->n_probe + d->n_red > 65535 || d->n_end > 65535 || d->n_nodes + d->n_arcs > 65535))
     return fail(WSI_ERR_UNSUPPORTED,
                 "more than 65535 probes / nodes+arcs / end items per template need the network engine%s");
   if (d->engine == 1 && (d->n_net_levels < 0 || !d->net_level_ptr || !d->net_level_ptr_host || !d->net_level_node ||
@@ -250,6 +250,9 @@ int wsi_validate(const WsiModelDesc* d) {
     return fail(WSI_ERR_BAD_DESC, "forcing arrays missing%s");
   if (d->n_probe > 0 && (!d->probe_group || !d->probe_plane || !d->probe_obj || !d->out_probe))
     return fail(WSI_ERR_BAD_DESC, "probe arrays missing%s");
+  if (d->n_red < 0 || (d->n_red > 0 && (!d->red_group || !d->red_plane || !d->red_obj || !d->red_out)))
+    return fail(WSI_ERR_BAD_DESC, "reduced-probe arrays missing%s");
+  if (d->rec_R < 0 || d->rec_r0 < 0 || d->rec_r0 + d->rec_R > d->R) return fail(WSI_ERR_BAD_DESC, "record member window outside [0, R)%s");
   if (d->record_mb && !d->out_mb) return fail(WSI_ERR_BAD_DESC, "record_mb without out_mb%s");
   if (d->mb_sums && !d->mb_partial) return fail(WSI_ERR_BAD_DESC, "mb_sums without mb_partial%s");
   if (d->n_nodes > 0 && (!d->mb_terms || !d->mb_term_slot)) return fail(WSI_ERR_BAD_DESC, "mb_terms missing%s");

@@ -192,8 +192,7 @@ __global__ void __launch_bounds__(kBlock, WSI_STEP_MINB)
   if (!active) return;
   if (flags & WSI_RUN_RECORD) {
     const int row = t_arg >= 0 ? row_arg : t - d.rec_t0;
-    if (row >= 0 && row < d.rec_T)
-      for (int k = 0; k < d.n_probe; k++) record_probe(c, row, k);
+    for (int k = 0; k < d.n_probe + d.n_red; k++) record_item(c, row, k);
   }
   if (flags & WSI_RUN_END_TIMESTEP)
     for (int i = 0; i < d.n_end; i++) end_item(c, d.end_kind[i], d.end_obj[i]);
@@ -261,11 +260,10 @@ __global__ void __launch_bounds__(kObjBlock, WSI_MB_MINB)
   const WsiModelDesc& d = g_wsi_desc[slot];
   const int t = step_of(d, t_arg);
   const int row = t_arg >= 0 ? row_arg : t - d.rec_t0;
-  if (row < 0 || row >= d.rec_T) return;
   int item, r;
-  if (!decode_item<FLAT>(d, d.n_probe, item, r)) return;
+  if (!decode_item<FLAT>(d, d.n_probe + d.n_red, item, r)) return;
   Ctx<CFG> c = make_ctx(nullptr, slot, cfg, r, t, 0u);
-  record_probe(c, row, item);
+  record_item(c, row, item);
 }
 
 // One thread per (end_timestep item, replica): arcs reset, DecayTank decay, QueueTank shift.
@@ -722,12 +720,15 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
     }
   }
   if (flags & WSI_RUN_RECORD) {
+    // series probes only inside the record window; reduced probes every step
     const int row = (int)t - d->rec_t0;
-    if (d->n_probe > 0 && (t < 0 || (row >= 0 && row < d->rec_T))) {
+    const bool in_window = d->n_probe > 0 && (t < 0 || (row >= 0 && row < d->rec_T));
+    const int items = d->n_probe + d->n_red;
+    if (d->n_red > 0 || in_window) {
       if (net) {
-        wsi_record_kernel<CFG, true><<<n_flat_blocks(d, d->n_probe), kObjBlock, 0, s>>>(slot, cfg, (int)t, row);
+        wsi_record_kernel<CFG, true><<<n_flat_blocks(d, items), kObjBlock, 0, s>>>(slot, cfg, (int)t, row);
       } else {
-        const dim3 grid(n_obj_blocks(d), d->n_probe);
+        const dim3 grid(n_obj_blocks(d), items);
         wsi_record_kernel<CFG, false><<<grid, kObjBlock, 0, s>>>(slot, cfg, (int)t, row);
       }
       WSI_CHECK_LAUNCH("wsi_record_kernel");

@@ -646,26 +646,51 @@ WSI_HDN void end_timestep(C& c) {
 
 // ---- recording (model.py:1063-1170): copy probe planes into out_probe[t, k, r] ---------------
 template <class C>
+WSI_HD const double* probe_src(const C& c, int group, int plane, int obj) {
+  switch (group) {
+    case 0: return c.arc(plane, obj);
+    case 1: return c.land(plane, obj);
+    case 2: return c.surf(plane, obj);
+    case 3: return c.tank(plane, obj);
+    case 4: return c.river(plane, obj);
+    default: return c.sewer(plane, obj);
+  }
+}
+// series probe k: only the members of the record window are kept (rec_R == 0: all of them)
+template <class C>
 WSI_HD void record_probe(const C& c, int row, int k) {
   const WsiModelDesc& d = c.D();
-  const int plane = d.probe_plane[k], obj = d.probe_obj[k];
-  const double* src;
-  switch (d.probe_group[k]) {
-    case 0: src = c.arc(plane, obj); break;
-    case 1: src = c.land(plane, obj); break;
-    case 2: src = c.surf(plane, obj); break;
-    case 3: src = c.tank(plane, obj); break;
-    case 4: src = c.river(plane, obj); break;
-    default: src = c.sewer(plane, obj); break;
+  const int nr = d.rec_R > 0 ? d.rec_R : d.R;
+  const int rr = c.r - (d.rec_R > 0 ? d.rec_r0 : 0);
+  if (rr < 0 || rr >= nr) return;
+  d.out_probe[((size_t)row * d.n_probe + k) * (size_t)nr + rr] = *probe_src(c, d.probe_group[k], d.probe_plane[k], d.probe_obj[k]);
+}
+// reduced probe k: running sum and maximum over the timesteps (what the objectives of
+// model.py:1177-1197 need of a member's series, without keeping the series)
+template <class C>
+WSI_HD void reduce_probe(const C& c, int k) {
+  const WsiModelDesc& d = c.D();
+  const double v = *probe_src(c, d.red_group[k], d.red_plane[k], d.red_obj[k]);
+  double* sum = d.red_out + (size_t)k * c.R + c.r;
+  double* mx = sum + (size_t)d.n_red * c.R;
+  *sum = *sum + v;
+  if (v > *mx) *mx = v;
+}
+// item k of the recording pass: series probes first, then the reduced ones
+template <class C>
+WSI_HD void record_item(const C& c, int row, int k) {
+  const WsiModelDesc& d = c.D();
+  if (k < d.n_probe) {
+    if (row >= 0 && row < d.rec_T) record_probe(c, row, k);
+  } else {
+    reduce_probe(c, k - d.n_probe);
   }
-  d.out_probe[((size_t)row * d.n_probe + k) * c.R + c.r] = *src;
 }
 template <class C>
 WSI_HD void record(const C& c) {
   const WsiModelDesc& d = c.D();
   const int row = c.t - d.rec_t0;
-  if (d.n_probe <= 0 || row < 0 || row >= d.rec_T) return;
-  for (int k = 0; k < d.n_probe; k++) record_probe(c, row, k);
+  for (int k = 0; k < d.n_probe + d.n_red; k++) record_item(c, row, k);
 }
 
 // Out-of-line ops receive a COPY of the context: a context whose address is handed to a function

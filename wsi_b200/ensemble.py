@@ -222,11 +222,53 @@ def algorithmic_bytes_per_replica_step(fm, n_recorded_planes):
     return 8 * (2 * S + Q + F + O), dict(S=S, Q=Q, F=F, O=O)
 
 
-def build_config3(R, template):
-    """``R`` members of the Oxford catchment's land + river-side subset.
+def config3_factors(R, seed=20261020):
+    """``[R, 6]`` parameter factors of the config-3 ensemble: member 0 is the Oxford
+    demo's own parameter set, every other member draws log-uniform(0.8, 1.25) factors for the
+    pervious area, field capacity, soil depth, impervious area, groundwater area and groundwater
+    residence time from ``default_rng(20261020)``, six per member in member order."""
+    rng = np.random.default_rng(seed)
+    f = np.ones((int(R), 6))
+    if R > 1:
+        f[1:] = np.exp(rng.uniform(np.log(0.8), np.log(1.25), (int(R) - 1, 6)))
+    return f
 
-    ``template`` is a flat model holding a few distinct members (the golden fixture
-    ``tests/golden/config3.npz`` generated from the reference's own Oxford data, which is not
-    shipped here); member ``i`` of the ensemble is template member ``i mod R0``.  Forcing and the
-    four catchment inflow series are shared by all members (broadcast loads)."""
-    return template.take_replicas(np.arange(int(R)) % template.R)
+
+def build_config3(R, template, factors=None):
+    """``R`` distinct members of the Oxford catchment's land + river-side subset.
+
+    ``template`` is a flat model whose member 0 is the Oxford demo's own parameter set (the golden
+    fixture ``tests/golden/config3.npz``, generated from the reference's Oxford data, which is not
+    shipped here).  Member ``i`` is that member with the factors ``config3_factors(R)[i]`` applied to
+    the flat planes exactly as the constructors of ``nodes/land.py`` / ``nodes/storage.py`` derive
+    them (``land.py:794-814``: field_capacity_m = field_capacity * depth, the tank's depth =
+    depth * total_porosity, capacity = area * depth; ``tests/golden/config3_members16.npz`` holds
+    the same members built object by object with the reference).  Forcing and the four catchment
+    inflow series are shared by all members (broadcast loads)."""
+    R = int(R)
+    f = config3_factors(R) if factors is None else np.asarray(factors, dtype=np.float64)
+    fm = template.take_replicas(np.zeros(R, dtype=np.int64))
+    types = fm.view("surf", "type")[0, :, 0].astype(int)
+    perv = [i for i, t in enumerate(types) if t == L.ST["PerviousSurface"]]
+    imp = [i for i, t in enumerate(types) if t == L.ST["ImperviousSurface"]]
+
+    def mul(group, name, objs, factor, planes=None):
+        v = fm.view(group, name)
+        rows = range(v.shape[0]) if planes is None else planes
+        for o in objs:
+            for p in rows:
+                v[p, o, :] *= factor
+
+    mul("surf", "area", perv, f[:, 0])
+    mul("surf", "capacity", perv, f[:, 0] * f[:, 2])
+    mul("surf", "depth", perv, f[:, 2])
+    mul("surf", "field_capacity_m", perv, f[:, 1] * f[:, 2])
+    mul("surf", "wilting_point_m", perv, f[:, 2])
+    mul("surf", "storage", perv, f[:, 0] * f[:, 2], planes=[0])
+    mul("surf", "area", imp, f[:, 3])
+    mul("surf", "capacity", imp, f[:, 3])
+    mul("surf", "storage", imp, f[:, 3], planes=[0])
+    gw = [int(fm.node_gidx[i]) for i, t in enumerate(fm.node_type) if int(t) == L.NT["Groundwater"]]
+    mul("tank", "area", gw, f[:, 4])
+    mul("tank", "residence_time", gw, f[:, 5])
+    return fm
