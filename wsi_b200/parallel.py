@@ -33,12 +33,30 @@ def reduce_mass_balance(mb_sums, mb_count, group=None):
     return mb_sums, mb_count
 
 
-def reduce_flags(node_flags_any, group=None):
-    """Bitwise-OR of per-node status words across ranks (``[n_nodes]`` int32 tensor)."""
+def reduce_mass_balance_async(mb_sums, mb_count, group=None):
+    """The same reduction without blocking the launching stream: returns the work handles (call
+    ``wait()`` on each before reading the tensors); the caller keeps stepping meanwhile."""
     import torch.distributed as dist
 
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(node_flags_any, op=dist.ReduceOp.BOR, group=group)
+        return [dist.all_reduce(mb_sums, op=dist.ReduceOp.SUM, group=group, async_op=True),
+                dist.all_reduce(mb_count, op=dist.ReduceOp.SUM, group=group, async_op=True)]
+    return []
+
+
+def reduce_flags(node_flags_any, group=None):
+    """Bitwise-OR of per-node status words across ranks (``[n_nodes]`` int32 tensor).  NCCL has no
+    bitwise reductions, so the words travel as one 0/1 plane per status bit under MAX (gloo would take
+    BOR directly; one code path serves both)."""
+    import torch
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        n_bits = 8  # WSI_FLAG_* uses 6
+        shifts = torch.arange(n_bits, dtype=node_flags_any.dtype, device=node_flags_any.device)
+        bits = (node_flags_any.unsqueeze(-1) >> shifts) & 1
+        dist.all_reduce(bits, op=dist.ReduceOp.MAX, group=group)
+        node_flags_any.copy_((bits << shifts).sum(dim=-1))
     return node_flags_any
 
 
