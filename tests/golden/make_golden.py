@@ -195,7 +195,7 @@ def build_quickstart(land_inputs, load_pol="phosphate"):
     return m
 
 
-def scenario_quickstart(T=500):
+def scenario_quickstart(T=1456):
     set_default_pollutants()
     land_inputs, dates = oxford_land_inputs()
     dates = dates[:T]
@@ -239,6 +239,61 @@ def scenario_fixture3607(T=730):
     fm = flatten_ref(m, dates)
     ref = run_reference(m, dates)
     save("fixture3607", fm, ref, "reference test fixture 3607 reduced to supported nodes, %d days, csv dates" % T)
+
+
+def scenario_hourly(T=1080):
+    """Hourly timestep (config 5's regime): dates are the reference's own ``to_datetime`` objects
+    parsed from 'YYYY-MM-DD HH:MM:SS' (model.py:139-162), 45 days from 2001-03-06.  The crop calendar
+    advances per TIMESTEP (land.py:1531-1544): days_after_sow counts hours, sowing and harvest fire on
+    the first hour of their day, and -- to_datetime.is_leap_year being a method -- the day of year is
+    shifted in this non-leap year too."""
+    from datetime import datetime, timedelta
+
+    set_default_pollutants()
+    t0 = datetime(2001, 3, 6)
+    dates = [to_datetime((t0 + timedelta(hours=i)).strftime("%Y-%m-%d %H:%M:%S")) for i in range(T)]
+    rng = np.random.default_rng(20261105)
+    hours = np.arange(T)
+    temperature = 8 + 5 * np.sin(2 * np.pi * (hours % 24 - 9) / 24) + rng.normal(0, 0.7, T)
+    et0 = np.maximum(0.0, 2.5e-4 * np.sin(2 * np.pi * (hours % 24 - 6) / 24))
+    wet = rng.random(T) < 0.12
+    precipitation = wet * rng.gamma(0.7, 1.2e-3, T)
+    forcing = {}
+    for t, d in enumerate(dates):
+        forcing[("precipitation", d)] = float(precipitation[t])
+        forcing[("et0", d)] = float(et0[t])
+        forcing[("temperature", d)] = float(temperature[t])
+    monthly = {(var, to_datetime(m)): 1e-7 / 24 for var in L.DEP_COLS for m in ("2001-03", "2001-04")}
+    a_grow = 3.0e4
+    vol = a_grow * 1.25 * 0.4 * 0.9
+    init = {"do": 0.01, "org-phosphorus": vol * 1e-4, "phosphate": vol * 1e-4, "ammonia": vol * 5e-5,
+            "solids": vol * 1e-2, "bod": vol * 1e-3, "cod": vol * 2e-2, "ph": 7.0, "temperature": 9.0,
+            "nitrate": vol * 4e-3, "nitrite": vol * 2e-5, "org-nitrogen": vol * 5e-3, "volume": vol}
+    soil = {"org-phosphorus": vol * 5e-3, "phosphate": vol * 5e-3, "ammonia": 0.0, "nitrate": vol,
+            "nitrite": 0.0, "org-nitrogen": vol, "volume": vol}
+    grow = dict(GROWING_TEMPLATE)
+    grow.update(type_="GrowingSurface", surface="crop", area=a_grow, pollutant_load={}, initial_storage=init,
+                initial_soil_storage=soil, data_input_dict=monthly, sowing_day=74, harvest_day=95,
+                crop_factor_stage_dates=[0, 73, 74, 80, 86, 90, 95, 96, 366], infiltration_capacity=0.004,
+                decays={"ammonia": {"constant": 0.1 / 24, "exponent": 1.005},
+                        "nitrite": {"constant": 0.05 / 24, "exponent": 1.005}})
+    imp = {"type_": "ImperviousSurface", "surface": "urban", "area": 5e3, "pore_depth": 0.002,
+           "pollutant_load": {"phosphate": 1e-11, "solids": 1e-6}}
+    land = {"type_": "Land", "name": "land", "data_input_dict": forcing, "surfaces": [imp, grow],
+            "surface_residence_time": 6.0, "subsurface_residence_time": 60.0, "percolation_residence_time": 400.0}
+    sewer = {"type_": "Sewer", "name": "sewer", "capacity": 40.0, "pipe_time": 2}
+    gw = {"type_": "Groundwater", "name": "gw", "area": a_grow, "capacity": a_grow * 0.5, "residence_time": 900.0,
+          "initial_storage": a_grow * 0.01}
+    arcs = [("land-sewer", "land", "sewer"), ("land-gw", "land", "gw"), ("land-river", "land", "river"),
+            ("sewer-river", "sewer", "river"), ("gw-river", "gw", "river"), ("river-outlet", "river", "outlet")]
+    m = Model()
+    m.add_nodes([sewer, land, gw, {"type_": "Node", "name": "river"}, {"type_": "Waste", "name": "outlet"}])
+    m.add_arcs([{"type_": "Arc", "name": a, "in_port": i, "out_port": o} for a, i, o in arcs])
+    fm = flatten_ref(m, dates)
+    ref = run_reference(m, dates)
+    das = ref["surf_state"][:, 1, 1]
+    assert das.max() > 24 * 15, "days_after_sow must count hours"
+    save("hourly", fm, ref, "hourly timestep, to_datetime dates, crop calendar counting timesteps, %d steps" % T)
 
 
 def synthetic_forcing(dates, rng):
@@ -579,6 +634,7 @@ SCENARIOS = {
     "rivernet": scenario_rivernet,
     "rivertree": scenario_rivertree,
     "config3": scenario_config3,
+    "hourly": scenario_hourly,
     "config3_members16": scenario_config3_members,
 }
 

@@ -6,7 +6,7 @@ import pytest
 from parity_util import load_golden
 
 
-def _quickstart_model(T=500):
+def _quickstart_model(T=1456):
     import pandas as pd
 
     from wsi_b200.core import constants
@@ -143,3 +143,41 @@ def test_records_and_scatter_back_from_oracle_arrays():
     assert np.array_equal(fm2.groups["tank"], run.groups["tank"])
     assert np.array_equal(fm2.groups["surf"][: fm.plane("surf", "out_percolation")],
                           run.groups["surf"][: fm.plane("surf", "out_percolation")])
+
+
+@pytest.mark.reference
+def test_model_load_of_the_reference_yaml_fixture_flattens_like_the_golden(tmp_path):
+    """``Model.load`` on a YAML model file + csv.gz inputs (model.py:216-274): the reference's own
+    real-catchment fixture (tests/test_model_data.zip, reduced to the nodes on the GPU path exactly as
+    tests/golden/make_golden.py reduces it) loaded through THIS package's Model must flatten to the
+    very planes the golden holds, which were flattened from the reference's objects after ITS load."""
+    import contextlib
+    import io
+    import zipfile
+
+    import yaml
+
+    from wsi_b200.orchestration.model import Model
+
+    fm_ref, _ = load_golden("fixture3607")
+    zipfile.ZipFile("/root/reference/tests/test_model_data.zip").extractall(tmp_path)
+    cfg = yaml.safe_load(open(tmp_path / "config.yml"))
+    keep = {k: v for k, v in cfg["nodes"].items()
+            if v["type_"] in ("Land", "Sewer", "Groundwater", "River", "Node", "Waste") and "foul" not in k}
+    cfg["nodes"] = keep
+    cfg["arcs"] = {k: a for k, a in cfg["arcs"].items() if a["in_port"] in keep and a["out_port"] in keep}
+    cfg["dates"] = cfg["dates"][:fm_ref.T]
+    cfg.pop("extensions", None)
+    yaml.safe_dump(cfg, open(tmp_path / "reduced.yml", "w"))
+    m = Model()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.load(str(tmp_path), config_name="reduced.yml")
+    fm = m.flatten()
+    assert fm.node_names == fm_ref.node_names and fm.arc_names == fm_ref.arc_names
+    for name in ("node_type", "node_gidx", "arc_in", "arc_out", "cand_ptr", "cand_arcs", "sched_op", "sched_node",
+                 "month_idx", "dayofyear", "doy_adj", "land_surf_ptr", "land_surf"):
+        assert np.array_equal(getattr(fm, name), getattr(fm_ref, name)), name
+    for g in fm.groups:
+        assert np.array_equal(fm.groups[g], fm_ref.groups[g]), g
+    for name in ("node_forcing", "surf_inputs", "catch_inputs"):
+        assert np.array_equal(getattr(fm, name), getattr(fm_ref, name)), name

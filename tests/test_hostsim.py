@@ -8,7 +8,7 @@ import pytest
 
 from parity_util import compare_blocks, compare_mb, load_golden
 
-GOLDENS = ["quickstart", "quickstart_simple", "fixture3607", "config2", "rivernet", "rivertree", "config3"]
+GOLDENS = ["quickstart", "quickstart_simple", "fixture3607", "config2", "rivernet", "rivertree", "config3", "hourly"]
 
 
 @pytest.fixture(scope="module")
