@@ -435,15 +435,14 @@ def main():
 
     n_sched = len(fm.sched_op)
     runner.buffers.set_rec_window(W)  # timestep W must fall inside the record window for RUN_RECORD to launch
-    phases = {
-        "wsi_surface_kernel (x3 classes)": _phase_ms(_c.RUN_SURFACES | _c.RUN_MASS_BALANCE) - _phase_ms(_c.RUN_MASS_BALANCE),
-        "wsi_step_kernel": _phase_ms(_c.RUN_SCHEDULE | _c.RUN_MASS_BALANCE, 0, n_sched) - _phase_ms(_c.RUN_MASS_BALANCE),
-        "wsi_mb_kernel + wsi_mb_finalize": _phase_ms(_c.RUN_MASS_BALANCE),
-        "wsi_record_kernel": _phase_ms(_c.RUN_RECORD),
-        "wsi_end_kernel": _phase_ms(_c.RUN_END_TIMESTEP),
-    }
     empty = _phase_ms(0)
-    kernel_ms = {k: max(v - (0 if "step" in k or "surface" in k else empty), 0.0) for k, v in phases.items()}
+    settle = _phase_ms(_c.RUN_MASS_BALANCE | _c.RUN_END_TIMESTEP)
+    kernel_ms = {
+        "wsi_surfaces_kernel (all surface classes, one launch)":
+            max(_phase_ms(_c.RUN_SURFACES | _c.RUN_MASS_BALANCE | _c.RUN_END_TIMESTEP) - settle, 0.0),
+        "wsi_step_kernel (schedule + recording)": _phase_ms(_c.RUN_SCHEDULE | _c.RUN_RECORD, 0, n_sched),
+        "wsi_settle_kernel (mass balance + end_timestep) + wsi_mb_finalize": max(settle - empty, 0.0),
+    }
 
     # ---------------- end to end through host buffers ------------------------------------------
     e2e = None
@@ -534,8 +533,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_by_kernel": traffic_by_kernel, "peak_source": peak_src, "algorithmic_bytes_per_member_step": int(alg_bytes),
                          "field_counts": {k: int(v) for k, v in parts.items()},
-                         "kernel": "one timestep = wsi_surface_kernel x3 + wsi_step_kernel + wsi_mb_kernel + "
-                                   "wsi_mb_finalize + wsi_record_kernel + wsi_end_kernel (dominant: wsi_step_kernel)",
+                         "kernel": "one timestep = wsi_surfaces_kernel + wsi_step_kernel (schedule + recording) + "
+                                   "wsi_settle_kernel (mass balance + end_timestep) + wsi_mb_finalize (dominant: wsi_step_kernel)",
                          "avg_launch_ms": ms / K,
                          "kernel_ms": {k: round(v, 4) for k, v in kernel_ms.items()}},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -455,7 +455,19 @@ class ModelBuffers:
         return a.detach().cpu().numpy()
 
     def groups_numpy(self):
-        return {g: self.to_numpy("group_" + g) for g in self.fm.groups}
+        """Group planes as the model stands BETWEEN timesteps.  The replica engine does not zero the
+        arcs at end_timestep (their transients expire by ``stamp``, csrc/wsi_device.cuh); what
+        Arc.end_timestep leaves behind (arcs.py:259-265) is restored here."""
+        out = {g: self.to_numpy("group_" + g) for g in self.fm.groups}
+        if self.engine == 0 and out["arc"].size:
+            a = np.array(out["arc"], copy=True)
+            V = self.fm.V
+            a[L.ARC.offset("flow_in", V)] = 0.0
+            o = L.ARC.offset("vqip_in", V)
+            a[o:o + V] = 0.0
+            a[L.ARC.offset("stamp", V)] = -1.0
+            out["arc"] = a
+        return out
 
     def set_rec_window(self, rec_t0):
         """Move the recording window (out_probe row 0 == timestep rec_t0)."""

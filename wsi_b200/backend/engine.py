@@ -36,6 +36,15 @@ class GpuRunner:
         if self.lib.wsi_num_blocks(C.byref(self.desc)) > self.buffers.partial_rows():
             raise RuntimeError("mb_partial scratch smaller than the library needs (block sizes out of sync)")
         capi.check(self.lib, self.lib.wsi_validate(C.byref(self.desc)))
+        self._last_t = -1
+
+    def _fresh_arcs(self, t0, stream):
+        """Arc transients are valid for the timestep their stamp names (replica engine): stepping a
+        timestep again, or going back in time on the same buffers, must not find old stamps."""
+        if self.buffers.engine == 0 and int(t0) <= self._last_t and self.fm.n_obj["arc"]:
+            plane = self.buffers.group("arc")[self.fm.plane("arc", "stamp")]
+            with self.torch.cuda.stream(stream if stream is not None else self.torch.cuda.current_stream(self.device)):
+                plane.fill_(-1.0)
 
     def _stream(self, stream):
         if stream is None:
@@ -45,10 +54,14 @@ class GpuRunner:
     def run(self, t0, t1, stream=None):
         """Timesteps [t0, t1) back to back (asynchronous on the stream)."""
         with self.torch.cuda.device(self.device):
+            self._fresh_arcs(t0, stream)
+            self._last_t = max(self._last_t, int(t1) - 1)
             capi.check(self.lib, self.lib.wsi_run_steps(C.byref(self.desc), int(t0), int(t1), self._stream(stream)))
 
     def step(self, t, stream=None):
         with self.torch.cuda.device(self.device):
+            self._fresh_arcs(t, stream)
+            self._last_t = max(self._last_t, int(t))
             capi.check(self.lib, self.lib.wsi_step(C.byref(self.desc), int(t), self._stream(stream)))
 
     def sched_range(self, t, begin, end, flags, stream=None):

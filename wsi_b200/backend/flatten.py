@@ -201,6 +201,11 @@ class FlatModel:
         n_obj = {k: int(v) for k, v in zip(L.GROUPS, d["meta_n_obj"])}
         surf_names = [tuple(x.split("\t")) for x in d["meta_surf_names"].tolist() if x]
         kw = {k: np.ascontiguousarray(d[k]) for k in cls._ARRAYS}
+        V = len(d["meta_pollutants"]) + 1
+        groups = {k: np.ascontiguousarray(d["group_" + k]) for k in L.GROUPS}
+        # fixtures written before the arc group had its `stamp` plane: insert it (no arc carries anything)
+        if groups["arc"].shape[0] == L.ARC.n_fields(V) - 1:
+            groups["arc"] = np.ascontiguousarray(np.insert(groups["arc"], L.ARC.offset("stamp", V), -1.0, axis=0))
         return cls(
             pollutants=[str(x) for x in d["meta_pollutants"].tolist()],
             additive=[str(x) for x in d["meta_additive"].tolist()],
@@ -212,7 +217,7 @@ class FlatModel:
             node_names=[str(x) for x in d["meta_node_names"].tolist()],
             arc_names=[str(x) for x in d["meta_arc_names"].tolist()],
             surf_names=surf_names,
-            groups={k: np.ascontiguousarray(d["group_" + k]) for k in L.GROUPS},
+            groups=groups,
             n_obj=n_obj,
             **kw,
         )
@@ -447,6 +452,8 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
         gb["arc"].set(col, "preference", a.preference)
         gb["arc"].set(col, "flow_in", a.flow_in)
         gb["arc"].set(col, "vqip_in", _vq(a.vqip_in, pollutants))
+        carried = a.flow_in != 0 or any(x != 0 for x in _vq(a.vqip_in, pollutants))
+        gb["arc"].set(col, "stamp", 0.0 if carried else -1.0)  # an arc flattened mid-step keeps what it carries
 
     def add_store(n):
         col = gb["tank"].new()

@@ -143,6 +143,8 @@ ARC = Group(
         S("flow_in"),  # per-step transient (arcs.py:64,152)
         S("pending_mode"),  # network engine: 0 = the sender already booked `pending` on the arc and
         #                     the receiver only adds it to its tank; 1 = the receiver runs the whole push
+        S("stamp"),  # replica engine: the timestep flow_in / vqip_in belong to (anything else reads as the
+        #              empty arc of arcs.py:259-265, so end_timestep never has to zero the arcs); -1 = none
         Q("vqip_in"),  # per-step transient; vqip_out aliases it (arcs.py:155-156)
         Q("pending"),  # network engine: the release the arc's sender parked for its receiver
     ],

@@ -162,6 +162,44 @@ struct Ctx {
 };
 
 // =========================================================================================
+// Arc transients.  An arc's flow_in / vqip_in (arcs.py:64-66, 152-156) live for one timestep and
+// Arc.end_timestep resets them (arcs.py:259-265).  The replica engine never writes those zeros:
+// the arc's `stamp` plane names the timestep its transients belong to, and anything else reads as
+// the empty arc -- the first booking of a step simply overwrites.  (The network engine keeps its
+// own bookkeeping and zeroes the arcs in its end_timestep pass: there every arc is live.)
+// =========================================================================================
+template <class C>
+WSI_HD bool arc_live(const C& c, int a) {
+  return c.D().engine == 1 || *c.arc(WSI_ARC_STAMP, a) == (double)c.t;
+}
+template <class C>
+WSI_HD double arc_flow_in(const C& c, int a) {
+  return arc_live(c, a) ? *c.arc(WSI_ARC_FLOW_IN, a) : 0.0;
+}
+template <class C>
+WSI_HD double arc_lane(const C& c, int a, int lane) {  // one lane of vqip_in
+  return arc_live(c, a) ? *c.arc(WSI_ARC_VQIP_IN(C::V) + lane, a) : 0.0;
+}
+template <class C>
+WSI_HD typename C::Vq arc_vqip_add(const C& c, int a) {  // volume + additive lanes of vqip_in
+  return arc_live(c, a) ? c.ldv_add(c.arc(WSI_ARC_VQIP_IN(C::V), a), c.s_arc()) : vq_zero<C::P>();
+}
+// book `sent` on the arc: flow_in += volume, vqip_in = sum_vqip(vqip_in, sent) (arcs.py:152-156)
+template <class C>
+WSI_HD void arc_book(C& c, int a, const typename C::Vq& sent) {
+  double* fi = c.arc(WSI_ARC_FLOW_IN, a);
+  double* vi = c.arc(WSI_ARC_VQIP_IN(C::V), a);
+  if (arc_live(c, a)) {
+    *fi = *fi + sent.x[0];
+    c.stv(vi, c.s_arc(), c.sum(c.ldv(vi, c.s_arc()), sent));
+  } else {  // first booking of the step: the arc is empty
+    *fi = 0.0 + sent.x[0];
+    c.stv(vi, c.s_arc(), c.sum(vq_zero<C::P>(), sent));
+    *c.arc(WSI_ARC_STAMP, a) = (double)c.t;
+  }
+}
+
+// =========================================================================================
 // Tanks addressed in place (global memory read-modify-write)
 // =========================================================================================
 template <class C>
@@ -398,7 +436,7 @@ WSI_HD typename C::Vq node_push_set(C& c, int node, const typename C::Vq& vqip) 
 // Arc.get_excess(direction="push")["volume"] arcs.py:230-257
 template <int D, class C>
 WSI_HD double arc_excess_vol(C& c, int a, bool has_v, double v_vol) {
-  const double pipe_excess = *c.arc(WSI_ARC_CAPACITY, a) - *c.arc(WSI_ARC_FLOW_IN, a);
+  const double pipe_excess = *c.arc(WSI_ARC_CAPACITY, a) - arc_flow_in(c, a);
   const double ne = node_push_check_vol<D>(c, c.D().arc_out[a], has_v, v_vol);
   return vol_vchange(ne, pymin(pipe_excess, ne));
 }
@@ -411,7 +449,6 @@ WSI_HD double arc_excess_vol(C& c, int a, bool has_v, double v_vol) {
 template <int D, class C>
 WSI_HD typename C::Vq arc_send_push_request(C& c, int a, const typename C::Vq& vqip) {
   using Vq = typename C::Vq;
-  constexpr int V = C::V;
   const double excess_in = arc_excess_vol<D>(c, a, true, vqip.x[0]);
   const double np = pymax(vqip.x[0] - excess_in, 0.0);
   const bool admitted = np == 0.0 && vqip.x[0] > 0;
@@ -431,10 +468,7 @@ WSI_HD typename C::Vq arc_send_push_request(C& c, int a, const typename C::Vq& v
     sent = c.extract(v, reply);
     reply = c.sum(reply, not_pushed);
   }
-  double* fi = c.arc(WSI_ARC_FLOW_IN, a);
-  *fi = *fi + sent.x[0];
-  double* vi = c.arc(WSI_ARC_VQIP_IN(V), a);
-  c.stv(vi, c.s_arc(), c.sum(c.ldv(vi, c.s_arc()), sent));
+  arc_book(c, a, sent);
   return reply;
 }
 
@@ -565,20 +599,12 @@ WSI_HD void chain_excess(C& c, const int* arcs, int n, double (&pipe)[kMaxChain]
     pipe[k] = 0.0;
     E[k] = 0.0;
     if (k < n) {
-      pipe[k] = *c.arc(WSI_ARC_CAPACITY, arcs[k]) - *c.arc(WSI_ARC_FLOW_IN, arcs[k]);
+      pipe[k] = *c.arc(WSI_ARC_CAPACITY, arcs[k]) - arc_flow_in(c, arcs[k]);
       u = clamp_to(u, pipe[k]);
       E[k] = u;
       u = 0.0 + u;  // the junction above sums its candidates' excesses from zero
     }
   }
-}
-
-template <class C>
-WSI_HD void arc_book(C& c, int a, const typename C::Vq& sent) {  // arcs.py:152-156
-  double* fi = c.arc(WSI_ARC_FLOW_IN, a);
-  *fi = *fi + sent.x[0];
-  double* vi = c.arc(WSI_ARC_VQIP_IN(C::V), a);
-  c.stv(vi, c.s_arc(), c.sum(c.ldv(vi, c.s_arc()), sent));
 }
 
 template <class C>
@@ -630,7 +656,8 @@ WSI_HD void chain_push_empty(C& c, const int* arcs, int k0, int n, int X) {
       break;
   }
 #pragma unroll 1
-  for (int k = k0; k < n; k++) tank_push_force(c, c.arc(WSI_ARC_VQIP_IN(V), arcs[k]), c.s_arc(), none);
+  for (int k = k0; k < n; k++)  // an arc nothing was booked on this step is empty: nothing to re-blend
+    if (arc_live(c, arcs[k])) tank_push_force(c, c.arc(WSI_ARC_VQIP_IN(V), arcs[k]), c.s_arc(), none);
 }
 
 template <class C>
@@ -957,7 +984,7 @@ WSI_HD typename C::Vq total_in(const C& c, int node) {
   const WsiModelDesc& d = c.D();
   typename C::Vq v = vq_zero<C::P>();
   for (int i = d.in_ptr[node]; i < d.in_ptr[node + 1]; i++) {
-    const typename C::Vq a = c.ldv_add(c.arc(WSI_ARC_VQIP_IN(C::V), d.in_arcs[i]), c.s_arc());
+    const typename C::Vq a = arc_vqip_add(c, d.in_arcs[i]);
 #pragma unroll
     for (int p = 0; p <= C::P; p++) v.x[p] += a.x[p];
   }
@@ -968,7 +995,7 @@ WSI_HD typename C::Vq total_out(const C& c, int node) {
   const WsiModelDesc& d = c.D();
   typename C::Vq v = vq_zero<C::P>();
   for (int i = d.out_ptr[node]; i < d.out_ptr[node + 1]; i++) {
-    const typename C::Vq a = c.ldv_add(c.arc(WSI_ARC_VQIP_IN(C::V), d.out_arcs[i]), c.s_arc());
+    const typename C::Vq a = arc_vqip_add(c, d.out_arcs[i]);
 #pragma unroll
     for (int p = 0; p <= C::P; p++) v.x[p] += a.x[p];
   }

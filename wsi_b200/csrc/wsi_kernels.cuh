@@ -169,7 +169,13 @@ __global__ void __launch_bounds__(kBlock, WSI_STEP_MINB)
 #endif
     }
   }
-  if (!fused) return;  // the object-parallel kernels run the other phases
+  // recording: the thread copies what it has just written (recording precedes end_timestep,
+  // model.py:1063-1176, and the settle pass below must not race with it)
+  if (active && (flags & WSI_RUN_RECORD)) {
+    const int row = t_arg >= 0 ? row_arg : t - d.rec_t0;
+    for (int k = 0; k < d.n_probe + d.n_red; k++) record_item(c, row, k);
+  }
+  if (!fused) return;  // wsi_settle_kernel runs mass balance and end_timestep one thread per (node, replica)
   if (flags & WSI_RUN_MASS_BALANCE) {
     const bool want_sums = d.mb_sums != nullptr;
     MbBlockSink<V> sink = {s_w, 0};
@@ -190,10 +196,6 @@ __global__ void __launch_bounds__(kBlock, WSI_STEP_MINB)
     }
   }
   if (!active) return;
-  if (flags & WSI_RUN_RECORD) {
-    const int row = t_arg >= 0 ? row_arg : t - d.rec_t0;
-    for (int k = 0; k < d.n_probe + d.n_red; k++) record_item(c, row, k);
-  }
   if (flags & WSI_RUN_END_TIMESTEP)
     for (int i = 0; i < d.n_end; i++) end_item(c, d.end_kind[i], d.end_obj[i]);
 }
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(kObjBlock, WSI_MB_MINB)
     if (item < d.n_nodes) {
       node_mass_balance(c, item, term[0], term[1], term[2]);
     } else {  // arcs are trivially balanced; they only feed the system totals
-      term[0] = c.ldv_add(c.arc(WSI_ARC_VQIP_IN(V), item - d.n_nodes), c.s_arc());
+      term[0] = arc_vqip_add(c, item - d.n_nodes);
       term[2] = term[0];
     }
   }
@@ -251,6 +253,65 @@ __global__ void __launch_bounds__(kObjBlock, WSI_MB_MINB)
       d.mb_partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 3 * V + threadIdx.x] = acc;
     }
   }
+}
+
+// Replica engine, large ensembles: one thread per (node, replica) checks the node's mass balance
+// (core.py:370-429; its in-arcs also stand for the arcs' own -- trivially balanced -- terms in the
+// system totals of model.py:1016-1036: every arc is the in-arc of exactly one node) and then ends
+// the timestep of what the node owns (model.py:1172-1176).  Arcs need no pass of their own: their
+// transients expire by stamp (wsi_device.cuh).  Block-reduced like wsi_mb_kernel.
+template <class CFG>
+__global__ void __launch_bounds__(kObjBlock, WSI_MB_MINB)
+    wsi_settle_kernel(const int slot, const CFG cfg, const int t_arg, const uint32_t flags) {
+  constexpr int V = CFG::P + 1;
+  constexpr int kWarps = kObjBlock / 32;
+  __shared__ double s_w[kWarps][3 * V];
+  const WsiModelDesc& d = g_wsi_desc[slot];
+  const int t = step_of(d, t_arg);
+  int node, r;
+  const bool active = decode_item<false>(d, d.n_nodes, node, r);
+  Ctx<CFG> c = make_ctx(nullptr, slot, cfg, active ? r : 0, t, flags);
+  if (flags & WSI_RUN_MASS_BALANCE) {
+    using Vq = typename Ctx<CFG>::Vq;
+    const bool want_sums = d.mb_sums != nullptr;
+    Vq term[3];
+    term[0] = vq_zero<CFG::P>();
+    term[1] = vq_zero<CFG::P>();
+    term[2] = vq_zero<CFG::P>();
+    if (active) {
+      node_mass_balance(c, node, term[0], term[1], term[2]);
+      if (want_sums) {
+        const Vq tin = total_in(c, node);
+        ds_add(c, term[0], tin);
+        ds_add(c, term[2], tin);
+      }
+    }
+    int v = active ? c.viol : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0 && d.mb_count) atomicAdd(&d.mb_count[t], v);
+    if (want_sums) {
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        double a[16];
+#pragma unroll
+        for (int p = 0; p < 16; p++) a[p] = (p < V && active && (p == 0 || bit(c.addm(), p))) ? term[k].x[p < V ? p : 0] : 0.0;
+        int p_mine;
+        const double x = warp_sum_16(a, lane, p_mine);
+        if ((lane & 1) == 0 && p_mine < V && (p_mine == 0 || bit(c.addm(), p_mine))) s_w[warp][k * V + p_mine] = x;
+      }
+      __syncthreads();
+      if (threadIdx.x < 3 * V) {
+        const int p = threadIdx.x % V;
+        double acc = 0.0;
+        if (p == 0 || bit(c.addm(), p))
+          for (int w = 0; w < kWarps; w++) acc += s_w[w][threadIdx.x];
+        d.mb_partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 3 * V + threadIdx.x] = acc;
+      }
+    }
+  }
+  if (active && (flags & WSI_RUN_END_TIMESTEP)) end_node(c, node);
 }
 
 // One thread per (probe, replica): Model.run's recording (model.py:1063-1170) is a strided copy.
@@ -691,27 +752,39 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
       wsi_step_kernel<CFG><<<n_blocks(d), kBlock, kDescSmem, s>>>(slot, cfg, (int)t, b, e, flags, (int)t - d->rec_t0,
                                                                     fused ? 1 : 0);
       WSI_CHECK_LAUNCH("wsi_step_kernel");
-      if (fused) {
-        if (want_sums) {
-          const int n = 3 * V;
-          wsi_mb_finalize<<<n, kFinBlock, 0, s>>>(slot, (int)t, n_blocks(d), n);
-          WSI_CHECK_LAUNCH("wsi_mb_finalize");
-        }
-        return WSI_OK;
+      int rows = n_blocks(d);
+      if (!fused && (flags & (WSI_RUN_MASS_BALANCE | WSI_RUN_END_TIMESTEP)) && d->n_nodes > 0) {
+        const dim3 grid(n_obj_blocks(d), d->n_nodes);
+        wsi_settle_kernel<CFG><<<grid, kObjBlock, 0, s>>>(slot, cfg, (int)t, flags);
+        WSI_CHECK_LAUNCH("wsi_settle_kernel");
+        rows = d->n_nodes * n_obj_blocks(d);
       }
+      if (want_sums) {
+        const int n = 3 * V;
+        wsi_mb_finalize<<<n, kFinBlock, 0, s>>>(slot, (int)t, rows, n);
+        WSI_CHECK_LAUNCH("wsi_mb_finalize");
+      }
+      return WSI_OK;
     }
   }
+  // What follows runs when the schedule kernel did not (phase-by-phase callers) and for the network
+  // engine.  Replica engine: the settle pass in two halves around the recording, network engine: the
+  // flat (item, replica) kernels -- in the order of model.py:1016-1176.
+  auto settle = [&](uint32_t f) {
+    const dim3 grid(n_obj_blocks(d), d->n_nodes);
+    wsi_settle_kernel<CFG><<<grid, kObjBlock, 0, s>>>(slot, cfg, (int)t, f);
+  };
   if (want_mb) {
-    const int items = d->n_nodes + (want_sums ? d->n_arcs : 0);
-    const int rows = net ? n_flat_blocks(d, items) : items * n_obj_blocks(d);
+    const int items = d->n_nodes + (want_sums && net ? d->n_arcs : 0);
+    const int rows = net ? n_flat_blocks(d, items) : d->n_nodes * n_obj_blocks(d);
     if (items > 0) {
       if (net) {
         wsi_mb_kernel<CFG, true><<<rows, kObjBlock, 0, s>>>(slot, cfg, (int)t, flags, items);
+        WSI_CHECK_LAUNCH("wsi_mb_kernel");
       } else {
-        const dim3 grid(n_obj_blocks(d), items);
-        wsi_mb_kernel<CFG, false><<<grid, kObjBlock, 0, s>>>(slot, cfg, (int)t, flags, items);
+        settle(flags & ~WSI_RUN_END_TIMESTEP);
+        WSI_CHECK_LAUNCH("wsi_settle_kernel");
       }
-      WSI_CHECK_LAUNCH("wsi_mb_kernel");
     }
     if (want_sums) {
       const int n = 3 * V;
@@ -734,14 +807,14 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
       WSI_CHECK_LAUNCH("wsi_record_kernel");
     }
   }
-  if ((flags & WSI_RUN_END_TIMESTEP) && d->n_end > 0) {
-    if (net) {
+  if (flags & WSI_RUN_END_TIMESTEP) {
+    if (net && d->n_end > 0) {
       wsi_end_kernel<CFG, true><<<n_flat_blocks(d, d->n_end), kObjBlock, 0, s>>>(slot, cfg, (int)t);
-    } else {
-      const dim3 grid(n_obj_blocks(d), d->n_end);
-      wsi_end_kernel<CFG, false><<<grid, kObjBlock, 0, s>>>(slot, cfg, (int)t);
+      WSI_CHECK_LAUNCH("wsi_end_kernel");
+    } else if (!net && d->n_nodes > 0) {
+      settle(flags & ~WSI_RUN_MASS_BALANCE);
+      WSI_CHECK_LAUNCH("wsi_settle_kernel");
     }
-    WSI_CHECK_LAUNCH("wsi_end_kernel");
   }
   return WSI_OK;
 }

@@ -320,8 +320,7 @@ WSI_HD void boundary_release(C& c, int node, bool deliver) {
   const typename C::Vq v = boundary_flow(c, node);
   c.stv(A(WSI_ARC_PENDING(V)), A.s, v);
   *A(WSI_ARC_PENDING_MODE) = 0.0;
-  *A(WSI_ARC_FLOW_IN) = *A(WSI_ARC_FLOW_IN) + v.x[0];
-  c.stv(A(WSI_ARC_VQIP_IN(V)), A.s, c.sum(c.ldv(A(WSI_ARC_VQIP_IN(V)), A.s), v));
+  arc_book(c, a0, v);
   if (deliver) {
     const int recv = d.arc_out[a0];
     if (d.node_type[recv] == WSI_NT_RIVER) {
@@ -339,7 +338,7 @@ WSI_HD void catchment_route_pre(C& c, int node, typename C::Vq& v) {
   const int g = d.node_gidx[node];
   v = catch_get_flow(c, g);
   for (int i = d.out_ptr[node]; i < d.out_ptr[node + 1]; i++)  // get_avail catchment.py:90-104
-    v = c.vchange(v, v.x[0] - *c.arc(WSI_ARC_VQIP_IN(C::V), d.out_arcs[i]));
+    v = c.vchange(v, v.x[0] - arc_lane(c, d.out_arcs[i], 0));
 }
 template <class C>
 WSI_HD void catchment_route_post(C& c, int node, const typename C::Vq& reply) {
@@ -375,7 +374,7 @@ WSI_HD typename C::Vq tank_ds(const C& c, int tk) {  // tanks.py:70-76 / 449-457
 // system totals of model.py:1016-1023
 template <class C>
 WSI_HD void arc_system_totals(C& c, int a) {
-  const typename C::Vq v = c.ldv_add(c.arc(WSI_ARC_VQIP_IN(C::V), a), c.s_arc());
+  const typename C::Vq v = arc_vqip_add(c, a);
 #pragma unroll
   for (int p = 0; p <= C::P; p++)
     if (p == 0 || bit(c.addm(), p)) {
@@ -443,7 +442,7 @@ WSI_HD void node_mass_balance(C& c, int node, typename C::Vq& in_, typename C::V
 template <int LANE, class C>
 WSI_HD double arcs_lane_sum(const C& c, const int* ptr, const int* list, int node) {
   double v = 0.0;
-  for (int i = ptr[node]; i < ptr[node + 1]; i++) v += *c.arc(WSI_ARC_VQIP_IN(C::V) + LANE, list[i]);
+  for (int i = ptr[node]; i < ptr[node + 1]; i++) v += arc_lane(c, list[i], LANE);
   return v;
 }
 template <int LANE, class C>
@@ -534,7 +533,7 @@ WSI_HD int replica_mb_lane(C& c, bool with_arcs, double& sys_in, double& sys_ds,
   sys_out = 0.0;
   if (with_arcs)
     for (int a = 0; a < d.n_arcs; a++) {
-      const double v = *c.arc(WSI_ARC_VQIP_IN(V) + LANE, a);
+      const double v = arc_lane(c, a, LANE);
       sys_in += v;
       sys_out += v;
     }
@@ -607,9 +606,11 @@ template <class C>
 WSI_HD void end_item(C& c, int kind, int obj) {
   constexpr int V = C::V;
   switch (kind) {
-    case 0:  // Arc.end_timestep arcs.py:259-265
-      *c.arc(WSI_ARC_FLOW_IN, obj) = 0.0;
-      c.stv(c.arc(WSI_ARC_VQIP_IN(V), obj), c.s_arc(), vq_zero<C::P>());
+    case 0:  // Arc.end_timestep arcs.py:259-265 (network engine; the replica engine's arcs expire by stamp)
+      if (c.D().engine == 1) {
+        *c.arc(WSI_ARC_FLOW_IN, obj) = 0.0;
+        c.stv(c.arc(WSI_ARC_VQIP_IN(V), obj), c.s_arc(), vq_zero<C::P>());
+      }
       break;
     case 2: {  // Surface (DecayTank) end_timestep tanks.py:442-447, land.py:266-275
       const Obj S = c.surf_obj(obj);
@@ -638,6 +639,33 @@ WSI_HD void end_item(C& c, int kind, int obj) {
   }
 }
 
+// end_timestep of everything a node owns (the replica engine's settle pass: one thread per
+// (node, replica) checks the node's mass balance and then ends its timestep)
+template <class C>
+WSI_HD void end_node(C& c, int node) {
+  const WsiModelDesc& d = c.D();
+  const int g = d.node_gidx[node];
+  switch (d.node_type[node]) {
+    case WSI_NT_LAND:
+      for (int i = d.land_surf_ptr[g]; i < d.land_surf_ptr[g + 1]; i++) end_item(c, 2, d.land_surf[i]);
+      break;
+    case WSI_NT_GROUNDWATER:
+    case WSI_NT_STORAGE:
+    case WSI_NT_RESERVOIR:
+      end_item(c, 3, g);
+      break;
+    case WSI_NT_RIVER:
+      end_item(c, 4, g);
+      end_item(c, 3, (int)*c.river(WSI_RIVER_TANK, g));
+      break;
+    case WSI_NT_SEWER:
+      end_item(c, 5, g);
+      break;
+    default:
+      break;
+  }
+}
+
 template <class C>
 WSI_HDN void end_timestep(C& c) {
   const WsiModelDesc& d = c.D();
@@ -657,20 +685,28 @@ WSI_HD const double* probe_src(const C& c, int group, int plane, int obj) {
   }
 }
 // series probe k: only the members of the record window are kept (rec_R == 0: all of them)
+// value of a probed plane; the transients of an arc nothing was booked on this step read as zero
+template <class C>
+WSI_HD double probe_value(const C& c, int group, int plane, int obj) {
+  if (group == 0 && (plane == WSI_ARC_FLOW_IN || (plane >= WSI_ARC_VQIP_IN(C::V) && plane < WSI_ARC_VQIP_IN(C::V) + C::V)) &&
+      !arc_live(c, obj))
+    return 0.0;
+  return *probe_src(c, group, plane, obj);
+}
 template <class C>
 WSI_HD void record_probe(const C& c, int row, int k) {
   const WsiModelDesc& d = c.D();
   const int nr = d.rec_R > 0 ? d.rec_R : d.R;
   const int rr = c.r - (d.rec_R > 0 ? d.rec_r0 : 0);
   if (rr < 0 || rr >= nr) return;
-  d.out_probe[((size_t)row * d.n_probe + k) * (size_t)nr + rr] = *probe_src(c, d.probe_group[k], d.probe_plane[k], d.probe_obj[k]);
+  d.out_probe[((size_t)row * d.n_probe + k) * (size_t)nr + rr] = probe_value(c, d.probe_group[k], d.probe_plane[k], d.probe_obj[k]);
 }
 // reduced probe k: running sum and maximum over the timesteps (what the objectives of
 // model.py:1177-1197 need of a member's series, without keeping the series)
 template <class C>
 WSI_HD void reduce_probe(const C& c, int k) {
   const WsiModelDesc& d = c.D();
-  const double v = *probe_src(c, d.red_group[k], d.red_plane[k], d.red_obj[k]);
+  const double v = probe_value(c, d.red_group[k], d.red_plane[k], d.red_obj[k]);
   double* sum = d.red_out + (size_t)k * c.R + c.r;
   double* mx = sum + (size_t)d.n_red * c.R;
   *sum = *sum + v;

@@ -169,6 +169,7 @@ def build_dendritic(N, T=365, seed=SEED, n_variants=8, n_series=64, binding_frac
     arc = np.zeros((L.GROUPS["arc"].n_fields(V), n_arcs))
     arc[L.GROUPS["arc"].offset("capacity", V)] = constants.UNBOUNDED_CAPACITY
     arc[L.GROUPS["arc"].offset("preference", V)] = 1.0
+    arc[L.GROUPS["arc"].offset("stamp", V)] = -1.0
     if binding_frac > 0:  # a sample of river arcs whose capacity binds at high flow
         pick = rng.random(N) < binding_frac
         arc[L.GROUPS["arc"].offset("capacity", V), :N][pick] = rng.uniform(3e3, 3e4, int(pick.sum()))
