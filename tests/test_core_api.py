@@ -60,10 +60,13 @@ def test_every_helper_equals_the_reference_method_on_random_vqips():
     """Same method names, same results bit for bit, default 12-pollutant set."""
     import sys
 
-    sys.path.insert(0, "/root/reference")
+    sys.path.append("/root/reference")  # appended: its own `tests` package must not shadow this one
     sys.dont_write_bytecode = True
-    from wsimod.core import constants as rc
-    from wsimod.core.core import WSIObj as Ref
+    try:
+        from wsimod.core import constants as rc
+        from wsimod.core.core import WSIObj as Ref
+    finally:
+        sys.path.remove("/root/reference")
 
     from wsi_b200.core import constants as mc
     from wsi_b200.core.core import WSIObj as Mine
