@@ -39,7 +39,8 @@ extern "C" {
 #define WSI_FLAG_POOL_MISMATCH 4u  /* "nutrient pool not tracking soil tank" land.py:1808 */
 #define WSI_FLAG_NAN 8u            /* reference would raise ZeroDivisionError (land.py:1462) */
 #define WSI_FLAG_DEPTH 16u         /* junction chain deeper than the kernel supports */
-#define WSI_FLAG_DENY 32u          /* push to a node whose handler denies (nodes.py:579) */
+#define WSI_FLAG_DENY 32u          /* push to / pull from a node whose handler denies (nodes.py:563-609) */
+#define WSI_FLAG_DEFICIT 64u       /* "Service reservoirs not filled" / "demand deficit" (wtw.py:583, demand.py:91) */
 
 /* run flags for wsi_sched_range */
 #define WSI_RUN_SCHEDULE 1u      /* execute schedule entries [begin, end) */
@@ -171,6 +172,16 @@ typedef struct WsiModelDesc {
   const int32_t* red_obj;
   double* red_out;    /* [2][n_red][R]: running sum and running maximum over the timesteps stepped so far
                          (caller-initialised: 0 and -inf) */
+
+  /* ---- treatment works and demand (ABI 2): SoA groups like the ones above ---- */
+  int32_t n_works, n_demand;
+  double* works;      /* WWTW / FWTW (wtw.py) */
+  double* demand;     /* ResidentialDemand (demand.py) */
+  double* distrib;    /* UnlimitedDistribution (distribution.py) */
+  int32_t n_distrib;
+  int32_t sched_split; /* > 0: schedule entries [0, sched_split) run BEFORE the surfaces of the timestep (they reach into
+                          a Land's surfaces: garden irrigation by a Demand node, demand.py:250 / land.py:2402);
+                          0: surfaces first, then the whole schedule (nothing before Land.run touches them) */
 } WsiModelDesc;
 
 /* ABI version of the loaded library (== WSI_ABI_VERSION). */

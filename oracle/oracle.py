@@ -66,6 +66,9 @@ def run(fm, probes=(), t0=0, t1=None, record_mb=False, n_threads=0, rec_t0=None,
     )
     assert buf.desc.n_red == 0 and buf.desc.rec_R == 0  # device-side output reductions are not restated here
     rc = lib().wsi_oracle_run(C.byref(buf.desc), int(t0), int(t1), int(n_threads))
+    if rc == 3:
+        raise NotImplementedError("the oracle does not restate treatment works / demand / the pull side "
+                                  "(their goldens come straight from the reference)")
     if rc != 0:
         raise RuntimeError(f"oracle returned {rc}")
     return OracleRun(buf)

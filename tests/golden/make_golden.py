@@ -296,6 +296,129 @@ def scenario_hourly(T=1080):
     save("hourly", fm, ref, "hourly timestep, to_datetime dates, crop calendar counting timesteps, %d steps" % T)
 
 
+def scenario_fixture3607_full(T=730):
+    """tests/test_model_data.zip as it is: 14 nodes / 21 arcs -- Land with 9 surfaces (GardenSurface
+    irrigated by a ResidentialDemand through the ("Demand", "Garden") tag), storm and two foul Sewers
+    exchanging through tiny-capacity arcs, Groundwater, River with biochemistry, WWTW, two
+    ResidentialDemands drawing on an UnlimitedDistribution, junction, 3 Waste; csv date regime."""
+    set_default_pollutants()
+    tmp = tempfile.mkdtemp()
+    zipfile.ZipFile(os.path.join(REF, "tests/test_model_data.zip")).extractall(tmp)
+    cfg = yaml.safe_load(open(os.path.join(tmp, "config.yml")))
+    cfg["dates"] = cfg["dates"][:T]
+    cfg.pop("extensions", None)
+    yaml.safe_dump(cfg, open(os.path.join(tmp, "full.yml"), "w"))
+    m = Model()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.load(tmp, config_name="full.yml")
+    dates = m.dates
+    fm = flatten_ref(m, dates)
+    ref = run_reference(m, dates)
+    save("fixture3607_full", fm, ref, "reference test fixture 3607, every node, %d days, csv dates" % T)
+
+
+def scenario_city(D=3, T=480):
+    """BASELINE.json configs[4] at a size the reference runs in seconds: a synthetic city of D
+    districts x {Land(Impervious, Garden, Pervious), storm Sewer, foul Sewer, Groundwater,
+    ResidentialDemand (house -> foul sewer, garden -> Land)} on a shared chain of three Rivers, a
+    Reservoir abstracting from the middle river (minimum required flow, capacity-limited arc), FWTW
+    -> distribution junction -> demands, foul sewers -> WWTW -> river; HOURLY timestep
+    (to_datetime dates, 'YYYY-MM-DD HH:MM:SS'), 20 days."""
+    from datetime import datetime, timedelta
+
+    set_default_pollutants()
+    t0 = datetime(2001, 6, 1)
+    dates = [to_datetime((t0 + timedelta(hours=i)).strftime("%Y-%m-%d %H:%M:%S")) for i in range(T)]
+    rng = np.random.default_rng(20261106)
+    hours = np.arange(T)
+    months = [to_datetime("2001-06")]
+
+    def land_forcing(k):
+        temperature = 15 + 6 * np.sin(2 * np.pi * (hours % 24 - 9) / 24) + rng.normal(0, 0.5, T) + 0.3 * k
+        et0 = np.maximum(0.0, 3.0e-4 * np.sin(2 * np.pi * (hours % 24 - 6) / 24))
+        precipitation = (rng.random(T) < 0.10) * rng.gamma(0.7, 1.5e-3, T)
+        d = {}
+        for t, date in enumerate(dates):
+            d[("precipitation", date)] = float(precipitation[t])
+            d[("et0", date)] = float(et0[t])
+            d[("temperature", date)] = float(temperature[t])
+        return d
+
+    tdata = {("temperature", d): float(14 + 2 * np.sin(2 * np.pi * (h % 24 - 12) / 24)) for h, d in zip(hours, dates)}
+    monthly = {(var, m): 1e-7 / 24 for var in L.DEP_COLS for m in months}
+    init = lambda v: {"volume": v, "do": 0.008, "org-phosphorus": v * 2e-5, "phosphate": v * 5e-5,  # noqa: E731
+                      "ammonia": v * 1e-4, "solids": v * 1e-3, "bod": v * 1e-3, "cod": v * 2e-3, "ph": 7.1,
+                      "temperature": 13.0, "nitrate": v * 2e-3, "nitrite": v * 1e-5, "org-nitrogen": v * 3e-4}
+    house = {"do": 0.004, "org-phosphorus": 2e-7, "phosphate": 5e-7, "ammonia": 3e-6, "solids": 1e-5, "bod": 2e-5,
+             "cod": 4e-5, "ph": 7.4, "temperature": 14.0, "nitrate": 1e-6, "nitrite": 1e-8, "org-nitrogen": 2e-6}
+    nodes, arcs = [], []
+    arc = lambda n, a, b, **kw: arcs.append(dict({"type_": "Arc", "name": n, "in_port": a, "out_port": b}, **kw))  # noqa: E731
+    for k in range(D):
+        a_g = 2.0e4 * (1 + 0.5 * k)
+        vol = a_g * 1.25 * 0.4 * 0.9
+        garden = dict(GROWING_TEMPLATE)
+        garden.update(type_="GardenSurface", surface="garden", area=a_g, pollutant_load={}, data_input_dict=monthly,
+                      initial_storage=dict(init(vol), volume=vol),
+                      initial_soil_storage={"org-phosphorus": vol * 5e-3, "phosphate": vol * 5e-3, "ammonia": 0.0,
+                                            "nitrate": vol, "nitrite": 0.0, "org-nitrogen": vol, "volume": vol},
+                      sowing_day=1, harvest_day=365, infiltration_capacity=0.004,
+                      decays={"ammonia": {"constant": 0.1 / 24, "exponent": 1.005},
+                              "nitrite": {"constant": 0.05 / 24, "exponent": 1.005}})
+        imp = {"type_": "ImperviousSurface", "surface": "urban", "area": 3e4 * (1 + k), "pore_depth": 0.002,
+               "pollutant_load": {"phosphate": 1e-11, "solids": 1e-6}}
+        perv = {"type_": "PerviousSurface", "surface": "park", "area": 4e4, "depth": 0.5,
+                "pollutant_load": {"phosphate": 1e-9}, "initial_storage": 4e4 * 0.5 * 0.4 * 0.5,
+                "infiltration_capacity": 0.003}
+        nodes += [
+            {"type_": "Land", "name": f"land{k}", "data_input_dict": land_forcing(k), "surfaces": [imp, garden, perv],
+             "surface_residence_time": 4.0, "subsurface_residence_time": 48.0, "percolation_residence_time": 300.0},
+            {"type_": "Sewer", "name": f"storm{k}", "capacity": 60.0 * (1 + k), "pipe_time": k % 2},
+            {"type_": "Sewer", "name": f"foul{k}", "capacity": 500.0, "pipe_timearea": {0: 0.6, 1: 0.3, 2: 0.1}},
+            {"type_": "Groundwater", "name": f"gw{k}", "area": 1e5, "capacity": 5e4, "residence_time": 700.0,
+             "initial_storage": 2e3},
+            {"type_": "Demand", "node_type_override": "ResidentialDemand", "name": f"demand{k}", "population": 4e3 * (1 + k), "per_capita": 0.15 / 24,
+             "pollutant_load": house, "data_input_dict": tdata, "gardening_efficiency": 0.4},
+        ]
+        arc(f"land{k}-storm{k}", f"land{k}", f"storm{k}")
+        arc(f"land{k}-gw{k}", f"land{k}", f"gw{k}")
+        arc(f"land{k}-river{k}", f"land{k}", f"river{k}")
+        arc(f"storm{k}-river{k}", f"storm{k}", f"river{k}", capacity=25.0 * (1 + k))
+        arc(f"gw{k}-river{k}", f"gw{k}", f"river{k}")
+        arc(f"dist-demand{k}", "distribution", f"demand{k}")
+        arc(f"demand{k}-foul{k}", f"demand{k}", f"foul{k}")
+        arc(f"demand{k}-land{k}", f"demand{k}", f"land{k}", preference=0.3)
+        arc(f"foul{k}-wwtw", f"foul{k}", "wwtw", preference=1e10)
+        arc(f"foul{k}-river{k}", f"foul{k}", f"river{k}", preference=1e-10)
+    for k in range(3):
+        nodes.append({"type_": "River", "name": f"river{k}", "length": 3000.0 * (1 + k), "width": 8.0 + 4 * k,
+                      "data_input_dict": tdata, "initial_storage": init(4e3 * (1 + k)), "mrf": 20.0 if k == 1 else 0})
+    for k in range(3, D):  # further districts drain to the last river
+        pass
+    nodes += [
+        {"type_": "Reservoir", "name": "reservoir", "capacity": 4e5, "initial_storage": init(3.5e5), "area": 5e4, "datum": 10},
+        {"type_": "FWTW", "name": "fwtw", "service_reservoir_storage_capacity": 1e4, "service_reservoir_storage_area": 500,
+         "service_reservoir_initial_storage": 1.5e3, "treatment_throughput_capacity": 400.0},
+        {"type_": "WWTW", "name": "wwtw", "stormwater_storage_capacity": 300.0, "stormwater_storage_area": 100,
+         "treatment_throughput_capacity": 300.0},
+        {"type_": "Node", "name": "distribution"},
+        {"type_": "Waste", "name": "sea"},
+    ]
+    arc("river0-river1", "river0", "river1")
+    arc("river1-river2", "river1", "river2")
+    arc("river2-sea", "river2", "sea")
+    arc("river1-reservoir", "river1", "reservoir", capacity=150.0)
+    arc("reservoir-fwtw", "reservoir", "fwtw")
+    arc("fwtw-dist", "fwtw", "distribution")
+    arc("fwtw-foul0", "fwtw", "foul0")
+    arc("wwtw-river2", "wwtw", "river2")
+    m = Model()
+    m.add_nodes(nodes)
+    m.add_arcs(arcs)
+    fm = flatten_ref(m, dates)
+    ref = run_reference(m, dates)
+    save("city", fm, ref, "synthetic city, %d districts, hourly, %d steps" % (D, T))
+
+
 def synthetic_forcing(dates, rng):
     """SURVEY 8d config 2 forcing generator."""
     doy = np.array([d.dayofyear for d in dates], dtype=float)
@@ -626,6 +749,23 @@ def scenario_config3_members(R=16):
     set_default_pollutants()
 
 
+def scenario_oxford():
+    """BASELINE.json configs[0], second half: the reference's own Oxford demo
+    (wsimod/demo/create_oxford.py:149-394) -- 18 nodes, 21 arcs, 12 Oxford pollutants, 1456 days:
+    four Catchments, junctions, Land, Groundwater, combined Sewer with a pipe time-area diagram and
+    a preference split between WWTW and overflow, WWTW, FWTW fed from the Farmoor Reservoir, the
+    reservoir's abstraction through a capacity-limited arc, ResidentialDemand drawing through a
+    distribution junction."""
+    from wsimod.demo.create_oxford import create_oxford_model
+
+    m = create_oxford_model(os.path.join(REF, "docs", "demo", "data"))
+    dates = m.dates
+    fm = flatten_ref(m, dates)
+    ref = run_reference(m, dates)
+    save("oxford", fm, ref, "create_oxford_model, %d days" % len(dates))
+    set_default_pollutants()
+
+
 SCENARIOS = {
     "quickstart": scenario_quickstart,
     "quickstart_simple": scenario_quickstart_simple,
@@ -635,6 +775,9 @@ SCENARIOS = {
     "rivertree": scenario_rivertree,
     "config3": scenario_config3,
     "hourly": scenario_hourly,
+    "oxford": scenario_oxford,
+    "city": scenario_city,
+    "fixture3607_full": scenario_fixture3607_full,
     "config3_members16": scenario_config3_members,
 }
 

@@ -9,7 +9,7 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "wsi_b200", "csrc")
 
 def build(force=False):
     deps = [os.path.join(HERE, "hostsim.cpp")] + [
-        os.path.join(CSRC, f) for f in ("wsi_vq.cuh", "wsi_device.cuh", "wsi_land.cuh", "wsi_nodes.cuh", "wsi_net.cuh")
+        os.path.join(CSRC, f) for f in ("wsi_vq.cuh", "wsi_device.cuh", "wsi_land.cuh", "wsi_nodes.cuh", "wsi_net.cuh", "wsi_works.cuh")
     ] + [os.path.join(os.path.dirname(CSRC), "..", "include", f) for f in ("wsi_b200.h", "wsi_layout.h")]
     if not force and os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
         return SO

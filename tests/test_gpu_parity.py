@@ -7,7 +7,8 @@ from parity_util import compare_blocks, compare_mb, load_golden
 
 pytestmark = pytest.mark.gpu
 
-GOLDENS = ["quickstart", "quickstart_simple", "fixture3607", "config2", "rivernet", "rivertree", "config3", "hourly"]
+GOLDENS = ["quickstart", "quickstart_simple", "fixture3607", "config2", "rivernet", "rivertree", "config3", "hourly",
+           "oxford", "fixture3607_full", "city"]
 
 
 def _run_gpu(fm, ps, record_mb=True, chunks=1, engine="replica"):
@@ -48,8 +49,11 @@ def test_status_flags_and_violation_counts_match_oracle(name):
 
     fm, _ = load_golden(name)
     ps = ProbeSet(fm).add_flows()
+    try:
+        ora = oracle.run(fm, probes=ps.probes)
+    except NotImplementedError as exc:  # treatment works / demand / pulls: pinned on the reference's golden instead
+        pytest.skip(str(exc))
     run = _run_gpu(fm, ps, record_mb=False)
-    ora = oracle.run(fm, probes=ps.probes)
     got_cnt, exp_cnt = run.mb_count()[: fm.T], ora.mb_count[: fm.T]
     differing = int(np.count_nonzero(got_cnt != exp_cnt))
     assert differing <= fm.T // 1000, (differing, np.nonzero(got_cnt != exp_cnt)[0][:10])

@@ -84,7 +84,7 @@ def test_unsupported_features_are_refused_not_ignored():
 
     m = Model()
     with pytest.raises(UnsupportedModelError):
-        m.add_nodes([{"type_": "WWTW", "name": "works"}])
+        m.add_nodes([{"type_": "NonResidentialDemand", "name": "factory"}])
     m, _ = _quickstart_model(T=10)
     with pytest.raises(UnsupportedModelError):
         m.add_arcs([{"type_": "PullArc", "name": "x", "in_port": "my_river", "out_port": "my_outlet"}])
@@ -180,4 +180,63 @@ def test_model_load_of_the_reference_yaml_fixture_flattens_like_the_golden(tmp_p
     for g in fm.groups:
         assert np.array_equal(fm.groups[g], fm_ref.groups[g]), g
     for name in ("node_forcing", "surf_inputs", "catch_inputs"):
+        assert np.array_equal(getattr(fm, name), getattr(fm_ref, name)), name
+
+
+@pytest.mark.reference
+def test_oxford_demo_built_with_this_package_flattens_like_the_reference_build():
+    """``wsi_b200.demo.create_oxford.create_oxford_model`` on the reference's demo data -> the very
+    flat model tests/golden/oxford.npz was flattened from the REFERENCE's create_oxford_model
+    (18 nodes / 21 arcs: FWTW, WWTW, ResidentialDemand, Reservoir abstraction, Sewer time-area)."""
+    from wsi_b200.core import constants
+    from wsi_b200.demo.create_oxford import create_oxford_model
+
+    fm_ref, _ = load_golden("oxford")
+    try:
+        m = create_oxford_model("/root/reference/docs/demo/data")
+        fm = m.flatten()
+    finally:
+        constants.set_default_pollutants()
+        constants.FLOAT_ACCURACY = 1e-11
+    assert fm.pollutants == fm_ref.pollutants and sorted(fm.additive) == sorted(fm_ref.additive)
+    assert fm.node_names == fm_ref.node_names and fm.arc_names == fm_ref.arc_names
+    for name in ("node_type", "node_gidx", "arc_in", "arc_out", "in_ptr", "in_arcs", "out_ptr", "cand_ptr", "cand_arcs",
+                 "sched_op", "sched_node"):
+        assert np.array_equal(getattr(fm, name), getattr(fm_ref, name)), name
+    for g in fm.groups:
+        assert np.array_equal(fm.groups[g], fm_ref.groups[g]), g
+    for name in ("node_forcing", "catch_inputs"):
+        assert np.array_equal(getattr(fm, name), getattr(fm_ref, name)), name
+
+
+@pytest.mark.reference
+def test_model_load_of_the_unreduced_reference_fixture(tmp_path):
+    """The reference's real-catchment fixture AS IT IS (14 nodes: ResidentialDemand x2 on an
+    UnlimitedDistribution, WWTW, storm + foul Sewers, garden irrigation, River, Groundwater ...)
+    through this package's ``Model.load``: same flat model as the reference's own load gives."""
+    import contextlib
+    import io
+    import zipfile
+
+    import yaml
+
+    from wsi_b200.orchestration.model import Model
+
+    fm_ref, _ = load_golden("fixture3607_full")
+    zipfile.ZipFile("/root/reference/tests/test_model_data.zip").extractall(tmp_path)
+    cfg = yaml.safe_load(open(tmp_path / "config.yml"))
+    cfg["dates"] = cfg["dates"][:fm_ref.T]
+    cfg.pop("extensions", None)
+    yaml.safe_dump(cfg, open(tmp_path / "full.yml", "w"))
+    m = Model()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.load(str(tmp_path), config_name="full.yml")
+    fm = m.flatten()
+    assert fm.node_names == fm_ref.node_names and fm.arc_names == fm_ref.arc_names
+    for name in ("node_type", "node_gidx", "arc_in", "arc_out", "in_ptr", "in_arcs", "cand_ptr", "cand_arcs", "sched_op",
+                 "sched_node", "doy_adj"):
+        assert np.array_equal(getattr(fm, name), getattr(fm_ref, name)), name
+    for g in fm.groups:
+        assert np.array_equal(fm.groups[g], fm_ref.groups[g]), g
+    for name in ("node_forcing", "surf_inputs"):
         assert np.array_equal(getattr(fm, name), getattr(fm_ref, name)), name

@@ -33,6 +33,7 @@ FLAG_NAMES = {
     8: "nan",
     16: "junction_depth",
     32: "push_denied",
+    64: "supply_deficit",
 }
 
 _i32p = C.POINTER(C.c_int32)
@@ -144,6 +145,13 @@ class WsiModelDesc(C.Structure):
         ("red_plane", _i32p),
         ("red_obj", _i32p),
         ("red_out", _f64p),
+        ("n_works", C.c_int32),
+        ("n_demand", C.c_int32),
+        ("works", _f64p),
+        ("demand", _f64p),
+        ("distrib", _f64p),
+        ("n_distrib", C.c_int32),
+        ("sched_split", C.c_int32),
     ]
 
 
@@ -156,7 +164,7 @@ _INT_ARRAYS = _NET_ARRAYS + [
 ]
 _F64_ARRAYS = ["node_forcing", "surf_inputs", "catch_inputs"]
 _GROUP_FIELD = {"arc": "arc", "land": "land", "surf": "surf", "tank": "tank", "river": "river",
-                "sewer": "sewer", "catchm": "catchm"}
+                "sewer": "sewer", "catchm": "catchm", "works": "works", "demand": "demand", "distrib": "distrib"}
 
 _LIB = None
 _LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "libwsi_b200.so")
@@ -243,6 +251,18 @@ def simple_chains(fm):
     return ptr, np.array(flat or [0], dtype=np.int32)
 
 
+def sched_split(fm):
+    """Index of the first Land.run entry when something scheduled before it reaches into a Land's
+    surfaces -- a Demand node with an arc to a Land (garden irrigation reads last step's evaporation
+    and waters the garden before the surfaces run, demand.py:250-272, land.py:2402-2437) -- else 0."""
+    land, demand = L.NT["Land"], L.NT["Demand"]
+    if not any(int(fm.node_type[fm.arc_in[a]]) == demand and int(fm.node_type[fm.arc_out[a]]) == land
+               for a in range(len(fm.arc_names))):
+        return 0
+    ops = [int(x) for x in fm.sched_op]
+    return ops.index(L.OP["LAND_RUN"]) if L.OP["LAND_RUN"] in ops else 0
+
+
 class ModelBuffers:
     """Owns the buffers of one flattened model on a device and its C descriptor."""
 
@@ -274,6 +294,8 @@ class ModelBuffers:
         items = [(0, a) for a in range(fm.n_obj["arc"])] + [(2, u) for u in range(fm.n_obj["surf"]) if nd[u] > 0]
         items += [(3, i) for i in range(fm.n_obj["tank"])] + [(4, i) for i in range(fm.n_obj["river"])]
         items += [(5, i) for i in range(fm.n_obj["sewer"])]
+        items += [(6, i) for i in range(fm.n_obj.get("works", 0))] + [(7, i) for i in range(fm.n_obj.get("demand", 0))]
+        items += [(8, i) for i in range(fm.n_obj.get("distrib", 0))]
         self.n_end = len(items)
         it = np.array(items or [(0, 0)], dtype=np.int32).reshape(-1, 2)
         fused = [int(t) in (L.NT["Land"], L.NT["Catchment"]) for t in fm.node_type]
@@ -308,6 +330,18 @@ class ModelBuffers:
             self._init_torch(device)
         self.desc = self._build_desc()
 
+    def _all_groups(self):
+        """Every group of the layout; builders that predate a group simply have no object of it."""
+        fm = self.fm
+        out = {}
+        for g in L.GROUPS:
+            if g in fm.groups:
+                out[g] = fm.groups[g]
+            else:
+                fm.n_obj.setdefault(g, 0)
+                out[g] = np.zeros((fm.n_fields(g), 0), dtype=np.float64)
+        return out
+
     # ---------------------------------------------------------------- backends
     def _init_numpy(self):
         fm = self.fm
@@ -317,7 +351,7 @@ class ModelBuffers:
             k[name] = np.ascontiguousarray(src, dtype=np.int32)
         for name in _F64_ARRAYS:
             k[name] = np.ascontiguousarray(getattr(fm, name), dtype=np.float64)
-        for g, arr in fm.groups.items():
+        for g, arr in self._all_groups().items():
             k["group_" + g] = np.ascontiguousarray(arr, dtype=np.float64).copy()
         pr = np.array(self.probes or [(0, 0, 0)], dtype=np.int32).reshape(-1, 3)
         k["probe_group"] = np.ascontiguousarray(pr[:, 0])
@@ -358,7 +392,7 @@ class ModelBuffers:
             k[name] = up(self._extra_int[name] if name in self._extra_int else getattr(fm, name), torch.int32)
         for name in _F64_ARRAYS:
             k[name] = up(getattr(fm, name), torch.float64)
-        for g, arr in fm.groups.items():
+        for g, arr in self._all_groups().items():
             k["group_" + g] = up(arr, torch.float64)
         pr = np.array(self.probes or [(0, 0, 0)], dtype=np.int32).reshape(-1, 3)
         k["probe_group"] = up(pr[:, 0], torch.int32)
@@ -398,6 +432,10 @@ class ModelBuffers:
         d.n_river = fm.n_obj["river"]
         d.n_sewer = fm.n_obj["sewer"]
         d.n_catch = fm.n_obj["catchm"]
+        d.n_works = fm.n_obj.get("works", 0)
+        d.n_demand = fm.n_obj.get("demand", 0)
+        d.n_distrib = fm.n_obj.get("distrib", 0)
+        d.sched_split = sched_split(fm)
         d.n_sched = int(len(fm.sched_op))
         for i, v in enumerate(self.surf_class_ptr):
             d.surf_class_ptr[i] = v

@@ -47,6 +47,10 @@ ORCHESTRATION_OPS = {
     ("Catchment", "route"): "CATCHMENT_ROUTE",
     ("Storage", "distribute"): "STORAGE_DISTRIBUTE",
     ("Reservoir", "distribute"): "STORAGE_DISTRIBUTE",
+    ("FWTW", "treat_water"): "FWTW_TREAT",
+    ("Demand", "create_demand"): "DEMAND_CREATE",
+    ("WWTW", "calculate_discharge"): "WWTW_CALC",
+    ("WWTW", "make_discharge"): "WWTW_DISCHARGE",
 }
 
 
@@ -198,14 +202,35 @@ class FlatModel:
     @classmethod
     def from_npz_dict(cls, d):
         sc = d["meta_scalars"]
-        n_obj = {k: int(v) for k, v in zip(L.GROUPS, d["meta_n_obj"])}
         surf_names = [tuple(x.split("\t")) for x in d["meta_surf_names"].tolist() if x]
         kw = {k: np.ascontiguousarray(d[k]) for k in cls._ARRAYS}
         V = len(d["meta_pollutants"]) + 1
-        groups = {k: np.ascontiguousarray(d["group_" + k]) for k in L.GROUPS}
-        # fixtures written before the arc group had its `stamp` plane: insert it (no arc carries anything)
+        nq = int(sc[3])
+        n_obj = {k: 0 for k in L.GROUPS}
+        n_obj.update({k: int(v) for k, v in zip(L.GROUPS, d["meta_n_obj"])})
+        groups = {}
+        for k in L.GROUPS:
+            nf = L.sewer_n_fields(V, nq) if k == "sewer" else L.GROUPS[k].n_fields(V)
+            groups[k] = np.ascontiguousarray(d["group_" + k]) if "group_" + k in d else np.zeros((nf, 0))
+        # fixtures written before a group gained planes are brought up to the current layout:
+        if groups["surf"].shape[0] == L.SURF.n_fields(V) - 1 - V:  # irrigated_at: never, pre_irrigation: unused
+            g = np.insert(groups["surf"], L.SURF.offset("irrigated_at", V), -1.0, axis=0)
+            groups["surf"] = np.ascontiguousarray(np.concatenate([g, np.zeros((V, g.shape[1]))], axis=0))
+        if groups["river"].shape[0] == L.RIVER.n_fields(V) - 1:  # mrf: none
+            groups["river"] = np.ascontiguousarray(np.insert(groups["river"], L.RIVER.offset("mrf", V), 0.0, axis=0))
+        if groups["land"].shape[0] == L.LAND.n_fields(V) - 1:  # garden_surf: none
+            groups["land"] = np.ascontiguousarray(np.insert(groups["land"], L.LAND.offset("garden_surf", V), -1.0, axis=0))
+        # the arc group's `stamp` (no arc carries anything) ...
         if groups["arc"].shape[0] == L.ARC.n_fields(V) - 1:
             groups["arc"] = np.ascontiguousarray(np.insert(groups["arc"], L.ARC.offset("stamp", V), -1.0, axis=0))
+        # ... and the sewer's pipe_timearea table (the default {0: 1}, sewer.py:62-66)
+        n_ta = 1 + 2 * L.MAX_TIMEAREA
+        if groups["sewer"].shape[0] == L.sewer_n_fields(V, nq) - n_ta:
+            o = L.SEWER.offset("n_timearea", V)
+            ins = np.zeros((n_ta, groups["sewer"].shape[1]))
+            ins[0] = 1.0
+            ins[1 + L.MAX_TIMEAREA] = 1.0
+            groups["sewer"] = np.ascontiguousarray(np.concatenate([groups["sewer"][:o], ins, groups["sewer"][o:]], axis=0))
         return cls(
             pollutants=[str(x) for x in d["meta_pollutants"].tolist()],
             additive=[str(x) for x in d["meta_additive"].tolist()],
@@ -341,8 +366,10 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
     for a in arcs:
         if _cls(a) != "Arc":
             raise UnsupportedModelError(f"arc {a.name!r} of class {_cls(a)} is not supported (plain Arc only)")
-        if _cls(a.out_port) in ("Land", "Catchment"):
+        if _cls(a.out_port) == "Catchment" or (_cls(a.out_port) == "Land" and _cls(a.in_port) != "Demand"):
             raise UnsupportedModelError(f"arc {a.name!r} pushes into a {_cls(a.out_port)} node")
+        if _cls(a.in_port) == "Land" and _cls(a.out_port) not in ("Sewer", "Groundwater", "River", "Node", "Waste"):
+            raise UnsupportedModelError(f"arc {a.name!r}: Land only pushes to Sewer / Groundwater / River / Node / Waste")
 
     # ---- graph CSR -----------------------------------------------------------
     node_type = np.array([L.NT[_cls(n)] for n in nodes], dtype=np.int32)
@@ -436,7 +463,8 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
     nq = 2
     for w in sewers:
         keys = list(w.sewer_tank.internal_arc.queue.keys())
-        nq = max(nq, max([1, int(w.pipe_time)] + [int(k) for k in keys]) + 1)
+        ta = getattr(w, "pipe_timearea", None) or {0: 1}
+        nq = max(nq, max([1, int(w.pipe_time)] + [int(k) for k in keys] + [int(k) for k in ta]) + 1)
     if nq > 16:
         raise UnsupportedModelError("sewer travel time > 15 timesteps")
 
@@ -496,6 +524,7 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
             b.set(col, "res_percolation", n.percolation.residence_time)
             b.set(col, "forcing_id", forcing_series(n.data_input_dict, ("precipitation", "et0", "temperature")))
             b.set(col, "node", i)
+            b.set(col, "garden_surf", -1.0)
             b.set(col, "surface_runoff", _vq(n.surface_runoff.storage, pollutants))
             b.set(col, "subsurface_runoff", _vq(n.subsurface_runoff.storage, pollutants))
             b.set(col, "percolation", _vq(n.percolation.storage, pollutants))
@@ -505,11 +534,11 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
                 surf_names.append((n.name, str(s.surface)))
                 _flatten_surface(gb["surf"], s, pollutants, additive, has_nitrate, dep_series_id)
                 gb["surf"].set(gb["surf"].cols[-1], "land", node_gidx[i])
+                if _cls(s) == "GardenSurface":  # the LAST garden answers the ("Demand", "Garden") tag (land.py:120-128)
+                    b.set(col, "garden_surf", float(lst[-1]))
             land_surf_lists.append(lst)
         elif c in STORE_TYPES:
             ti = add_store(n)
-            if c == "Reservoir" and len(n.in_arcs) > 0:
-                raise UnsupportedModelError(f"{n.name}: Reservoir abstractions (pulls) are not on the GPU path yet")
             if c == "River":
                 node_gidx[i] = len(gb["river"].cols)
                 _flatten_river(gb["river"], n, ti)
@@ -526,6 +555,12 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
                 raise UnsupportedModelError("non-integer pipe_time")
             b.set(col, "capacity", tk.capacity)
             b.set(col, "pipe_time", n.pipe_time)
+            ta = getattr(n, "pipe_timearea", None) or {0: 1}
+            if len(ta) > L.MAX_TIMEAREA or any(int(k) != k or k < 0 for k in ta):
+                raise UnsupportedModelError(f"{n.name}: pipe_timearea with more than {L.MAX_TIMEAREA} / non-integer entries")
+            b.set(col, "n_timearea", len(ta))
+            b.set(col, "ta_time", [float(k) for k in ta.keys()])
+            b.set(col, "ta_frac", [float(v) for v in ta.values()])
             qmask = 0
             for k, v in tk.internal_arc.queue.items():
                 qmask |= 1 << int(k)
@@ -539,6 +574,28 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
             col = gb["catchm"].new()
             col[0] = len(catch_series)
             catch_series.append(_series_from_dict(n.data_input_dict, dates, ["flow"] + pollutants))
+        elif c in ("WWTW", "FWTW"):
+            node_gidx[i] = len(gb["works"].cols)
+            _flatten_works(gb["works"], n, add_store, pollutants, additive, non_additive)
+        elif c == "Demand":
+            if not hasattr(n, "population"):
+                raise UnsupportedModelError(f"{n.name}: only ResidentialDemand is on the GPU path (demand.py:153)")
+            missing = [p for p in pollutants if p not in n.pollutant_load]
+            if missing:  # the reference raises KeyError in get_house_demand (demand.py:303-324)
+                raise UnsupportedModelError(f"{n.name}: pollutant_load lacks {missing}")
+            node_gidx[i] = len(gb["demand"].cols)
+            b = gb["demand"]
+            col = b.new()
+            for f in ("population", "per_capita", "gardening_efficiency", "constant_weighting", "constant_temp"):
+                b.set(col, f, getattr(n, f))
+            b.set(col, "forcing_id", forcing_series(n.data_input_dict, (None, None, "temperature")))
+            b.set(col, "pollutant_load", [0.0] + [float(n.pollutant_load[p]) for p in pollutants])
+            for f in ("total_demand", "total_backup", "total_received"):
+                b.set(col, f, _vq(getattr(n, f), pollutants))
+        elif c == "UnlimitedDistribution":
+            node_gidx[i] = len(gb["distrib"].cols)
+            col = gb["distrib"].new()
+            gb["distrib"].set(col, "supplied", _vq(n.supplied, pollutants))
         else:  # Node, Waste
             node_gidx[i] = 0
 
@@ -608,6 +665,50 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
     )
 
 
+def _flatten_works(b, n, add_store, pollutants, additive, non_additive):
+    """WWTW / FWTW (wtw.py:14-657): process parameters, state and the works' own tank."""
+    if "temperature" not in pollutants:
+        raise UnsupportedModelError(f"{n.name}: treatment works read the influent temperature (wtw.py:138)")
+    for key in additive:
+        if key not in n.process_parameters or key not in n.liquor_multiplier:
+            raise UnsupportedModelError(f"{n.name}: process_parameters / liquor_multiplier lack {key!r}")
+    kind = 1 if _cls(n) == "FWTW" else 0
+
+    class _TankHolder:  # the works' tank as a Storage-like object for add_store
+        pass
+
+    h = _TankHolder()
+    h.tank = n.service_reservoir_tank if kind else n.stormwater_tank
+    h.residence_time = h.infiltration_threshold = h.infiltration_pct = 0.0
+    h.data_input_dict = None
+    h.name = n.name
+    col = b.new()
+    b.set(col, "kind", kind)
+    b.set(col, "tank", add_store(h))
+    b.set(col, "throughput_capacity", n.treatment_throughput_capacity)
+    b.set(col, "percent_solids", n.percent_solids)
+    pidx = {p: i + 1 for i, p in enumerate(pollutants)}
+    lm = [0.0] * (len(pollutants) + 1)
+    pc = [0.0] * (len(pollutants) + 1)
+    pe = [1.0] * (len(pollutants) + 1)
+    lm[0] = float(n.liquor_multiplier["volume"])
+    pc[0] = float(n.process_parameters["volume"]["constant"])
+    for key in additive:
+        lm[pidx[key]] = float(n.liquor_multiplier[key])
+        pc[pidx[key]] = float(n.process_parameters[key]["constant"])
+        pe[pidx[key]] = float(n.process_parameters[key]["exponent"])
+    b.set(col, "liquor_mult", lm)
+    b.set(col, "proc_const", pc)
+    b.set(col, "proc_exp", pe)
+    for f in ("current_input", "treated", "liquor", "solids"):
+        b.set(col, f, _vq(getattr(n, f), pollutants))
+    if kind:
+        for f in ("total_deficit", "total_pulled", "previous_pulled", "unpushed_sludge"):
+            b.set(col, f, _vq(getattr(n, f), pollutants))
+    else:
+        b.set(col, "liquor_", _vq(n.liquor_, pollutants))
+
+
 def _flatten_surface(b, s, pollutants, additive, has_nitrate, dep_series_id):
     cname = _cls(s)
     if cname not in SURFACE_CLASS_MAP:
@@ -617,6 +718,7 @@ def _flatten_surface(b, s, pollutants, additive, has_nitrate, dep_series_id):
     kind = SURFACE_CLASS_MAP[cname]
     col = b.new()
     b.set(col, "type", L.ST[kind])
+    b.set(col, "irrigated_at", -1.0)
     b.set(col, "area", s.area)
     b.set(col, "capacity", s.capacity)
     b.set(col, "depth", s.depth)
@@ -698,6 +800,7 @@ def _flatten_river(b, n, tank_index):
     kt = n.damp * total_time
     riverrc = 1 - kt + kt * math.exp(-1 / kt) if kt != 0 else 1
     b.set(col, "riverrc", riverrc)
+    b.set(col, "mrf", getattr(n, "mrf", 0.0))
     b.set(col, "area", n.area)
     for name in (
         "uptake_PNratio", "denpar_w", "T_wdays", "halfsatINwater", "hsatTP", "limpppar", "prodNpar",

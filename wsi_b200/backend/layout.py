@@ -24,6 +24,7 @@ MAX_STAGE = 16  # crop_factor_stages table length (fixture uses 9)
 LAG_T = 21  # River.max_temp_lag + 1 (storage.py:560,753)
 LAG_TP = 366  # River.max_phosphorus_lag + 1 (storage.py:563,758)
 MAXP = 16  # compile-time bound on pollutants
+MAX_TIMEAREA = 8  # entries of a Sewer's pipe_timearea
 MAX_CAND = 8  # candidate out-arcs one push_distributed call may split over (kMaxCand in csrc/wsi_device.cuh)
 
 # node types (Node.__class__.__name__ in the reference)
@@ -39,6 +40,10 @@ NODE_TYPES = [
     "Catchment",
     "Boundary",  # not a reference class: the downstream end of a cut arc of a partitioned network --
     #              releases a prescribed VQIP series (totals) where the upstream river used to discharge
+    "WWTW",  # wtw.py:165-420
+    "FWTW",  # wtw.py:423-657
+    "Demand",  # demand.py:14-324 (ResidentialDemand files itself under this name, demand.py:214)
+    "UnlimitedDistribution",  # distribution.py:144-200: supplies whatever is pulled
 ]
 NT = {n: i for i, n in enumerate(NODE_TYPES)}
 
@@ -73,6 +78,10 @@ OPS = [
     "STORAGE_DISTRIBUTE",  # Storage.distribute          storage.py:120
     "NOP",  # e.g. Land.apply_irrigation without IrrigationSurface
     "BOUNDARY_RELEASE",  # partitioned networks: stands where the cut-off river's distribute stood
+    "FWTW_TREAT",  # FWTW.treat_water            wtw.py:559
+    "DEMAND_CREATE",  # Demand.create_demand        demand.py:79
+    "WWTW_CALC",  # WWTW.calculate_discharge    wtw.py:278
+    "WWTW_DISCHARGE",  # WWTW.make_discharge         wtw.py:306
 ]
 OP = {n: i for i, n in enumerate(OPS)}
 
@@ -158,6 +167,8 @@ LAND = Group(
         S("res_percolation"),
         S("forcing_id"),
         S("node"),  # node slot of this Land (status flags)
+        S("garden_surf"),  # surface slot of the Land's GardenSurface (-1: none): it answers pushes tagged
+        #                    ("Demand", "Garden") (land.py:120-128, 2384-2437)
         Q("surface_runoff"),  # ResidenceTank storages (land.py:138-149)
         Q("subsurface_runoff"),
         Q("percolation"),
@@ -256,6 +267,7 @@ SURF = Group(
         S("out_evaporation"),
         S("out_precipitation"),
         S("out_tank_recharge"),
+        S("irrigated_at"),  # GardenSurface: timestep whose irrigation arrived before the surface ran (-1: none)
         Q("storage"),
         Q("load"),  # pollutant_load (plane 0 unused)
         # per-step exchange between the surface kernels and the land phase (scratch)
@@ -265,6 +277,7 @@ SURF = Group(
         Q("mb_in"),  # this surface's share of running_inflow_mb (volume + additive lanes)
         Q("mb_out"),  # ... of running_outflow_mb
         Q("mb_ds"),  # surface.ds() (tanks.py:449-457)
+        Q("pre_irrigation"),  # GardenSurface: storage before this step's irrigation (= storage_ for ds())
     ],
 )
 
@@ -302,6 +315,7 @@ RIVER = Group(
         S("muptPpar"),
         S("max_temp_lag"),
         S("max_phosphorus_lag"),
+        S("mrf"),  # minimum required flow, volume per timestep (storage.py:477, 676-680)
         S("n_lag_T"),  # state: len(lagged_temperatures)
         S("head_T"),  # state: ring index of the oldest entry
         S("n_lag_TP"),
@@ -320,6 +334,9 @@ SEWER = Group(
         S("pipe_time"),
         S("qmask"),  # state: which travel-time keys exist in internal_arc.queue
         S("ia_flow_in"),  # per-step transient: internal_arc.flow_in (arcs.py:427)
+        S("n_timearea"),  # pipe_timearea (sewer.py:62-66): pushes tagged "Land"/"Demand" spread over travel times
+        S("ta_time", MAX_TIMEAREA),
+        S("ta_frac", MAX_TIMEAREA),
         Q("storage"),
         Q("storage_"),
         Q("active_storage"),
@@ -331,7 +348,51 @@ SEWER = Group(
 
 CATCH = Group("catchm", [S("cid")])
 
-GROUPS = {g.name: g for g in (ARC, LAND, SURF, TANK, RIVER, SEWER, CATCH)}
+# WWTW / FWTW (wtw.py): the WTW process model plus the works' own tank (stormwater tank / service
+# reservoir: an object of the tank group)
+WORKS = Group(
+    "works",
+    [
+        S("kind"),  # 0 WWTW, 1 FWTW
+        S("tank"),  # index into the tank group
+        S("throughput_capacity"),  # treatment_throughput_capacity
+        S("percent_solids"),
+        Q("liquor_mult"),  # liquor_multiplier: plane 0 = volume, additive planes per pollutant
+        Q("proc_const"),  # process_parameters[...]["constant"]: plane 0 = volume (wtw.py:101-107)
+        Q("proc_exp"),  # process_parameters[...]["exponent"] (plane 0 unused)
+        Q("current_input"),  # state (wtw.py:92-95)
+        Q("treated"),
+        Q("liquor"),
+        Q("solids"),
+        Q("liquor_"),  # WWTW: liquor at the end of the previous step (mass balance)
+        Q("total_deficit"),  # FWTW (wtw.py:512-515)
+        Q("total_pulled"),
+        Q("previous_pulled"),
+        Q("unpushed_sludge"),
+    ],
+)
+
+# ResidentialDemand (demand.py:153-324)
+DEMAND = Group(
+    "demand",
+    [
+        S("population"),
+        S("per_capita"),
+        S("gardening_efficiency"),
+        S("constant_weighting"),
+        S("constant_temp"),
+        S("forcing_id"),  # temperature series
+        Q("pollutant_load"),  # per person and timestep (plane 0 unused)
+        Q("total_demand"),  # per-step trackers (mass balance, demand.py:57-64)
+        Q("total_backup"),
+        Q("total_received"),
+    ],
+)
+
+# UnlimitedDistribution (distribution.py:144-200)
+DISTRIB = Group("distrib", [Q("supplied")])
+
+GROUPS = {g.name: g for g in (ARC, LAND, SURF, TANK, RIVER, SEWER, CATCH, WORKS, DEMAND, DISTRIB)}
 GROUP_ID = {n: i for i, n in enumerate(GROUPS)}
 
 # surface monthly data columns (land.py:540-569,1659-1691)
@@ -386,6 +447,7 @@ def c_header() -> str:
         ("WSI_LAG_TP", LAG_TP),
         ("WSI_MAXP", MAXP),
         ("WSI_MAX_CAND", MAX_CAND),
+        ("WSI_MAX_TIMEAREA", MAX_TIMEAREA),
         ("WSI_NF", NF),
         ("WSI_N_DEP", N_DEP),
     ):

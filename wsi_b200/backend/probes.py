@@ -81,7 +81,12 @@ class ProbeSet:
             self.add_fields("surf_out", "surf", SURF_OUT)
             self.add_fields("surf_state", "surf", SURF_STATE + SURF_POOLS)
         if fm.n_obj["tank"]:
-            self.add_field("tank_storage", "tank", "storage")
+            # the tanks of the store nodes, in node order (a treatment works' own tank is not one of them)
+            works_tanks = set()
+            if fm.n_obj.get("works", 0):
+                works_tanks = set(fm.view("works", "tank")[0, :, 0].astype(int).tolist())
+            self.add_field("tank_storage", "tank", "storage",
+                           objs=[i for i in range(fm.n_obj["tank"]) if i not in works_tanks])
         if fm.n_obj["sewer"]:
             self.add_field("sewer_storage", "sewer", "storage")
             self.add_field("sewer_active", "sewer", "active_storage")

@@ -17,6 +17,7 @@ HEADERS = [
     os.path.join(CSRC, "wsi_land.cuh"),
     os.path.join(CSRC, "wsi_nodes.cuh"),
     os.path.join(CSRC, "wsi_net.cuh"),
+    os.path.join(CSRC, "wsi_works.cuh"),
     os.path.join(CSRC, "wsi_kernels.cuh"),
     os.path.join(CSRC, "wsi_warp.cuh"),
     os.path.join(CSRC, "wsi_host.h"),

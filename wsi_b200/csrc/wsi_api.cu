@@ -165,7 +165,7 @@ int run_steps_graph(const WsiModelDesc* d, int slot, int64_t t0, int64_t t1, cud
   const int32_t baked[] = {slot, d->P, (int32_t)d->additive_mask, d->idx[0], d->idx[1], d->idx[2], d->idx[3], d->idx[4],
                            d->idx[5], d->idx[6], d->idx[7], d->R, d->n_nodes, d->n_arcs, d->n_surf, d->surf_class_ptr[0],
                            d->surf_class_ptr[1], d->surf_class_ptr[2], d->surf_class_ptr[3], d->surf_class_ptr[4],
-                           d->n_probe, d->n_red, d->n_end, d->n_sched, d->engine, d->n_net_levels, d->n_net_calc, d->n_net_final,
+                           d->n_probe, d->n_red, d->n_end, d->n_sched, d->sched_split, d->engine, d->n_net_levels, d->n_net_calc, d->n_net_final,
                            d->n_net_bnd, d->mb_sums ? 1 : 0};
   unsigned long long h = fnv(1469598103934665603ull, baked, sizeof baked);
   if (d->engine == 1) h = fnv(h, d->net_level_ptr_host, sizeof(int32_t) * (size_t)(d->n_net_levels + 1));

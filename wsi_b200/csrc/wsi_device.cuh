@@ -82,6 +82,8 @@ struct Ctx {
   double FA;
   uint32_t run_flags;
   bool block_sync;  // device: every thread of the block walks the same schedule -> WSI_BLOCK_ALIGN may sync
+  int tag;         // tag of the push being made: 0 "default", 1 "Demand" (Sewer.push_set_land, sewer.py:95-98),
+                   // 2 ("Demand", "Garden") (a Land's GardenSurface, land.py:120-128)
   int viol;        // mass-balance violations found for this replica this step
   double* mb_acc;  // [3*V] per-thread system-total accumulators (stride mb_stride) or null
   int mb_stride;
@@ -110,6 +112,12 @@ struct Ctx {
   WSI_HD double* tank(int plane, int i) const { return pl(D().tank, D().n_tank, plane, i); }
   WSI_HD double* river(int plane, int i) const { return pl(D().river, D().n_river, plane, i); }
   WSI_HD double* sewer(int plane, int i) const { return pl(D().sewer, D().n_sewer, plane, i); }
+  WSI_HD double* works(int plane, int i) const { return pl(D().works, D().n_works, plane, i); }
+  WSI_HD double* demand(int plane, int i) const { return pl(D().demand, D().n_demand, plane, i); }
+  WSI_HD size_t s_works() const { return (size_t)D().n_works * R; }
+  WSI_HD size_t s_demand() const { return (size_t)D().n_demand * R; }
+  WSI_HD double* distrib(int plane, int i) const { return pl(D().distrib, D().n_distrib, plane, i); }
+  WSI_HD size_t s_distrib() const { return (size_t)D().n_distrib * R; }
   WSI_HD Obj arc_obj(int a) const { return Obj{D().arc + (size_t)a * R + r, (size_t)D().n_arcs * R}; }
   WSI_HD Obj land_obj(int i) const { return Obj{D().land + (size_t)i * R + r, (size_t)D().n_land * R}; }
   WSI_HD Obj surf_obj(int i) const { return Obj{D().surf + (size_t)i * R + r, (size_t)D().n_surf * R}; }
@@ -306,6 +314,20 @@ WSI_HD typename C::Vq node_push_set(C& c, int node, const typename C::Vq& vqip);
 template <int D, class C>
 WSI_HD typename C::Vq push_distributed(C& c, int node, const typename C::Vq& vqip, int filter);
 
+// treatment works as push receivers (wsi_works.cuh)
+// (out of line, and handed a COPY of the context: rare receivers must neither grow every
+// instantiation of the push code nor force the caller's context into memory)
+template <class C>
+WSI_HDN double wwtw_push_check_vol(C c, int g, bool has_v, double v_vol);
+template <class C>
+WSI_HDN typename C::Vq wwtw_push_set(C c, int g, typename C::Vq vqip);
+template <class C>
+WSI_HDN typename C::Vq sewer_push_timearea(C c, int w, typename C::Vq vqip);
+template <class C>
+WSI_HDN double garden_irrigation_demand(C c, int land);
+template <class C>
+WSI_HDN void garden_receive_irrigation(C c, int land, typename C::Vq vqip);
+
 // sewer QueueTank helpers -------------------------------------------------------------------
 template <class C>
 WSI_HD void sewer_update_queue(C& c, int w) {  // AltQueueArc.update_queue arcs.py:603-638
@@ -394,7 +416,13 @@ WSI_HD double node_push_check_vol(C& c, int node, bool has_v, double v_vol) {
       if (!has_v) return ex;
       return vol_vchange(ex, pymin(ex, v_vol));
     }
-    default:  // Land / Catchment deny pushes (nodes.py:595-609)
+    case WSI_NT_WWTW:  // push_check_sewer wtw.py:319-342 (its "Sewer" and "default" handlers)
+      return wwtw_push_check_vol(c, g, has_v, v_vol);
+    case WSI_NT_LAND:  // only the ("Demand", "Garden") tag is answered (land.py:93, 120-128): irrigation demand
+      if (c.tag == 2) return garden_irrigation_demand(c, g);
+      c.flag(node, WSI_FLAG_DENY);
+      return 0.0;
+    default:  // Land / Catchment / FWTW / Demand deny pushes (nodes.py:595-609)
       c.flag(node, WSI_FLAG_DENY);
       return 0.0;
   }
@@ -410,8 +438,12 @@ WSI_HD typename C::Vq node_push_set(C& c, int node, const typename C::Vq& vqip) 
       if constexpr (D == 0) {
         c.flag(node, WSI_FLAG_DEPTH);
         return vqip;
-      } else {
-        return push_distributed<D - 1>(c, node, vqip, WSI_FILTER_NRWR);
+      } else {  // a junction forwards with the default tag (nodes.py:62-66)
+        const int tag = c.tag;
+        c.tag = 0;
+        const typename C::Vq r = push_distributed<D - 1>(c, node, vqip, WSI_FILTER_NRWR);
+        c.tag = tag;
+        return r;
       }
     case WSI_NT_WASTE:  // waste.py:40-49
       return vq_zero<C::P>();
@@ -425,8 +457,18 @@ WSI_HD typename C::Vq node_push_set(C& c, int node, const typename C::Vq& vqip) 
     case WSI_NT_RESERVOIR:  // push_set_storage storage.py:106-118
       return tank_push(c, c.tank(WSI_TANK_STORAGE(V), g), c.s_tank(), *c.tank(WSI_TANK_CAPACITY, g),
                        vqip);
-    case WSI_NT_SEWER:  // push_set_sewer sewer.py:163-176
+    case WSI_NT_SEWER:  // push_set_sewer sewer.py:163-176; tagged "Demand": push_set_land sewer.py:178-199
+      if (c.tag == 1) return sewer_push_timearea(c, g, vqip);
       return sewer_push_storage(c, g, vqip, (int)*c.sewer(WSI_SEWER_PIPE_TIME, g));
+    case WSI_NT_WWTW:  // push_set_sewer wtw.py:344-374
+      return wwtw_push_set(c, g, vqip);
+    case WSI_NT_LAND:  // ("Demand", "Garden"): GardenSurface.receive_irrigation_demand land.py:2425-2437
+      if (c.tag == 2) {
+        garden_receive_irrigation(c, g, vqip);
+        return vq_zero<C::P>();
+      }
+      c.flag(node, WSI_FLAG_DENY);
+      return vqip;
     default:
       c.flag(node, WSI_FLAG_DENY);
       return vqip;
@@ -631,6 +673,17 @@ WSI_HDN typename C::Vq push_general_call(C c, int node, typename C::Vq vqip, int
 // storage.py:711-721, Tank.push_storage tanks.py:160-205, QueueTank.push_storage below
 // FLOAT_ACCURACY tanks.py:513-539) and of every arc's vqip_in (arcs.py:152-156); Waste takes
 // nothing.
+// push_set of the chain's receiver; a tag only reaches a receiver right behind the first arc --
+// junctions forward with the default one (nodes.py:62-66)
+template <class C>
+WSI_HD typename C::Vq chain_push_set(C& c, int X, const typename C::Vq& v, int n) {
+  const int tag = c.tag;
+  if (n > 1) c.tag = 0;
+  const typename C::Vq r = node_push_set<0>(c, X, v);
+  c.tag = tag;
+  return r;
+}
+
 template <class C>
 WSI_HD void chain_push_empty(C& c, const int* arcs, int k0, int n, int X) {
   constexpr int V = C::V;
@@ -646,8 +699,13 @@ WSI_HD void chain_push_empty(C& c, const int* arcs, int k0, int n, int X) {
     case WSI_NT_RESERVOIR:
       tank_push_force(c, c.tank(WSI_TANK_STORAGE(V), g), c.s_tank(), none);
       break;
-    case WSI_NT_SEWER:
-      tank_push_force(c, c.sewer(WSI_SEWER_STORAGE(V), g), c.s_sewer(), none);
+    case WSI_NT_SEWER: {  // once per push_storage call: one, or one per pipe_timearea entry (push_set_land)
+      const int reps = (c.tag == 1 && n == 1) ? (int)*c.sewer(WSI_SEWER_N_TIMEAREA, g) : 1;
+      for (int i = 0; i < reps; i++) tank_push_force(c, c.sewer(WSI_SEWER_STORAGE(V), g), c.s_sewer(), none);
+      break;
+    }
+    case WSI_NT_WWTW:  // current_input = sum_vqip(current_input, empty) wtw.py:359
+      tank_push_force(c, c.works(WSI_WORKS_CURRENT_INPUT(V), g), c.s_works(), none);
       break;
     case WSI_NT_WASTE:
       break;
@@ -707,7 +765,7 @@ WSI_HD bool arc_send(C& c, int a, const typename C::Vq& vqip, typename C::Vq& re
     }
     if (j < 0 && v0 > 0) {
       WSI_STAT(0);
-      reply = node_push_set<0>(c, X, vqip);
+      reply = chain_push_set(c, X, vqip, n);
       if (vq_is_empty(c, reply)) {
 #pragma unroll 1
         for (int k = 0; k < n; k++) arc_book(c, arcs[k], vqip);
@@ -743,7 +801,7 @@ WSI_HD bool arc_send(C& c, int a, const typename C::Vq& vqip, typename C::Vq& re
         chain_push_empty(c, arcs, j + 1, n, X);
         reply = vq_zero<C::P>();
       } else {
-        reply = node_push_set<0>(c, X, w);
+        reply = chain_push_set(c, X, w, n);
         const bool rempty = vq_is_empty(c, reply);
         const Vq np_w = c.vchange(w, 0.0);
 #pragma unroll 1

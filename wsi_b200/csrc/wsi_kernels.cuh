@@ -658,6 +658,12 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
   constexpr int V = CFG::P + 1;
   const bool want_mb = (flags & WSI_RUN_MASS_BALANCE) != 0;
   const bool want_sums = want_mb && d->mb_sums != nullptr;
+  // schedule entries that reach into the surfaces before Land.run (garden irrigation) run first
+  if (d->engine == 0 && (flags & WSI_RUN_SCHEDULE) && (flags & WSI_RUN_SURFACES) && d->sched_split > b && d->sched_split < e) {
+    wsi_step_kernel<CFG><<<n_blocks(d), kBlock, kDescSmem, s>>>(slot, cfg, (int)t, b, d->sched_split, WSI_RUN_SCHEDULE, 0, 0);
+    WSI_CHECK_LAUNCH("wsi_step_kernel");
+    b = d->sched_split;
+  }
 #ifndef WSI_SURF_SPLIT
   if ((flags & WSI_RUN_SURFACES) && d->n_surf > 0 && d->n_surf <= 65535) {
     const dim3 grid((d->R + kSurfBlock - 1) / kSurfBlock, d->n_surf);

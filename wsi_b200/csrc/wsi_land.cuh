@@ -612,8 +612,10 @@ WSI_HD void surface_phase(C& c, int u) {
     }
   }
   if (want_ds) {
-    // storage_ is what is still in memory, except for the decayed pollutants (pre_decay)
-    Vq old = c.ldv_add(stp, ss);
+    // storage_ is what is still in memory (or what was, before this step's garden irrigation arrived),
+    // except for the decayed pollutants (pre_decay)
+    const bool irrigated = growing && *S(WSI_SURF_IRRIGATED_AT) == (double)c.t;
+    Vq old = c.ldv_add(irrigated ? S(WSI_SURF_PRE_IRRIGATION(V)) : stp, ss);
     const int n = (int)*S(WSI_SURF_N_DECAY);
     for (int i = 0; i < WSI_MAX_DECAY; i++) {
       if (i >= n) break;
@@ -649,7 +651,9 @@ WSI_HD void surface_phase(C& c, int u) {
       *S(WSI_SURF_POOL_ADS_INORG + k) = pl.ads_inorg[k];
     }
   }
-  if (c.D().n_probe > 0) {  // per-step diagnostics recorded by Model.run (model.py:1081-1118)
+  // per-step diagnostics recorded by Model.run (model.py:1081-1118); a GardenSurface's evaporation and
+  // precipitation are also what next step's irrigation demand is worked out from (land.py:2402-2423)
+  if (c.D().n_probe > 0 || (int)*Lo(WSI_LAND_GARDEN_SURF) == u) {
     *S(WSI_SURF_OUT_PERCOLATION) = pc.x[0];
     *S(WSI_SURF_OUT_SUBSURFACE) = sf.x[0];
     *S(WSI_SURF_OUT_SURFACE) = type == WSI_ST_IMPERVIOUSSURFACE ? 0.0 : ie.x[0];

@@ -35,17 +35,6 @@ WSI_HD void storage_distribute_pre(C& c, int node, typename C::Vq& v) {  // stor
   double* st = c.tank(WSI_TANK_STORAGE(V), g);
   v = tank_pull(c, st, c.s_tank(), st[0]);
 }
-// Reservoir.make_abstractions storage.py:983-989 with no in-arcs: pull_distributed returns
-// an empty VQIP (nodes.py:376-407), which is then pushed (twice) into the tank.
-template <class C>
-WSI_HD void reservoir_abstract(C& c, int node) {
-  constexpr int V = C::V;
-  const int g = c.D().node_gidx[node];
-  double* st = c.tank(WSI_TANK_STORAGE(V), g);
-  typename C::Vq spill = tank_push(c, st, c.s_tank(), *c.tank(WSI_TANK_CAPACITY, g), vq_zero<C::P>());
-  tank_push_force(c, st, c.s_tank(), spill);
-}
-
 // ---- River --------------------------------------------------------------------------------
 // Python's sum() over a list slice (CPython >= 3.12: Neumaier compensated summation) on a
 // ring buffer stored as planes; entries [first, first+n) counted from the oldest.
@@ -332,13 +321,13 @@ WSI_HD void boundary_release(C& c, int node, bool deliver) {
 
 // Catchment.route catchment.py:77-88: what is still to be routed, and -- after the push -- the
 // mass-balance terms, which need unrouted_water (the reply)
+}  // namespace wsi
+#include "wsi_works.cuh"  // pull side, treatment works, demand (needs catch_get_flow above)
+namespace wsi {
+
 template <class C>
 WSI_HD void catchment_route_pre(C& c, int node, typename C::Vq& v) {
-  const WsiModelDesc& d = c.D();
-  const int g = d.node_gidx[node];
-  v = catch_get_flow(c, g);
-  for (int i = d.out_ptr[node]; i < d.out_ptr[node + 1]; i++)  // get_avail catchment.py:90-104
-    v = c.vchange(v, v.x[0] - arc_lane(c, d.out_arcs[i], 0));
+  v = catchment_avail(c, node);  // get_avail catchment.py:90-104: what abstractions have left
 }
 template <class C>
 WSI_HD void catchment_route_post(C& c, int node, const typename C::Vq& reply) {
@@ -420,6 +409,14 @@ WSI_HD void node_mass_balance(C& c, int node, typename C::Vq& in_, typename C::V
       case WSI_NT_STORAGE:
       case WSI_NT_RESERVOIR:
         ds_add(c, ds, tank_ds(c, g));
+        break;
+      case WSI_NT_WWTW:
+      case WSI_NT_FWTW:
+      case WSI_NT_DEMAND:
+      case WSI_NT_UNLIMITEDDISTRIBUTION:
+#pragma unroll
+        for (int p = 0; p <= C::P; p++)
+          if (p == 0 || bit(c.addm(), p)) (void)works_mb_lane(c, type, g, p, in_.x[p], ds.x[p], out_.x[p]);
         break;
       case WSI_NT_RIVER: {
         ds_add(c, in_, c.ldv_add(c.river(WSI_RIVER_BIO_IN(V), g), c.s_river()));
@@ -508,6 +505,12 @@ WSI_HD void node_mb_lane(const C& c, int node, double& in_, double& ds, double& 
       case WSI_NT_STORAGE:
       case WSI_NT_RESERVOIR:
         ds += tank_ds_lane<LANE>(c, g);
+        break;
+      case WSI_NT_WWTW:
+      case WSI_NT_FWTW:
+      case WSI_NT_DEMAND:
+      case WSI_NT_UNLIMITEDDISTRIBUTION:
+        (void)works_mb_lane(c, type, g, LANE, in_, ds, out_);
         break;
       case WSI_NT_RIVER:
         in_ += *c.river(WSI_RIVER_BIO_IN(V) + LANE, g);
@@ -634,6 +637,15 @@ WSI_HD void end_item(C& c, int kind, int obj) {
     case 5:
       sewer_end_timestep(c, obj);
       break;
+    case 6:  // WWTW / FWTW (their tank is a kind-3 item)
+      works_end_timestep(c, obj);
+      break;
+    case 7:
+      demand_end_timestep(c, obj);
+      break;
+    case 8:  // UnlimitedDistribution.end_timestep distribution.py:191-200
+      c.stv(c.distrib(WSI_DISTRIB_SUPPLIED(V), obj), c.s_distrib(), vq_zero<C::P>());
+      break;
     default:
       break;
   }
@@ -661,6 +673,17 @@ WSI_HD void end_node(C& c, int node) {
     case WSI_NT_SEWER:
       end_item(c, 5, g);
       break;
+    case WSI_NT_WWTW:
+    case WSI_NT_FWTW:
+      end_item(c, 6, g);
+      end_item(c, 3, (int)*c.works(WSI_WORKS_TANK, g));
+      break;
+    case WSI_NT_DEMAND:
+      end_item(c, 7, g);
+      break;
+    case WSI_NT_UNLIMITEDDISTRIBUTION:
+      end_item(c, 8, g);
+      break;
     default:
       break;
   }
@@ -681,6 +704,9 @@ WSI_HD const double* probe_src(const C& c, int group, int plane, int obj) {
     case 2: return c.surf(plane, obj);
     case 3: return c.tank(plane, obj);
     case 4: return c.river(plane, obj);
+    case 7: return c.works(plane, obj);
+    case 8: return c.demand(plane, obj);
+    case 9: return c.distrib(plane, obj);
     default: return c.sewer(plane, obj);
   }
 }
@@ -767,6 +793,10 @@ WSI_HD void run_op(C& c, int op, int node) {
       case WSI_OP_RIVER_DISTRIBUTE: river_distribute_pre(c, node, v); filter = WSI_FILTER_NRW; break;
       case WSI_OP_STORAGE_DISTRIBUTE: storage_distribute_pre(c, node, v); filter = WSI_FILTER_ALL; break;
       case WSI_OP_BOUNDARY_RELEASE: boundary_release(c, node, true); push = false; break;
+      case WSI_OP_FWTW_TREAT: fwtw_treat_water(c, node); push = false; break;
+      case WSI_OP_DEMAND_CREATE: demand_create(c, node); push = false; break;
+      case WSI_OP_WWTW_CALC: wwtw_calculate_discharge(c, node); push = false; break;
+      case WSI_OP_WWTW_DISCHARGE: wwtw_make_discharge(c, node); push = false; break;
       default: push = false; break;
     }
     WSI_BLOCK_ALIGN(c);
@@ -792,14 +822,23 @@ WSI_HD void run_op(C& c, int op, int node) {
     }
   }
 }
-// out-of-line entry points of single ops for the network engine's scalar fall-backs (wsi_net.cuh)
+// out-of-line entry points of single ops for the network engine's scalar fall-backs (wsi_net.cuh);
+// written out rather than routed through run_op, which would instantiate every other op for the
+// network kernels' context as well
 template <class C>
 WSI_HDN void catchment_route(C& c, int node) {
-  run_op(c, WSI_OP_CATCHMENT_ROUTE, node);
+  typename C::Vq v, reply;
+  catchment_route_pre(c, node, v);
+  (void)push_out(c, node, v, WSI_FILTER_NRW, reply);
+  catchment_route_post(c, node, reply);
 }
 template <class C>
 WSI_HDN void river_distribute(C& c, int node) {
-  run_op(c, WSI_OP_RIVER_DISTRIBUTE, node);
+  typename C::Vq v, reply;
+  river_distribute_pre(c, node, v);
+  (void)push_out(c, node, v, WSI_FILTER_NRW, reply);
+  tank_push_force(c, c.tank(WSI_TANK_STORAGE(C::V), (int)*c.river(WSI_RIVER_TANK, c.D().node_gidx[node])), c.s_tank(),
+                  reply);
 }
 
 template <class C>
@@ -811,6 +850,10 @@ WSI_HD void net_schedule(C& c);  // wsi_net.cuh
 template <bool FUSED_SURFACES, class C>
 WSI_HD void replica_step(C& c, int sched_begin, int sched_end) {
   const WsiModelDesc& d = c.D();
+  // entries that reach into a Land's surfaces before Land.run (garden irrigation) come first
+  const int split = (d.engine == 0 && d.sched_split > sched_begin && d.sched_split < sched_end) ? d.sched_split : sched_begin;
+  if (c.run_flags & WSI_RUN_SCHEDULE)
+    for (int k = sched_begin; k < split; k++) run_op(c, d.sched_op[k], d.sched_node[k]);
   if constexpr (FUSED_SURFACES) {
     if (c.run_flags & WSI_RUN_SURFACES)
       for (int u = 0; u < d.n_surf; u++) surface_phase<-1>(c, u);
@@ -818,7 +861,7 @@ WSI_HD void replica_step(C& c, int sched_begin, int sched_end) {
   if (c.run_flags & WSI_RUN_SCHEDULE) {
     if (d.engine == 1) net_schedule(c);
     else
-      for (int k = sched_begin; k < sched_end; k++) run_op(c, d.sched_op[k], d.sched_node[k]);
+      for (int k = split; k < sched_end; k++) run_op(c, d.sched_op[k], d.sched_node[k]);
   }
   if (c.run_flags & WSI_RUN_MASS_BALANCE) {
     MbHostSink sink;
@@ -840,6 +883,7 @@ WSI_HD Ctx<CFG, SMEM> make_ctx(const WsiModelDesc* host_d, int slot, const CFG& 
   c.FA = c.D().float_accuracy;
   c.run_flags = flags;
   c.viol = 0;
+  c.tag = 0;
   c.block_sync = false;
   c.mb_acc = nullptr;
   c.mb_stride = 1;
