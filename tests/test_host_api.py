@@ -240,3 +240,24 @@ def test_model_load_of_the_unreduced_reference_fixture(tmp_path):
         assert np.array_equal(fm.groups[g], fm_ref.groups[g]), g
     for name in ("node_forcing", "surf_inputs"):
         assert np.array_equal(getattr(fm, name), getattr(fm_ref, name)), name
+
+
+def test_pickle_round_trip_and_result_files(tmp_path):
+    """save_pickle / load_pickle (model.py:604-640) keep parameters and state; write_results writes
+    the three csv files of the reference's command line (__main__.py:59-63)."""
+    import pandas as pd
+
+    from wsi_b200.orchestration.model import Model
+
+    m, _ = _quickstart_model(T=5)
+    m.nodes["my_groundwater"].tank.storage["volume"] = 12.5
+    m.save_pickle(tmp_path / "m.pkl")
+    m2 = Model().load_pickle(tmp_path / "m.pkl")
+    assert list(m2.nodes) == list(m.nodes) and list(m2.arcs) == list(m.arcs)
+    assert m2.nodes["my_groundwater"].tank.storage["volume"] == 12.5
+    assert np.array_equal(m2.flatten().groups["tank"], m.flatten().groups["tank"])
+    flows = [{"arc": "runoff", "flow": 0.05, "time": "2009-03-03", "phosphate": 1e-7}]
+    Model.write_results(flows, [{"node": "my_sewer", "storage": 0.03, "time": "2009-03-03"}], [], tmp_path / "out")
+    got = pd.read_csv(tmp_path / "out" / "flows.csv", index_col=0)
+    assert got.loc[0, "arc"] == "runoff" and got.loc[0, "flow"] == 0.05
+    assert (tmp_path / "out" / "tanks.csv").exists() and (tmp_path / "out" / "surfaces.csv").exists()

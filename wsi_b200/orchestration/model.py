@@ -13,7 +13,6 @@ from __future__ import annotations
 import csv
 import gzip
 import os
-import sys
 from collections.abc import Sequence
 from datetime import datetime
 
@@ -392,6 +391,33 @@ class Model(WSIObj):
         for node in self.nodes.values():
             node.reinit()
 
+    # ---- persistence (model.py:604-640) and result files (__main__.py:59-63) -----------------
+    def save_pickle(self, fid):
+        """Pickle the whole object graph including its state (``run`` scatters the device state
+        back into the objects, so a model saved after a run resumes where it stopped)."""
+        import dill as pickle
+
+        with open(fid, "wb") as file:
+            pickle.dump(self, file)
+
+    def load_pickle(self, fid):
+        import dill as pickle
+
+        with open(fid, "rb") as file:
+            return pickle.load(file)
+
+    @staticmethod
+    def write_results(flows, tanks, surfaces, outputs):
+        """``flows.csv`` / ``tanks.csv`` / ``surfaces.csv`` exactly as the reference's command line
+        writes them (``pd.DataFrame(records).to_csv``, __main__.py:59-63)."""
+        import os
+
+        import pandas as pd
+
+        os.makedirs(outputs, exist_ok=True)
+        for name, records in (("flows", flows), ("tanks", tanks), ("surfaces", surfaces)):
+            pd.DataFrame(list(records)).to_csv(os.path.join(str(outputs), name + ".csv"))
+
 
 class _RecordPlan:
     """Which probes back ``tanks`` / ``surfaces`` records and how to turn them into the
@@ -515,4 +541,3 @@ class _RecordPlan:
 
 
 __all__ = ["Model", "to_datetime", "read_csv", "UnsupportedModelError"]
-_ = sys  # keep the import surface close to the reference module
