@@ -419,6 +419,43 @@ def scenario_city(D=3, T=480):
     save("city", fm, ref, "synthetic city, %d districts, hourly, %d steps" % (D, T))
 
 
+def scenario_queuegw(T=400):
+    """QueueGroundwater (storage.py:248-449) both ways: with ``decays`` -- a DecayQueueTank whose
+    DecayArcAlt decays what enters and what waits (tanks.py:645-696, arcs.py:731-805; built-in delay of
+    one timestep) -- and without (a plain QueueTank), each fed by a Land through a time-area diagram
+    and releasing to a river junction."""
+    set_default_pollutants()
+    dates = [pd.Timestamp("2001-01-01") + pd.Timedelta(days=i) for i in range(T)]
+    rng = np.random.default_rng(20261107)
+    forcing = synthetic_forcing(dates, rng)
+    tdata = {k: v for k, v in forcing.items() if k[0] == "temperature"}
+    nodes, arcs = [], []
+    for k, decays in enumerate([{"ammonia": {"constant": 0.04, "exponent": 1.02}, "bod": {"constant": 0.1, "exponent": 1.0}},
+                                None]):
+        perv = {"type_": "PerviousSurface", "surface": "rural", "area": 5e4 * (1 + k), "depth": 0.5,
+                "pollutant_load": {"phosphate": 1e-7, "ammonia": 2e-7, "bod": 1e-6}, "initial_storage": 5e4 * (1 + k) * 0.5 * 0.4 * 0.5,
+                "infiltration_capacity": 0.05}
+        nodes += [
+            {"type_": "Land", "name": f"land{k}", "data_input_dict": forcing, "surfaces": [perv],
+             "percolation_residence_time": 5.0},
+            {"type_": "QueueGroundwater", "name": f"qgw{k}", "area": 1e5, "capacity": 4e4, "initial_storage": 3e3,
+             "timearea": {0: 0.5, 1: 0.3, 3: 0.2}, "decays": decays, "data_input_dict": tdata},
+        ]
+        arcs += [(f"land{k}-qgw{k}", f"land{k}", f"qgw{k}"), (f"land{k}-river", f"land{k}", "river"),
+                 (f"qgw{k}-river", f"qgw{k}", "river")]
+    nodes += [{"type_": "Node", "name": "river"}, {"type_": "Waste", "name": "outlet"}]
+    arcs.append(("river-outlet", "river", "outlet"))
+    m = Model()
+    m.add_nodes(nodes)
+    m.add_arcs([{"type_": "Arc", "name": a, "in_port": i, "out_port": o} for a, i, o in arcs])
+    # Node.__init__ resets data_input_dict to None after QueueGroundwater stored it (storage.py:296-297,
+    # nodes.py:58), so the temperature its queue decays with has to be attached afterwards
+    m.nodes["qgw0"].data_input_dict = tdata
+    fm = flatten_ref(m, dates)
+    ref = run_reference(m, dates)
+    save("queuegw", fm, ref, "QueueGroundwater with and without decays, %d days" % T)
+
+
 def synthetic_forcing(dates, rng):
     """SURVEY 8d config 2 forcing generator."""
     doy = np.array([d.dayofyear for d in dates], dtype=float)
@@ -776,6 +813,7 @@ SCENARIOS = {
     "config3": scenario_config3,
     "hourly": scenario_hourly,
     "oxford": scenario_oxford,
+    "queuegw": scenario_queuegw,
     "city": scenario_city,
     "fixture3607_full": scenario_fixture3607_full,
     "config3_members16": scenario_config3_members,

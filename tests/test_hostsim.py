@@ -9,7 +9,7 @@ import pytest
 from parity_util import compare_blocks, compare_mb, load_golden
 
 GOLDENS = ["quickstart", "quickstart_simple", "fixture3607", "config2", "rivernet", "rivertree", "config3", "hourly",
-           "oxford", "fixture3607_full", "city"]
+           "oxford", "fixture3607_full", "city", "queuegw"]
 
 
 @pytest.fixture(scope="module")

@@ -40,6 +40,8 @@ ORCHESTRATION_OPS = {
     ("Land", "apply_irrigation"): "NOP",
     ("Groundwater", "infiltrate"): "GW_INFILTRATE",
     ("Groundwater", "distribute"): "GW_DISTRIBUTE",
+    ("QueueGroundwater", "infiltrate"): "NOP",  # storage.py:365-367
+    ("QueueGroundwater", "distribute"): "QGW_DISTRIBUTE",
     ("Sewer", "make_discharge"): "SEWER_DISCHARGE",
     ("River", "calculate_discharge"): "RIVER_CALC",
     ("River", "distribute"): "RIVER_DISTRIBUTE",
@@ -223,13 +225,19 @@ class FlatModel:
         # the arc group's `stamp` (no arc carries anything) ...
         if groups["arc"].shape[0] == L.ARC.n_fields(V) - 1:
             groups["arc"] = np.ascontiguousarray(np.insert(groups["arc"], L.ARC.offset("stamp", V), -1.0, axis=0))
-        # ... and the sewer's pipe_timearea table (the default {0: 1}, sewer.py:62-66)
-        n_ta = 1 + 2 * L.MAX_TIMEAREA
-        if groups["sewer"].shape[0] == L.sewer_n_fields(V, nq) - n_ta:
+        # ... and the sewer group's pipe_timearea table (the default {0: 1}, sewer.py:62-66) and, later,
+        # its QueueGroundwater / queue-decay planes (none)
+        n_ta, n_q = 1 + 2 * L.MAX_TIMEAREA, 5 + 1 + 4 * L.MAX_DECAY
+        full = L.sewer_n_fields(V, nq)
+        if groups["sewer"].shape[0] == full - n_ta - n_q:
             o = L.SEWER.offset("n_timearea", V)
             ins = np.zeros((n_ta, groups["sewer"].shape[1]))
             ins[0] = 1.0
             ins[1 + L.MAX_TIMEAREA] = 1.0
+            groups["sewer"] = np.concatenate([groups["sewer"][:o], ins, groups["sewer"][o:]], axis=0)
+        if groups["sewer"].shape[0] == full - n_q:
+            o = L.SEWER.offset("kind", V)
+            ins = np.zeros((n_q, groups["sewer"].shape[1]))
             groups["sewer"] = np.ascontiguousarray(np.concatenate([groups["sewer"][:o], ins, groups["sewer"][o:]], axis=0))
         return cls(
             pollutants=[str(x) for x in d["meta_pollutants"].tolist()],
@@ -250,7 +258,11 @@ class FlatModel:
 
 # ---------------------------------------------------------------------- helpers
 def _cls(obj):
-    return obj.__class__.__name__
+    name = obj.__class__.__name__
+    # QueueGroundwater files itself under its parent's name (storage.py:299)
+    if name == "Groundwater" and hasattr(obj, "timearea"):
+        return "QueueGroundwater"
+    return name
 
 
 def _vq(vqip, pollutants):
@@ -368,7 +380,7 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
             raise UnsupportedModelError(f"arc {a.name!r} of class {_cls(a)} is not supported (plain Arc only)")
         if _cls(a.out_port) == "Catchment" or (_cls(a.out_port) == "Land" and _cls(a.in_port) != "Demand"):
             raise UnsupportedModelError(f"arc {a.name!r} pushes into a {_cls(a.out_port)} node")
-        if _cls(a.in_port) == "Land" and _cls(a.out_port) not in ("Sewer", "Groundwater", "River", "Node", "Waste"):
+        if _cls(a.in_port) == "Land" and _cls(a.out_port) not in ("Sewer", "Groundwater", "QueueGroundwater", "River", "Node", "Waste"):
             raise UnsupportedModelError(f"arc {a.name!r}: Land only pushes to Sewer / Groundwater / River / Node / Waste")
 
     # ---- graph CSR -----------------------------------------------------------
@@ -465,6 +477,11 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
         keys = list(w.sewer_tank.internal_arc.queue.keys())
         ta = getattr(w, "pipe_timearea", None) or {0: 1}
         nq = max(nq, max([1, int(w.pipe_time)] + [int(k) for k in keys] + [int(k) for k in ta]) + 1)
+    for w in nodes:
+        if _cls(w) == "QueueGroundwater":
+            delay = int(w.tank.internal_arc.number_of_timesteps)
+            keys = [int(k) for k in w.tank.internal_arc.queue.keys()]
+            nq = max(nq, max([1] + keys + [int(k) + delay for k in w.timearea]) + 1)
     if nq > 16:
         raise UnsupportedModelError("sewer travel time > 15 timesteps")
 
@@ -537,6 +554,9 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
                 if _cls(s) == "GardenSurface":  # the LAST garden answers the ("Demand", "Garden") tag (land.py:120-128)
                     b.set(col, "garden_surf", float(lst[-1]))
             land_surf_lists.append(lst)
+        elif c == "QueueGroundwater":
+            node_gidx[i] = len(gb["sewer"].cols)
+            _flatten_queue_groundwater(gb["sewer"], n, pollutants, V, forcing_series)
         elif c in STORE_TYPES:
             ti = add_store(n)
             if c == "River":
@@ -663,6 +683,49 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
         doy_adj=doy_adj,
         dates=dates,
     )
+
+
+def _flatten_queue_groundwater(b, n, pollutants, V, forcing_series):
+    """QueueGroundwater (storage.py:248-449): a QueueTank -- or, with decays, a DecayQueueTank whose
+    internal DecayArcAlt decays what enters and what waits (tanks.py:645-696, arcs.py:731-805) -- in
+    the queue-store group."""
+    tk = n.tank
+    ia = tk.internal_arc
+    ta = n.timearea or {0: 1}
+    if len(ta) > L.MAX_TIMEAREA or any(int(k) != k or k < 0 for k in ta):
+        raise UnsupportedModelError(f"{n.name}: timearea with more than {L.MAX_TIMEAREA} / non-integer entries")
+    if len(n.in_arcs) and any(_cls(a.in_port) in ("Reservoir", "FWTW", "Demand") for a in n.out_arcs.values()):
+        raise UnsupportedModelError(f"{n.name}: abstraction from a QueueGroundwater (pull_set_active) is not supported")
+    # push checks are answered by the Tank the Storage base class created first (storage.py:60): stale
+    handler = getattr(n, "push_check_handler", {}).get("default")
+    stale = getattr(handler, "__self__", None) or getattr(n, "_stale_tank", None) or tk
+    col = b.new()
+    b.set(col, "capacity", tk.capacity)
+    b.set(col, "pipe_time", 0)
+    b.set(col, "n_timearea", len(ta))
+    b.set(col, "ta_time", [float(k) for k in ta.keys()])
+    b.set(col, "ta_frac", [float(v) for v in ta.values()])
+    b.set(col, "kind", 1)
+    b.set(col, "queue_delay", int(ia.number_of_timesteps))
+    b.set(col, "stale_capacity", stale.capacity)
+    b.set(col, "stale_volume", stale.storage["volume"])
+    decays = getattr(ia, "decays", None) or {}
+    if decays:
+        nd, pol, const, exp_, total, _ = _decay_fields(ia, pollutants)
+        b.set(col, "n_decay", nd)
+        b.set(col, "decay_pol", pol)
+        b.set(col, "decay_const", const)
+        b.set(col, "decay_exp", exp_)
+        b.set(col, "total_decayed", total)
+        b.set(col, "forcing_id", forcing_series(n.data_input_dict, (None, None, "temperature")))
+    qmask = 0
+    for k, v in ia.queue.items():
+        qmask |= 1 << int(k)
+        b.set(col, "queue", _vq(v, pollutants), k=int(k) * V)
+    b.set(col, "qmask", qmask)
+    b.set(col, "storage", _vq(tk.storage, pollutants))
+    b.set(col, "storage_", _vq(tk.storage_, pollutants))
+    b.set(col, "active_storage", _vq(tk.active_storage, pollutants))
 
 
 def _flatten_works(b, n, add_store, pollutants, additive, non_additive):

@@ -44,6 +44,7 @@ NODE_TYPES = [
     "FWTW",  # wtw.py:423-657
     "Demand",  # demand.py:14-324 (ResidentialDemand files itself under this name, demand.py:214)
     "UnlimitedDistribution",  # distribution.py:144-200: supplies whatever is pulled
+    "QueueGroundwater",  # storage.py:248-449 (files itself under "Groundwater"): a QueueTank / DecayQueueTank store
 ]
 NT = {n: i for i, n in enumerate(NODE_TYPES)}
 
@@ -82,6 +83,7 @@ OPS = [
     "DEMAND_CREATE",  # Demand.create_demand        demand.py:79
     "WWTW_CALC",  # WWTW.calculate_discharge    wtw.py:278
     "WWTW_DISCHARGE",  # WWTW.make_discharge         wtw.py:306
+    "QGW_DISTRIBUTE",  # QueueGroundwater.distribute storage.py:345-363
 ]
 OP = {n: i for i, n in enumerate(OPS)}
 
@@ -337,6 +339,16 @@ SEWER = Group(
         S("n_timearea"),  # pipe_timearea (sewer.py:62-66): pushes tagged "Land"/"Demand" spread over travel times
         S("ta_time", MAX_TIMEAREA),
         S("ta_frac", MAX_TIMEAREA),
+        S("kind"),  # 0 Sewer (sewer.py), 1 QueueGroundwater (storage.py:248)
+        S("queue_delay"),  # internal_arc.number_of_timesteps, added to every travel time (arcs.py:385)
+        S("stale_capacity"),  # QueueGroundwater answers push checks from the Tank its Storage base class
+        S("stale_volume"),  # created first and no longer updates (storage.py:60, 301-315)
+        S("forcing_id"),  # temperature series for the queue's decays
+        S("n_decay"),  # DecayQueueTank / DecayArcAlt (tanks.py:645-696, arcs.py:731-805)
+        S("decay_pol", MAX_DECAY),
+        S("decay_const", MAX_DECAY),
+        S("decay_exp", MAX_DECAY),
+        S("total_decayed", MAX_DECAY),  # state: internal_arc.total_decayed
         Q("storage"),
         Q("storage_"),
         Q("active_storage"),

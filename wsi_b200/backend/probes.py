@@ -80,16 +80,27 @@ class ProbeSet:
             self.add_field("surf_storage", "surf", "storage")
             self.add_fields("surf_out", "surf", SURF_OUT)
             self.add_fields("surf_state", "surf", SURF_STATE + SURF_POOLS)
-        if fm.n_obj["tank"]:
-            # the tanks of the store nodes, in node order (a treatment works' own tank is not one of them)
-            works_tanks = set()
-            if fm.n_obj.get("works", 0):
-                works_tanks = set(fm.view("works", "tank")[0, :, 0].astype(int).tolist())
-            self.add_field("tank_storage", "tank", "storage",
-                           objs=[i for i in range(fm.n_obj["tank"]) if i not in works_tanks])
-        if fm.n_obj["sewer"]:
-            self.add_field("sewer_storage", "sewer", "storage")
-            self.add_field("sewer_active", "sewer", "active_storage")
+        # the storage of every store node in node order (what Model.run's tank record walks): the tank of
+        # a Groundwater / Storage / Reservoir / River, the queue store of a QueueGroundwater
+        store_probes, n_stores = [], 0
+        for i, t in enumerate(fm.node_type):
+            name = L.NODE_TYPES[int(t)]
+            g = int(fm.node_gidx[i])
+            if name in ("Groundwater", "Storage", "Reservoir"):
+                store_probes += fm.probes_for_field("tank", "storage", g)
+            elif name == "River":
+                store_probes += fm.probes_for_field("tank", "storage", int(fm.view("river", "tank")[0, g, 0]))
+            elif name == "QueueGroundwater":
+                store_probes += fm.probes_for_field("sewer", "storage", g)
+            else:
+                continue
+            n_stores += 1
+        if n_stores:
+            self._add("tank_storage", store_probes, (n_stores, fm.V))
+        sewers = [int(fm.node_gidx[i]) for i, t in enumerate(fm.node_type) if L.NODE_TYPES[int(t)] == "Sewer"]
+        if sewers:
+            self.add_field("sewer_storage", "sewer", "storage", objs=sewers)
+            self.add_field("sewer_active", "sewer", "active_storage", objs=sewers)
         return self
 
     def split(self, out_probe):

@@ -344,6 +344,27 @@ WSI_HD void sewer_update_queue(C& c, int w) {  // AltQueueArc.update_queue arcs.
       if (!bit(c.addm(), p)) q0[(size_t)p * s] = 0.0;
   }
 }
+// DecayObj.make_decay (core.py:474-521) of a VQIP entering or waiting in a DecayQueueTank's delay
+// line (DecayArcAlt, arcs.py:731-805): diff = x * min(k * theta^(T - 20), 1) leaves the VQIP and
+// accumulates in the arc's total_decayed.  A store without decays is left alone.
+template <class C>
+WSI_HD void queue_make_decay(C& c, int w, typename C::Vq& v) {
+  const int n = (int)*c.sewer(WSI_SEWER_N_DECAY, w);
+  if (n <= 0) return;
+  const double temperature = c.forcing((int)*c.sewer(WSI_SEWER_FORCING_ID, w), 2);
+  for (int i = 0; i < WSI_MAX_DECAY; i++) {
+    if (i >= n) break;
+    const int pol = (int)*c.sewer(WSI_SEWER_DECAY_POL + i, w);
+    const double f = *c.sewer(WSI_SEWER_DECAY_CONST + i, w) * pow(*c.sewer(WSI_SEWER_DECAY_EXP + i, w), temperature - 20.0);
+    const double x = vget<C::P>(v, pol);
+    const double diff = x * pymin(f, 1.0);
+    vset<C::P>(v, pol, x - diff);
+    // total_decayed = sum_vqip(total_decayed, diff): a zero-volume VQIP, so only additive lanes accumulate
+    double* td = c.sewer(WSI_SEWER_TOTAL_DECAYED + i, w);
+    if (bit(c.addm(), pol)) *td = *td + diff;
+  }
+}
+
 // QueueTank.push_storage(vqip, time) tanks.py:513-539 through AltQueueArc (arcs.py:360-407).
 template <class C>
 WSI_HD typename C::Vq sewer_push_storage(C& c, int w, const typename C::Vq& v0, int time) {
@@ -364,7 +385,9 @@ WSI_HD typename C::Vq sewer_push_storage(C& c, int w, const typename C::Vq& v0, 
     const double excess_in = vol_vchange(ne, pymin(pipe_excess, ne));
     Vq not_pushed = c.vchange(v0, pymax(v0.x[0] - excess_in, 0.0));
     Vq v = c.extract(v0, not_pushed);
+    time += (int)*c.sewer(WSI_SEWER_QUEUE_DELAY, w);  // + internal_arc.number_of_timesteps (arcs.py:385)
     *ia_flow_in = *ia_flow_in + v.x[0] / (double)(time + 1);  // enter_arc arcs.py:423-427
+    queue_make_decay(c, w, v);  // DecayArcAlt.enter_queue arcs.py:750-776: decay on entry
     double* qm = c.sewer(WSI_SEWER_QMASK, w);
     unsigned qmask = (unsigned)*qm;
     double* q = c.sewer(WSI_SEWER_QUEUE(V) + time * V, w);
@@ -416,6 +439,8 @@ WSI_HD double node_push_check_vol(C& c, int node, bool has_v, double v_vol) {
       if (!has_v) return ex;
       return vol_vchange(ex, pymin(ex, v_vol));
     }
+    case WSI_NT_QUEUEGROUNDWATER:  // the stale Tank's get_excess (storage.py:60, 301-315)
+      return tank_excess_vol(*c.sewer(WSI_SEWER_STALE_CAPACITY, g), *c.sewer(WSI_SEWER_STALE_VOLUME, g), has_v, v_vol);
     case WSI_NT_WWTW:  // push_check_sewer wtw.py:319-342 (its "Sewer" and "default" handlers)
       return wwtw_push_check_vol(c, g, has_v, v_vol);
     case WSI_NT_LAND:  // only the ("Demand", "Garden") tag is answered (land.py:93, 120-128): irrigation demand
@@ -460,6 +485,8 @@ WSI_HD typename C::Vq node_push_set(C& c, int node, const typename C::Vq& vqip) 
     case WSI_NT_SEWER:  // push_set_sewer sewer.py:163-176; tagged "Demand": push_set_land sewer.py:178-199
       if (c.tag == 1) return sewer_push_timearea(c, g, vqip);
       return sewer_push_storage(c, g, vqip, (int)*c.sewer(WSI_SEWER_PIPE_TIME, g));
+    case WSI_NT_QUEUEGROUNDWATER:  // push_set_timearea storage.py:329-343
+      return sewer_push_timearea(c, g, vqip);
     case WSI_NT_WWTW:  // push_set_sewer wtw.py:344-374
       return wwtw_push_set(c, g, vqip);
     case WSI_NT_LAND:  // ("Demand", "Garden"): GardenSurface.receive_irrigation_demand land.py:2425-2437
@@ -699,8 +726,10 @@ WSI_HD void chain_push_empty(C& c, const int* arcs, int k0, int n, int X) {
     case WSI_NT_RESERVOIR:
       tank_push_force(c, c.tank(WSI_TANK_STORAGE(V), g), c.s_tank(), none);
       break;
-    case WSI_NT_SEWER: {  // once per push_storage call: one, or one per pipe_timearea entry (push_set_land)
-      const int reps = (c.tag == 1 && n == 1) ? (int)*c.sewer(WSI_SEWER_N_TIMEAREA, g) : 1;
+    case WSI_NT_QUEUEGROUNDWATER:
+    case WSI_NT_SEWER: {  // once per push_storage call: one, or one per time-area entry (push_set_land / _timearea)
+      const int reps = ((c.tag == 1 && n == 1) || d.node_type[X] == WSI_NT_QUEUEGROUNDWATER)
+                           ? (int)*c.sewer(WSI_SEWER_N_TIMEAREA, g) : 1;
       for (int i = 0; i < reps; i++) tank_push_force(c, c.sewer(WSI_SEWER_STORAGE(V), g), c.s_sewer(), none);
       break;
     }

@@ -236,13 +236,26 @@ WSI_HD void sewer_discharge_post(C& c, int node, const typename C::Vq& remaining
   c.stv(st, s, storage);
 }
 
-// QueueTank._end_timestep tanks.py:631-635 + AltQueueArc.end_timestep arcs.py:640-660
+// QueueTank._end_timestep tanks.py:631-635 + AltQueueArc.end_timestep arcs.py:640-660; with decays:
+// DecayQueueTank._end_timestep tanks.py:688-696 + DecayArcAlt._end_timestep arcs.py:778-805
 template <class C>
 WSI_HD void sewer_end_timestep(C& c, int w) {
   using Vq = typename C::Vq;
   constexpr int V = C::V;
   const size_t s = c.s_sewer();
   const int nq = c.D().nq;
+  const int n_decay = (int)*c.sewer(WSI_SEWER_N_DECAY, w);
+  double* stp = c.sewer(WSI_SEWER_STORAGE(V), w);
+  if (n_decay > 0) {  // what decayed in the delay line this step leaves the storage, then the tally restarts
+    Vq st = c.ldv(stp, s);
+    for (int i = 0; i < WSI_MAX_DECAY; i++) {
+      if (i >= n_decay) break;
+      const int pol = (int)*c.sewer(WSI_SEWER_DECAY_POL + i, w);
+      if (bit(c.addm(), pol)) vsub<C::P>(st, pol, *c.sewer(WSI_SEWER_TOTAL_DECAYED + i, w));
+      *c.sewer(WSI_SEWER_TOTAL_DECAYED + i, w) = 0.0;
+    }
+    c.stv(stp, s, st);
+  }
   *c.sewer(WSI_SEWER_IA_FLOW_IN, w) = 0.0;
   unsigned keys = (unsigned)*c.sewer(WSI_SEWER_QMASK, w);
   int max_travel = 1;
@@ -250,26 +263,59 @@ WSI_HD void sewer_end_timestep(C& c, int w) {
     if (keys & (1u << k)) max_travel = k;
   double* q = c.sewer(WSI_SEWER_QUEUE(V), w);
   const Vq q0 = c.ldv(q, s);
-  const Vq q1 = c.ldv(q + (size_t)V * s, s);
+  Vq q1 = c.ldv(q + (size_t)V * s, s);
+  queue_make_decay(c, w, q1);  // i = 0: queue[0] = make_decay(queue_[1])
   // arcs.py:653-658: queue[i] = queue_[i+1]; queue[i+1] = empty, for the keys that exist
   unsigned newkeys = keys | 1u;
   for (int i = 1; i < nq; i++) {
     const bool take = (i < max_travel) && ((keys >> (i + 1)) & 1u);
     if (take) {
-      c.stv(q + (size_t)i * V * s, s, c.ldv(q + (size_t)(i + 1) * V * s, s));
+      Vq moved = c.ldv(q + (size_t)(i + 1) * V * s, s);
+      queue_make_decay(c, w, moved);
+      c.stv(q + (size_t)i * V * s, s, moved);
       newkeys |= 1u << i;
     } else if ((keys >> i) & 1u) {
       c.stv(q + (size_t)i * V * s, s, vq_zero<C::P>());
     }
   }
   *c.sewer(WSI_SEWER_QMASK, w) = (double)newkeys;
-  // queue[0] = sum_vqip(queue_[0], queue_[1]), then update_queue() empties it into active
-  const Vq merged = c.sum(q0, q1);
-  double* act = c.sewer(WSI_SEWER_ACTIVE_STORAGE(V), w);
-  c.stv(act, s, c.sum(c.ldv(act, s), merged));
-  c.stv(q, s, vq_zero<C::P>());
+  if (n_decay > 0) {
+    // queue[0] = sum_vqip(queue[0], make_decay(queue_[0])); it waits there for the next update_queue
+    Vq d0 = q0;
+    queue_make_decay(c, w, d0);
+    c.stv(q, s, c.sum(q1, d0));
+  } else {
+    // queue[0] = sum_vqip(queue_[0], queue_[1]), then update_queue() empties it into active
+    const Vq merged = c.sum(q0, q1);
+    double* act = c.sewer(WSI_SEWER_ACTIVE_STORAGE(V), w);
+    c.stv(act, s, c.sum(c.ldv(act, s), merged));
+    c.stv(q, s, vq_zero<C::P>());
+  }
   // storage_ = copy(storage)
-  c.stv(c.sewer(WSI_SEWER_STORAGE_LAG(V), w), s, c.ldv(c.sewer(WSI_SEWER_STORAGE(V), w), s));
+  c.stv(c.sewer(WSI_SEWER_STORAGE_LAG(V), w), s, c.ldv(stp, s));
+}
+
+// ---- QueueGroundwater.distribute storage.py:345-363 ------------------------------------------
+template <class C>
+WSI_HD void qgw_distribute_pre(C& c, int node, typename C::Vq& v) {
+  const int w = c.D().node_gidx[node];
+  sewer_update_queue(c, w);
+  v = c.ldv(c.sewer(WSI_SEWER_ACTIVE_STORAGE(C::V), w), c.s_sewer());
+}
+template <class C>
+WSI_HD void qgw_distribute_post(C& c, int node, const typename C::Vq& remaining) {
+  using Vq = typename C::Vq;
+  constexpr int V = C::V;
+  const int w = c.D().node_gidx[node];
+  const size_t s = c.s_sewer();
+  double* act = c.sewer(WSI_SEWER_ACTIVE_STORAGE(V), w);
+  double* st = c.sewer(WSI_SEWER_STORAGE(V), w);
+  Vq active = c.ldv(act, s);
+  const Vq sent = c.vchange(active, active.x[0] - remaining.x[0]);
+  // QueueTank.pull_storage tanks.py:541-564
+  const Vq reply = c.vchange(active, pymin(sent.x[0], active.x[0]));
+  c.stv(act, s, c.extract(active, reply));
+  c.stv(st, s, c.extract(c.ldv(st, s), reply));
 }
 
 // ---- Catchment ------------------------------------------------------------------------------
@@ -397,6 +443,7 @@ WSI_HD void node_mass_balance(C& c, int node, typename C::Vq& in_, typename C::V
       case WSI_NT_WASTE:  // waste.py:38
         ds_add(c, out_, tin);
         break;
+      case WSI_NT_QUEUEGROUNDWATER:
       case WSI_NT_SEWER: {
         const Vq st = c.ldv_add(c.sewer(WSI_SEWER_STORAGE(V), g), c.s_sewer());
         const Vq st_ = c.ldv_add(c.sewer(WSI_SEWER_STORAGE_LAG(V), g), c.s_sewer());
@@ -498,6 +545,7 @@ WSI_HD void node_mb_lane(const C& c, int node, double& in_, double& ds, double& 
       case WSI_NT_WASTE:
         out_ += tin;
         break;
+      case WSI_NT_QUEUEGROUNDWATER:
       case WSI_NT_SEWER:
         ds += *c.sewer(WSI_SEWER_STORAGE(V) + LANE, g) - *c.sewer(WSI_SEWER_STORAGE_LAG(V) + LANE, g);
         break;
@@ -670,6 +718,7 @@ WSI_HD void end_node(C& c, int node) {
       end_item(c, 4, g);
       end_item(c, 3, (int)*c.river(WSI_RIVER_TANK, g));
       break;
+    case WSI_NT_QUEUEGROUNDWATER:
     case WSI_NT_SEWER:
       end_item(c, 5, g);
       break;
@@ -797,6 +846,7 @@ WSI_HD void run_op(C& c, int op, int node) {
       case WSI_OP_DEMAND_CREATE: demand_create(c, node); push = false; break;
       case WSI_OP_WWTW_CALC: wwtw_calculate_discharge(c, node); push = false; break;
       case WSI_OP_WWTW_DISCHARGE: wwtw_make_discharge(c, node); push = false; break;
+      case WSI_OP_QGW_DISTRIBUTE: qgw_distribute_pre(c, node, v); filter = WSI_FILTER_ALL; break;
       default: push = false; break;
     }
     WSI_BLOCK_ALIGN(c);
@@ -808,6 +858,7 @@ WSI_HD void run_op(C& c, int op, int node) {
     switch (op) {
       case WSI_OP_LAND_RUN: land_post(c, node, sub, reply, aux); break;
       case WSI_OP_SEWER_DISCHARGE: sewer_discharge_post(c, node, reply); break;
+      case WSI_OP_QGW_DISTRIBUTE: qgw_distribute_post(c, node, reply); break;
       case WSI_OP_CATCHMENT_ROUTE: catchment_route_post(c, node, reply); break;
       case WSI_OP_GW_INFILTRATE:
       case WSI_OP_GW_DISTRIBUTE:

@@ -8,7 +8,7 @@ import warnings
 
 from ..core import constants
 from .nodes import Node
-from .tanks import DecayTank, Tank
+from .tanks import DecayQueueTank, DecayTank, QueueTank, Tank
 
 
 class Storage(Node):
@@ -115,3 +115,24 @@ class River(Storage):
 class Reservoir(Storage):
     def __init__(self, **kwargs):
         super().__init__(**kwargs)
+
+
+class QueueGroundwater(Storage):
+    """Groundwater whose baseflow follows a time-area diagram (reference: storage.py:248-449): pushes
+    enter a QueueTank (a DecayQueueTank when ``decays`` are given) spread over ``timearea``;
+    ``distribute`` releases what has arrived.  Like the reference it files itself under
+    "Groundwater" and keeps answering push checks from the Tank its base class created first."""
+
+    def __init__(self, timearea=None, data_input_dict=None, **kwargs):
+        self.timearea = {0: 1} if timearea is None else timearea
+        super().__init__(**kwargs)
+        self.data_input_dict = {} if data_input_dict is None else data_input_dict
+        self.__class__.__name__ = "Groundwater"
+        self._stale_tank = self.tank
+        args = dict(capacity=self.capacity, area=self.area, datum=self.datum, initial_storage=self.initial_storage)
+        self.tank = QueueTank(**args) if self.decays is None else DecayQueueTank(decays=self.decays, parent=self, **args)
+
+    def apply_overrides(self, overrides=None):
+        overrides = overrides or {}
+        self.timearea = overrides.pop("timearea", self.timearea)
+        super().apply_overrides(overrides)

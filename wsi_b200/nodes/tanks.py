@@ -90,4 +90,26 @@ class QueueTank(Tank):
         self.internal_arc = _InternalQueue(self, self.number_of_timesteps)
 
 
-__all__ = ["Tank", "ResidenceTank", "DecayTank", "QueueTank", "constants"]
+class DecayQueueTank(QueueTank):
+    """QueueTank whose delay line decays what enters it and what waits in it (reference:
+    tanks.py:645-696 with DecayArcAlt, arcs.py:731-805); built-in delay of one timestep."""
+
+    def __init__(self, decays=None, parent=None, number_of_timesteps=1, **kwargs):
+        super().__init__(number_of_timesteps=number_of_timesteps, **kwargs)
+        self.parent = parent
+        self.internal_arc.decays = {} if decays is None else decays
+        self.internal_arc.total_decayed = self.empty_vqip()
+
+    def apply_overrides(self, overrides=None):
+        overrides = overrides or {}
+        self.internal_arc.decays.update(overrides.pop("decays", {}))
+        super().apply_overrides(overrides)
+
+    def reinit(self):
+        decays = self.internal_arc.decays
+        super().reinit()
+        self.internal_arc.decays = decays
+        self.internal_arc.total_decayed = self.empty_vqip()
+
+
+__all__ = ["Tank", "ResidenceTank", "DecayTank", "QueueTank", "DecayQueueTank", "constants"]
