@@ -85,7 +85,8 @@ typedef struct WsiModelDesc {
   const int32_t* land_surf;
   const int32_t* surf_order; /* [n_surf] surface slots sorted by surface class */
   int32_t surf_class_ptr[5]; /* CSR over surf_order: class k = [ptr[k], ptr[k+1]) */
-  int32_t reserved0;
+  int32_t features;          /* bit 0: the model has treatment works, demand, distribution, queue groundwater or
+                                abstractions (pulls); 0 lets the library use the schedule kernel without them */
   const int32_t* end_kind;   /* [n_end] end_timestep items: group id (0 arc, 2 surf, 3 tank, 4 river, 5 sewer) */
   const int32_t* end_obj;    /* [n_end] object slot */
   int32_t n_end;

@@ -13,15 +13,15 @@
 
 using namespace wsi;
 
-template <class CFG>
-static int run_cfg(const WsiModelDesc* d, const CFG& cfg, int64_t t0, int64_t t1) {
+template <bool LEAN, class CFG>
+static int run_cfg_as(const WsiModelDesc* d, const CFG& cfg, int64_t t0, int64_t t1) {
   const int V = d->V;
   double* acc = (double*)calloc((size_t)3 * V, sizeof(double));
   for (int64_t t = t0; t < t1; t++) {
     memset(acc, 0, sizeof(double) * 3 * V);
     int viol = 0;
     for (int r = 0; r < d->R; r++) {
-      Ctx<CFG> c = make_ctx(d, 0, cfg, r, (int)t, WSI_RUN_ALL);
+      Ctx<CFG, false, LEAN> c = make_ctx<false, LEAN>(d, 0, cfg, r, (int)t, WSI_RUN_ALL);
       c.mb_acc = d->mb_sums ? acc : nullptr;
       c.mb_stride = 1;
       replica_step<true>(c, 0, d->n_sched);
@@ -32,6 +32,12 @@ static int run_cfg(const WsiModelDesc* d, const CFG& cfg, int64_t t0, int64_t t1
   }
   free(acc);
   return 0;
+}
+
+// the library's choice (wsi_kernels.cuh launch()): the lean instantiation when desc.features == 0
+template <class CFG>
+static int run_cfg(const WsiModelDesc* d, const CFG& cfg, int64_t t0, int64_t t1) {
+  return d->features == 0 ? run_cfg_as<true>(d, cfg, t0, t1) : run_cfg_as<false>(d, cfg, t0, t1);
 }
 
 template <int P>

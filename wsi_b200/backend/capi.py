@@ -83,7 +83,7 @@ class WsiModelDesc(C.Structure):
         ("land_surf", _i32p),
         ("surf_order", _i32p),
         ("surf_class_ptr", C.c_int32 * 5),
-        ("reserved0", C.c_int32),
+        ("features", C.c_int32),
         ("end_kind", _i32p),
         ("end_obj", _i32p),
         ("n_end", C.c_int32),
@@ -436,6 +436,9 @@ class ModelBuffers:
         d.n_demand = fm.n_obj.get("demand", 0)
         d.n_distrib = fm.n_obj.get("distrib", 0)
         d.sched_split = sched_split(fm)
+        rare = {L.NT[k] for k in ("WWTW", "FWTW", "Demand", "UnlimitedDistribution", "QueueGroundwater")}
+        pulls = any(int(t) == L.NT["Reservoir"] and fm.in_ptr[i + 1] > fm.in_ptr[i] for i, t in enumerate(fm.node_type))
+        d.features = 1 if (pulls or any(int(t) in rare for t in fm.node_type)) else 0
         d.n_sched = int(len(fm.sched_op))
         for i, v in enumerate(self.surf_class_ptr):
             d.surf_class_ptr[i] = v

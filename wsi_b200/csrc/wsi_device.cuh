@@ -66,9 +66,13 @@ struct Obj {
 
 // SMEM: the kernel staged its descriptor in shared memory (wsi_stage_desc) and device functions
 // read it from there; otherwise from the constant-memory slot.
-template <class CFG, bool SMEM = false>
+// LEAN: the schedule kernel's context for models without treatment works, demand, distribution,
+// queue groundwater or abstractions (WsiModelDesc.features == 0) -- their handlers are compiled out,
+// which keeps the hot kernel's code and register pressure where they were before those nodes existed.
+template <class CFG, bool SMEM = false, bool LEAN = false>
 struct Ctx {
   static constexpr bool kInlinePush = SMEM;  // the schedule kernel's context (see push_distributed)
+  static constexpr bool kLean = LEAN;
   static constexpr int P = CFG::P;
   static constexpr int V = P + 1;
   using Vq = VQ<P>;
@@ -385,9 +389,9 @@ WSI_HD typename C::Vq sewer_push_storage(C& c, int w, const typename C::Vq& v0, 
     const double excess_in = vol_vchange(ne, pymin(pipe_excess, ne));
     Vq not_pushed = c.vchange(v0, pymax(v0.x[0] - excess_in, 0.0));
     Vq v = c.extract(v0, not_pushed);
-    time += (int)*c.sewer(WSI_SEWER_QUEUE_DELAY, w);  // + internal_arc.number_of_timesteps (arcs.py:385)
+    if constexpr (!C::kLean) time += (int)*c.sewer(WSI_SEWER_QUEUE_DELAY, w);  // + number_of_timesteps (arcs.py:385)
     *ia_flow_in = *ia_flow_in + v.x[0] / (double)(time + 1);  // enter_arc arcs.py:423-427
-    queue_make_decay(c, w, v);  // DecayArcAlt.enter_queue arcs.py:750-776: decay on entry
+    if constexpr (!C::kLean) queue_make_decay(c, w, v);  // DecayArcAlt.enter_queue arcs.py:750-776: decay on entry
     double* qm = c.sewer(WSI_SEWER_QMASK, w);
     unsigned qmask = (unsigned)*qm;
     double* q = c.sewer(WSI_SEWER_QUEUE(V) + time * V, w);
@@ -440,17 +444,21 @@ WSI_HD double node_push_check_vol(C& c, int node, bool has_v, double v_vol) {
       return vol_vchange(ex, pymin(ex, v_vol));
     }
     case WSI_NT_QUEUEGROUNDWATER:  // the stale Tank's get_excess (storage.py:60, 301-315)
-      return tank_excess_vol(*c.sewer(WSI_SEWER_STALE_CAPACITY, g), *c.sewer(WSI_SEWER_STALE_VOLUME, g), has_v, v_vol);
+      if constexpr (!C::kLean)
+        return tank_excess_vol(*c.sewer(WSI_SEWER_STALE_CAPACITY, g), *c.sewer(WSI_SEWER_STALE_VOLUME, g), has_v, v_vol);
+      break;
     case WSI_NT_WWTW:  // push_check_sewer wtw.py:319-342 (its "Sewer" and "default" handlers)
-      return wwtw_push_check_vol(c, g, has_v, v_vol);
+      if constexpr (!C::kLean) return wwtw_push_check_vol(c, g, has_v, v_vol);
+      break;
     case WSI_NT_LAND:  // only the ("Demand", "Garden") tag is answered (land.py:93, 120-128): irrigation demand
-      if (c.tag == 2) return garden_irrigation_demand(c, g);
-      c.flag(node, WSI_FLAG_DENY);
-      return 0.0;
+      if constexpr (!C::kLean)
+        if (c.tag == 2) return garden_irrigation_demand(c, g);
+      break;
     default:  // Land / Catchment / FWTW / Demand deny pushes (nodes.py:595-609)
-      c.flag(node, WSI_FLAG_DENY);
-      return 0.0;
+      break;
   }
+  c.flag(node, WSI_FLAG_DENY);
+  return 0.0;
 }
 
 template <int D, class C>
@@ -483,23 +491,27 @@ WSI_HD typename C::Vq node_push_set(C& c, int node, const typename C::Vq& vqip) 
       return tank_push(c, c.tank(WSI_TANK_STORAGE(V), g), c.s_tank(), *c.tank(WSI_TANK_CAPACITY, g),
                        vqip);
     case WSI_NT_SEWER:  // push_set_sewer sewer.py:163-176; tagged "Demand": push_set_land sewer.py:178-199
-      if (c.tag == 1) return sewer_push_timearea(c, g, vqip);
+      if constexpr (!C::kLean)
+        if (c.tag == 1) return sewer_push_timearea(c, g, vqip);
       return sewer_push_storage(c, g, vqip, (int)*c.sewer(WSI_SEWER_PIPE_TIME, g));
     case WSI_NT_QUEUEGROUNDWATER:  // push_set_timearea storage.py:329-343
-      return sewer_push_timearea(c, g, vqip);
+      if constexpr (!C::kLean) return sewer_push_timearea(c, g, vqip);
+      break;
     case WSI_NT_WWTW:  // push_set_sewer wtw.py:344-374
-      return wwtw_push_set(c, g, vqip);
+      if constexpr (!C::kLean) return wwtw_push_set(c, g, vqip);
+      break;
     case WSI_NT_LAND:  // ("Demand", "Garden"): GardenSurface.receive_irrigation_demand land.py:2425-2437
-      if (c.tag == 2) {
-        garden_receive_irrigation(c, g, vqip);
-        return vq_zero<C::P>();
-      }
-      c.flag(node, WSI_FLAG_DENY);
-      return vqip;
+      if constexpr (!C::kLean)
+        if (c.tag == 2) {
+          garden_receive_irrigation(c, g, vqip);
+          return vq_zero<C::P>();
+        }
+      break;
     default:
-      c.flag(node, WSI_FLAG_DENY);
-      return vqip;
+      break;
   }
+  c.flag(node, WSI_FLAG_DENY);
+  return vqip;
 }
 
 // Arc.get_excess(direction="push")["volume"] arcs.py:230-257
@@ -728,13 +740,14 @@ WSI_HD void chain_push_empty(C& c, const int* arcs, int k0, int n, int X) {
       break;
     case WSI_NT_QUEUEGROUNDWATER:
     case WSI_NT_SEWER: {  // once per push_storage call: one, or one per time-area entry (push_set_land / _timearea)
-      const int reps = ((c.tag == 1 && n == 1) || d.node_type[X] == WSI_NT_QUEUEGROUNDWATER)
-                           ? (int)*c.sewer(WSI_SEWER_N_TIMEAREA, g) : 1;
+      int reps = 1;
+      if constexpr (!C::kLean)
+        if ((c.tag == 1 && n == 1) || d.node_type[X] == WSI_NT_QUEUEGROUNDWATER) reps = (int)*c.sewer(WSI_SEWER_N_TIMEAREA, g);
       for (int i = 0; i < reps; i++) tank_push_force(c, c.sewer(WSI_SEWER_STORAGE(V), g), c.s_sewer(), none);
       break;
     }
     case WSI_NT_WWTW:  // current_input = sum_vqip(current_input, empty) wtw.py:359
-      tank_push_force(c, c.works(WSI_WORKS_CURRENT_INPUT(V), g), c.s_works(), none);
+      if constexpr (!C::kLean) tank_push_force(c, c.works(WSI_WORKS_CURRENT_INPUT(V), g), c.s_works(), none);
       break;
     case WSI_NT_WASTE:
       break;

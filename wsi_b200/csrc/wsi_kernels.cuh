@@ -144,7 +144,7 @@ struct MbBlockSink {
 // the replica's mass balances (lane by lane, wsi_nodes.cuh), recording and end_timestep: the
 // thread reads back what it has just written (L1 / L2) instead of three more kernels re-streaming
 // the state from HBM.  Routing is sequential inside a replica by construction.
-template <class CFG>
+template <class CFG, bool LEAN>
 __global__ void __launch_bounds__(kBlock, WSI_STEP_MINB)
     wsi_step_kernel(const int slot, const CFG cfg, const int t_arg, const int sched_begin, const int sched_end,
                     const uint32_t flags, const int row_arg, const int fused) {
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kBlock, WSI_STEP_MINB)
   const int t = step_of(d, t_arg);
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = r < d.R;
-  Ctx<CFG, true> c = make_ctx<true>(nullptr, slot, cfg, active ? r : 0, t, flags);
+  Ctx<CFG, true, LEAN> c = make_ctx<true, LEAN>(nullptr, slot, cfg, active ? r : 0, t, flags);
   c.block_sync = (blockIdx.x + 1) * blockDim.x <= (unsigned)d.R;  // full block: all threads walk the schedule
   if (flags & WSI_RUN_SCHEDULE) {
     for (int k = sched_begin; k < sched_end; k++) {
@@ -660,7 +660,7 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
   const bool want_sums = want_mb && d->mb_sums != nullptr;
   // schedule entries that reach into the surfaces before Land.run (garden irrigation) run first
   if (d->engine == 0 && (flags & WSI_RUN_SCHEDULE) && (flags & WSI_RUN_SURFACES) && d->sched_split > b && d->sched_split < e) {
-    wsi_step_kernel<CFG><<<n_blocks(d), kBlock, kDescSmem, s>>>(slot, cfg, (int)t, b, d->sched_split, WSI_RUN_SCHEDULE, 0, 0);
+    wsi_step_kernel<CFG, false><<<n_blocks(d), kBlock, kDescSmem, s>>>(slot, cfg, (int)t, b, d->sched_split, WSI_RUN_SCHEDULE, 0, 0);
     WSI_CHECK_LAUNCH("wsi_step_kernel");
     b = d->sched_split;
   }
@@ -755,8 +755,19 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
       // the tail's dependent loads only when it runs one thread per (object, replica): measured on
       // config 2 at R = 1e5, fused 0.228 ms vs 0.13 ms for the three object-parallel kernels.
       const bool fused = d->R <= kFusedTailMaxR;
-      wsi_step_kernel<CFG><<<n_blocks(d), kBlock, kDescSmem, s>>>(slot, cfg, (int)t, b, e, flags, (int)t - d->rec_t0,
-                                                                    fused ? 1 : 0);
+      // the lean instantiation for models without treatment works / demand / distribution / queue groundwater /
+      // abstractions (desc.features == 0): those handlers are compiled out of the hot kernel
+      bool lean = false;
+      if constexpr (CFG::kLeanKernel) {
+        if (d->features == 0) {
+          lean = true;
+          wsi_step_kernel<CFG, true><<<n_blocks(d), kBlock, kDescSmem, s>>>(slot, cfg, (int)t, b, e, flags,
+                                                                              (int)t - d->rec_t0, fused ? 1 : 0);
+        }
+      }
+      if (!lean)
+        wsi_step_kernel<CFG, false><<<n_blocks(d), kBlock, kDescSmem, s>>>(slot, cfg, (int)t, b, e, flags,
+                                                                             (int)t - d->rec_t0, fused ? 1 : 0);
       WSI_CHECK_LAUNCH("wsi_step_kernel");
       int rows = n_blocks(d);
       if (!fused && (flags & (WSI_RUN_MASS_BALANCE | WSI_RUN_END_TIMESTEP)) && d->n_nodes > 0) {

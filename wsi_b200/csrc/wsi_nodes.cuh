@@ -814,6 +814,16 @@ template <class C>
 WSI_HDN void reservoir_abstract_call(C c, int node) {
   reservoir_abstract(c, node);
 }
+// Reservoir.make_abstractions without in-arcs: pull_distributed returns an empty VQIP (nodes.py:376-407),
+// which is then pushed (twice) into the tank (storage.py:983-989)
+template <class C>
+WSI_HDN void reservoir_settle_call(C c, int node) {
+  constexpr int V = C::V;
+  const int g = c.D().node_gidx[node];
+  double* st = c.tank(WSI_TANK_STORAGE(V), g);
+  const typename C::Vq spill = tank_push(c, st, c.s_tank(), *c.tank(WSI_TANK_CAPACITY, g), vq_zero<C::P>());
+  tank_push_force(c, st, c.s_tank(), spill);
+}
 
 // ---- one schedule entry -----------------------------------------------------------------------
 // An entry runs as one or more sub-steps (Land.run: one per surface, then its tanks); each sub-step
@@ -837,16 +847,39 @@ WSI_HD void run_op(C& c, int op, int node) {
       case WSI_OP_SEWER_DISCHARGE: sewer_discharge_pre(c, node, v); filter = WSI_FILTER_ALL; break;
       case WSI_OP_GW_DISTRIBUTE: gw_distribute_pre(c, node, v); filter = WSI_FILTER_NRW; break;
       case WSI_OP_RIVER_CALC: river_calc_call(c, node); push = false; break;
-      case WSI_OP_RESERVOIR_ABSTRACT: reservoir_abstract_call(c, node); push = false; break;
+      case WSI_OP_RESERVOIR_ABSTRACT:
+        if constexpr (C::kLean) reservoir_settle_call(c, node);  // no in-arcs: nothing to pull
+        else reservoir_abstract_call(c, node);
+        push = false;
+        break;
       case WSI_OP_CATCHMENT_ROUTE: catchment_route_pre(c, node, v); filter = WSI_FILTER_NRW; break;
       case WSI_OP_RIVER_DISTRIBUTE: river_distribute_pre(c, node, v); filter = WSI_FILTER_NRW; break;
       case WSI_OP_STORAGE_DISTRIBUTE: storage_distribute_pre(c, node, v); filter = WSI_FILTER_ALL; break;
       case WSI_OP_BOUNDARY_RELEASE: boundary_release(c, node, true); push = false; break;
-      case WSI_OP_FWTW_TREAT: fwtw_treat_water(c, node); push = false; break;
-      case WSI_OP_DEMAND_CREATE: demand_create(c, node); push = false; break;
-      case WSI_OP_WWTW_CALC: wwtw_calculate_discharge(c, node); push = false; break;
-      case WSI_OP_WWTW_DISCHARGE: wwtw_make_discharge(c, node); push = false; break;
-      case WSI_OP_QGW_DISTRIBUTE: qgw_distribute_pre(c, node, v); filter = WSI_FILTER_ALL; break;
+      case WSI_OP_FWTW_TREAT:
+        if constexpr (!C::kLean) fwtw_treat_water(c, node);
+        push = false;
+        break;
+      case WSI_OP_DEMAND_CREATE:
+        if constexpr (!C::kLean) demand_create(c, node);
+        push = false;
+        break;
+      case WSI_OP_WWTW_CALC:
+        if constexpr (!C::kLean) wwtw_calculate_discharge(c, node);
+        push = false;
+        break;
+      case WSI_OP_WWTW_DISCHARGE:
+        if constexpr (!C::kLean) wwtw_make_discharge(c, node);
+        push = false;
+        break;
+      case WSI_OP_QGW_DISTRIBUTE:
+        if constexpr (!C::kLean) {
+          qgw_distribute_pre(c, node, v);
+          filter = WSI_FILTER_ALL;
+        } else {
+          push = false;
+        }
+        break;
       default: push = false; break;
     }
     WSI_BLOCK_ALIGN(c);
@@ -858,7 +891,9 @@ WSI_HD void run_op(C& c, int op, int node) {
     switch (op) {
       case WSI_OP_LAND_RUN: land_post(c, node, sub, reply, aux); break;
       case WSI_OP_SEWER_DISCHARGE: sewer_discharge_post(c, node, reply); break;
-      case WSI_OP_QGW_DISTRIBUTE: qgw_distribute_post(c, node, reply); break;
+      case WSI_OP_QGW_DISTRIBUTE:
+        if constexpr (!C::kLean) qgw_distribute_post(c, node, reply);
+        break;
       case WSI_OP_CATCHMENT_ROUTE: catchment_route_post(c, node, reply); break;
       case WSI_OP_GW_INFILTRATE:
       case WSI_OP_GW_DISTRIBUTE:
@@ -922,9 +957,9 @@ WSI_HD void replica_step(C& c, int sched_begin, int sched_end) {
   if (c.run_flags & WSI_RUN_END_TIMESTEP) end_timestep(c);
 }
 
-template <bool SMEM = false, class CFG>
-WSI_HD Ctx<CFG, SMEM> make_ctx(const WsiModelDesc* host_d, int slot, const CFG& cfg, int r, int t, uint32_t flags) {
-  Ctx<CFG, SMEM> c;
+template <bool SMEM = false, bool LEAN = false, class CFG>
+WSI_HD Ctx<CFG, SMEM, LEAN> make_ctx(const WsiModelDesc* host_d, int slot, const CFG& cfg, int r, int t, uint32_t flags) {
+  Ctx<CFG, SMEM, LEAN> c;
   c.host_d = host_d;
   c.slot = slot;
   c.cfg = cfg;

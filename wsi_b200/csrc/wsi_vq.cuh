@@ -34,6 +34,7 @@ struct VQ {
 struct CfgDefault12 {
   static constexpr int P = 12;
   static constexpr bool kStatic = true;
+  static constexpr bool kLeanKernel = true;  // also build the schedule kernel without the rare node classes
   WSI_HD uint32_t add_mask() const { return 0x1CFCu; }  // planes 2-7 and 10-12, see below
   WSI_HD int no3() const { return 10; }
   WSI_HD int no2() const { return 11; }
@@ -54,6 +55,7 @@ template <int P_>
 struct CfgRuntime {
   static constexpr int P = P_;
   static constexpr bool kStatic = false;
+  static constexpr bool kLeanKernel = false;
   uint32_t mask;
   int i_no3, i_no2, i_nh4, i_po4, i_orgp, i_orgn, i_solids, i_temp;
   WSI_HD uint32_t add_mask() const { return mask; }
@@ -72,6 +74,7 @@ struct CfgRuntime {
 // set (12 pollutants, temperature the only non-additive one: mask 0x1FFC minus its bit).
 template <int P_, uint32_t MASK>
 struct CfgStaticMask : CfgRuntime<P_> {
+  static constexpr bool kLeanKernel = true;
   WSI_HD uint32_t add_mask() const { return MASK; }
 };
 
