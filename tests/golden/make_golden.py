@@ -151,8 +151,23 @@ def merge_replicas(fms):
     return F.FlatModel(**kw)
 
 
+def pad_ref(ref, V_ref, V):
+    """The flat model pads its pollutant set up to a compiled width (flatten.py): the reference's
+    outputs get the same -- all-zero -- planes, so a comparison also checks that they stay zero."""
+    if V == V_ref:
+        return ref
+    out = dict(ref)
+    grow = lambda a: np.concatenate([a, np.zeros(a.shape[:-1] + (V - V_ref,))], axis=-1)  # noqa: E731
+    for k in ("flows", "mb", "surf_storage", "tank_storage", "sewer_storage", "sewer_active"):
+        out[k] = grow(ref[k])
+    lt = ref["land_tanks"]
+    out["land_tanks"] = grow(lt.reshape(lt.shape[:-1] + (3, V_ref))).reshape(lt.shape[:-1] + (3 * V,))
+    return out
+
+
 def save(name, fm, ref, note):
     d = fm.to_npz_dict()
+    ref = pad_ref(ref, ref["flows"].shape[-1], fm.V)
     for k, v in ref.items():
         d["ref_" + k] = v
     d["meta_note"] = np.array(note)
@@ -214,6 +229,37 @@ def scenario_quickstart_simple(T=300):
     fm = flatten_ref(m, dates)
     ref = run_reference(m, dates)
     save("quickstart_simple", fm, ref, "quickstart model with set_simple_pollutants (P=2)")
+    set_default_pollutants()
+
+
+def scenario_quickstart_p5(T=400):
+    """Five pollutants (three additive, two not): a count the library has no kernels for, so the
+    flat model is padded to twelve (flatten.py) -- the reference runs the five."""
+    constants.POLLUTANTS = ["phosphate", "solids", "bod", "temperature", "ph"]
+    constants.NON_ADDITIVE_POLLUTANTS = ["temperature", "ph"]
+    constants.ADDITIVE_POLLUTANTS = ["phosphate", "solids", "bod"]
+    constants.FLOAT_ACCURACY = 1e-11
+    land_inputs, dates = oxford_land_inputs()
+    dates = dates[100 : 100 + T]
+    m = build_quickstart(land_inputs, load_pol="solids")
+    fm = flatten_ref(m, dates)
+    ref = run_reference(m, dates)
+    save("quickstart_p5", fm, ref, "quickstart model with 5 pollutants (padded to 12 in the flat model)")
+    set_default_pollutants()
+
+
+def scenario_quickstart_p14(T=300):
+    """The default twelve pollutants plus two more additive ones: padded to fifteen in the flat model."""
+    constants.set_default_pollutants()
+    constants.POLLUTANTS = list(constants.POLLUTANTS) + ["chloride", "zinc"]
+    constants.ADDITIVE_POLLUTANTS = list(constants.ADDITIVE_POLLUTANTS) + ["chloride", "zinc"]
+    constants.FLOAT_ACCURACY = 1e-11
+    land_inputs, dates = oxford_land_inputs()
+    dates = dates[300 : 300 + T]
+    m = build_quickstart(land_inputs, load_pol="zinc")
+    fm = flatten_ref(m, dates)
+    ref = run_reference(m, dates)
+    save("quickstart_p14", fm, ref, "quickstart model with 14 pollutants (padded to 15 in the flat model)")
     set_default_pollutants()
 
 
@@ -806,6 +852,8 @@ def scenario_oxford():
 SCENARIOS = {
     "quickstart": scenario_quickstart,
     "quickstart_simple": scenario_quickstart_simple,
+    "quickstart_p5": scenario_quickstart_p5,
+    "quickstart_p14": scenario_quickstart_p14,
     "fixture3607": scenario_fixture3607,
     "config2": scenario_config2,
     "rivernet": scenario_rivernet,

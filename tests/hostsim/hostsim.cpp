@@ -62,5 +62,6 @@ extern "C" int wsi_hostsim_run(const WsiModelDesc* d, int64_t t0, int64_t t1, in
   if (is_default && !force_runtime_cfg) return run_cfg(d, CfgDefault12(), t0, t1);
   if (d->P == 12) return run_cfg(d, runtime_cfg<12>(d), t0, t1);
   if (d->P == 2) return run_cfg(d, runtime_cfg<2>(d), t0, t1);
+  if (d->P == 15) return run_cfg(d, runtime_cfg<15>(d), t0, t1);
   return WSI_ERR_UNSUPPORTED;
 }

@@ -7,7 +7,7 @@ from parity_util import compare_blocks, compare_mb, load_golden
 
 pytestmark = pytest.mark.gpu
 
-GOLDENS = ["quickstart", "quickstart_simple", "fixture3607", "config2", "rivernet", "rivertree", "config3", "hourly",
+GOLDENS = ["quickstart", "quickstart_simple", "quickstart_p5", "quickstart_p14", "fixture3607", "config2", "rivernet", "rivertree", "config3", "hourly",
            "oxford", "fixture3607_full", "city", "queuegw"]
 
 

@@ -261,3 +261,50 @@ def test_pickle_round_trip_and_result_files(tmp_path):
     got = pd.read_csv(tmp_path / "out" / "flows.csv", index_col=0)
     assert got.loc[0, "arc"] == "runoff" and got.loc[0, "flow"] == 0.05
     assert (tmp_path / "out" / "tanks.csv").exists() and (tmp_path / "out" / "surfaces.csv").exists()
+
+
+def test_pollutant_sets_without_kernels_are_padded_with_zero_additive_planes():
+    """libwsi_b200.so has kernels for 2, 12 and 15 pollutants (layout.COMPILED_P); flatten pads any other
+    count with additive pollutants that are zero everywhere, and neither results nor the objects'
+    scattered-back state ever show them (goldens quickstart_p5 / quickstart_p14 pin the numbers)."""
+    from oracle import oracle
+    from wsi_b200.backend import flatten as F
+    from wsi_b200.backend import layout as L
+    from wsi_b200.backend.probes import ProbeSet
+    from wsi_b200.core import constants
+    from wsi_b200.orchestration.model import _RecordPlan
+
+    m, _ = _quickstart_model(T=20)
+    try:
+        constants.POLLUTANTS = ["phosphate", "solids", "bod", "temperature", "ph"]
+        constants.NON_ADDITIVE_POLLUTANTS = ["temperature", "ph"]
+        constants.ADDITIVE_POLLUTANTS = ["phosphate", "solids", "bod"]
+        m2, _ = None, None
+        from wsi_b200.orchestration.model import Model
+
+        m2 = Model()
+        m2.add_nodes([
+            {"type_": "Land", "data_input_dict": m.nodes["my_land"].data_input_dict, "name": "my_land", "surfaces": [
+                {"type_": "ImperviousSurface", "surface": "urban", "area": 10, "pollutant_load": {"solids": 1e-7}}]},
+            {"type_": "Sewer", "capacity": 0.04, "name": "my_sewer"},
+            {"type_": "Waste", "name": "my_outlet"}])
+        m2.add_arcs([{"type_": "Arc", "name": "drain", "in_port": "my_land", "out_port": "my_sewer"},
+                     {"type_": "Arc", "name": "out", "in_port": "my_sewer", "out_port": "my_outlet"}])
+        m2.dates = m.dates
+        fm = m2.flatten()
+        assert fm.P == 12 and fm.P in L.COMPILED_P
+        assert F.model_pollutants(fm) == constants.POLLUTANTS
+        assert set(fm.pollutants[5:]) <= set(fm.additive) and all(p.startswith(F.PAD_PREFIX) for p in fm.pollutants[5:])
+        ps = ProbeSet(fm)
+        ps.add_flows(list(m2.arcs))
+        run = oracle.run(fm, probes=ps.probes)
+        flows, _, _ = _RecordPlan(m2, fm, ps, [], [], False).records(ps.split(run.out_probe), m2.dates)
+        assert set(flows[0]) == {"arc", "flow", "time", *constants.POLLUTANTS}
+        assert not run.out_probe[:, :, 0].reshape(20, -1, fm.V)[:, :, 6:].any()  # padding planes stay zero
+        F.scatter_back(m2, fm, run.groups, m2.dates[-1])
+        assert set(m2.nodes["my_sewer"].sewer_tank.storage) == {"volume", *constants.POLLUTANTS}
+        with pytest.raises(F.UnsupportedModelError):
+            F.flatten(m2, m2.dates, [f"p{i}" for i in range(16)], [f"p{i}" for i in range(16)], [], 1e-11)
+    finally:
+        constants.set_default_pollutants()
+        constants.FLOAT_ACCURACY = 1e-11

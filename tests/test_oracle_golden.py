@@ -6,7 +6,7 @@ import pytest
 
 from parity_util import compare_blocks, compare_mb, load_golden
 
-GOLDENS = ["quickstart", "quickstart_simple", "fixture3607", "config2", "rivernet", "rivertree", "config3", "hourly"]
+GOLDENS = ["quickstart", "quickstart_simple", "quickstart_p5", "quickstart_p14", "fixture3607", "config2", "rivernet", "rivertree", "config3", "hourly"]
 
 
 @pytest.mark.parametrize("name", GOLDENS)

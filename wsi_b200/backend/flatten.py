@@ -335,6 +335,14 @@ def _series_from_dict(did, dates, variables, required=True):
     return out
 
 
+PAD_PREFIX = "_pad"  # padding pollutants (see flatten): never shown to the caller
+
+
+def model_pollutants(fm):
+    """The model's own pollutants: fm.pollutants without the padding ones."""
+    return [p for p in fm.pollutants if not p.startswith(PAD_PREFIX)]
+
+
 # --------------------------------------------------------------------- flatten
 def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
     """Flatten ``model`` for the timesteps ``dates`` (the objects used as
@@ -348,6 +356,17 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
         raise UnsupportedModelError(f"{P} pollutants > {L.MAXP}")
     if set(additive) | set(non_additive) != set(pollutants) or set(additive) & set(non_additive):
         raise UnsupportedModelError("POLLUTANTS must be the disjoint union of additive and non-additive")
+    # The library is compiled for L.COMPILED_P pollutant counts.  Any other count runs on the next
+    # compiled one with additive padding pollutants that are zero everywhere: a zero additive plane
+    # stays zero through every VQIP operation (core.py:90-200) and no operation on another plane
+    # reads it, so the model's own planes are bit-identical to an exact-width run.
+    target = next((c for c in L.COMPILED_P if c >= P), None)
+    if target is None:
+        raise UnsupportedModelError(f"{P} pollutants > {max(L.COMPILED_P)}")
+    pads = [f"{PAD_PREFIX}{i}" for i in range(target - P)]
+    model_pollutants = list(pollutants)
+    pollutants, additive = pollutants + pads, additive + pads
+    P, V = len(pollutants), len(pollutants) + 1
     has_nitrate = "nitrate" in pollutants
     if has_nitrate:
         # River.biochemical_processes (storage.py:727) and the GrowingSurface nutrient processes read
@@ -593,14 +612,14 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
             node_gidx[i] = len(gb["catchm"].cols)
             col = gb["catchm"].new()
             col[0] = len(catch_series)
-            catch_series.append(_series_from_dict(n.data_input_dict, dates, ["flow"] + pollutants))
+            catch_series.append(_series_from_dict(n.data_input_dict, dates, ["flow"] + model_pollutants + [None] * len(pads)))
         elif c in ("WWTW", "FWTW"):
             node_gidx[i] = len(gb["works"].cols)
             _flatten_works(gb["works"], n, add_store, pollutants, additive, non_additive)
         elif c == "Demand":
             if not hasattr(n, "population"):
                 raise UnsupportedModelError(f"{n.name}: only ResidentialDemand is on the GPU path (demand.py:153)")
-            missing = [p for p in pollutants if p not in n.pollutant_load]
+            missing = [p for p in model_pollutants if p not in n.pollutant_load]
             if missing:  # the reference raises KeyError in get_house_demand (demand.py:303-324)
                 raise UnsupportedModelError(f"{n.name}: pollutant_load lacks {missing}")
             node_gidx[i] = len(gb["demand"].cols)
@@ -609,7 +628,7 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
             for f in ("population", "per_capita", "gardening_efficiency", "constant_weighting", "constant_temp"):
                 b.set(col, f, getattr(n, f))
             b.set(col, "forcing_id", forcing_series(n.data_input_dict, (None, None, "temperature")))
-            b.set(col, "pollutant_load", [0.0] + [float(n.pollutant_load[p]) for p in pollutants])
+            b.set(col, "pollutant_load", [0.0] + [float(n.pollutant_load.get(p, 0.0)) for p in pollutants])
             for f in ("total_demand", "total_backup", "total_received"):
                 b.set(col, f, _vq(getattr(n, f), pollutants))
         elif c == "UnlimitedDistribution":
@@ -895,7 +914,7 @@ def scatter_back(model, fm, groups, last_date=None):
     ``node.tank.storage[...]`` inspection and pickling keep working."""
     if fm.R != 1:
         raise ValueError("scatter_back needs an R == 1 model")
-    pol = fm.pollutants
+    pol = model_pollutants(fm)  # the padding pollutants never reach the objects (they lead nowhere: all zero)
     V = fm.V
 
     def vq_dict(group, name, obj, k=0):

@@ -24,6 +24,7 @@ MAX_STAGE = 16  # crop_factor_stages table length (fixture uses 9)
 LAG_T = 21  # River.max_temp_lag + 1 (storage.py:560,753)
 LAG_TP = 366  # River.max_phosphorus_lag + 1 (storage.py:563,758)
 MAXP = 16  # compile-time bound on pollutants
+COMPILED_P = (2, 12, 15)  # pollutant counts libwsi_b200.so has kernels for (csrc/wsi_cfg_*.cu); others are padded up
 MAX_TIMEAREA = 8  # entries of a Sewer's pipe_timearea
 MAX_CAND = 8  # candidate out-arcs one push_distributed call may split over (kMaxCand in csrc/wsi_device.cuh)
 

@@ -10,7 +10,8 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 SO = os.path.join(CSRC, "libwsi_b200.so")
 # one translation unit per pollutant configuration (compiled in parallel) + the host API
-SOURCES = ["wsi_api.cu", "wsi_cfg_default12.cu", "wsi_cfg_oxford12.cu", "wsi_cfg_runtime12.cu", "wsi_cfg_runtime2.cu"]
+SOURCES = ["wsi_api.cu", "wsi_cfg_default12.cu", "wsi_cfg_oxford12.cu", "wsi_cfg_runtime12.cu", "wsi_cfg_runtime2.cu",
+           "wsi_cfg_runtime15.cu"]
 HEADERS = [
     os.path.join(CSRC, "wsi_vq.cuh"),
     os.path.join(CSRC, "wsi_device.cuh"),

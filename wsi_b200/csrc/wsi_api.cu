@@ -61,6 +61,7 @@ const ConfigUnit* unit_of(const WsiModelDesc* d) {
   if (d->P == 12 && d->additive_mask == kOxfordMask) return &wsi_unit_oxford12;
   if (d->P == 12) return &wsi_unit_runtime12;
   if (d->P == 2) return &wsi_unit_runtime2;
+  if (d->P == 15) return &wsi_unit_runtime15;
 #endif
   return nullptr;
 }
@@ -257,8 +258,8 @@ int wsi_validate(const WsiModelDesc* d) {
   if (d->mb_sums && !d->mb_partial) return fail(WSI_ERR_BAD_DESC, "mb_sums without mb_partial%s");
   if (d->n_nodes > 0 && (!d->mb_terms || !d->mb_term_slot)) return fail(WSI_ERR_BAD_DESC, "mb_terms missing%s");
   if (!d->node_flags) return fail(WSI_ERR_BAD_DESC, "node_flags missing%s");
-  if (!(is_default12(d) || d->P == 12 || d->P == 2))
-    return fail(WSI_ERR_UNSUPPORTED, "kernels are instantiated for P in {2, 12}%s");
+  if (!unit_of(d))  // other counts: the caller pads with zero additive pollutants (wsi_b200/backend/flatten.py)
+    return fail(WSI_ERR_UNSUPPORTED, "kernels are instantiated for P in {2, 12, 15}%s");
   return WSI_OK;
 }
 

@@ -49,7 +49,7 @@ struct ConfigUnit {
   void (*set_step)(int slot, int t, cudaStream_t s);                        // device-side step counter
   void (*advance)(int slot, cudaStream_t s);
 };
-extern const ConfigUnit wsi_unit_default12, wsi_unit_oxford12, wsi_unit_runtime12, wsi_unit_runtime2;
+extern const ConfigUnit wsi_unit_default12, wsi_unit_oxford12, wsi_unit_runtime12, wsi_unit_runtime2, wsi_unit_runtime15;
 
 constexpr uint32_t kOxfordMask = 0x1FFCu;  // 12 pollutants, every one additive but plane 1 (temperature)
 

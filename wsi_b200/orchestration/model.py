@@ -425,7 +425,7 @@ class _RecordPlan:
 
     def __init__(self, model, fm, ps, record_tanks, record_surfaces, record_all):
         self.model, self.fm, self.ps = model, fm, ps
-        self.pol = list(fm.pollutants)
+        self.pol = F.model_pollutants(fm)  # results never carry the padding pollutants
         V = fm.V
         self.tank_items = []  # (kind, node name, prop or None, block name, index)
         self.surf_items = []
