@@ -42,6 +42,10 @@ extern "C" {
 #define WSI_FLAG_DENY 32u          /* push to / pull from a node whose handler denies (nodes.py:563-609) */
 #define WSI_FLAG_DEFICIT 64u       /* "Service reservoirs not filled" / "demand deficit" (wtw.py:583, demand.py:91) */
 
+/* arc_flags bits */
+#define WSI_ARC_DENY_PUSH 1 /* PullArc: pushes and push checks answer "nothing" (arcs.py:808-850) */
+#define WSI_ARC_DENY_PULL 2 /* PushArc: pulls and pull checks answer "nothing" (arcs.py:852-893) */
+
 /* run flags for wsi_sched_range */
 #define WSI_RUN_SCHEDULE 1u      /* execute schedule entries [begin, end) */
 #define WSI_RUN_MASS_BALANCE 2u  /* per-node mass balance (core.py:370) */
@@ -85,8 +89,9 @@ typedef struct WsiModelDesc {
   const int32_t* land_surf;
   const int32_t* surf_order; /* [n_surf] surface slots sorted by surface class */
   int32_t surf_class_ptr[5]; /* CSR over surf_order: class k = [ptr[k], ptr[k+1]) */
-  int32_t features;          /* bit 0: the model has treatment works, demand, distribution, queue groundwater or
-                                abstractions (pulls); 0 lets the library use the schedule kernel without them */
+  int32_t features;          /* bit 0: the model has treatment works, demand, distribution, queue groundwater, river
+                                reservoirs, irrigation or abstractions (pulls); 0 lets the library use the schedule
+                                kernel without them.  bit 1: IrrigationSurface / VariableAreaSurface planes are in use */
   const int32_t* end_kind;   /* [n_end] end_timestep items: group id (0 arc, 2 surf, 3 tank, 4 river, 5 sewer) */
   const int32_t* end_obj;    /* [n_end] object slot */
   int32_t n_end;
@@ -183,6 +188,8 @@ typedef struct WsiModelDesc {
   int32_t sched_split; /* > 0: schedule entries [0, sched_split) run BEFORE the surfaces of the timestep (they reach into
                           a Land's surfaces: garden irrigation by a Demand node, demand.py:250 / land.py:2402);
                           0: surfaces first, then the whole schedule (nothing before Land.run touches them) */
+  const int32_t* arc_flags; /* [n_arcs] WSI_ARC_DENY_PUSH: PullArc (arcs.py:808-850; the caller also leaves such arcs
+                               out of cand_arcs), WSI_ARC_DENY_PULL: PushArc (arcs.py:852-893) */
 } WsiModelDesc;
 
 /* ABI version of the loaded library (== WSI_ABI_VERSION). */

@@ -672,6 +672,137 @@ def scenario_rivernet(T=420):
     save("rivernet", fm, ref, "synthetic river/sewer network with decays, splits and binding capacities")
 
 
+def scenario_reservoirs(T=400):
+    """A RiverReservoir on a river (spill, environmental flow, a binding arc downstream so that some
+    spill comes back) and the arc variants: a PullArc to an abstracting Reservoir, a PushArc to a
+    Reservoir that also tries to abstract, a WeirArc and a SewerArc."""
+    set_default_pollutants()
+    dates = [pd.Timestamp("2003-01-01") + pd.Timedelta(days=i) for i in range(T)]
+    rng = np.random.default_rng(20261022)
+    forcing = synthetic_forcing(dates, rng)
+
+    def catch_data(seed, q):
+        r = np.random.default_rng(seed)
+        d = {}
+        flow = q * (1 + 0.8 * np.sin(np.arange(T) / 25.0)) * r.lognormal(0, 0.5, T)
+        for t, date in enumerate(dates):
+            d[("flow", date)] = float(flow[t])
+            for p in constants.POLLUTANTS:
+                if p == "temperature":
+                    d[(p, date)] = forcing[("temperature", date)] + 1.0
+                elif p == "ph":
+                    d[(p, date)] = 7.2
+                elif p == "do":
+                    d[(p, date)] = 0.009
+                else:
+                    d[(p, date)] = float(r.uniform(1e-5, 2e-3))
+        return d
+
+    tdata = {k: v for k, v in forcing.items() if k[0] == "temperature"}
+    init = lambda v: {"volume": v, "do": 0.008, "org-phosphorus": v * 2e-5, "phosphate": v * 5e-5,  # noqa: E731
+                      "ammonia": v * 1e-4, "solids": v * 1e-3, "bod": v * 1e-3, "cod": v * 2e-3, "ph": 7.1,
+                      "temperature": 8.0, "nitrate": v * 2e-3, "nitrite": v * 1e-5, "org-nitrogen": v * 3e-4}
+    decays = {"ammonia": {"constant": 0.03, "exponent": 1.01}}
+    nodes = [
+        {"type_": "Catchment", "name": "c1", "data_input_dict": catch_data(1, 3e4)},
+        {"type_": "Catchment", "name": "c2", "data_input_dict": catch_data(2, 8e3)},
+        {"type_": "River", "name": "r1", "length": 6000, "width": 10, "data_input_dict": tdata, "initial_storage": init(4e4)},
+        {"type_": "Node", "name": "j"},
+        {"type_": "RiverReservoir", "name": "rr", "capacity": 2.5e5, "area": 4e4, "initial_storage": init(2.3e5),
+         "environmental_flow": 9e3, "decays": dict(decays), "data_input_dict": tdata},
+        {"type_": "Reservoir", "name": "farm", "capacity": 6e4, "area": 1e4, "initial_storage": init(1e4)},
+        {"type_": "Reservoir", "name": "pond", "capacity": 3e4, "area": 1e4, "initial_storage": init(2e4)},
+        {"type_": "River", "name": "r2", "length": 4000, "width": 15, "data_input_dict": tdata, "initial_storage": init(2e4)},
+        {"type_": "Node", "name": "j2"},
+        {"type_": "Waste", "name": "out"},
+        {"type_": "Waste", "name": "out2"},
+    ]
+    arcs = [
+        ("Arc", "c1-r1", "c1", "r1", {}), ("Arc", "r1-j", "r1", "j", {}),
+        ("Arc", "j-rr", "j", "rr", {"preference": 2.0}),
+        ("PullArc", "j-farm", "j", "farm", {"capacity": 4e3}),
+        ("PushArc", "j-pond", "j", "pond", {"preference": 0.5, "capacity": 1.5e3}),
+        ("WeirArc", "rr-j2", "rr", "j2", {}), ("Arc", "c2-j2", "c2", "j2", {}),
+        ("Arc", "j2-r2", "j2", "r2", {"capacity": 2.2e4}), ("Arc", "j2-out2", "j2", "out2", {"capacity": 3e3, "preference": 0.2}),
+        ("SewerArc", "r2-out", "r2", "out", {}),
+    ]
+    m = Model()
+    m.orchestration.append({"Reservoir": "satisfy_environmental"})  # after the abstractions, before river routing
+    m.add_nodes(nodes)
+    m.add_arcs([dict({"type_": ty, "name": a, "in_port": i, "out_port": o}, **kw) for ty, a, i, o, kw in arcs])
+    # only the RiverReservoir has satisfy_environmental: run it for that node alone, as a user would
+    m.orchestration[-1] = {"RiverReservoirOnly": "satisfy_environmental"}
+    m.nodes_type["RiverReservoirOnly"] = {"rr": m.nodes["rr"]}
+    fm = flatten_ref(m, dates)
+    ref = run_reference(m, dates)
+    save("reservoirs", fm, ref, "RiverReservoir (spill, environmental flow) and PullArc / PushArc / WeirArc / SewerArc")
+
+
+def scenario_irrigation(T=500):
+    """A Land with an IrrigationSurface (pulls its crop water demand from a River, a Groundwater and a
+    Reservoir through the Land's in-arcs, after the surfaces have run) and a VariableAreaSurface."""
+    set_default_pollutants()
+    dates = [pd.Timestamp("2004-01-01") + pd.Timedelta(days=i) for i in range(T)]
+    rng = np.random.default_rng(20261023)
+    forcing = synthetic_forcing(dates, rng)
+    months = sorted({(d.year, d.month) for d in dates})
+    monthly = {}
+    for var in L.DEP_COLS:
+        for (y, mth) in months:
+            monthly[(var, pd.Timestamp(year=y, month=mth, day=1).to_period("M"))] = 1e-7
+    tdata = {k: v for k, v in forcing.items() if k[0] == "temperature"}
+    init = lambda v: {"volume": v, "do": 0.008, "org-phosphorus": v * 2e-5, "phosphate": v * 5e-5,  # noqa: E731
+                      "ammonia": v * 1e-4, "solids": v * 1e-3, "bod": v * 1e-3, "cod": v * 2e-3, "ph": 7.1,
+                      "temperature": 8.0, "nitrate": v * 2e-3, "nitrite": v * 1e-5, "org-nitrogen": v * 3e-4}
+
+    def crop(kind, name, area, **extra):
+        vol = area * 1.25 * 0.4 * 0.8
+        soil = {"org-phosphorus": vol * 5e-3, "phosphate": vol * 5e-3, "ammonia": 0.0, "nitrate": vol,
+                "nitrite": 0.0, "org-nitrogen": vol, "volume": vol}
+        g = dict(GROWING_TEMPLATE)
+        g.update(type_=kind, surface=name, area=area, pollutant_load={}, initial_storage=init(vol),
+                 initial_soil_storage=soil, data_input_dict=monthly, rooting_depth=1.25,
+                 decays={"ammonia": {"constant": 0.1, "exponent": 1.005}}, **extra)
+        return g
+
+    def catch_data(seed, q):
+        r = np.random.default_rng(seed)
+        d = {}
+        flow = q * (1 + 0.5 * np.sin(np.arange(T) / 30.0)) * r.lognormal(0, 0.3, T)
+        for t, date in enumerate(dates):
+            d[("flow", date)] = float(flow[t])
+            for p in constants.POLLUTANTS:
+                d[(p, date)] = (forcing[("temperature", date)] + 1.0 if p == "temperature" else 7.2 if p == "ph"
+                                else 0.009 if p == "do" else float(r.uniform(1e-5, 2e-3)))
+        return d
+
+    nodes = [
+        {"type_": "Catchment", "name": "c1", "data_input_dict": catch_data(5, 2e3)},
+        {"type_": "River", "name": "r1", "length": 4000, "width": 8, "data_input_dict": tdata, "initial_storage": init(8e3)},
+        {"type_": "Reservoir", "name": "res", "capacity": 5e4, "area": 1e4, "initial_storage": init(3e4)},
+        {"type_": "Land", "name": "farm", "data_input_dict": forcing, "surfaces": [
+            crop("IrrigationSurface", "irrigated", 3e5, irrigation_coefficient=0.6),
+            crop("VariableAreaSurface", "variable", 1e5, current_surface_area=6.5e4),
+            {"type_": "PerviousSurface", "surface": "rural", "area": 5e4, "depth": 0.5, "initial_storage": init(5e3)},
+        ]},
+        {"type_": "Groundwater", "name": "gw", "area": 4e5, "capacity": 2e5, "residence_time": 60.0, "initial_storage": init(2e4)},
+        {"type_": "Node", "name": "j"},
+        {"type_": "Waste", "name": "out"},
+    ]
+    arcs = [
+        ("c1-r1", "c1", "r1", {}), ("r1-j", "r1", "j", {}), ("j-out", "j", "out", {}),
+        ("r1-farm", "r1", "farm", {"capacity": 900.0}), ("gw-farm", "gw", "farm", {"preference": 0.5}),
+        ("res-farm", "res", "farm", {"preference": 0.2, "capacity": 150.0}),
+        ("farm-gw", "farm", "gw", {}), ("farm-j", "farm", "j", {}), ("gw-j", "gw", "j", {}),
+    ]
+    m = Model()
+    m.add_nodes(nodes)
+    m.add_arcs([dict({"type_": "Arc", "name": a, "in_port": i, "out_port": o}, **kw) for a, i, o, kw in arcs])
+    fm = flatten_ref(m, dates)
+    ref = run_reference(m, dates)
+    save("irrigation", fm, ref, "IrrigationSurface pulling through its Land (River / Groundwater / Reservoir) + VariableAreaSurface")
+
+
 def scenario_rivertree(T=380):
     """Dendritic river network (the network engine's case): catchments and rivers joined through
     junctions (also chained and shared ones), a binding river-arc capacity, decays, a dry
@@ -857,6 +988,8 @@ SCENARIOS = {
     "fixture3607": scenario_fixture3607,
     "config2": scenario_config2,
     "rivernet": scenario_rivernet,
+    "reservoirs": scenario_reservoirs,
+    "irrigation": scenario_irrigation,
     "rivertree": scenario_rivertree,
     "config3": scenario_config3,
     "hourly": scenario_hourly,

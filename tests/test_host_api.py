@@ -87,7 +87,7 @@ def test_unsupported_features_are_refused_not_ignored():
         m.add_nodes([{"type_": "NonResidentialDemand", "name": "factory"}])
     m, _ = _quickstart_model(T=10)
     with pytest.raises(UnsupportedModelError):
-        m.add_arcs([{"type_": "PullArc", "name": "x", "in_port": "my_river", "out_port": "my_outlet"}])
+        m.add_arcs([{"type_": "DecayArc", "name": "x", "in_port": "my_river", "out_port": "my_outlet"}])
     m, _ = _quickstart_model(T=10)
     m.orchestration.append({"Land": "some_custom_function"})
     with pytest.raises(UnsupportedModelError):
@@ -308,3 +308,49 @@ def test_pollutant_sets_without_kernels_are_padded_with_zero_additive_planes():
     finally:
         constants.set_default_pollutants()
         constants.FLOAT_ACCURACY = 1e-11
+
+
+def test_arc_variants_and_river_reservoir_through_the_mirror_api():
+    """PullArc / PushArc / SewerArc / WeirArc (arcs.py:808-905) and RiverReservoir (storage.py:992-1133) are
+    accepted by Model.add_nodes / add_arcs and flatten to what golden 'reservoirs' (built with the
+    reference's classes) holds; the queueing arcs are still refused."""
+    import pandas as pd
+
+    from wsi_b200.backend import layout as L
+    from wsi_b200.backend.flatten import UnsupportedModelError
+    from wsi_b200.core import constants
+    from wsi_b200.orchestration.model import Model
+
+    constants.set_default_pollutants()
+    constants.FLOAT_ACCURACY = 1e-11
+    fm_ref, _ = load_golden("reservoirs")
+    dates = [pd.Timestamp("2003-01-01") + pd.Timedelta(days=i) for i in range(5)]
+    tdata = {("temperature", d): 10.0 for d in dates}
+    m = Model()
+    m.add_nodes([
+        {"type_": "River", "name": "r1", "length": 6000, "width": 10, "data_input_dict": tdata},
+        {"type_": "Node", "name": "j"},
+        {"type_": "RiverReservoir", "name": "rr", "capacity": 2.5e5, "area": 4e4, "environmental_flow": 9e3},
+        {"type_": "Reservoir", "name": "farm", "capacity": 6e4, "area": 1e4},
+        {"type_": "Reservoir", "name": "pond", "capacity": 3e4, "area": 1e4},
+        {"type_": "Waste", "name": "out"}])
+    m.add_arcs([
+        {"type_": "Arc", "name": "r1-j", "in_port": "r1", "out_port": "j"},
+        {"type_": "Arc", "name": "j-rr", "in_port": "j", "out_port": "rr"},
+        {"type_": "PullArc", "name": "j-farm", "in_port": "j", "out_port": "farm"},
+        {"type_": "PushArc", "name": "j-pond", "in_port": "j", "out_port": "pond"},
+        {"type_": "WeirArc", "name": "rr-out", "in_port": "rr", "out_port": "out"}])
+    m.orchestration.append({"RROnly": "satisfy_environmental"})
+    m.nodes_type["RROnly"] = {"rr": m.nodes["rr"]}
+    m.dates = dates
+    fm = m.flatten()
+    assert list(fm.arc_flags) == [0, 0, L.ARC_DENY_PUSH, L.ARC_DENY_PULL, 0]
+    assert fm.node_type[2] == L.NT["RiverReservoir"] == fm_ref.node_type[4]
+    assert fm.view("tank", "environmental_flow")[0, int(fm.node_gidx[2]), 0] == 9e3
+    assert L.OP["RESERVOIR_ENVIRONMENTAL"] in list(fm.sched_op)
+    # j pushes to [Node, River, Waste, Reservoir]: the PullArc is not a candidate
+    nrwr = L.FI["NRWR"]
+    cand = list(fm.cand_arcs[fm.cand_ptr[1 * L.NF + nrwr]: fm.cand_ptr[1 * L.NF + nrwr + 1]])
+    assert cand == [1, 3]
+    with pytest.raises(UnsupportedModelError):
+        m.add_arcs([{"type_": "QueueArc", "name": "q", "in_port": "r1", "out_port": "j"}])

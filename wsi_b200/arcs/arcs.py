@@ -34,6 +34,25 @@ class Arc(WSIObj):
             print(f"No override behaviour defined for: {overrides.keys()}")
 
 
-# Queue/decay/pull/weir arcs of the reference (arcs.py:272-905) are outside the GPU path;
+class PullArc(Arc):
+    """Only pulls travel along it: pushes and push checks are answered with "nothing" (reference:
+    arcs.py:808-850) -- the flattener leaves it out of every push candidate list."""
+
+
+class PushArc(Arc):
+    """Only pushes travel along it (reference: arcs.py:852-893) -- WsiModelDesc.arc_flags tells the
+    pull code."""
+
+
+class SewerArc(Arc):
+    """A plain Arc under another name (reference: arcs.py:896-899)."""
+
+
+class WeirArc(SewerArc):
+    """A plain Arc under another name (reference: arcs.py:902-905)."""
+
+
+SUPPORTED_ARCS = ("Arc", "PullArc", "PushArc", "SewerArc", "WeirArc")
+# The arcs that keep a list of individual requests (arcs.py:272-805) are outside the GPU path;
 # Model.add_arcs raises for them rather than silently treating them as plain arcs.
-UNSUPPORTED_ARCS = ("QueueArc", "AltQueueArc", "DecayArc", "DecayArcAlt", "PullArc", "PushArc", "SewerArc", "WeirArc")
+UNSUPPORTED_ARCS = ("QueueArc", "AltQueueArc", "DecayArc", "DecayArcAlt")

@@ -152,6 +152,7 @@ class WsiModelDesc(C.Structure):
         ("distrib", _f64p),
         ("n_distrib", C.c_int32),
         ("sched_split", C.c_int32),
+        ("arc_flags", _i32p),
     ]
 
 
@@ -160,7 +161,7 @@ _NET_ARRAYS = ["net_level_ptr", "net_level_node", "net_calc_node", "net_final_no
 _INT_ARRAYS = _NET_ARRAYS + [
     "arc_chain_ptr", "arc_chain", "surf_order", "end_kind", "end_obj", "mb_term_slot", "node_type", "node_gidx", "arc_in", "arc_out", "out_ptr", "out_arcs", "in_ptr", "in_arcs",
     "cand_ptr", "cand_arcs", "land_surf_ptr", "land_surf", "sched_op", "sched_node", "month_idx",
-    "dayofyear", "doy_adj",
+    "dayofyear", "doy_adj", "arc_flags",
 ]
 _F64_ARRAYS = ["node_forcing", "surf_inputs", "catch_inputs"]
 _GROUP_FIELD = {"arc": "arc", "land": "land", "surf": "surf", "tank": "tank", "river": "river",
@@ -245,6 +246,8 @@ def simple_chains(fm):
             nxt = int(fm.out_arcs[fm.out_ptr[node]])
             arcs.append(nxt)
             node = int(fm.arc_out[nxt])
+        if int(fm.node_type[node]) == L.NT["RiverReservoir"]:
+            ok = False  # its push handlers look and push further downstream themselves (storage.py:1062-1107)
         if ok:
             flat.extend(arcs)
         ptr[a + 1] = len(flat)
@@ -296,6 +299,7 @@ class ModelBuffers:
         items += [(5, i) for i in range(fm.n_obj["sewer"])]
         items += [(6, i) for i in range(fm.n_obj.get("works", 0))] + [(7, i) for i in range(fm.n_obj.get("demand", 0))]
         items += [(8, i) for i in range(fm.n_obj.get("distrib", 0))]
+        items += [(9, int(fm.node_gidx[i])) for i, t in enumerate(fm.node_type) if int(t) == L.NT["RiverReservoir"]]
         self.n_end = len(items)
         it = np.array(items or [(0, 0)], dtype=np.int32).reshape(-1, 2)
         fused = [int(t) in (L.NT["Land"], L.NT["Catchment"]) for t in fm.node_type]
@@ -436,9 +440,11 @@ class ModelBuffers:
         d.n_demand = fm.n_obj.get("demand", 0)
         d.n_distrib = fm.n_obj.get("distrib", 0)
         d.sched_split = sched_split(fm)
-        rare = {L.NT[k] for k in ("WWTW", "FWTW", "Demand", "UnlimitedDistribution", "QueueGroundwater")}
-        pulls = any(int(t) == L.NT["Reservoir"] and fm.in_ptr[i + 1] > fm.in_ptr[i] for i, t in enumerate(fm.node_type))
+        rare = {L.NT[k] for k in ("WWTW", "FWTW", "Demand", "UnlimitedDistribution", "QueueGroundwater", "RiverReservoir")}
+        pulls = any(int(t) in (L.NT["Reservoir"], L.NT["RiverReservoir"]) and fm.in_ptr[i + 1] > fm.in_ptr[i] for i, t in enumerate(fm.node_type))
         d.features = 1 if (pulls or any(int(t) in rare for t in fm.node_type)) else 0
+        if fm.n_obj["surf"] and ((fm.view("surf", "irrigation_coefficient") >= 0).any() or (fm.view("surf", "climate_scale") != 1.0).any()):
+            d.features |= 3  # bit 1: irrigation / variable-area surfaces (read by the surface kernel)
         d.n_sched = int(len(fm.sched_op))
         for i, v in enumerate(self.surf_class_ptr):
             d.surf_class_ptr[i] = v

@@ -31,8 +31,13 @@ SURFACE_CLASS_MAP = {
     # GardenSurface only differs through Demand push handlers (land.py:2384-2437);
     # Demand nodes are not on this path, so it behaves as a GrowingSurface.
     "GardenSurface": "GrowingSurface",
+    # IrrigationSurface: a GrowingSurface that also pulls water through its Land (land.py:2314-2381);
+    # VariableAreaSurface: a GrowingSurface whose climate scales with current_surface_area (land.py:2440-2461)
+    "IrrigationSurface": "GrowingSurface",
+    "VariableAreaSurface": "GrowingSurface",
 }
-STORE_TYPES = ("Groundwater", "Storage", "River", "Reservoir")
+STORE_TYPES = ("Groundwater", "Storage", "River", "Reservoir", "RiverReservoir")
+ARC_CLASSES = ("Arc", "SewerArc", "WeirArc", "PullArc", "PushArc")  # arcs.py:18, 808-905 (no queues)
 
 # (class name, orchestration function) -> op
 ORCHESTRATION_OPS = {
@@ -49,6 +54,9 @@ ORCHESTRATION_OPS = {
     ("Catchment", "route"): "CATCHMENT_ROUTE",
     ("Storage", "distribute"): "STORAGE_DISTRIBUTE",
     ("Reservoir", "distribute"): "STORAGE_DISTRIBUTE",
+    ("RiverReservoir", "make_abstractions"): "RESERVOIR_ABSTRACT",
+    ("RiverReservoir", "distribute"): "STORAGE_DISTRIBUTE",
+    ("RiverReservoir", "satisfy_environmental"): "RESERVOIR_ENVIRONMENTAL",
     ("FWTW", "treat_water"): "FWTW_TREAT",
     ("Demand", "create_demand"): "DEMAND_CREATE",
     ("WWTW", "calculate_discharge"): "WWTW_CALC",
@@ -95,8 +103,13 @@ class FlatModel:
     month_idx: np.ndarray
     dayofyear: np.ndarray
     doy_adj: np.ndarray
+    arc_flags: np.ndarray = None  # [n_arcs] L.ARC_DENY_PUSH / L.ARC_DENY_PULL bits (PullArc / PushArc)
     dates: list = field(default_factory=list)
     recipe: dict = None  # what a synthetic builder drew (tests); not part of the model
+
+    def __post_init__(self):
+        if self.arc_flags is None:  # plain arcs
+            self.arc_flags = np.zeros(max(len(self.arc_names), 1), dtype=np.int32)
 
     # ------------------------------------------------------------------ basics
     @property
@@ -184,7 +197,7 @@ class FlatModel:
         "node_type", "node_gidx", "arc_in", "arc_out", "out_ptr", "out_arcs", "in_ptr",
         "in_arcs", "cand_ptr", "cand_arcs", "land_surf_ptr", "land_surf", "sched_op",
         "sched_node", "node_forcing", "surf_inputs", "catch_inputs", "month_idx",
-        "dayofyear", "doy_adj",
+        "dayofyear", "doy_adj", "arc_flags",
     ]
 
     def to_npz_dict(self):
@@ -205,7 +218,8 @@ class FlatModel:
     def from_npz_dict(cls, d):
         sc = d["meta_scalars"]
         surf_names = [tuple(x.split("\t")) for x in d["meta_surf_names"].tolist() if x]
-        kw = {k: np.ascontiguousarray(d[k]) for k in cls._ARRAYS}
+        kw = {k: np.ascontiguousarray(d[k]) for k in cls._ARRAYS if k in d}
+        kw.setdefault("arc_flags", np.zeros(max(len(d["meta_arc_names"]), 1), dtype=np.int32))  # plain arcs
         V = len(d["meta_pollutants"]) + 1
         nq = int(sc[3])
         n_obj = {k: 0 for k in L.GROUPS}
@@ -215,9 +229,17 @@ class FlatModel:
             nf = L.sewer_n_fields(V, nq) if k == "sewer" else L.GROUPS[k].n_fields(V)
             groups[k] = np.ascontiguousarray(d["group_" + k]) if "group_" + k in d else np.zeros((nf, 0))
         # fixtures written before a group gained planes are brought up to the current layout:
-        if groups["surf"].shape[0] == L.SURF.n_fields(V) - 1 - V:  # irrigated_at: never, pre_irrigation: unused
+        if groups["surf"].shape[0] == L.SURF.n_fields(V) - 3 - V:  # irrigated_at: never, pre_irrigation: unused
             g = np.insert(groups["surf"], L.SURF.offset("irrigated_at", V), -1.0, axis=0)
             groups["surf"] = np.ascontiguousarray(np.concatenate([g, np.zeros((V, g.shape[1]))], axis=0))
+        if groups["surf"].shape[0] == L.SURF.n_fields(V) - 2:  # irrigation_coefficient: none, climate_scale: 1
+            o = L.SURF.offset("irrigation_coefficient", V)
+            g = np.insert(groups["surf"], [o, o], 0.0, axis=0)
+            g[o], g[o + 1] = -1.0, 1.0
+            groups["surf"] = np.ascontiguousarray(g)
+        if groups["tank"].shape[0] == L.TANK.n_fields(V) - 2:  # environmental_flow, env_satisfied: none
+            o = L.TANK.offset("environmental_flow", V)
+            groups["tank"] = np.ascontiguousarray(np.insert(groups["tank"], [o, o], 0.0, axis=0))
         if groups["river"].shape[0] == L.RIVER.n_fields(V) - 1:  # mrf: none
             groups["river"] = np.ascontiguousarray(np.insert(groups["river"], L.RIVER.offset("mrf", V), 0.0, axis=0))
         if groups["land"].shape[0] == L.LAND.n_fields(V) - 1:  # garden_surf: none
@@ -262,6 +284,9 @@ def _cls(obj):
     # QueueGroundwater files itself under its parent's name (storage.py:299)
     if name == "Groundwater" and hasattr(obj, "timearea"):
         return "QueueGroundwater"
+    # ... and so does RiverReservoir (storage.py:1041)
+    if name == "Reservoir" and hasattr(obj, "environmental_flow"):
+        return "RiverReservoir"
     return name
 
 
@@ -395,9 +420,10 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
                 f"(supported: {sorted(SUPPORTED_NODES)})"
             )
     for a in arcs:
-        if _cls(a) != "Arc":
-            raise UnsupportedModelError(f"arc {a.name!r} of class {_cls(a)} is not supported (plain Arc only)")
-        if _cls(a.out_port) == "Catchment" or (_cls(a.out_port) == "Land" and _cls(a.in_port) != "Demand"):
+        if _cls(a) not in ARC_CLASSES:
+            raise UnsupportedModelError(f"arc {a.name!r} of class {_cls(a)} is not supported (arcs without queues only)")
+        irrigated = _cls(a.out_port) == "Land" and any(_cls(x) == "IrrigationSurface" for x in a.out_port.surfaces)
+        if _cls(a.out_port) == "Catchment" or (_cls(a.out_port) == "Land" and _cls(a.in_port) != "Demand" and not irrigated):
             raise UnsupportedModelError(f"arc {a.name!r} pushes into a {_cls(a.out_port)} node")
         if _cls(a.in_port) == "Land" and _cls(a.out_port) not in ("Sewer", "Groundwater", "QueueGroundwater", "River", "Node", "Waste"):
             raise UnsupportedModelError(f"arc {a.name!r}: Land only pushes to Sewer / Groundwater / River / Node / Waste")
@@ -415,6 +441,12 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
             ptr[i + 1] = len(flat)
         return ptr, np.array(flat if flat else [0], dtype=np.int32)[: max(len(flat), 1)]
 
+    # PullArc answers every push (check) with "nothing" and PushArc every pull (arcs.py:808-893): an arc whose
+    # check returns zero never takes part in a distribution (nodes.py:271-317), so a PullArc is simply not a
+    # push candidate; pulls read arc_flags on the device
+    arc_flags = np.array([(L.ARC_DENY_PUSH if _cls(a) == "PullArc" else 0) | (L.ARC_DENY_PULL if _cls(a) == "PushArc" else 0)
+                          for a in arcs] or [0], dtype=np.int32)
+    pushable = lambda k: not (arc_flags[arc_index[k]] & L.ARC_DENY_PUSH)  # noqa: E731
     out_lists = [[arc_index[k] for k in n.out_arcs.keys()] for n in nodes]
     in_lists = [[arc_index[k] for k in n.in_arcs.keys()] for n in nodes]
     out_ptr, out_arcs = csr(out_lists)
@@ -424,12 +456,12 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
         for fname in L.FILTER_NAMES:
             types = L.FILTERS[fname]
             if types is None:
-                cand_lists.append([arc_index[k] for k in n.out_arcs.keys()])
+                cand_lists.append([arc_index[k] for k in n.out_arcs.keys() if pushable(k)])
             else:
                 # get_direction_arcs (nodes.py:257-265): per type, in of_type order
                 lst = []
                 for ty in types:
-                    lst += [arc_index[k] for k in n.out_arcs_type.get(ty, {}).keys()]
+                    lst += [arc_index[k] for k in n.out_arcs_type.get(ty, {}).keys() if pushable(k)]
                 cand_lists.append(lst)
     for n_i, n in enumerate(nodes):
         longest = max(len(l) for l in cand_lists[n_i * L.NF : (n_i + 1) * L.NF])
@@ -532,6 +564,8 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
         if _cls(tk) not in ("Tank", "DecayTank"):
             raise UnsupportedModelError(f"{n.name}: tank class {_cls(tk)} unsupported")
         b.set(col, "is_decay", 1.0 if is_decay else 0.0)
+        b.set(col, "environmental_flow", getattr(n, "environmental_flow", 0.0))
+        b.set(col, "env_satisfied", getattr(n, "total_environmental_satisfied", 0.0))
         need_T = (is_decay and len(tk.decays) > 0) or (_cls(n) == "River" and has_nitrate)
         fid = 0
         if need_T:
@@ -646,6 +680,8 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
         for type_key, fn in item.items():
             for n in model.nodes_type.get(type_key, {}).values():
                 op = ORCHESTRATION_OPS.get((_cls(n), fn))
+                if op == "NOP" and fn == "apply_irrigation" and any(_cls(x) == "IrrigationSurface" for x in n.surfaces):
+                    op = "LAND_IRRIGATE"
                 if op is None:
                     raise UnsupportedModelError(f"orchestration entry {type_key}.{fn} on {_cls(n)} {n.name!r} unsupported")
                 if op != "NOP":
@@ -690,6 +726,7 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
         land_surf_ptr=land_surf_ptr,
         land_surf=land_surf,
         surf_names=surf_names,
+        arc_flags=arc_flags,
         sched_op=sched_op,
         sched_node=sched_node,
         groups=groups,
@@ -713,7 +750,7 @@ def _flatten_queue_groundwater(b, n, pollutants, V, forcing_series):
     ta = n.timearea or {0: 1}
     if len(ta) > L.MAX_TIMEAREA or any(int(k) != k or k < 0 for k in ta):
         raise UnsupportedModelError(f"{n.name}: timearea with more than {L.MAX_TIMEAREA} / non-integer entries")
-    if len(n.in_arcs) and any(_cls(a.in_port) in ("Reservoir", "FWTW", "Demand") for a in n.out_arcs.values()):
+    if len(n.in_arcs) and any(_cls(a.in_port) in ("Reservoir", "RiverReservoir", "FWTW", "Demand") for a in n.out_arcs.values()):
         raise UnsupportedModelError(f"{n.name}: abstraction from a QueueGroundwater (pull_set_active) is not supported")
     # push checks are answered by the Tank the Storage base class created first (storage.py:60): stale
     handler = getattr(n, "push_check_handler", {}).get("default")
@@ -801,6 +838,8 @@ def _flatten_surface(b, s, pollutants, additive, has_nitrate, dep_series_id):
     col = b.new()
     b.set(col, "type", L.ST[kind])
     b.set(col, "irrigated_at", -1.0)
+    b.set(col, "irrigation_coefficient", float(s.irrigation_coefficient) if cname == "IrrigationSurface" else -1.0)
+    b.set(col, "climate_scale", s.current_surface_area / s.area if cname == "VariableAreaSurface" else 1.0)
     b.set(col, "area", s.area)
     b.set(col, "capacity", s.capacity)
     b.set(col, "depth", s.depth)
@@ -977,6 +1016,8 @@ def scatter_back(model, fm, groups, last_date=None):
             n.tank.storage_ = vq_dict("tank", "storage_", ti)
             if _cls(n.tank) == "DecayTank":
                 decay_back(n.tank, "tank", ti)
+            if c == "RiverReservoir":
+                n.total_environmental_satisfied = sc("tank", "env_satisfied", ti)
             if c == "River":
                 nT, hT = int(sc("river", "n_lag_T", ri)), int(sc("river", "head_T", ri))
                 n.lagged_temperatures = [sc("river", "lag_T", ri, (hT + k) % L.LAG_T) for k in range(nT)]

@@ -26,6 +26,7 @@ LAG_TP = 366  # River.max_phosphorus_lag + 1 (storage.py:563,758)
 MAXP = 16  # compile-time bound on pollutants
 COMPILED_P = (2, 12, 15)  # pollutant counts libwsi_b200.so has kernels for (csrc/wsi_cfg_*.cu); others are padded up
 MAX_TIMEAREA = 8  # entries of a Sewer's pipe_timearea
+ARC_DENY_PUSH, ARC_DENY_PULL = 1, 2  # arc_flags bits: PullArc / PushArc (arcs.py:808-893)
 MAX_CAND = 8  # candidate out-arcs one push_distributed call may split over (kMaxCand in csrc/wsi_device.cuh)
 
 # node types (Node.__class__.__name__ in the reference)
@@ -46,6 +47,7 @@ NODE_TYPES = [
     "Demand",  # demand.py:14-324 (ResidentialDemand files itself under this name, demand.py:214)
     "UnlimitedDistribution",  # distribution.py:144-200: supplies whatever is pulled
     "QueueGroundwater",  # storage.py:248-449 (files itself under "Groundwater"): a QueueTank / DecayQueueTank store
+    "RiverReservoir",  # storage.py:992-1133 (files itself under "Reservoir"): spills downstream, environmental flow
 ]
 NT = {n: i for i, n in enumerate(NODE_TYPES)}
 
@@ -85,6 +87,8 @@ OPS = [
     "WWTW_CALC",  # WWTW.calculate_discharge    wtw.py:278
     "WWTW_DISCHARGE",  # WWTW.make_discharge         wtw.py:306
     "QGW_DISTRIBUTE",  # QueueGroundwater.distribute storage.py:345-363
+    "RESERVOIR_ENVIRONMENTAL",  # RiverReservoir.satisfy_environmental storage.py:1109-1127
+    "LAND_IRRIGATE",  # Land.apply_irrigation land.py:192-198 -> IrrigationSurface.irrigate land.py:2347-2381
 ]
 OP = {n: i for i, n in enumerate(OPS)}
 
@@ -271,6 +275,8 @@ SURF = Group(
         S("out_precipitation"),
         S("out_tank_recharge"),
         S("irrigated_at"),  # GardenSurface: timestep whose irrigation arrived before the surface ran (-1: none)
+        S("irrigation_coefficient"),  # IrrigationSurface (land.py:2317-2329); -1: not one
+        S("climate_scale"),  # VariableAreaSurface: current_surface_area / area (land.py:2449-2461); 1 otherwise
         Q("storage"),
         Q("load"),  # pollutant_load (plane 0 unused)
         # per-step exchange between the surface kernels and the land phase (scratch)
@@ -294,6 +300,8 @@ TANK = Group(
         S("infiltration_pct"),
         S("forcing_id"),
         S("is_decay"),  # DecayTank vs Tank (storage.py:53-68)
+        S("environmental_flow"),  # RiverReservoir (storage.py:995, 1031)
+        S("env_satisfied"),  # state: total_environmental_satisfied (storage.py:1035), reset at end_timestep
         *_DECAY,
         Q("storage"),
         Q("storage_"),  # lagged storage for mass balance (tanks.py:40,351)

@@ -86,7 +86,7 @@ class ProbeSet:
         for i, t in enumerate(fm.node_type):
             name = L.NODE_TYPES[int(t)]
             g = int(fm.node_gidx[i])
-            if name in ("Groundwater", "Storage", "Reservoir"):
+            if name in ("Groundwater", "Storage", "Reservoir", "RiverReservoir"):
                 store_probes += fm.probes_for_field("tank", "storage", g)
             elif name == "River":
                 store_probes += fm.probes_for_field("tank", "storage", int(fm.view("river", "tank")[0, g, 0]))

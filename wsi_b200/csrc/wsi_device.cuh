@@ -321,6 +321,10 @@ WSI_HD typename C::Vq push_distributed(C& c, int node, const typename C::Vq& vqi
 // treatment works as push receivers (wsi_works.cuh)
 // (out of line, and handed a COPY of the context: rare receivers must neither grow every
 // instantiation of the push code nor force the caller's context into memory)
+template <int D, class C>
+WSI_HDN double rres_push_check_vol(C c, int node, bool has_v, double v_vol);
+template <int D, class C>
+WSI_HDN typename C::Vq rres_push_set(C c, int node, typename C::Vq vqip);
 template <class C>
 WSI_HDN double wwtw_push_check_vol(C c, int g, bool has_v, double v_vol);
 template <class C>
@@ -443,6 +447,9 @@ WSI_HD double node_push_check_vol(C& c, int node, bool has_v, double v_vol) {
       if (!has_v) return ex;
       return vol_vchange(ex, pymin(ex, v_vol));
     }
+    case WSI_NT_RIVERRESERVOIR:  // push_check_river_reservoir storage.py:1084-1107
+      if constexpr (!C::kLean) return rres_push_check_vol<D>(c, node, has_v, v_vol);
+      break;
     case WSI_NT_QUEUEGROUNDWATER:  // the stale Tank's get_excess (storage.py:60, 301-315)
       if constexpr (!C::kLean)
         return tank_excess_vol(*c.sewer(WSI_SEWER_STALE_CAPACITY, g), *c.sewer(WSI_SEWER_STALE_VOLUME, g), has_v, v_vol);
@@ -494,6 +501,9 @@ WSI_HD typename C::Vq node_push_set(C& c, int node, const typename C::Vq& vqip) 
       if constexpr (!C::kLean)
         if (c.tag == 1) return sewer_push_timearea(c, g, vqip);
       return sewer_push_storage(c, g, vqip, (int)*c.sewer(WSI_SEWER_PIPE_TIME, g));
+    case WSI_NT_RIVERRESERVOIR:  // push_set_river_reservoir storage.py:1062-1082
+      if constexpr (!C::kLean) return rres_push_set<D>(c, node, vqip);
+      break;
     case WSI_NT_QUEUEGROUNDWATER:  // push_set_timearea storage.py:329-343
       if constexpr (!C::kLean) return sewer_push_timearea(c, g, vqip);
       break;

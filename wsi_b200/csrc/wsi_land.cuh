@@ -238,15 +238,21 @@ WSI_HD void surface_phase(C& c, int u) {
     const double capacity = ldp(S(WSI_SURF_CAPACITY));
     const double fc_m = ldp(S(WSI_SURF_FIELD_CAPACITY_M));
     const double wp_m = ldp(S(WSI_SURF_WILTING_POINT_M));
-    const double evaporation_depth = et0 * et0_coef;  // get_climate land.py:903-911
+    double evaporation_depth = et0 * et0_coef;  // get_climate land.py:903-911
+    double precip_s = precip;
+    if (c.D().features & 2) {  // VariableAreaSurface.get_climate_ land.py:2449-2461 (1 for every other class)
+      const double scale = ldp(S(WSI_SURF_CLIMATE_SCALE));
+      precip_s *= scale;
+      evaporation_depth *= scale;
+    }
     const double inf_cap = ldp(S(WSI_SURF_INFILTRATION_CAPACITY));
-    const double infiltrated = pymin(precip, inf_cap);
-    double infiltration_excess = pymax(precip - infiltrated, 0.0);
+    const double infiltrated = pymin(precip_s, inf_cap);
+    double infiltration_excess = pymax(precip_s - infiltrated, 0.0);
     const double cmd = tank_excess_vol(capacity, st.x[0], false, 0.0) / area;  // get_cmd land.py:886
     double evaporation = evaporation_depth * pymin(1.0, exp(2 * (1 - cmd / (depth - wp_m))));
     const double outflow =
         infiltrated * (1 - pymin(1.0, pow(cmd / (depth - fc_m), ldp(S(WSI_SURF_IHACRES_P)))));
-    evaporation = pymin(evaporation, precip + st.x[0] / area);
+    evaporation = pymin(evaporation, precip_s + st.x[0] / area);
     const double surf_coef = ldp(S(WSI_SURF_SURFACE_COEFFICIENT));
     const double surface = outflow * surf_coef * area;
     const double percolation = outflow * (1 - surf_coef) * ldp(S(WSI_SURF_PERCOLATION_COEFFICIENT)) * area;
@@ -255,7 +261,7 @@ WSI_HD void surface_phase(C& c, int u) {
     infiltration_excess *= area;
     infiltration_excess += surface;
     evaporation *= area;
-    const double precipitation = precip * area;
+    const double precipitation = precip_s * area;
     const double total = tank_recharge + subsurface_flow + percolation;
     if (total > 0) {
       Vq tw = vq_volume<P>(total);
@@ -621,6 +627,10 @@ WSI_HD void surface_phase(C& c, int u) {
       if (i >= n) break;
       vset<P>(old, (int)*S(WSI_SURF_DECAY_POL + i), *S(WSI_SURF_PRE_DECAY + i));
     }
+    // an IrrigationSurface is watered AFTER it has run (Land.apply_irrigation, land.py:192-198, 2347-2381):
+    // land_irrigate re-forms this step's ds from the storage_ kept here
+    if (growing && (c.D().features & 2) && *S(WSI_SURF_IRRIGATION_COEFFICIENT) >= 0.0)
+      c.stv_add(S(WSI_SURF_PRE_IRRIGATION(V)), ss, old);
     if (type == WSI_ST_IMPERVIOUSSURFACE) {
       // the tank still receives the sewers' reply: land_phase forms ds from storage_
       c.stv_add(S(WSI_SURF_MB_DS(V)), ss, old);
@@ -653,7 +663,7 @@ WSI_HD void surface_phase(C& c, int u) {
   }
   // per-step diagnostics recorded by Model.run (model.py:1081-1118); a GardenSurface's evaporation and
   // precipitation are also what next step's irrigation demand is worked out from (land.py:2402-2423)
-  if (c.D().n_probe > 0 || (int)*Lo(WSI_LAND_GARDEN_SURF) == u) {
+  if (c.D().n_probe > 0 || (int)*Lo(WSI_LAND_GARDEN_SURF) == u || (c.D().features & 2)) {
     *S(WSI_SURF_OUT_PERCOLATION) = pc.x[0];
     *S(WSI_SURF_OUT_SUBSURFACE) = sf.x[0];
     *S(WSI_SURF_OUT_SURFACE) = type == WSI_ST_IMPERVIOUSSURFACE ? 0.0 : ie.x[0];

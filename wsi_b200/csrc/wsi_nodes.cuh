@@ -455,6 +455,7 @@ WSI_HD void node_mass_balance(C& c, int node, typename C::Vq& in_, typename C::V
       case WSI_NT_GROUNDWATER:
       case WSI_NT_STORAGE:
       case WSI_NT_RESERVOIR:
+      case WSI_NT_RIVERRESERVOIR:
         ds_add(c, ds, tank_ds(c, g));
         break;
       case WSI_NT_WWTW:
@@ -552,6 +553,7 @@ WSI_HD void node_mb_lane(const C& c, int node, double& in_, double& ds, double& 
       case WSI_NT_GROUNDWATER:
       case WSI_NT_STORAGE:
       case WSI_NT_RESERVOIR:
+      case WSI_NT_RIVERRESERVOIR:
         ds += tank_ds_lane<LANE>(c, g);
         break;
       case WSI_NT_WWTW:
@@ -691,6 +693,9 @@ WSI_HD void end_item(C& c, int kind, int obj) {
     case 7:
       demand_end_timestep(c, obj);
       break;
+    case 9:  // RiverReservoir.end_timestep_ storage.py:1129-1133 (its tank is a kind-3 item)
+      *c.tank(WSI_TANK_ENV_SATISFIED, obj) = 0.0;
+      break;
     case 8:  // UnlimitedDistribution.end_timestep distribution.py:191-200
       c.stv(c.distrib(WSI_DISTRIB_SUPPLIED(V), obj), c.s_distrib(), vq_zero<C::P>());
       break;
@@ -713,6 +718,10 @@ WSI_HD void end_node(C& c, int node) {
     case WSI_NT_STORAGE:
     case WSI_NT_RESERVOIR:
       end_item(c, 3, g);
+      break;
+    case WSI_NT_RIVERRESERVOIR:
+      end_item(c, 3, g);
+      end_item(c, 9, g);
       break;
     case WSI_NT_RIVER:
       end_item(c, 4, g);
@@ -870,6 +879,14 @@ WSI_HD void run_op(C& c, int op, int node) {
         break;
       case WSI_OP_WWTW_DISCHARGE:
         if constexpr (!C::kLean) wwtw_make_discharge(c, node);
+        push = false;
+        break;
+      case WSI_OP_LAND_IRRIGATE:
+        if constexpr (!C::kLean) land_irrigate(c, node);
+        push = false;
+        break;
+      case WSI_OP_RESERVOIR_ENVIRONMENTAL:
+        if constexpr (!C::kLean) rres_satisfy_environmental(c, node);
         push = false;
         break;
       case WSI_OP_QGW_DISTRIBUTE:

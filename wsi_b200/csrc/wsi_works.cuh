@@ -30,7 +30,7 @@ WSI_HD typename C::Vq pull_distributed(C& c, int node, double volume, int of_typ
 // in-arcs a pull may use: every one (of_type None), or -- of_type ["River", "Node"] -- those that
 // come from a River, then those from a junction Node (get_direction_arcs nodes.py:218-256).
 // Returns the count; arcs[] holds at most kMaxCand of them.
-constexpr int kPullAll = 0, kPullRiverNode = 1;
+constexpr int kPullAll = 0, kPullRiverNode = 1, kPullIrrigation = 2;
 template <class C>
 WSI_HD int pull_arcs(const C& c, int node, int of_type, int* arcs) {
   const WsiModelDesc& d = c.D();
@@ -38,6 +38,21 @@ WSI_HD int pull_arcs(const C& c, int node, int of_type, int* arcs) {
   if (of_type == kPullAll) {
     for (int i = d.in_ptr[node]; i < d.in_ptr[node + 1]; i++, n++)
       if (n < kMaxCand) arcs[n] = d.in_arcs[i];
+    return n;
+  }
+  if (of_type == kPullIrrigation) {  // ["River", "Node", "Groundwater", "Reservoir"] land.py:2364-2367, by class NAME
+    for (int pass = 0; pass < 4; pass++)
+      for (int i = d.in_ptr[node]; i < d.in_ptr[node + 1]; i++) {
+        const int ty = d.node_type[d.arc_in[d.in_arcs[i]]];
+        const bool hit = pass == 0   ? ty == WSI_NT_RIVER
+                         : pass == 1 ? ty == WSI_NT_NODE
+                         : pass == 2 ? (ty == WSI_NT_GROUNDWATER || ty == WSI_NT_QUEUEGROUNDWATER)
+                                     : (ty == WSI_NT_RESERVOIR || ty == WSI_NT_RIVERRESERVOIR);
+        if (hit) {
+          if (n < kMaxCand) arcs[n] = d.in_arcs[i];
+          n++;
+        }
+      }
     return n;
   }
   for (int pass = 0; pass < 2; pass++)
@@ -101,7 +116,8 @@ WSI_HD double node_pull_check_vol(C& c, int node, bool has_v, double v_vol) {
     }
     case WSI_NT_GROUNDWATER:
     case WSI_NT_STORAGE:
-    case WSI_NT_RESERVOIR: {  // tank.get_avail tanks.py:102-130
+    case WSI_NT_RESERVOIR:
+    case WSI_NT_RIVERRESERVOIR: {  // tank.get_avail tanks.py:102-130
       const double vol = *c.tank(WSI_TANK_STORAGE(V), g);
       return has_v ? vol_vchange(vol, pymin(vol, v_vol)) : vol;
     }
@@ -121,9 +137,74 @@ WSI_HD double node_pull_check_vol(C& c, int node, bool has_v, double v_vol) {
   }
 }
 
+// ---- RiverReservoir (storage.py:992-1133): a Reservoir on a river -- what it cannot hold spills on
+// downstream, and the spill counts towards its environmental flow ----------------------------------
+// push_check_river_reservoir storage.py:1084-1107
+template <int D, class C>
+WSI_HDN double rres_push_check_vol(C c, int node, bool has_v, double v_vol) {
+  constexpr int V = C::V;
+  const WsiModelDesc& d = c.D();
+  const int g = d.node_gidx[node];
+  double downstream = 0.0;  // get_connected(direction="push", of_type=[Node, River, Waste])["avail"]
+  if constexpr (D > 0) {
+    const int b = d.cand_ptr[node * WSI_NF + WSI_FILTER_NRW], e = d.cand_ptr[node * WSI_NF + WSI_FILTER_NRW + 1];
+#pragma unroll 1
+    for (int i = b; i < e; i++) {
+      double a = arc_excess_vol<D - 1>(c, d.cand_arcs[i], false, 0.0);
+      if (a < c.FA) a = 0.0;
+      downstream += a;
+    }
+  } else {
+    c.flag(node, WSI_FLAG_DEPTH);
+  }
+  const double vol = *c.tank(WSI_TANK_STORAGE(V), g);
+  const double excess = tank_excess_vol(*c.tank(WSI_TANK_CAPACITY, g), vol, false, 0.0);
+  double new_v = excess + downstream;
+  if (has_v) new_v = pymin(v_vol, new_v);
+  return vol_vchange(excess, new_v);
+}
+// push_set_river_reservoir storage.py:1062-1082
+template <int D, class C>
+WSI_HDN typename C::Vq rres_push_set(C c, int node, typename C::Vq vqip) {
+  constexpr int V = C::V;
+  using Vq = typename C::Vq;
+  const int g = c.D().node_gidx[node];
+  double* st = c.tank(WSI_TANK_STORAGE(V), g);
+  tank_push_force(c, st, c.s_tank(), vqip);
+  const Vq spill = tank_pull(c, st, c.s_tank(), pymax(*st - *c.tank(WSI_TANK_CAPACITY, g), 0.0));  // pull_ponded tanks.py:78-100
+  Vq reply = spill;
+  if constexpr (D > 0) {
+    const int tag = c.tag;
+    c.tag = 0;
+    reply = push_distributed<D - 1>(c, node, spill, WSI_FILTER_NRW);
+    c.tag = tag;
+  } else {
+    c.flag(node, WSI_FLAG_DEPTH);
+  }
+  double* sat = c.tank(WSI_TANK_ENV_SATISFIED, g);
+  *sat = *sat + (spill.x[0] - reply.x[0]);
+  return reply;
+}
+// satisfy_environmental storage.py:1109-1127
+template <class C>
+WSI_HDN void rres_satisfy_environmental(C c, int node) {
+  constexpr int V = C::V;
+  using Vq = typename C::Vq;
+  const int g = c.D().node_gidx[node];
+  double* st = c.tank(WSI_TANK_STORAGE(V), g);
+  double* sat = c.tank(WSI_TANK_ENV_SATISFIED, g);
+  const double to_satisfy = pymax(*c.tank(WSI_TANK_ENVIRONMENTAL_FLOW, g) - *sat, 0.0);
+  const Vq environmental = tank_pull(c, st, c.s_tank(), to_satisfy);
+  const Vq reply = push_distributed<kJunctionDepth>(c, node, environmental, WSI_FILTER_ALL);
+  tank_push_force(c, st, c.s_tank(), reply);
+  if (reply.x[0] > c.FA) c.flag(node, WSI_FLAG_DEFICIT);  // "warning: environmental not able to push"
+  *sat = *sat + environmental.x[0];
+}
+
 // Arc.get_excess(direction="pull")["volume"] arcs.py:230-257
 template <int D, class C>
 WSI_HDN double arc_pull_check_vol(C& c, int a, bool has_v, double v_vol) {
+  if (c.D().arc_flags[a] & WSI_ARC_DENY_PULL) return 0.0;  // PushArc.send_pull_check_deny arcs.py:881-893
   const double pipe_excess = *c.arc(WSI_ARC_CAPACITY, a) - arc_flow_in(c, a);
   const double ne = node_pull_check_vol<D>(c, c.D().arc_in[a], has_v, v_vol);
   return vol_vchange(ne, pymin(pipe_excess, ne));
@@ -150,7 +231,8 @@ WSI_HD typename C::Vq node_pull_set(C& c, int node, double volume) {
     }
     case WSI_NT_GROUNDWATER:
     case WSI_NT_STORAGE:
-    case WSI_NT_RESERVOIR:  // tank.pull_storage storage.py:98
+    case WSI_NT_RESERVOIR:
+    case WSI_NT_RIVERRESERVOIR:  // tank.pull_storage storage.py:98
       return tank_pull(c, c.tank(WSI_TANK_STORAGE(V), g), c.s_tank(), volume);
     case WSI_NT_FWTW: {  // pull_set_fwtw wtw.py:625-639
       const Vq pulled = tank_pull(c, c.tank(WSI_TANK_STORAGE(V), (int)*c.works(WSI_WORKS_TANK, g)), c.s_tank(), volume);
@@ -191,6 +273,7 @@ WSI_HD typename C::Vq node_pull_set(C& c, int node, double volume) {
 // Arc.send_pull_request({"volume": volume}) arcs.py:160-197
 template <int D, class C>
 WSI_HDN typename C::Vq arc_send_pull_request(C& c, int a, double volume) {
+  if (c.D().arc_flags[a] & WSI_ARC_DENY_PULL) return vq_zero<C::P>();  // PushArc.send_pull_deny arcs.py:865-879
   const double excess_in = arc_pull_check_vol<D>(c, a, true, volume);
   const double not_pulled = pymax(volume - excess_in, 0.0);
   volume -= not_pulled;
@@ -305,6 +388,52 @@ WSI_HDN void garden_receive_irrigation(C c, int land, typename C::Vq vqip) {  //
     *c.surf(WSI_SURF_IRRIGATED_AT, u) = (double)c.t;
   }
   tank_push_force(c, st, c.s_surf(), vqip);
+}
+
+// Land.apply_irrigation land.py:192-198 -> IrrigationSurface.irrigate land.py:2347-2381: what the crop
+// evaporated beyond the rain, pulled through the Land's in-arcs, into the soil tank and its nutrient pools
+template <class C>
+WSI_HDN void land_irrigate(C c, int node) {
+  using Vq = typename C::Vq;
+  constexpr int P = C::P;
+  constexpr int V = C::V;
+  const WsiModelDesc& d = c.D();
+  const int L = d.node_gidx[node];
+  const auto& cfg = c.cfg;
+#pragma unroll 1
+  for (int i = d.land_surf_ptr[L]; i < d.land_surf_ptr[L + 1]; i++) {
+    const int u = d.land_surf[i];
+    const double coef = *c.surf(WSI_SURF_IRRIGATION_COEFFICIENT, u);
+    if (coef < 0.0) continue;
+    if (!(*c.surf(WSI_SURF_DAYS_AFTER_SOW, u) > 0.0)) continue;  // `if self.days_after_sow:` (None and 0 are falsy)
+    double demand = pymax(*c.surf(WSI_SURF_OUT_EVAPORATION, u) - *c.surf(WSI_SURF_OUT_PRECIPITATION, u), 0.0) * coef;
+    if (!(demand > c.FA)) continue;
+    double* st = c.surf(WSI_SURF_STORAGE(V), u);
+    const double cmd = tank_excess_vol(*c.surf(WSI_SURF_CAPACITY, u), *st, false, 0.0) / *c.surf(WSI_SURF_AREA, u);
+    if (cmd <= c.FA) demand = 0.0;
+    const Vq supplied = pull_distributed_call<kJunctionDepth>(c, node, demand, kPullIrrigation);
+    tank_push_force(c, st, c.s_surf(), supplied);
+    // allocate_organic_irrigation / allocate_inorganic_irrigation nutrient_pool.py:192-224
+    if (cfg.orgn() >= 0) {
+      double* org = c.surf(WSI_SURF_POOL_DIS_ORG, u);
+      double* ino = c.surf(WSI_SURF_POOL_DIS_INORG, u);
+      const size_t ss = c.s_surf();
+      org[0] = org[0] + vget<P>(supplied, cfg.orgn());
+      org[ss] = org[ss] + vget<P>(supplied, cfg.orgp());
+      ino[0] = ino[0] + (vget<P>(supplied, cfg.nh4()) + vget<P>(supplied, cfg.no3()));
+      ino[ss] = ino[ss] + vget<P>(supplied, cfg.po4());
+    }
+    if (c.run_flags & WSI_RUN_MASS_BALANCE) {  // decay_ds tanks.py:449-457 again, on the watered tank
+      const Obj S = c.surf_obj(u);
+      const Vq now = c.ldv_add(st, c.s_surf());
+      const Vq old = c.ldv_add(S(WSI_SURF_PRE_IRRIGATION(V)), c.s_surf());
+      Vq dsv;
+#pragma unroll
+      for (int p = 0; p <= P; p++) dsv.x[p] = (p == 0 || bit(c.addm(), p)) ? now.x[p] - old.x[p] : 0.0;
+      dsv = c.sum(dsv, decay_total<C>(c, S, WSI_SURF_N_DECAY));
+      c.stv_add(S(WSI_SURF_MB_DS(V)), c.s_surf(), dsv);
+    }
+  }
 }
 
 // ---- WTW.treat_current_input wtw.py:118-160 ---------------------------------------------------

@@ -223,8 +223,9 @@ class GrowingSurface(PerviousSurface):
 
 
 class IrrigationSurface(GrowingSurface):
-    """Pull-driven irrigation (land.py:2314-2381) is outside the GPU path: a model containing
-    one is refused by the flattener."""
+    """A GrowingSurface whose crop water demand not met by rain is pulled through the parent Land's
+    in-arcs after the surfaces have run (reference: land.py:2314-2381; the kernels: land_irrigate in
+    csrc/wsi_works.cuh, scheduled by the Land's ``apply_irrigation`` orchestration entry)."""
 
     def __init__(self, irrigation_coefficient=0.1, **kwargs):
         self.irrigation_coefficient = irrigation_coefficient

@@ -117,6 +117,23 @@ class Reservoir(Storage):
         super().__init__(**kwargs)
 
 
+class RiverReservoir(Reservoir):
+    """A reservoir on a river (reference: storage.py:992-1133): what it cannot hold spills on to the
+    Node / River / Waste nodes downstream and counts towards ``environmental_flow``, which
+    ``satisfy_environmental`` (an orchestration function) tops up.  Files itself under "Reservoir"."""
+
+    def __init__(self, environmental_flow=0, **kwargs):
+        self.environmental_flow = environmental_flow
+        super().__init__(**kwargs)
+        self.total_environmental_satisfied = 0
+        self.__class__.__name__ = "Reservoir"
+
+    def apply_overrides(self, overrides=None):
+        overrides = overrides or {}
+        self.environmental_flow = overrides.pop("environmental_flow", self.environmental_flow)
+        super().apply_overrides(overrides)
+
+
 class QueueGroundwater(Storage):
     """Groundwater whose baseflow follows a time-area diagram (reference: storage.py:248-449): pushes
     enter a QueueTank (a DecayQueueTank when ``decays`` are given) spread over ``timearea``;

@@ -247,11 +247,11 @@ class Model(WSIObj):
         for arc in arclist:
             arc = dict(arc)
             type_ = arc.pop("type_")
-            if type_ != "Arc":
-                raise UnsupportedModelError(f"Arc type {type_} is not available on the GPU path (plain Arc only)")
+            if type_ not in arcs_mod.SUPPORTED_ARCS:
+                raise UnsupportedModelError(f"Arc type {type_} is not available on the GPU path (arcs without queues only)")
             arc["in_port"] = self.nodes[arc["in_port"]]
             arc["out_port"] = self.nodes[arc["out_port"]]
-            self.arcs[arc["name"]] = arcs_mod.Arc(**arc)
+            self.arcs[arc["name"]] = getattr(arcs_mod, type_)(**arc)
         self._derive_river_order()
 
     def add_instantiated_arcs(self, arclist):
