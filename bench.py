@@ -123,7 +123,8 @@ def reference_throughput(steps, warmup):
 
     if not RA.available():
         return None
-    per_core = max(4, int(round(1100.0 / max(steps + warmup, 1))))  # ~1.5 s of Model.run per process
+    # ~10 s of Model.run per process (the reference does ~9e3 node-timesteps/s on a core): 18 000 member-steps
+    per_core = min(400, max(4, int(round(18000.0 / max(steps, 1)))))
     r = RA.run(steps=steps, warmup=warmup, members_per_core=per_core)
     r["sample"] = (f"{r['members']} catchments ({per_core} per core) x {steps} timed steps (+{warmup} warm-up) of the "
                    f"config-2 ensemble through wsimod Model.run (baseline/_ref), one process per core, "
@@ -486,7 +487,7 @@ def main():
         port = {"value": v, "unit": "node-timesteps/s", "cores": cores, "kind": "port",
                 "sample": f"{args.cpu_members} members x {steps_cpu} steps of the same ensemble, oracle/wsi_oracle.c "
                           f"(C restatement of the reference, OpenMP over members), {dt:.1f} s"}
-        ref = reference_throughput(min(K, 40), 5)
+        ref = reference_throughput(min(K, 180), 5)
         if ref is not None:
             cpu = {"value": ref["value"], "unit": "node-timesteps/s", "cores": ref["cores"], "kind": "reference",
                    "sample": ref["sample"], "single_core": ref["single_core"], "port": port}
