@@ -178,6 +178,49 @@ def _timed_max(ms, world, device):
     return ms
 
 
+def e2e_reduced(run, fm, t_begin, K, REC, world, device):
+    """End to end with the outputs an ensemble run is specified with: every step
+    the forcing rows come from pinned host memory and the step's violation count and the full series of
+    the record-window members go back to pinned host memory; the per-member reductions (running sum and
+    maximum of every recorded plane, kept on the device) are read once the steps are done -- inside the
+    timed region.  Steps go through wsi_run_steps in chunks of the record ring (REC rows).
+    Returns (seconds, max over ranks; h2d bytes per step; d2h bytes per step; the reductions)."""
+    import torch
+    import torch.distributed as dist
+
+    cin, nf = run.buffers.array("catch_inputs"), run.buffers.array("node_forcing")
+    h_cin, h_nf = torch.from_numpy(fm.catch_inputs).pin_memory(), torch.from_numpy(fm.node_forcing).pin_memory()
+    cnt = run.buffers.array("mb_count")
+    h_cnt = torch.zeros(fm.T, dtype=torch.int32).pin_memory()
+    d_red = run.buffers.array("red_out")
+    h_red = torch.empty(d_red.shape, dtype=torch.float64).pin_memory()
+    d_ser = run.buffers.array("out_probe")  # [REC, planes, members of the record window]
+    h_ser = torch.empty((K + REC,) + tuple(d_ser.shape[1:]), dtype=torch.float64).pin_memory()
+    rows = 0
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_start = time.perf_counter()
+    t = t_begin
+    while t < t_begin + K:
+        n = min(REC, t_begin + K - t)
+        if cin.numel():
+            cin[t:t + n].copy_(h_cin[t:t + n], non_blocking=True)
+        nf[t:t + n].copy_(h_nf[t:t + n], non_blocking=True)
+        run.buffers.set_rec_window(t)
+        run.run(t, t + n)
+        h_cnt[t:t + n].copy_(cnt[t:t + n], non_blocking=True)
+        h_ser[rows:rows + n].copy_(d_ser[:n], non_blocking=True)  # stream-ordered before the ring is reused
+        rows += n
+        t += n
+    h_red.copy_(d_red, non_blocking=True)
+    torch.cuda.synchronize()
+    e2e_s = _timed_max(time.perf_counter() - t_start, world, device)
+    h2d = (fm.catch_inputs[0].size + fm.node_forcing[0].size) * 8
+    d2h = 4 + h_ser[0].numel() * 8 + h_red.numel() * 8 / K
+    return e2e_s, int(h2d), int(d2h), h_red
+
+
 def bench_config3(args, rank, world, device, K, W, peak):
     """SURVEY 8d config 3 / BASELINE.json configs[2]: the parameter ensemble of the Oxford catchment's
     land + river-side nodes, ``--members3`` distinct members per GPU (members are independent: weak
@@ -224,42 +267,10 @@ def bench_config3(args, rank, world, device, K, W, peak):
     e1.record(stream)
     torch.cuda.synchronize()
     ms = _timed_max(e0.elapsed_time(e1), world, device)
-    # end to end: every step the forcing rows come from pinned host memory and the step's violation
-    # count goes back; the reductions and the 16 series are read once the steps are done
-    cin, nf = run.buffers.array("catch_inputs"), run.buffers.array("node_forcing")
-    h_cin, h_nf = torch.from_numpy(fm.catch_inputs).pin_memory(), torch.from_numpy(fm.node_forcing).pin_memory()
-    cnt = run.buffers.array("mb_count")
-    h_cnt = torch.zeros(fm.T, dtype=torch.int32).pin_memory()
-    d_red = run.buffers.array("red_out")
-    h_red = torch.empty(d_red.shape, dtype=torch.float64).pin_memory()
-    d_ser = run.buffers.array("out_probe")  # [REC, 13, 16]: the 16 members whose series are kept
-    h_ser = torch.empty((K + REC,) + tuple(d_ser.shape[1:]), dtype=torch.float64).pin_memory()
-    rows = 0
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t_start = time.perf_counter()
-    t = W + K
-    while t < W + 2 * K:
-        n = min(REC, W + 2 * K - t)
-        cin[t:t + n].copy_(h_cin[t:t + n], non_blocking=True)
-        nf[t:t + n].copy_(h_nf[t:t + n], non_blocking=True)
-        run.buffers.set_rec_window(t)
-        run.run(t, t + n)
-        h_cnt[t:t + n].copy_(cnt[t:t + n], non_blocking=True)
-        h_ser[rows:rows + n].copy_(d_ser[:n], non_blocking=True)  # stream-ordered before the ring is reused
-        rows += n
-        t += n
-    h_red.copy_(d_red, non_blocking=True)
-    torch.cuda.synchronize()
-    red = h_red
-    e2e_s = time.perf_counter() - t_start
-    e2e_s = _timed_max(e2e_s, world, device)
+    e2e_s, h2d, d2h, red = e2e_reduced(run, fm, W + K, K, REC, world, device)
     alg, parts = E.algorithmic_bytes_per_replica_step(fm, 0)
     alg += 8 * 2 * 2 * len(ps.probes)  # the running sum and maximum of every reduced plane: read + written
     value = world * R * n_nodes * K / (ms * 1e-3)
-    h2d = (fm.catch_inputs[0].size + fm.node_forcing[0].size) * 8
-    d2h = 4 + h_ser[0].numel() * 8 + red.numel() * 8 / K
     return {
         "workload": "config3 (BASELINE.json configs[2]): parameter ensemble of the Oxford catchment's land + river-side "
                     "nodes, 12 Oxford pollutants, members = Oxford parameters x log-uniform(0.8, 1.25)",
@@ -473,10 +484,38 @@ def main():
             tm = torch.tensor([e2e_s], device=device, dtype=torch.float64)
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             e2e_s = float(tm.item())
-        e2e = {"value": world * R * NODES_PER_MEMBER * K / e2e_s, "unit": "node-timesteps/s",
-               "h2d_bytes_per_step": int(sess.h2d_bytes_per_step), "d2h_bytes_per_step": int(sess.d2h_bytes_per_step),
-               "outputs": "river-outlet VQIP of every member + mass-balance violation count, every step",
-               "checksum": float(np.sum(results[-1])) if results else None}
+        every_member = {"value": world * R * NODES_PER_MEMBER * K / e2e_s, "unit": "node-timesteps/s",
+                        "h2d_bytes_per_step": int(sess.h2d_bytes_per_step), "d2h_bytes_per_step": int(sess.d2h_bytes_per_step),
+                        "outputs": "river-outlet VQIP of EVERY member + mass-balance violation count, every step "
+                                   "(wsi_b200.session.EnsembleSession, one Python call per step)",
+                        "checksum": float(np.sum(results[-1])) if results else None}
+        del sess, results
+        # The headline end-to-end number moves the outputs the workload is specified with (SURVEY 8d config 2:
+        # full series of the first 64 members for parity; per-member objective reductions -- running sum and
+        # maximum of the outlet's flow and every pollutant -- kept on the device and read at the end).  The
+        # every-member variant above stays on the line: at N = 8 its 8 x 20 GB/s of D2H meets the host's
+        # aggregate DMA bandwidth (~100 GB/s on this pool's 8-GPU boxes), which is a property of the box.
+        from wsi_b200.backend.engine import GpuRunner
+        from wsi_b200.backend.probes import ProbeSet
+
+        ps2 = ProbeSet(fm).add_flows(outlet)
+        run2 = GpuRunner(fm, probes=ps2.probes, rec_t0=0, rec_T=8, device=device, engine="replica",
+                         reduce_probes=ps2.probes, rec_members=(0, 64))
+        t = 0
+        while t < W:
+            n = min(8, W - t)
+            run2.buffers.set_rec_window(t)
+            run2.run(t, t + n)
+            t += n
+        red_s, h2d2, d2h2, red = e2e_reduced(run2, fm, W, K, 8, world, device)
+        e2e = {"value": world * R * NODES_PER_MEMBER * K / red_s, "unit": "node-timesteps/s",
+               "h2d_bytes_per_step": h2d2, "d2h_bytes_per_step": d2h2,
+               "outputs": "per-member sum and maximum of the river-outlet VQIP (13 planes) reduced on the device, read "
+                          "once at the end (inside the timed region); full outlet series of the first 64 members and "
+                          "the mass-balance violation count every step; forcing from pinned host memory every step",
+               "objective_checksum": float(np.nansum(red[0].numpy())),
+               "every_member_outputs": every_member}
+        del run2
 
     # ---------------- CPU baseline (rank 0, N == 1) ----------------------------------------------
     cpu = None
