@@ -2,7 +2,9 @@
 """Markdown summary of an ncu report (--set full) for profiles/: per kernel the headline metrics,
 the stall picture and the DRAM traffic; also rewrites profiles/traffic.json for the step kernel.
 
-    python tools/ncu_summary.py gpurun_out/x.ncu-rep "<title>" "<command>" > profiles/rNN_ncu_kernels.md
+    python tools/ncu_summary.py gpurun_out/x.ncu-rep "<title>" "<command>" [--no-traffic] > profiles/rNN_ncu_kernels.md
+
+--no-traffic: leave profiles/traffic.json alone (captures of other workloads than bench.py's headline one).
 """
 import csv, json, os, re, subprocess, sys
 
@@ -30,6 +32,8 @@ for r in rows[2:]:
                  for i, x in enumerate(h) if 'issue_stalled' in x and 'per_issue_active' in x), reverse=True)
     print("\nStall cycles per issued instruction: " + ", ".join(f"{n} {v:.1f}" for v, n in st if v > 0.5) + "\n")
     traffic[short] = (float(r[h.index('dram__bytes_read.sum')]) + float(r[h.index('dram__bytes_write.sum')])) * 1e6
+if "--no-traffic" in sys.argv[4:]:
+    sys.exit(0)
 # one entry per kernel of the captured timestep; the total is what bench.py reports as roofline.traffic
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 json.dump({"dram_bytes_per_step": int(sum(traffic.values())),
