@@ -1,0 +1,1 @@
+"""wsi_b200.demo: host-side mirror of the reference interface."""
