@@ -37,6 +37,31 @@ def test_golden_parity(name):
     assert run.launch_count() > 0
 
 
+@pytest.mark.parametrize("name", ["quickstart", "fixture3607", "config2", "rivernet", "oxford", "city", "reservoirs", "irrigation"])
+def test_large_ensemble_launch_sequence_on_goldens(name, monkeypatch):
+    """Ensembles beyond WSI_B200_FUSED_TAIL_MAX_R members (default 4096) run mass balance and end_timestep
+    in wsi_settle_kernel, one thread per (node, member), instead of the schedule kernel's fused tail
+    (DESIGN.md 2a).  Forcing that launch sequence on the goldens puts the settle kernel under the same
+    parity as everything else: flows, stores and every node's (in, ds, out) against the reference, and
+    violation counts, status flags and system totals against the fused sequence."""
+    from wsi_b200.backend.probes import ProbeSet
+
+    fm, ref = load_golden(name)
+    ps = ProbeSet(fm).add_standard()
+    fused = _run_gpu(fm, ps, chunks=2)
+    monkeypatch.setenv("WSI_B200_FUSED_TAIL_MAX_R", "0")
+    settle = _run_gpu(fm, ps, chunks=2)
+    ok, reports = compare_blocks(ps.split(settle.out_probe()), ref, fm)
+    ok2, rep = compare_mb(settle.out_mb(), ref["mb"], fm)
+    assert ok and ok2, "\n".join(reports + [rep])
+    assert np.array_equal(settle.out_probe(), fused.out_probe())  # the same device functions in the same order
+    assert np.array_equal(settle.out_mb(), fused.out_mb())
+    assert np.array_equal(settle.mb_count()[: fm.T], fused.mb_count()[: fm.T])
+    assert np.array_equal(settle.node_flags(), fused.node_flags())
+    a, b = settle.mb_sums()[: fm.T], fused.mb_sums()[: fm.T]  # block-reduced in a different (fixed) order
+    assert np.allclose(a, b, rtol=1e-12, atol=1e-9 * max(1.0, float(np.abs(b).max())))
+
+
 @pytest.mark.parametrize("name", GOLDENS)
 def test_status_flags_and_violation_counts_match_oracle(name):
     """The advisories are under parity too: the sticky per-node status words (mass balance,

@@ -33,6 +33,14 @@ bool cluster_enabled() {
   return on;
 }
 
+// Replicas up to which the schedule kernel runs mass balance and end_timestep itself (two launches per step)
+// instead of handing them to wsi_settle_kernel.  WSI_B200_FUSED_TAIL_MAX_R overrides the
+// measured default -- the tests use it to run small models through the large-ensemble path.
+int fused_tail_max_r() {
+  const char* e = getenv("WSI_B200_FUSED_TAIL_MAX_R");
+  return e && e[0] ? atoi(e) : 4096;
+}
+
 }  // namespace wsi_host
 
 using namespace wsi_host;
@@ -167,7 +175,7 @@ int run_steps_graph(const WsiModelDesc* d, int slot, int64_t t0, int64_t t1, cud
                            d->idx[5], d->idx[6], d->idx[7], d->R, d->n_nodes, d->n_arcs, d->n_surf, d->surf_class_ptr[0],
                            d->surf_class_ptr[1], d->surf_class_ptr[2], d->surf_class_ptr[3], d->surf_class_ptr[4],
                            d->n_probe, d->n_red, d->n_end, d->n_sched, d->sched_split, d->engine, d->n_net_levels, d->n_net_calc, d->n_net_final,
-                           d->n_net_bnd, d->mb_sums ? 1 : 0};
+                           d->n_net_bnd, d->mb_sums ? 1 : 0, fused_tail_max_r()};
   unsigned long long h = fnv(1469598103934665603ull, baked, sizeof baked);
   if (d->engine == 1) h = fnv(h, d->net_level_ptr_host, sizeof(int32_t) * (size_t)(d->n_net_levels + 1));
   DeviceState* ds = device_state();

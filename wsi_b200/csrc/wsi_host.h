@@ -23,6 +23,7 @@ extern thread_local char g_err[512];
 extern std::atomic<long long> g_launches;
 int fail(int code, const char* fmt, const char* detail = "");
 bool cluster_enabled();
+int fused_tail_max_r();
 
 constexpr int kBlock = WSI_STEP_BLOCK;  // replicas per block of the per-replica schedule kernel
 #ifndef WSI_SURF_BLOCK

@@ -47,8 +47,7 @@ namespace {
 #ifndef WSI_MB_MINB  // mass balance / record / end_timestep: streaming kernels
 #define WSI_MB_MINB 5  // 96 registers: 6 (80) spills more, 4 (128) starves the end_timestep copy (gpurun sweep, round 1)
 #endif
-constexpr size_t kDescSmem = sizeof(WsiModelDesc);
-constexpr int kFusedTailMaxR = 4096;  // replicas up to which the schedule kernel runs mb / record / end itself  // dynamic shared memory: the staged descriptor
+constexpr size_t kDescSmem = sizeof(WsiModelDesc);  // dynamic shared memory: the staged descriptor
 
 // Work-item decode of the object-parallel kernels.  Replica engine (FLAT = false): blockIdx.y is
 // the item and blockIdx.x tiles the replicas, so every block is homogeneous in item.  Network
@@ -754,7 +753,7 @@ int launch(const WsiModelDesc* d, int slot, const CFG& cfg, int64_t t, int b, in
       // phases asked for (fused tail, one thread per replica).  Large ones have the threads to hide
       // the tail's dependent loads only when it runs one thread per (object, replica): measured on
       // config 2 at R = 1e5, fused 0.228 ms vs 0.13 ms for the three object-parallel kernels.
-      const bool fused = d->R <= kFusedTailMaxR;
+      const bool fused = d->R <= fused_tail_max_r();
       // the lean instantiation for models without treatment works / demand / distribution / queue groundwater /
       // abstractions (desc.features == 0): those handlers are compiled out of the hot kernel
       bool lean = false;
