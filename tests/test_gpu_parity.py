@@ -375,6 +375,43 @@ def test_config3_sixteen_members_match_the_reference():
     assert not (run.node_flags() & ~np.uint32(1)).any()
 
 
+def test_config3_full_size_repeats_the_reference_members():
+    """BASELINE.json configs[2] at its per-GPU size (125 000 members), through a size-independent property:
+    with the 16 reference-run parameter sets tiled over the ensemble, member r must reproduce member r % 16
+    bit for bit in the per-member reductions (running sum and maximum of the outlet VQIP, formed on the
+    device), whatever block or warp it lands in; the first 16 members' full series are compared with what
+    the reference produced for them (tests/golden/config3_members16.npz); no violation, no status flag."""
+    from parity_util import compare, nonadditive_mask
+    from wsi_b200 import ensemble as E
+    from wsi_b200.backend.engine import GpuRunner
+    from wsi_b200.backend.probes import ProbeSet
+
+    template, _ = load_golden("config3")
+    fm16, ref = load_golden("config3_members16")
+    R = 125_000
+    factors = np.tile(E.config3_factors(16), (R // 16 + 1, 1))[:R]
+    fm = E.build_config3(R, template, factors=factors)
+    outlet = fm.arc_names.index("mixer_to_waste")
+    ps = ProbeSet(fm).add_flows([outlet])
+    run = GpuRunner(fm, probes=ps.probes, rec_t0=0, rec_T=fm.T, record_mb=False, engine="replica",
+                    reduce_probes=ps.probes, rec_members=(0, 16))
+    run.run(0, fm.T)
+    run.synchronize()
+    rsum, rmax = run.reduced()
+    assert np.isfinite(rsum).all() and np.isfinite(rmax).all()
+    for red in (rsum, rmax):
+        first = red[:, :16]
+        assert np.array_equal(red, np.tile(first, (1, R // 16 + 1))[:, :R])
+    assert len(np.unique(rsum[0, :16])) == 16  # sixteen different members
+    got = run.out_probe().reshape(fm.T, 1, fm.V, 16)
+    kept = [str(a) for a in ref["kept_arcs"]]
+    exp = ref["flows_kept"].reshape(fm.T, len(kept), fm.V, 16)[:, [kept.index("mixer_to_waste")]]
+    ok, rep = compare("config3 full size, first 16 members", got, exp, fm.float_accuracy,
+                      ignore=nonadditive_mask(got, exp, fm, 1))
+    assert ok, rep
+    assert int(run.mb_count()[: fm.T].sum()) == 0 and not run.node_flags().any()
+
+
 def test_config3_ensemble_equals_oracle():
     """SURVEY 8d config 3 (Oxford land + river-side subset, 12 Oxford pollutants with only
     temperature non-additive -> CfgStaticMask<12>, junction chains three deep) as an ensemble of 96
