@@ -433,18 +433,13 @@ def test_config3_ensemble_equals_oracle():
     assert not run.node_flags().any()
 
 
-@pytest.mark.parametrize("segments,chunk", [(1, None), (1, 3), (3, 2)])
-def test_partitioned_network_is_bit_identical_on_gpu(segments, chunk):
-    """SURVEY 8e config 4: upland shards + trunk segments (boundary series on the cut arcs) == the
-    whole network on one device, bit for bit -- also when every part runs on its own stream in
-    chunks of timesteps (shards ahead of the trunk, the trunk's segments as a pipeline)."""
+def _partition_equals_whole(N, T, n_parts, segments, chunk, binding_frac):
     from wsi_b200 import rivernet
     from wsi_b200.backend import partition as P
     from wsi_b200.backend.engine import GpuRunner
     from wsi_b200.parallel import build_partition_runners, run_partitioned
 
-    N, T = 20000, 10
-    fm = rivernet.build_dendritic(N, T=T, binding_frac=0.01, names=False)
+    fm = rivernet.build_dendritic(N, T=T, binding_frac=binding_frac, names=False)
 
     def outlet_probes(sub):
         nodes = list(sub.recipe["nodes"]) if "nodes" in (sub.recipe or {}) else None
@@ -462,19 +457,35 @@ def test_partitioned_network_is_bit_identical_on_gpu(segments, chunk):
     whole = make(fm, outlet_probes(fm), T)
     whole.run(0, T)
     whole.synchronize()
-    parts = P.partition_network(fm, 4, stem_segments=segments)
+    parts = P.partition_network(fm, n_parts, stem_segments=segments)
     subs = parts["parts"]
     runners = run_partitioned(parts, build_partition_runners(parts, make, T, extra_probes=outlet_probes), T,
                               chunk=chunk)
     assert np.array_equal(runners[len(subs) - 1].out_probe(), whole.out_probe())
     o = fm.plane("tank", "storage")
-    ref = whole.groups()["tank"][o:o + fm.V]
+    ref = whole.buffers.to_numpy("group_tank")[o:o + fm.V]  # one group: at 10^6 rivers all of them are gigabytes
     got = np.full_like(ref, np.nan)
     for k, r in runners.items():
         nodes = subs[k].recipe["nodes"]
         rivers = nodes[fm.node_type[nodes] == 6] - 1  # river slots 1..N hold tanks 0..N-1
-        got[:, rivers] = r.groups()["tank"][o:o + fm.V][:, :len(rivers)]
+        got[:, rivers] = r.buffers.to_numpy("group_tank")[o:o + fm.V][:, :len(rivers)]
     assert np.array_equal(got, ref)
+    assert int(whole.mb_count()[:T].sum()) == sum(int(r.mb_count()[:T].sum()) for r in runners.values())
+
+
+@pytest.mark.parametrize("segments,chunk", [(1, None), (1, 3), (3, 2)])
+def test_partitioned_network_is_bit_identical_on_gpu(segments, chunk):
+    """SURVEY 8e config 4: upland shards + trunk segments (boundary series on the cut arcs) == the
+    whole network on one device, bit for bit -- also when every part runs on its own stream in
+    chunks of timesteps (shards ahead of the trunk, the trunk's segments as a pipeline)."""
+    _partition_equals_whole(20000, 10, 4, segments, chunk, 0.01)
+
+
+def test_partitioned_network_at_full_size():
+    """BASELINE.json configs[3] at its size (10^6 rivers, 2 000 001 nodes), as bench.py runs it: six upland
+    shards + trunk on seven streams in chunks of timesteps.  The outlet's inflow series and every river's
+    final tank are those of the unpartitioned run, bit for bit."""
+    _partition_equals_whole(1_000_000, 8, 6, 1, 4, 0.0)
 
 
 def test_cluster_tail_kernel_bitwise(monkeypatch):
