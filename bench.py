@@ -124,7 +124,7 @@ def reference_throughput(steps, warmup):
     if not RA.available():
         return None
     # ~10 s of Model.run per process (the reference does ~9e3 node-timesteps/s on a core): 18 000 member-steps
-    per_core = min(400, max(4, int(round(18000.0 / max(steps, 1)))))
+    per_core = min(int(os.environ.get("WSI_BENCH_REF_PER_CORE", "400")), max(4, int(round(18000.0 / max(steps, 1)))))
     r = RA.run(steps=steps, warmup=warmup, members_per_core=per_core)
     r["sample"] = (f"{r['members']} catchments ({per_core} per core) x {steps} timed steps (+{warmup} warm-up) of the "
                    f"config-2 ensemble through wsimod Model.run (baseline/_ref), one process per core, "
