@@ -803,6 +803,48 @@ def scenario_irrigation(T=500):
     save("irrigation", fm, ref, "IrrigationSurface pulling through its Land (River / Groundwater / Reservoir) + VariableAreaSurface")
 
 
+def scenario_distribution(T=300):
+    """A plain Distribution with leakage (pulls pass through it enlarged by the leak, the leak goes to a
+    Groundwater whose capacity binds now and then) supplying a base Demand (constant demand with its own
+    loads) and a ResidentialDemand from an FWTW fed by a Reservoir; the used water leaves through a Sewer."""
+    set_default_pollutants()
+    dates = [pd.Timestamp("2005-01-01") + pd.Timedelta(days=i) for i in range(T)]
+    rng = np.random.default_rng(20261024)
+    forcing = synthetic_forcing(dates, rng)
+    tdata = {k: v for k, v in forcing.items() if k[0] == "temperature"}
+    init = lambda v: {"volume": v, "do": 0.008, "org-phosphorus": v * 2e-5, "phosphate": v * 5e-5,  # noqa: E731
+                      "ammonia": v * 1e-4, "solids": v * 1e-3, "bod": v * 1e-3, "cod": v * 2e-3, "ph": 7.1,
+                      "temperature": 9.0, "nitrate": v * 2e-3, "nitrite": v * 1e-5, "org-nitrogen": v * 3e-4}
+    house = {"do": 0.004, "org-phosphorus": 2e-7, "phosphate": 5e-7, "ammonia": 3e-6, "solids": 1e-5, "bod": 2e-5,
+             "cod": 4e-5, "ph": 7.4, "temperature": 14.0, "nitrate": 1e-6, "nitrite": 1e-8, "org-nitrogen": 2e-6}
+    nodes = [
+        {"type_": "Reservoir", "name": "res", "capacity": 5e6, "area": 1e5, "initial_storage": init(7e5)},
+        {"type_": "FWTW", "name": "fwtw", "service_reservoir_storage_capacity": 6e3, "service_reservoir_storage_area": 400,
+         "service_reservoir_initial_storage": init(3e3), "treatment_throughput_capacity": 3.2e3, "data_input_dict": tdata},
+        {"type_": "Distribution", "name": "mains", "leakage": 0.08},
+        {"type_": "Groundwater", "name": "gw", "area": 1e5, "capacity": 4e3, "residence_time": 12.0, "initial_storage": init(3.2e3)},
+        {"type_": "Demand", "name": "works", "constant_demand": 650.0,
+         "pollutant_load": {"solids": 0.4, "bod": 0.6, "temperature": 21.0, "ph": 7.9}},
+        {"type_": "Demand", "node_type_override": "ResidentialDemand", "name": "houses", "population": 1.6e4, "per_capita": 0.14,
+         "pollutant_load": house, "data_input_dict": tdata},
+        {"type_": "Sewer", "name": "foul", "capacity": 2.6e3, "pipe_timearea": {0: 0.7, 1: 0.3}},
+        {"type_": "Node", "name": "j"},
+        {"type_": "Waste", "name": "out"},
+    ]
+    arcs = [
+        ("res-fwtw", "res", "fwtw", {}), ("fwtw-mains", "fwtw", "mains", {}), ("fwtw-foul", "fwtw", "foul", {}),
+        ("mains-works", "mains", "works", {"capacity": 640.0}), ("mains-houses", "mains", "houses", {}),
+        ("mains-gw", "mains", "gw", {}), ("works-foul", "works", "foul", {}), ("houses-foul", "houses", "foul", {}),
+        ("foul-j", "foul", "j", {}), ("gw-j", "gw", "j", {}), ("j-out", "j", "out", {}),
+    ]
+    m = Model()
+    m.add_nodes(nodes)
+    m.add_arcs([dict({"type_": "Arc", "name": a, "in_port": i, "out_port": o}, **kw) for a, i, o, kw in arcs])
+    fm = flatten_ref(m, dates)
+    ref = run_reference(m, dates)
+    save("distribution", fm, ref, "Distribution with leakage, base Demand with a constant demand, ResidentialDemand, FWTW")
+
+
 def scenario_rivertree(T=380):
     """Dendritic river network (the network engine's case): catchments and rivers joined through
     junctions (also chained and shared ones), a binding river-arc capacity, decays, a dry
@@ -990,6 +1032,7 @@ SCENARIOS = {
     "rivernet": scenario_rivernet,
     "reservoirs": scenario_reservoirs,
     "irrigation": scenario_irrigation,
+    "distribution": scenario_distribution,
     "rivertree": scenario_rivertree,
     "config3": scenario_config3,
     "hourly": scenario_hourly,

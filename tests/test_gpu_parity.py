@@ -8,7 +8,7 @@ from parity_util import compare_blocks, compare_mb, load_golden
 pytestmark = pytest.mark.gpu
 
 GOLDENS = ["quickstart", "quickstart_simple", "quickstart_p5", "quickstart_p14", "fixture3607", "config2", "rivernet", "rivertree", "config3", "hourly",
-           "oxford", "fixture3607_full", "city", "queuegw", "reservoirs", "irrigation"]
+           "oxford", "fixture3607_full", "city", "queuegw", "reservoirs", "irrigation", "distribution"]
 
 
 def _run_gpu(fm, ps, record_mb=True, chunks=1, engine="replica"):

@@ -354,3 +354,53 @@ def test_arc_variants_and_river_reservoir_through_the_mirror_api():
     assert cand == [1, 3]
     with pytest.raises(UnsupportedModelError):
         m.add_arcs([{"type_": "QueueArc", "name": "q", "in_port": "r1", "out_port": "j"}])
+
+
+def test_distribution_and_base_demand_through_the_mirror_api():
+    """Distribution with leakage (distribution.py:14-141) and the base Demand's constant demand
+    (demand.py:14-131), built with this package's classes, flatten to what golden 'distribution' -- built
+    with the reference's classes -- holds."""
+    import pandas as pd
+
+    from wsi_b200.backend import layout as L
+    from wsi_b200.core import constants
+    from wsi_b200.orchestration.model import Model
+
+    constants.set_default_pollutants()
+    constants.FLOAT_ACCURACY = 1e-11
+    fm_ref, _ = load_golden("distribution")
+    T = fm_ref.T
+    dates = [pd.Timestamp("2005-01-01") + pd.Timedelta(days=i) for i in range(T)]
+    tdata = {("temperature", d): float(fm_ref.node_forcing[t, 0, 2]) for t, d in enumerate(dates)}
+    init = lambda v: {"volume": v, "do": 0.008, "org-phosphorus": v * 2e-5, "phosphate": v * 5e-5,  # noqa: E731
+                      "ammonia": v * 1e-4, "solids": v * 1e-3, "bod": v * 1e-3, "cod": v * 2e-3, "ph": 7.1,
+                      "temperature": 9.0, "nitrate": v * 2e-3, "nitrite": v * 1e-5, "org-nitrogen": v * 3e-4}
+    house = {"do": 0.004, "org-phosphorus": 2e-7, "phosphate": 5e-7, "ammonia": 3e-6, "solids": 1e-5, "bod": 2e-5,
+             "cod": 4e-5, "ph": 7.4, "temperature": 14.0, "nitrate": 1e-6, "nitrite": 1e-8, "org-nitrogen": 2e-6}
+    m = Model()
+    m.add_nodes([
+        {"type_": "Reservoir", "name": "res", "capacity": 5e6, "area": 1e5, "initial_storage": init(7e5)},
+        {"type_": "FWTW", "name": "fwtw", "service_reservoir_storage_capacity": 6e3, "service_reservoir_storage_area": 400,
+         "service_reservoir_initial_storage": init(3e3), "treatment_throughput_capacity": 3.2e3, "data_input_dict": tdata},
+        {"type_": "Distribution", "name": "mains", "leakage": 0.08},
+        {"type_": "Groundwater", "name": "gw", "area": 1e5, "capacity": 4e3, "residence_time": 12.0, "initial_storage": init(3.2e3)},
+        {"type_": "Demand", "name": "works", "constant_demand": 650.0,
+         "pollutant_load": {"solids": 0.4, "bod": 0.6, "temperature": 21.0, "ph": 7.9}},
+        {"type_": "Demand", "node_type_override": "ResidentialDemand", "name": "houses", "population": 1.6e4, "per_capita": 0.14,
+         "pollutant_load": house, "data_input_dict": tdata},
+        {"type_": "Sewer", "name": "foul", "capacity": 2.6e3, "pipe_timearea": {0: 0.7, 1: 0.3}},
+        {"type_": "Node", "name": "j"},
+        {"type_": "Waste", "name": "out"}])
+    arcs = [("res-fwtw", "res", "fwtw", {}), ("fwtw-mains", "fwtw", "mains", {}), ("fwtw-foul", "fwtw", "foul", {}),
+            ("mains-works", "mains", "works", {"capacity": 640.0}), ("mains-houses", "mains", "houses", {}),
+            ("mains-gw", "mains", "gw", {}), ("works-foul", "works", "foul", {}), ("houses-foul", "houses", "foul", {}),
+            ("foul-j", "foul", "j", {}), ("gw-j", "gw", "j", {}), ("j-out", "j", "out", {})]
+    m.add_arcs([dict({"type_": "Arc", "name": a, "in_port": i, "out_port": o}, **kw) for a, i, o, kw in arcs])
+    m.dates = dates
+    fm = m.flatten()
+    assert fm.node_type[2] == L.NT["Distribution"] and fm.view("distrib", "leakage")[0, 0, 0] == 0.08
+    assert fm.view("demand", "population")[0, 0, 0] == -1 and fm.view("demand", "per_capita")[0, 0, 0] == 650.0
+    for g in fm.groups:
+        assert np.array_equal(fm.groups[g], fm_ref.groups[g]), g
+    for k in ("node_type", "node_gidx", "arc_in", "arc_out", "cand_ptr", "cand_arcs", "sched_op", "sched_node", "arc_flags"):
+        assert np.array_equal(getattr(fm, k), getattr(fm_ref, k)), k

@@ -9,7 +9,7 @@ import pytest
 from parity_util import compare_blocks, compare_mb, load_golden
 
 GOLDENS = ["quickstart", "quickstart_simple", "quickstart_p5", "quickstart_p14", "fixture3607", "config2", "rivernet", "rivertree", "config3", "hourly",
-           "oxford", "fixture3607_full", "city", "queuegw", "reservoirs", "irrigation"]
+           "oxford", "fixture3607_full", "city", "queuegw", "reservoirs", "irrigation", "distribution"]
 
 
 @pytest.fixture(scope="module")

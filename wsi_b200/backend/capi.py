@@ -440,7 +440,7 @@ class ModelBuffers:
         d.n_demand = fm.n_obj.get("demand", 0)
         d.n_distrib = fm.n_obj.get("distrib", 0)
         d.sched_split = sched_split(fm)
-        rare = {L.NT[k] for k in ("WWTW", "FWTW", "Demand", "UnlimitedDistribution", "QueueGroundwater", "RiverReservoir")}
+        rare = {L.NT[k] for k in ("WWTW", "FWTW", "Demand", "UnlimitedDistribution", "QueueGroundwater", "RiverReservoir", "Distribution")}
         pulls = any(int(t) in (L.NT["Reservoir"], L.NT["RiverReservoir"]) and fm.in_ptr[i + 1] > fm.in_ptr[i] for i, t in enumerate(fm.node_type))
         d.features = 1 if (pulls or any(int(t) in rare for t in fm.node_type)) else 0
         if fm.n_obj["surf"] and ((fm.view("surf", "irrigation_coefficient") >= 0).any() or (fm.view("surf", "climate_scale") != 1.0).any()):

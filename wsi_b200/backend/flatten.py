@@ -240,6 +240,8 @@ class FlatModel:
         if groups["tank"].shape[0] == L.TANK.n_fields(V) - 2:  # environmental_flow, env_satisfied: none
             o = L.TANK.offset("environmental_flow", V)
             groups["tank"] = np.ascontiguousarray(np.insert(groups["tank"], [o, o], 0.0, axis=0))
+        if groups["distrib"].shape[0] == L.DISTRIB.n_fields(V) - 1:  # leakage: none
+            groups["distrib"] = np.ascontiguousarray(np.insert(groups["distrib"], L.DISTRIB.offset("leakage", V), 0.0, axis=0))
         if groups["river"].shape[0] == L.RIVER.n_fields(V) - 1:  # mrf: none
             groups["river"] = np.ascontiguousarray(np.insert(groups["river"], L.RIVER.offset("mrf", V), 0.0, axis=0))
         if groups["land"].shape[0] == L.LAND.n_fields(V) - 1:  # garden_surf: none
@@ -651,17 +653,25 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
             node_gidx[i] = len(gb["works"].cols)
             _flatten_works(gb["works"], n, add_store, pollutants, additive, non_additive)
         elif c == "Demand":
-            if not hasattr(n, "population"):
-                raise UnsupportedModelError(f"{n.name}: only ResidentialDemand is on the GPU path (demand.py:153)")
+            residential = hasattr(n, "population")
+            if not residential and n.__class__.__mro__[0].__name__ == "NonResidentialDemand":
+                raise UnsupportedModelError(f"{n.name}: NonResidentialDemand.get_demand calls itself (demand.py:143-150)")
             missing = [p for p in model_pollutants if p not in n.pollutant_load]
-            if missing:  # the reference raises KeyError in get_house_demand (demand.py:303-324)
+            if residential and missing:  # the reference raises KeyError in get_house_demand (demand.py:303-324)
                 raise UnsupportedModelError(f"{n.name}: pollutant_load lacks {missing}")
+            unknown = [p for p in n.pollutant_load if p not in model_pollutants]
+            if unknown:  # Demand.get_demand would put a foreign key into the VQIP (demand.py:126-129)
+                raise UnsupportedModelError(f"{n.name}: pollutant_load names {unknown}, not modelled")
             node_gidx[i] = len(gb["demand"].cols)
             b = gb["demand"]
             col = b.new()
-            for f in ("population", "per_capita", "gardening_efficiency", "constant_weighting", "constant_temp"):
-                b.set(col, f, getattr(n, f))
-            b.set(col, "forcing_id", forcing_series(n.data_input_dict, (None, None, "temperature")))
+            if residential:
+                for f in ("population", "per_capita", "gardening_efficiency", "constant_weighting", "constant_temp"):
+                    b.set(col, f, getattr(n, f))
+                b.set(col, "forcing_id", forcing_series(n.data_input_dict, (None, None, "temperature")))
+            else:  # base Demand (demand.py:14-131): population -1 marks it, per_capita holds constant_demand,
+                b.set(col, "population", -1.0)  # pollutant_load the absolute loads of that demand
+                b.set(col, "per_capita", float(n.constant_demand))
             b.set(col, "pollutant_load", [0.0] + [float(n.pollutant_load.get(p, 0.0)) for p in pollutants])
             for f in ("total_demand", "total_backup", "total_received"):
                 b.set(col, f, _vq(getattr(n, f), pollutants))
@@ -669,6 +679,12 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
             node_gidx[i] = len(gb["distrib"].cols)
             col = gb["distrib"].new()
             gb["distrib"].set(col, "supplied", _vq(n.supplied, pollutants))
+        elif c == "Distribution":
+            if not 0 <= n.leakage < 1:
+                raise UnsupportedModelError(f"{n.name}: leakage must be in [0, 1)")
+            node_gidx[i] = len(gb["distrib"].cols)
+            col = gb["distrib"].new()
+            gb["distrib"].set(col, "leakage", float(n.leakage))
         else:  # Node, Waste
             node_gidx[i] = 0
 

@@ -48,6 +48,7 @@ NODE_TYPES = [
     "UnlimitedDistribution",  # distribution.py:144-200: supplies whatever is pulled
     "QueueGroundwater",  # storage.py:248-449 (files itself under "Groundwater"): a QueueTank / DecayQueueTank store
     "RiverReservoir",  # storage.py:992-1133 (files itself under "Reservoir"): spills downstream, environmental flow
+    "Distribution",  # distribution.py:101-141: conveys pulls, denies pushes, leaks a share to Groundwater
 ]
 NT = {n: i for i, n in enumerate(NODE_TYPES)}
 
@@ -411,7 +412,7 @@ DEMAND = Group(
 )
 
 # UnlimitedDistribution (distribution.py:144-200)
-DISTRIB = Group("distrib", [Q("supplied")])
+DISTRIB = Group("distrib", [S("leakage"), Q("supplied")])  # leakage: plain Distribution (distribution.py:101-141)
 
 GROUPS = {g.name: g for g in (ARC, LAND, SURF, TANK, RIVER, SEWER, CATCH, WORKS, DEMAND, DISTRIB)}
 GROUP_ID = {n: i for i, n in enumerate(GROUPS)}

@@ -90,6 +90,9 @@ WSI_HD double river_pull_check_vol(C& c, int node, bool has_v, double v_vol) {
   return vol_vchange(avail, has_v ? pymin(avail_vol, v_vol) : avail_vol);
 }
 
+template <class C>
+WSI_HD typename C::Vq push_from(C& c, int node, const typename C::Vq& v, int filter, int tag);
+
 // in_port.pull_check(vqip)["volume"]
 template <int D, class C>
 WSI_HD double node_pull_check_vol(C& c, int node, bool has_v, double v_vol) {
@@ -107,6 +110,22 @@ WSI_HD double node_pull_check_vol(C& c, int node, bool has_v, double v_vol) {
         for (int i = d.in_ptr[node]; i < d.in_ptr[node + 1]; i++)
           avail = avail + arc_pull_check_vol<D - 1>(c, d.in_arcs[i], false, 0.0);
         if (has_v) avail = vol_vchange(avail, pymin(avail, v_vol));
+        return avail;
+      }
+    }
+    case WSI_NT_DISTRIBUTION: {  // pull_check_basic under decorate_leakage_check distribution.py:63-98
+      if constexpr (D == 0) {
+        c.flag(node, WSI_FLAG_DEPTH);
+        return 0.0;
+      } else {
+        const double leakage = *c.distrib(WSI_DISTRIB_LEAKAGE, g);
+        const double want = (leakage > 0 && has_v) ? v_vol / (1 - leakage) : v_vol;
+        double avail = 0.0;
+#pragma unroll 1
+        for (int i = d.in_ptr[node]; i < d.in_ptr[node + 1]; i++)
+          avail = avail + arc_pull_check_vol<D - 1>(c, d.in_arcs[i], false, 0.0);
+        if (has_v) avail = vol_vchange(avail, pymin(avail, want));
+        if (leakage > 0) avail = avail - vol_vchange(avail, avail * leakage);
         return avail;
       }
     }
@@ -225,6 +244,23 @@ WSI_HD typename C::Vq node_pull_set(C& c, int node, double volume) {
       } else {
         return pull_distributed<D - 1>(c, node, volume);
       }
+    case WSI_NT_DISTRIBUTION:  // Node.pull_distributed under decorate_leakage_set distribution.py:14-60
+      if constexpr (D == 0) {
+        c.flag(node, WSI_FLAG_DEPTH);
+        return vq_zero<C::P>();
+      } else {
+        const double leakage = *c.distrib(WSI_DISTRIB_LEAKAGE, g);
+        if (!(leakage > 0)) return pull_distributed<D - 1>(c, node, volume);
+        Vq reply = pull_distributed<D - 1>(c, node, volume / (1 - leakage));
+        const Vq leaked = c.vchange(reply, reply.x[0] * leakage);
+        reply = c.extract(reply, leaked);
+        const Vq unsuccessful = push_from(c, node, leaked, WSI_FILTER_GROUNDWATER, 0);
+        if (unsuccessful.x[0] > c.FA) {  // "warning, distribution leakage not going to GW"
+          c.flag(node, WSI_FLAG_DEFICIT);
+          reply = c.sum(reply, unsuccessful);
+        }
+        return reply;
+      }
     case WSI_NT_CATCHMENT: {  // pull_set_abstraction catchment.py:123-138 (the arc keeps the books)
       const Vq avail = catchment_avail(c, node);
       return c.vchange(avail, pymin(avail.x[0], volume));
@@ -332,7 +368,7 @@ WSI_HD typename C::Vq pull_distributed(C& c, int node, double volume, int of_typ
 
 // a push made from inside one of the out-of-line ops below
 template <class C>
-WSI_HD typename C::Vq push_from(C& c, int node, const typename C::Vq& v, int filter, int tag = 0) {
+WSI_HD typename C::Vq push_from(C& c, int node, const typename C::Vq& v, int filter, int tag) {
   c.tag = tag;
   const typename C::Vq reply = push_distributed<kJunctionDepth>(c, node, v, filter);
   c.tag = 0;
@@ -534,7 +570,7 @@ WSI_HDN void wwtw_make_discharge(C c, int node) {
   constexpr int V = C::V;
   const int g = c.D().node_gidx[node];
   double* tr = c.works(WSI_WORKS_TREATED(V), g);
-  const Vq reply = push_from(c, node, c.ldv(tr, c.s_works()), WSI_FILTER_ALL);
+  const Vq reply = push_from(c, node, c.ldv(tr, c.s_works()), WSI_FILTER_ALL, 0);
   c.stv(tr, c.s_works(), vq_zero<C::P>());
   if (reply.x[0] > c.FA)
     tank_push_force(c, c.tank(WSI_TANK_STORAGE(V), (int)*c.works(WSI_WORKS_TANK, g)), c.s_tank(), reply);
@@ -562,7 +598,7 @@ WSI_HDN void fwtw_treat_water(C c, int node) {
   works_treat_current_input(c, node, g);
   // liquor and solids go back to the sewers
   const Vq push_back = c.sum(c.ldv(c.works(WSI_WORKS_LIQUOR(V), g), s), c.ldv(c.works(WSI_WORKS_SOLIDS(V), g), s));
-  const Vq rejected = push_from(c, node, push_back, WSI_FILTER_SEWER);
+  const Vq rejected = push_from(c, node, push_back, WSI_FILTER_SEWER, 0);
   double* us = c.works(WSI_WORKS_UNPUSHED_SLUDGE(V), g);
   c.stv(us, s, c.sum(c.ldv(us, s), rejected));
   // treated water into the service reservoirs
@@ -589,10 +625,23 @@ WSI_HDN void demand_create(C c, int node) {
     excess += a;
   }
   c.tag = 0;
+  const double population = *c.demand(WSI_DEMAND_POPULATION, g);
+  if (population < 0) {  // base Demand (demand.py:14-131): {"default": constant_demand carrying pollutant_load}
+    Vq pol = c.ldv(c.demand(WSI_DEMAND_POLLUTANT_LOAD(V), g), s);
+    pol.x[0] = *c.demand(WSI_DEMAND_PER_CAPITA, g);
+    const double requested = 0.0 + pol.x[0];
+    const Vq got = pull_distributed<kJunctionDepth>(c, node, requested);
+    c.stv(c.demand(WSI_DEMAND_TOTAL_RECEIVED(V), g), s, got);
+    if (requested - got.x[0] > c.FA) c.flag(node, WSI_FLAG_DEFICIT);  // "demand deficit"
+    double* tb0 = c.demand(WSI_DEMAND_TOTAL_BACKUP(V), g);
+    c.stv(tb0, s, c.sum(c.ldv(tb0, s), push_from(c, node, pol, WSI_FILTER_ALL, 0)));
+    double* td0 = c.demand(WSI_DEMAND_TOTAL_DEMAND(V), g);
+    c.stv(td0, s, c.sum(c.ldv(td0, s), pol));
+    return;
+  }
   Vq garden = vq_zero<P>();
   garden.x[0] = excess * *c.demand(WSI_DEMAND_GARDENING_EFFICIENCY, g);
   // house: per-capita consumption carrying the per-capita loads
-  const double population = *c.demand(WSI_DEMAND_POPULATION, g);
   Vq foul = c.ldv(c.demand(WSI_DEMAND_POLLUTANT_LOAD(V), g), s);
 #pragma unroll
   for (int p = 1; p <= P; p++)

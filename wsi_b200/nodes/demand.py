@@ -1,5 +1,7 @@
 """Demand nodes (reference: wsimod/nodes/demand.py:14-324): parameters and per-step trackers.
-``create_demand`` is schedule op DEMAND_CREATE on the device (csrc/wsi_works.cuh)."""
+``create_demand`` is schedule op DEMAND_CREATE on the device (csrc/wsi_works.cuh): the base class's
+constant demand carrying ``pollutant_load`` (demand.py:119-131) and ResidentialDemand's house and
+garden demands (demand.py:229-324)."""
 from __future__ import annotations
 
 from .nodes import Node

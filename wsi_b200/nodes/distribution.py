@@ -1,6 +1,8 @@
-"""Distribution nodes (reference: wsimod/nodes/distribution.py:101-200).  ``UnlimitedDistribution``
-answers every pull in full (its pull handlers replace the leakage decorators of its parent class,
-distribution.py:163-168); the handlers run on the device (csrc/wsi_works.cuh)."""
+"""Distribution nodes (reference: wsimod/nodes/distribution.py:14-200).  ``Distribution`` conveys pulls
+and denies pushes; with ``leakage`` > 0 every pull through it is enlarged by the leak, which is pushed
+to the attached Groundwater (the decorators of distribution.py:14-98).  ``UnlimitedDistribution``
+answers every pull in full (its pull handlers replace the decorators, distribution.py:163-168).  The
+handlers run on the device (csrc/wsi_works.cuh)."""
 from __future__ import annotations
 
 from .nodes import Node
