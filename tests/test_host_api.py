@@ -404,3 +404,76 @@ def test_distribution_and_base_demand_through_the_mirror_api():
         assert np.array_equal(fm.groups[g], fm_ref.groups[g]), g
     for k in ("node_type", "node_gidx", "arc_in", "arc_out", "cand_ptr", "cand_arcs", "sched_op", "sched_node", "arc_flags"):
         assert np.array_equal(getattr(fm, k), getattr(fm_ref, k)), k
+
+
+@pytest.mark.reference
+def test_patched_reference_objects_are_refused():
+    """SURVEY 8b eligibility: reference objects whose behaviour was changed after construction -- by
+    ``wsimod.extensions.apply_patches`` (extensions.py:94-119), by a user function assigned as a method or put
+    into a handler dict or a surface's function lists, or by re-pointing a handler at another reference method --
+    are refused by the flattener; the pristine model flattens (subprocess: the reference is imported)."""
+    import subprocess
+    import sys
+
+    code = r"""
+import sys; sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests/golden'); sys.dont_write_bytecode = True
+import make_golden as G
+from wsimod import extensions
+from wsi_b200 import ensemble as E
+from wsi_b200.backend.flatten import UnsupportedModelError
+dates = E.daily_dates(20)
+forcing = E.synthetic_forcing_arrays(dates, 1)
+G.set_default_pollutants()
+fdict = {(v, d): float(forcing[t, 0, j]) for t, d in enumerate(dates) for j, v in enumerate(('precipitation', 'et0', 'temperature'))}
+def fresh():
+    extensions.extensions_registry.clear()
+    return G.config2_member(fdict, dates, 1.0, 1.0)
+def refused(m, what):
+    try:
+        G.flatten_ref(m, dates)
+    except UnsupportedModelError as e:
+        assert what in str(e), (what, str(e))
+        return
+    raise AssertionError('accepted: ' + what)
+m = fresh()
+G.flatten_ref(m, dates)
+river = 'gw'  # the member's Groundwater
+land = next(n for n in m.nodes.values() if n.__class__.__name__ == 'Land')
+# 1. a method patch through the reference's own registry
+@extensions.register_node_patch(river, 'distribute')
+def slower(self):
+    return None
+extensions.apply_patches(m)
+refused(m, 'was patched')
+# 2. a handler replaced through the registry (item patch), no _patched_ marker left behind
+m = fresh()
+@extensions.register_node_patch(river, 'push_set_handler', item='default')
+def swallow(self, vqip):
+    return self.empty_vqip()
+extensions.apply_patches(m)
+refused(m, 'user function')
+# 3. a user function assigned as a method by hand
+m = fresh()
+m.nodes[river].infiltrate = lambda: None
+refused(m, 'user function')
+# 4. a handler re-pointed at another method of the reference
+m = fresh()
+m.nodes[river].push_set_handler['default'] = m.nodes[river].push_set_deny
+refused(m, 'differ from a pristine Groundwater')
+# 5. a function appended to a surface's list; 6. a reference method that does not belong to the class's lists
+m = fresh()
+s = m.nodes[land.name].surfaces[0]
+s.processes.append(lambda: (s.empty_vqip(), s.empty_vqip()))
+refused(m, 'user function')
+m = fresh()
+s = m.nodes[land.name].surfaces[0]
+s.inflows.append(s.get_avail)
+refused(m, 'function lists hold')
+# 7. a tank whose end_timestep was replaced
+m = fresh()
+m.nodes[river].tank.end_timestep = lambda: None
+refused(m, 'user function')
+print('refused all')
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "refused all" in r.stdout, r.stdout + r.stderr

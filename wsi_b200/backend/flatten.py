@@ -281,6 +281,51 @@ class FlatModel:
 
 
 # ---------------------------------------------------------------------- helpers
+_HANDLER_DICTS = ("push_set_handler", "push_check_handler", "pull_set_handler", "pull_check_handler")
+
+
+def _foreign(f):
+    """A callable that is not code of the reference (or of this package's mirror of it)."""
+    mod = getattr(getattr(f, "__func__", f), "__module__", None) or ""
+    return not (mod.startswith("wsimod.") or mod.startswith("wsi_b200.") or mod == "builtins")
+
+
+def _check_unpatched(obj, key, label):
+    """SURVEY 8b eligibility: the kernels run the behaviour of the reference's classes, so an object whose
+    behaviour was changed after construction must be refused, not silently run unpatched.  Caught here:
+    ``wsimod.extensions.apply_patches`` (extensions.py:94-119: ``_patched_<method>`` attributes, replaced
+    methods, replaced handler / list items), user functions assigned as methods or put into the handler
+    dicts or a surface's inflows / processes / outflows lists, and handler dicts re-pointed at another
+    reference method.  ``key`` indexes handler_table.HANDLER_TABLE (what a pristine object carries)."""
+    import types
+
+    from .handler_table import HANDLER_TABLE
+
+    for k, v in vars(obj).items():
+        if k.startswith("_patched_"):
+            raise UnsupportedModelError(f"{label}: method {k[9:]!r} was patched (wsimod/extensions.py:115-119)")
+        if isinstance(v, (types.MethodType, types.FunctionType)) and _foreign(v):
+            raise UnsupportedModelError(f"{label}: attribute {k!r} is a user function; patched behaviour cannot run in the kernels")
+        if isinstance(v, (list, dict)):
+            for f in (v.values() if isinstance(v, dict) else v):
+                if isinstance(f, (types.MethodType, types.FunctionType)) and _foreign(f):
+                    raise UnsupportedModelError(f"{label}: {k!r} holds a user function; patched behaviour cannot run in the kernels")
+    if not (hasattr(obj, "push_set_handler") or hasattr(obj, "inflows") or key.startswith("arc:")) or key not in HANDLER_TABLE:
+        return  # this package's own node classes carry no handlers
+    have = {h: {k: v.__name__ for k, v in getattr(obj, h).items()} for h in _HANDLER_DICTS if hasattr(obj, h)}
+    aliases = {k: v.__name__ for k, v in vars(obj).items() if isinstance(v, types.MethodType)}
+    ok = False
+    for want in HANDLER_TABLE[key]:
+        ok = ok or (all(have.get(h, want.get(h)) == want.get(h) for h in _HANDLER_DICTS) and aliases == want["aliases"])
+    if not ok:
+        raise UnsupportedModelError(f"{label}: handlers / method aliases differ from a pristine {key} ({have}, {aliases})")
+    if hasattr(obj, "inflows"):
+        names = {f.__name__ for lst in ("inflows", "processes", "outflows") for f in getattr(obj, lst)}
+        extra = names - set(HANDLER_TABLE[key][0]["functions"])
+        if extra:
+            raise UnsupportedModelError(f"{label}: function lists hold {sorted(extra)}, not part of a pristine {key}")
+
+
 def _cls(obj):
     name = obj.__class__.__name__
     # QueueGroundwater files itself under its parent's name (storage.py:299)
@@ -421,13 +466,22 @@ def flatten(model, dates, pollutants, additive, non_additive, float_accuracy):
                 f"node {n.name!r} of class {_cls(n)} is outside the GPU hot path "
                 f"(supported: {sorted(SUPPORTED_NODES)})"
             )
+        _check_unpatched(n, _cls(n), f"node {n.name!r}")
+        for s_ in getattr(n, "surfaces", []):
+            _check_unpatched(s_, "surface:" + s_.__class__.__name__, f"surface {s_.surface!r} of {n.name!r}")
+        for k_, v_ in vars(n).items():  # the node's tanks
+            if hasattr(v_, "storage") and hasattr(v_, "capacity") and not isinstance(v_, (list, dict)):
+                _check_unpatched(v_, "tank", f"{k_} of {n.name!r}")
     for a in arcs:
         if _cls(a) not in ARC_CLASSES:
             raise UnsupportedModelError(f"arc {a.name!r} of class {_cls(a)} is not supported (arcs without queues only)")
+        _check_unpatched(a, "arc:" + _cls(a), f"arc {a.name!r}")
         irrigated = _cls(a.out_port) == "Land" and any(_cls(x) == "IrrigationSurface" for x in a.out_port.surfaces)
         if _cls(a.out_port) == "Catchment" or (_cls(a.out_port) == "Land" and _cls(a.in_port) != "Demand" and not irrigated):
             raise UnsupportedModelError(f"arc {a.name!r} pushes into a {_cls(a.out_port)} node")
-        if _cls(a.in_port) == "Land" and _cls(a.out_port) not in ("Sewer", "Groundwater", "QueueGroundwater", "River", "Node", "Waste"):
+        # Land.run only pushes to these types (land.py:200-244); an arc to a plain Storage carries nothing either way
+        # (a Storage never pulls upstream); anything else downstream of a Land could pull through it -- refused
+        if _cls(a.in_port) == "Land" and _cls(a.out_port) not in ("Sewer", "Groundwater", "QueueGroundwater", "River", "Node", "Waste", "Storage"):
             raise UnsupportedModelError(f"arc {a.name!r}: Land only pushes to Sewer / Groundwater / River / Node / Waste")
 
     # ---- graph CSR -----------------------------------------------------------
