@@ -310,8 +310,8 @@ def _check_unpatched(obj, key, label):
             for f in (v.values() if isinstance(v, dict) else v):
                 if isinstance(f, (types.MethodType, types.FunctionType)) and _foreign(f):
                     raise UnsupportedModelError(f"{label}: {k!r} holds a user function; patched behaviour cannot run in the kernels")
-    if not (hasattr(obj, "push_set_handler") or hasattr(obj, "inflows") or key.startswith("arc:")) or key not in HANDLER_TABLE:
-        return  # this package's own node classes carry no handlers
+    if obj.__class__.__module__.startswith("wsi_b200.") or key not in HANDLER_TABLE:
+        return  # this package's own classes carry parameters and state only: no handlers, no method aliases
     have = {h: {k: v.__name__ for k, v in getattr(obj, h).items()} for h in _HANDLER_DICTS if hasattr(obj, h)}
     aliases = {k: v.__name__ for k, v in vars(obj).items() if isinstance(v, types.MethodType)}
     ok = False
