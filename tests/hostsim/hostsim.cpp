@@ -9,6 +9,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+// per-process switch of surface_phase (csrc/wsi_land.cuh WSI_PROC): all on unless a known-answer test says otherwise
+#define WSI_HOSTSIM_PROCESS_MASK
+namespace wsi {
+unsigned g_wsi_process_mask = ~0u;
+}
+extern "C" void wsi_hostsim_process_mask(unsigned mask) { wsi::g_wsi_process_mask = mask; }
+
 #include "../../wsi_b200/csrc/wsi_device.cuh"
 
 using namespace wsi;

@@ -7,6 +7,23 @@
 
 namespace wsi {
 
+// Test hook of the HOST build only (tests/hostsim, -DWSI_HOSTSIM_PROCESS_MASK): which entries of a surface's
+// inflows / processes lists run, so that the reference's per-process known answers (tests/test_land.py:627-1069:
+// one method of a GrowingSurface called on a prepared state) can be reproduced one process at a time through
+// surface_phase.  In every CUDA compilation WSI_PROC(...) is the constant true and folds away.
+#if !defined(__CUDACC__) && defined(WSI_HOSTSIM_PROCESS_MASK)
+extern unsigned g_wsi_process_mask;
+#define WSI_PROC(bit) (((g_wsi_process_mask >> (bit)) & 1u) != 0)
+#else
+#define WSI_PROC(bit) true
+#endif
+enum {
+  WSI_PROC_CROP_COVER = 0, WSI_PROC_DRY_DEPOSITION, WSI_PROC_WET_DEPOSITION, WSI_PROC_SIMPLE_DEPOSITION, WSI_PROC_IHACRES,
+  WSI_PROC_FLUSHING, WSI_PROC_FERTILISER, WSI_PROC_MANURE, WSI_PROC_SOIL_TEMPERATURE, WSI_PROC_TEMPERATURE_FACTOR,
+  WSI_PROC_MOISTURE_FACTOR, WSI_PROC_SOIL_POOL, WSI_PROC_CROP_UPTAKE, WSI_PROC_EROSION, WSI_PROC_DENITRIFICATION,
+  WSI_PROC_ADSORPTION
+};
+
 // vol + additive accumulation used for running_inflow_mb / running_outflow_mb
 // (land.py:441-449): the non-additive lanes of those VQIPs never reach a comparison.
 template <class C>
@@ -125,7 +142,7 @@ WSI_HD void surface_phase(C& c, int u) {
   double days_after_sow = 0.0, crop_cover = 0.0, ground_cover = 0.0, crop_factor_out = 0.0;
 
   // ---- inflows --------------------------------------------------------------------------
-  if (growing) {  // calc_crop_cover land.py:1514-1572
+  if (growing && WSI_PROC(WSI_PROC_CROP_COVER)) {  // calc_crop_cover land.py:1514-1572
     const double doy = (double)c.D().doy_adj[c.t];
     const double dayofyear = (double)c.D().dayofyear[c.t];
     days_after_sow = *S(WSI_SURF_DAYS_AFTER_SOW);
@@ -166,6 +183,7 @@ WSI_HD void surface_phase(C& c, int u) {
     // atmospheric_deposition / precipitation_deposition land.py:528-581 (dry, then wet)
 #pragma unroll
     for (int wet = 0; wet < 2; wet++) {
+      if (!WSI_PROC(wet ? WSI_PROC_WET_DEPOSITION : WSI_PROC_DRY_DEPOSITION)) continue;
       const int b = wet ? WSI_DEP_NHX_WET : WSI_DEP_NHX_DRY;
       const double nhx = c.dep(dep_id, b) * area;
       const double noy = c.dep(dep_id, b + 1) * area;
@@ -196,7 +214,7 @@ WSI_HD void surface_phase(C& c, int u) {
       mb_acc(c, mb_in, v);
     }
   }
-  if (ldp(S(WSI_SURF_HAS_LOAD)) != 0.0) {  // simple_deposition land.py:505-526
+  if (ldp(S(WSI_SURF_HAS_LOAD)) != 0.0 && WSI_PROC(WSI_PROC_SIMPLE_DEPOSITION)) {  // simple_deposition land.py:505-526
     Vq pol;
     pol.x[0] = 0.0;
     const double* lp = S(WSI_SURF_LOAD(V));
@@ -238,6 +256,7 @@ WSI_HD void surface_phase(C& c, int u) {
     const double capacity = ldp(S(WSI_SURF_CAPACITY));
     const double fc_m = ldp(S(WSI_SURF_FIELD_CAPACITY_M));
     const double wp_m = ldp(S(WSI_SURF_WILTING_POINT_M));
+    if (WSI_PROC(WSI_PROC_IHACRES)) {
     double evaporation_depth = et0 * et0_coef;  // get_climate land.py:903-911
     double precip_s = precip;
     if (c.D().features & 2) {  // VariableAreaSurface.get_climate_ land.py:2449-2461 (1 for every other class)
@@ -310,10 +329,11 @@ WSI_HD void surface_phase(C& c, int u) {
     out_recharge = tank_recharge;
     mb_in.x[0] += precipitation;
     mb_out.x[0] += evaporation;
+    }
 
     if (nutrients) {
       // effective_precipitation_flushing land.py:1605-1647
-      {
+      if (WSI_PROC(WSI_PROC_FLUSHING)) {
         const int a = cfg.nh4(), b = cfg.no2(), n3 = cfg.no3();
         double N = vget<P>(sf, a) + vget<P>(sf, b) + vget<P>(sf, n3) + vget<P>(pc, a) + vget<P>(pc, b) +
                    vget<P>(pc, n3) + vget<P>(ie, a) + vget<P>(ie, b) + vget<P>(ie, n3);
@@ -328,6 +348,7 @@ WSI_HD void surface_phase(C& c, int u) {
       // fertiliser land.py:1649-1679, manure land.py:1681-1710
 #pragma unroll
       for (int manure = 0; manure < 2; manure++) {
+        if (!WSI_PROC(manure ? WSI_PROC_MANURE : WSI_PROC_FERTILISER)) continue;
         const int b = manure ? WSI_DEP_NHX_MANURE : WSI_DEP_NHX_FERTILISER;
         const double nhx = c.dep(dep_id, b) * area;
         const double noy = c.dep(dep_id, b + 1) * area;
@@ -359,7 +380,7 @@ WSI_HD void surface_phase(C& c, int u) {
     }
 
     // ---- processes ----------------------------------------------------------------------
-    if (cfg.temp() >= 0) {  // calculate_soil_temperature land.py:1060-1079
+    if (cfg.temp() >= 0 && WSI_PROC(WSI_PROC_SOIL_TEMPERATURE)) {  // calculate_soil_temperature land.py:1060-1079
       const double w_prev = ldp(S(WSI_SURF_SOIL_TEMP_W_PREV)), w_air = ldp(S(WSI_SURF_SOIL_TEMP_W_AIR)),
                    w_deep = ldp(S(WSI_SURF_SOIL_TEMP_W_DEEP));
       const double au = vget<P>(st, cfg.temp()) * w_prev;
@@ -371,14 +392,16 @@ WSI_HD void surface_phase(C& c, int u) {
       const double rooting_depth = ldp(S(WSI_SURF_ROOTING_DEPTH));
       const double soilT = vget<P>(st, cfg.temp());
       // calc_temperature_dependence_factor land.py:1813-1831
-      if (soilT > 5)
+      if (!WSI_PROC(WSI_PROC_TEMPERATURE_FACTOR))
+        pl.tdf = 0.0;
+      else if (soilT > 5)
         pl.tdf = pow(2.0, (soilT - 20) / 10);
       else if (soilT > 0)
         pl.tdf = soilT / 5;
       else
         pl.tdf = 0.0;
       // calc_soil_moisture_dependence_factor land.py:1833-1856
-      {
+      if (WSI_PROC(WSI_PROC_MOISTURE_FACTOR)) {
         const double smc = st.x[0] / area;
         const double satact = ldp(S(WSI_SURF_SATACT));
         if (smc >= fc_m) {
@@ -394,7 +417,7 @@ WSI_HD void surface_phase(C& c, int u) {
         }
       }
       // soil_pool_transformation land.py:1744-1811 + nutrient_pool.py:396-450
-      {
+      if (WSI_PROC(WSI_PROC_SOIL_POOL)) {
         const double sno3 = vget<P>(st, cfg.no3()), snh4 = vget<P>(st, cfg.nh4());
         if (sno3 + snh4 == 0) c.flag((int)*Lo(WSI_LAND_NODE), WSI_FLAG_NAN);
         const double nitrate_proportion = sno3 / (sno3 + snh4);
@@ -442,7 +465,7 @@ WSI_HD void surface_phase(C& c, int u) {
         mb_acc(c, mb_out, out_);
       }
       // calc_crop_uptake land.py:1858-1926
-      if (days_after_sow > 0) {
+      if (days_after_sow > 0 && WSI_PROC(WSI_PROC_CROP_UPTAKE)) {
         double das = days_after_sow;
         double temp_func = 1.0;
         if (ldp(S(WSI_SURF_AUTUMN_SOW)) != 0.0) {
@@ -467,7 +490,7 @@ WSI_HD void surface_phase(C& c, int u) {
         mb_acc(c, mb_out, out_);
       }
       // erosion land.py:1928-2094
-      {
+      if (WSI_PROC(WSI_PROC_EROSION)) {
         const double precipitation_depth = precip * 1e3;  // M_TO_MM
         double mobilised_rain = 0.0, mobilised_flow = 0.0;
         if (precipitation_depth > 5) {
@@ -532,7 +555,7 @@ WSI_HD void surface_phase(C& c, int u) {
         }
       }
       // denitrification land.py:2096-2152
-      {
+      if (WSI_PROC(WSI_PROC_DENITRIFICATION)) {
         const double smc = st.x[0] / area;
         double dep_f = -1.0;
         const double limpar = ldp(S(WSI_SURF_LIMPAR));
@@ -553,7 +576,7 @@ WSI_HD void surface_phase(C& c, int u) {
         }
       }
       // adsorption land.py:2154-2265 (Freundlich isotherm, Newton-Raphson)
-      {
+      if (WSI_PROC(WSI_PROC_ADSORPTION)) {
         const double bulk_density = ldp(S(WSI_SURF_BULK_DENSITY));
         double ad_de_P_pool = pl.ads_inorg[1] + pl.dis_inorg[1];
         ad_de_P_pool /= area * 1e-6;
