@@ -64,11 +64,27 @@ def build_extension(force=False, verbose=False, only_default12=False, defines=()
     then one link.  ``only_default12``: development build with the default pollutant set only."""
     if out is None and not force and is_current():
         return SO
-    from concurrent.futures import ThreadPoolExecutor
+    import fcntl
 
     nvcc = nvcc_path()
     objdir = os.path.join(CSRC, "_obj" if out is None else "_obj_" + os.path.basename(out))
     os.makedirs(objdir, exist_ok=True)
+    # one build at a time per object directory: a second caller (a test session started while build() runs)
+    # waits here instead of rewriting the objects the first one is about to link
+    lock = open(os.path.join(objdir, ".lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if out is None and not force and is_current():
+            return SO
+        return _build_locked(nvcc, objdir, only_default12, defines, verbose, out)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(nvcc, objdir, only_default12, defines, verbose, out):
+    from concurrent.futures import ThreadPoolExecutor
+
     sources = SOURCES[:2] if only_default12 else SOURCES
     extra = (["-DWSI_ONLY_DEFAULT12"] if only_default12 else []) + ["-D" + x for x in defines]
     so = SO if out is None else out
@@ -82,7 +98,8 @@ def build_extension(force=False, verbose=False, only_default12=False, defines=()
 
     with ThreadPoolExecutor(max_workers=len(sources)) as pool:
         objs = list(pool.map(compile_one, sources))
-    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", so] + objs, cwd=CSRC)
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", so + ".tmp"] + objs, cwd=CSRC)
+    os.replace(so + ".tmp", so)  # a reader never sees a half-written library
     return so
 
 
