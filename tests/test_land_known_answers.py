@@ -1,5 +1,5 @@
-"""Known answers of the reference's land tests, surface class by surface class (CPU, host build of the
-kernel headers).  The reference calls one process of one surface (tests/test_land.py); here a Land node
+"""Known answers of the reference's land tests, surface class by surface class (CPU: host build of the
+kernel headers; ``-m gpu``: the CUDA library through the C ABI).  The reference calls one process of one surface (tests/test_land.py); here a Land node
 holding just that surface -- no deposition data, no pollutant load, so that process is the only one that
 acts -- is built through this package's Model API, flattened and stepped once, and the surface's own
 state and flow diagnostics are compared with the reference's expected values."""
@@ -11,8 +11,12 @@ import pandas as pd
 import pytest
 
 
-@pytest.fixture(scope="module")
-def hostsim():
+@pytest.fixture(scope="module", params=["host build", pytest.param("gpu", marks=pytest.mark.gpu)])
+def hostsim(request):
+    """Where the Land is stepped: the host build of the kernel headers (CPU suite), or libwsi_b200.so through the
+    C ABI on cuda:0 (``-m gpu``) -- the same assertions either way."""
+    if request.param == "gpu":
+        return None
     from hostsim.build import build
     from wsi_b200.backend.capi import WsiModelDesc
 
@@ -41,9 +45,17 @@ def _step(hostsim, surface, forcing_rows):
         m.dates = dates
         fm = m.flatten()
         ps = ProbeSet(fm).add_standard()
-        buf = ModelBuffers(fm, device="numpy", probes=ps.probes, rec_t0=0, rec_T=fm.T, record_mb=False, engine="replica")
-        assert hostsim.wsi_hostsim_run(C.byref(buf.desc), 0, fm.T, 0) == 0
-        blocks = ps.split(buf.array("out_probe"))
+        if hostsim is None:
+            from wsi_b200.backend.engine import GpuRunner
+
+            run = GpuRunner(fm, probes=ps.probes, rec_t0=0, rec_T=fm.T, record_mb=False, device="cuda:0")
+            run.run(0, fm.T)
+            run.synchronize()
+            blocks = ps.split(run.out_probe())
+        else:
+            buf = ModelBuffers(fm, device="numpy", probes=ps.probes, rec_t0=0, rec_T=fm.T, record_mb=False, engine="replica")
+            assert hostsim.wsi_hostsim_run(C.byref(buf.desc), 0, fm.T, 0) == 0
+            blocks = ps.split(buf.array("out_probe"))
         order = [fm.pollutants.index(p) + 1 for p in ("phosphate", "temperature")]
         storage = blocks["surf_storage"][:, 0, :, 0][:, [0] + order]  # volume, phosphate, temperature
         out = {k.replace("out_", ""): blocks["surf_out"][:, 0, i, 0] for i, k in enumerate(SURF_OUT)}
