@@ -197,3 +197,44 @@ def test_catchment_route(hostsim):  # tests/test_catchment.py:36-86 (get_flow ca
 
     r = Run(hostsim, [catchment, WASTE], [("a", "c", "waste", {})])
     assert np.array_equal(r.arc("a"), [10, 0.4 * 10, 10])
+
+
+def _two_stores(type_="Storage"):  # tests/test_nodes.py:62-88 get_simple_model2
+    return [{"type_": type_, "name": "1", "capacity": 20, "initial_storage": {"volume": 10, "phosphate": 0.5, "temperature": 15}},
+            {"type_": type_, "name": "2", "capacity": 30, "initial_storage": {"volume": 20, "phosphate": 0.2, "temperature": 12}},
+            {"type_": "Node", "name": "3"}, {"type_": "Node", "name": "4"}]
+
+
+def _two_stores_arcs():
+    return [("arc1", "1", "3", {"preference": 0.75}), ("arc2", "2", "3", {"preference": 1.25}),
+            ("arc3", "4", "1", {"preference": 0.5}), ("arc4", "4", "2", {"preference": 10})]
+
+
+def test_pull_distributed(hostsim):  # tests/test_nodes.py:308-337 (Node.pull_distributed nodes.py:345-407)
+    # the reference calls node3.pull_distributed({"volume": 10}); here a Demand downstream of node 3 pulls 10
+    r = Run(hostsim, _two_stores() + [{"type_": "Demand", "name": "user", "constant_demand": 10}, WASTE],
+            _two_stores_arcs() + [("pull", "3", "user", {}), ("used", "user", "waste", {})])
+    from_1 = 10 * 10 * 0.75 / (10 * 0.75 + 20 * 1.25)
+    from_2 = 10 * 20 * 1.25 / (10 * 0.75 + 20 * 1.25)
+    assert r.arc("arc1") == pytest.approx([from_1, 0.5 * from_1 / 10, 15], abs=1e-14)
+    assert r.arc("arc2") == pytest.approx([from_2, 0.2 * from_2 / 20, 12], abs=1e-14)
+    assert r.arc("pull") == pytest.approx([10, 0.5 * from_1 / 10 + 0.2 * from_2 / 20, (15 * from_1 + 12 * from_2) / 10], abs=1e-14)
+
+
+def test_push_distributed(hostsim):  # tests/test_nodes.py:339-354 (Node.push_distributed nodes.py:409-478)
+    # the reference calls node4.push_distributed({15, 0.01, 12}) with no of_type; here a Demand upstream of node 4
+    # discharges it, and a junction's own push handler forwards to Node / River / Waste / Reservoir only
+    # (nodes.py:62-71), so the two stores are Reservoirs (same push handlers as a Storage, storage.py:60-76)
+    r = Run(hostsim, _two_stores("Reservoir") + [{"type_": "Demand", "name": "src", "constant_demand": 15,
+                                                  "pollutant_load": {"phosphate": 0.01, "temperature": 12}}],
+            _two_stores_arcs() + [("push", "src", "4", {})])
+    assert np.array_equal(r.arc("push"), [15, 0.01, 12])  # nothing handed back
+    # "distributing is iterative so these won't be perfect" (the reference asserts 14 places)
+    assert r.arc("arc4") == pytest.approx([10, 0.01 * 2 / 3, 12], abs=1e-14)
+    assert r.arc("arc3") == pytest.approx([5, 0.01 / 3, 12], abs=1e-14)
+
+
+def test_junction_does_not_forward_to_a_storage(hostsim):  # nodes.py:62-71: of_type of a junction's default push handlers
+    r = Run(hostsim, _two_stores() + [{"type_": "Demand", "name": "src", "constant_demand": 15, "pollutant_load": {"phosphate": 0.01, "temperature": 12}}],
+            _two_stores_arcs() + [("push", "src", "4", {})])
+    assert not r.flows.any()
