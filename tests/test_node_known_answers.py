@@ -238,3 +238,16 @@ def test_junction_does_not_forward_to_a_storage(hostsim):  # nodes.py:62-71: of_
     r = Run(hostsim, _two_stores() + [{"type_": "Demand", "name": "src", "constant_demand": 15, "pollutant_load": {"phosphate": 0.01, "temperature": 12}}],
             _two_stores_arcs() + [("push", "src", "4", {})])
     assert not r.flows.any()
+
+
+def test_arc_capacity_is_per_timestep(hostsim):  # tests/test_arcs.py:57-88 (Arc.send_push_request / get_excess arcs.py:112-257)
+    # the reference pushes {10, 0.0001, 15} twice into an arc of capacity 10: the first travels, the second is handed
+    # back whole; here two Demands discharge into the junction upstream of that arc, one after the other
+    load = {"phosphate": 0.0001, "temperature": 15}
+    r = Run(hostsim, [{"type_": "Demand", "name": "first", "constant_demand": 10, "pollutant_load": load},
+                      {"type_": "Demand", "name": "second", "constant_demand": 10, "pollutant_load": load},
+                      {"type_": "Node", "name": "1"}, {"type_": "Waste", "name": "2"}],
+            [("f", "first", "1", {}), ("s", "second", "1", {}), ("arc1", "1", "2", {"capacity": 10})])
+    assert np.array_equal(r.arc("arc1"), [10, 0.0001, 15])
+    assert np.array_equal(r.arc("f"), [10, 0.0001, 15])
+    assert not r.arc("s").any()
