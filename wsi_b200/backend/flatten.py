@@ -297,6 +297,8 @@ def _check_unpatched(obj, key, label):
     methods, replaced handler / list items), user functions assigned as methods or put into the handler
     dicts or a surface's inflows / processes / outflows lists, and handler dicts re-pointed at another
     reference method.  ``key`` indexes handler_table.HANDLER_TABLE (what a pristine object carries)."""
+    if obj.__class__.__module__.startswith("wsi_b200."):
+        return  # this package's own classes carry parameters and state only: there is no behaviour to patch
     import types
 
     from .handler_table import HANDLER_TABLE
@@ -310,8 +312,8 @@ def _check_unpatched(obj, key, label):
             for f in (v.values() if isinstance(v, dict) else v):
                 if isinstance(f, (types.MethodType, types.FunctionType)) and _foreign(f):
                     raise UnsupportedModelError(f"{label}: {k!r} holds a user function; patched behaviour cannot run in the kernels")
-    if obj.__class__.__module__.startswith("wsi_b200.") or key not in HANDLER_TABLE:
-        return  # this package's own classes carry parameters and state only: no handlers, no method aliases
+    if key not in HANDLER_TABLE:
+        return  # tanks, nutrient pools: the scan above is the whole check
     have = {h: {k: v.__name__ for k, v in getattr(obj, h).items()} for h in _HANDLER_DICTS if hasattr(obj, h)}
     aliases = {k: v.__name__ for k, v in vars(obj).items() if isinstance(v, types.MethodType)}
     ok = False
