@@ -251,3 +251,20 @@ def test_arc_capacity_is_per_timestep(hostsim):  # tests/test_arcs.py:57-88 (Arc
     assert np.array_equal(r.arc("arc1"), [10, 0.0001, 15])
     assert np.array_equal(r.arc("f"), [10, 0.0001, 15])
     assert not r.arc("s").any()
+
+
+def test_wwtw_treatment(hostsim):  # tests/test_wtw.py:42-70 (WTW.treat_current_input wtw.py:112-160) through a WWTW
+    from wsi_b200.core import constants
+    from wsi_b200.nodes.wtw import WWTW
+
+    ref_t = constants.DECAY_REFERENCE_TEMPERATURE
+    par = WWTW(name="probe", treatment_throughput_capacity=10)
+    pp, lm = par.process_parameters, par.liquor_multiplier
+    r = Run(hostsim, [{"type_": "Demand", "name": "town", "constant_demand": 8, "pollutant_load": {"phosphate": 5, "temperature": ref_t}},
+                      {"type_": "WWTW", "name": "works", "treatment_throughput_capacity": 10}, WASTE],
+            [("in", "town", "works", {}), ("out", "works", "waste", {})])
+    assert np.array_equal(r.arc("in"), [8, 5, ref_t])
+    # at the reference temperature the exponent term of every process parameter is 1 (wtw.py:138-146)
+    assert r.arc("out") == pytest.approx([8 * pp["volume"]["constant"], 5 * pp["phosphate"]["constant"], ref_t], rel=1e-15)
+    # the liquor (what goes back to the head of the works) as the reference's test expects it
+    assert r.field("works", "liquor_")[:2] == pytest.approx([8 * lm["volume"], 5 * lm["phosphate"]], rel=1e-15)
