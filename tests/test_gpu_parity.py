@@ -518,3 +518,33 @@ def test_cluster_tail_kernel_bitwise(monkeypatch):
         launches.append(int(res.stdout.strip().splitlines()[-1]))
     assert np.array_equal(outs[0], outs[1])
     assert launches[1] < launches[0]  # fewer, fatter launches
+
+
+@pytest.mark.parametrize("name, R, T", [("oxford", 16384, 120), ("city", 8192, 96), ("distribution", 32768, 120)])
+def test_pull_side_models_replicated_are_member_independent(name, R, T):
+    """The models with the pull side, treatment works, demand and distribution (the schedule kernel's full
+    instantiation) as ensembles of thousands of identical members -- the four-launch sequence of large
+    ensembles: every member must reproduce, bit for bit, what the model gives when it runs alone (flows,
+    status flags), and that run is the one compared with the reference in test_golden_parity."""
+    from wsi_b200.backend.engine import GpuRunner
+    from wsi_b200.backend.probes import ProbeSet
+
+    fm1, _ = load_golden(name)
+    T = min(T, fm1.T)
+    ps1 = ProbeSet(fm1).add_flows()
+    alone = GpuRunner(fm1, probes=ps1.probes, rec_t0=0, rec_T=T)
+    alone.run(0, T)
+    alone.synchronize()
+    expect = alone.out_probe()[:T]  # [T, n_probe, 1]
+
+    fm = fm1.replicate(R)
+    ps = ProbeSet(fm).add_flows()
+    run = GpuRunner(fm, probes=ps.probes, rec_t0=0, rec_T=T)
+    run.run(0, T)
+    run.synchronize()
+    out = run.out_probe()[:T]
+    assert np.isfinite(out).all() and np.abs(expect).max() > 0
+    assert np.array_equal(out, np.broadcast_to(expect, out.shape))
+    flags = run.node_flags().reshape(len(fm.node_names), R)
+    assert np.array_equal(flags, np.broadcast_to(alone.node_flags().reshape(-1, 1), flags.shape))
+    assert np.array_equal(run.mb_count()[:T], alone.mb_count()[:T] * R)
