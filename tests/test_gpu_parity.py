@@ -39,16 +39,18 @@ def test_golden_parity(name):
 
 @pytest.mark.parametrize("name", ["quickstart", "fixture3607", "config2", "rivernet", "oxford", "city", "reservoirs", "irrigation"])
 def test_large_ensemble_launch_sequence_on_goldens(name, monkeypatch):
-    """Ensembles beyond WSI_B200_FUSED_TAIL_MAX_R members (default 4096) run mass balance and end_timestep
-    in wsi_settle_kernel, one thread per (node, member), instead of the schedule kernel's fused tail
-    (DESIGN.md 2a).  Forcing that launch sequence on the goldens puts the settle kernel under the same
-    parity as everything else: flows, stores and every node's (in, ds, out) against the reference, and
-    violation counts, status flags and system totals against the fused sequence."""
+    """Mass balance and end_timestep run in wsi_settle_kernel, one thread per (node, member); ensembles of up
+    to WSI_B200_FUSED_TAIL_MAX_R members (default 0: none) would run them in the schedule kernel's fused tail
+    instead.  Forcing each launch sequence in turn puts both under the same parity: flows,
+    stores and every node's (in, ds, out) against the reference, and violation counts, status flags and
+    system totals of one sequence against the other."""
     from wsi_b200.backend.probes import ProbeSet
 
     fm, ref = load_golden(name)
     ps = ProbeSet(fm).add_standard()
+    monkeypatch.setenv("WSI_B200_FUSED_TAIL_MAX_R", "1000000")
     fused = _run_gpu(fm, ps, chunks=2)
+    assert compare_blocks(ps.split(fused.out_probe()), ref, fm)[0]
     monkeypatch.setenv("WSI_B200_FUSED_TAIL_MAX_R", "0")
     settle = _run_gpu(fm, ps, chunks=2)
     ok, reports = compare_blocks(ps.split(settle.out_probe()), ref, fm)

@@ -34,11 +34,13 @@ bool cluster_enabled() {
 }
 
 // Replicas up to which the schedule kernel runs mass balance and end_timestep itself (two launches per step)
-// instead of handing them to wsi_settle_kernel.  WSI_B200_FUSED_TAIL_MAX_R overrides the
-// measured default -- the tests use it to run small models through the large-ensemble path.
+// instead of handing them to wsi_settle_kernel.  Default 0 = never: one thread per (node,
+// replica) beats one thread walking a replica's nodes at every ensemble size measured, a single model included
+// (profiles/r02_fused_tail_threshold.md: 35-45 % of the step at R = 1 ... 4096).  WSI_B200_FUSED_TAIL_MAX_R
+// overrides it -- the tests use it to put the fused sequence under the same parity.
 int fused_tail_max_r() {
   const char* e = getenv("WSI_B200_FUSED_TAIL_MAX_R");
-  return e && e[0] ? atoi(e) : 4096;
+  return e && e[0] ? atoi(e) : 0;
 }
 
 }  // namespace wsi_host
