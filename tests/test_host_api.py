@@ -477,3 +477,18 @@ print('refused all')
 """
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "refused all" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.reference
+def test_handler_table_is_current():
+    """backend/handler_table.py (what a pristine reference object carries) is what tools/gen_handler_table.py
+    derives from the mounted reference."""
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.path.insert(0, '/root/repo/tools'); sys.dont_write_bytecode = True\n"
+            "import gen_handler_table as G\n"
+            "from wsi_b200.backend.handler_table import HANDLER_TABLE\n"
+            "assert G.build_table() == HANDLER_TABLE\nprint('current')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "current" in r.stdout, r.stdout + r.stderr
